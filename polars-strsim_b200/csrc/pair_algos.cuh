@@ -1,0 +1,199 @@
+// pair_algos.cuh -- per-pair bit-parallel cores of the five measures.
+//
+// Every function here is `__host__ __device__` and free of memory-space assumptions: the position
+// masks of one string ("PM": codepoint -> bitmask of the positions where it occurs) and the
+// character streams are supplied by small functor/reader types.  On the device those are backed by
+// per-thread shared-memory slabs (short_kernel.cuh); in tests/test_pair_algos.py the same templates
+// are compiled for the host and checked against the oracle, so the arithmetic is validated without
+// a GPU.
+//
+// Behavioural contract: /root/reference/src/expressions/strsim.rs (lines cited per function) as
+// restated in SURVEY.md section 9.  All integer intermediates are exact; all f64 operations are
+// single IEEE-754 round-to-nearest operations in the reference's order, never contracted to FMA.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SS_HD __host__ __device__ __forceinline__
+#else
+#define SS_HD inline
+#endif
+
+namespace strsim {
+
+enum Measure : int {
+    LEVENSHTEIN = 0,
+    JARO = 1,
+    JARO_WINKLER = 2,
+    JACCARD = 3,
+    SORENSEN_DICE = 4,
+};
+
+// flags reported in the debug record (same convention as oracle/strsim_oracle.c)
+enum Flag : int { F_GENERAL = 0, F_EQUAL = 1, F_ONE_EMPTY = 2, F_SINGLE_CHAR = 3 };
+
+struct PairInts {
+    int flag, la, lb, x0, x1, x2;
+};
+
+// ---- f64 helpers: one rounding per written operation -------------------------------------------
+SS_HD double f_div(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __ddiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+SS_HD double f_add(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+SS_HD double f_sub(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+SS_HD double f_mul(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+
+// ---- bit helpers --------------------------------------------------------------------------------
+SS_HD int popc(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+SS_HD int popc(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return __popcll(x);
+#else
+    return __builtin_popcountll(x);
+#endif
+}
+
+// bits lo..hi inclusive (0 <= lo, hi < bits(M)); empty when lo > hi
+template <class M>
+SS_HD M mask_range(int lo, int hi) {
+    if (lo > hi) return M(0);
+    M upto_hi = (M(2) << hi) - M(1);  // hi == bits-1 wraps to all ones
+    M below_lo = (M(1) << lo) - M(1);
+    return upto_hi & ~below_lo;
+}
+
+// ---- final f64 formulas (reference order) --------------------------------------------------------
+// strsim.rs:160
+SS_HD double lev_value(int d, int la, int lb) {
+    int mx = la > lb ? la : lb;
+    return f_sub(1.0, f_div((double)d, (double)mx));
+}
+// strsim.rs:238-243 (m > 0); t/2 is the integer floor
+SS_HD double jaro_value(int m, int t, int la, int lb) {
+    double dm = (double)m;
+    double s = f_add(f_div(dm, (double)la), f_div(dm, (double)lb));
+    s = f_add(s, f_div((double)(m - t / 2), dm));
+    return f_div(s, 3.0);
+}
+// strsim.rs:260-270
+SS_HD double winkler_value(double js, int l) {
+    return f_add(js, f_mul(f_mul((double)l, 0.1), f_sub(1.0, js)));
+}
+// strsim.rs:306
+SS_HD double jaccard_value(int inter, int uni) { return f_div((double)inter, (double)uni); }
+// strsim.rs:343
+SS_HD double dice_value(int inter, int total) {
+    return f_div(f_mul(2.0, (double)inter), (double)total);
+}
+
+// ---- Levenshtein: Myers / Hyyro bit-parallel, single word ---------------------------------------
+// Unit-cost edit distance between a pattern of m <= bits(M) codepoints (described by `pm`) and a
+// text of n codepoints streamed from `text`.  Equals the two-row DP of strsim.rs:141-159.
+template <class M, class PM, class Text>
+SS_HD int myers_single_word(const PM& pm, int m, Text& text, int n) {
+    if (m == 0) return n;
+    M Pv = ~M(0), Mv = M(0);
+    int score = m;
+    const int top = m - 1;
+    for (int j = 0; j < n; j++) {
+        M Eq = pm(text.next());
+        M Xv = Eq | Mv;
+        M Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+        M Ph = Mv | ~(Xh | Pv);
+        M Mh = Pv & Xh;
+        score += (int)((Ph >> top) & M(1)) - (int)((Mh >> top) & M(1));
+        Ph = (Ph << 1) | M(1);
+        Mh = Mh << 1;
+        Pv = Mh | ~(Xv | Ph);
+        Mv = Ph & Xv;
+    }
+    return score;
+}
+
+// ---- Jaro: greedy windowed matching on bitmasks --------------------------------------------------
+// `pmb` describes b (lb <= bits(M)); a (la <= bits(M)) is streamed twice (match pass, then the
+// transposition pass).  Reproduces strsim.rs:200-237 exactly: a is the outer sequence, the first
+// unflagged equal position of b inside [i-bound, min(i+bound, lb-1)] is taken.
+template <class M, class PM, class TextA>
+SS_HD void jaro_match(const PM& pmb, TextA& a_first, TextA& a_second, int la, int lb, int& m_out,
+                      int& t_out) {
+    int mx = la > lb ? la : lb;
+    int bound = mx / 2 - 1;  // strsim.rs:200 (mx >= 2 here)
+    int outer = la < lb + bound ? la : lb + bound;
+    M flag_a = M(0), flag_b = M(0);
+    int m = 0;
+    for (int i = 0; i < outer; i++) {
+        uint32_t c = a_first.next();
+        int lo = i - bound;
+        if (lo < 0) lo = 0;
+        int hi = i + bound;
+        if (hi > lb - 1) hi = lb - 1;
+        M cand = pmb(c) & mask_range<M>(lo, hi) & ~flag_b;
+        if (cand) {
+            flag_b |= cand & (M(0) - cand);  // lowest candidate
+            flag_a |= M(1) << i;
+            m++;
+        }
+    }
+    // strsim.rs:220-237: k-th flagged char of a vs k-th flagged char of b
+    int t = 0;
+    M fb = flag_b;
+    for (int i = 0; i < outer && fb; i++) {
+        uint32_t c = a_second.next();
+        if ((flag_a >> i) & M(1)) {
+            M low = fb & (M(0) - fb);
+            fb ^= low;
+            if (!(pmb(c) & low)) t++;
+        }
+    }
+    m_out = m;
+    t_out = t;
+}
+
+// ---- character multiset intersection --------------------------------------------------------------
+// inter = sum_c min(count_a(c), count_b(c)) (strsim.rs:297-305): each character of a consumes one
+// not-yet-consumed equal character of b.
+template <class M, class PM, class TextA>
+SS_HD int multiset_intersection(const PM& pmb, TextA& a, int la) {
+    M used = M(0);
+    int inter = 0;
+    for (int i = 0; i < la; i++) {
+        M cand = pmb(a.next()) & ~used;
+        if (cand) {
+            used |= cand & (M(0) - cand);
+            inter++;
+        }
+    }
+    return inter;
+}
+
+}  // namespace strsim

@@ -1,0 +1,62 @@
+// Host build of the product's per-pair templates (polars-strsim_b200/csrc/row_short.cuh) so that
+// tests/test_pair_algos.py can check them against the oracle without a GPU.  Test code only.
+#include <cstdint>
+#include <cstring>
+
+#include "row_short.cuh"
+
+using namespace strsim;
+
+template <class M>
+struct HostStore {
+    static constexpr int CAP = (int)sizeof(M) * 8;
+    M table[128];
+    uint32_t cps[2 * CAP];
+    uint32_t a_words[CAP / 4], b_words[CAP / 4];
+    M& tab(uint32_t c) { return table[c]; }
+    const M& tab(uint32_t c) const { return table[c]; }
+    uint32_t& cp(int s) { return cps[s]; }
+    const uint32_t& cp(int s) const { return cps[s]; }
+    uint32_t wa(int k) const { return a_words[k]; }
+    uint32_t wb(int k) const { return b_words[k]; }
+};
+
+template <class M>
+static int run(int measure, const uint8_t* a, int na, const uint8_t* b, int nb, int force_unicode,
+               int* ints, double* value) {
+    static thread_local HostStore<M> s;  // table must stay all-zero between rows
+    if (na > HostStore<M>::CAP || nb > HostStore<M>::CAP) return -2;
+    std::memset(s.a_words, 0, sizeof s.a_words);
+    std::memset(s.b_words, 0, sizeof s.b_words);
+    std::memcpy(s.a_words, a, na);
+    std::memcpy(s.b_words, b, nb);
+    bool equal = na == nb && std::memcmp(a, b, na) == 0;
+    bool ascii = !force_unicode;
+    for (int i = 0; i < na; i++) ascii = ascii && a[i] < 0x80;
+    for (int i = 0; i < nb; i++) ascii = ascii && b[i] < 0x80;
+    PairInts pi;
+    *value = row_short<M>(measure, s, na, nb, equal, ascii, pi);
+    ints[0] = pi.flag; ints[1] = pi.la; ints[2] = pi.lb; ints[3] = pi.x0; ints[4] = pi.x1; ints[5] = pi.x2;
+    for (int c = 0; c < 128; c++)
+        if (s.table[c] != 0) return -1;  // invariant broken
+    return 0;
+}
+
+extern "C" int algos_row(int measure, int bits, const uint8_t* a, int na, const uint8_t* b, int nb,
+                         int force_unicode, int* ints, double* value) {
+    return bits == 32 ? run<uint32_t>(measure, a, na, b, nb, force_unicode, ints, value)
+                      : run<uint64_t>(measure, a, na, b, nb, force_unicode, ints, value);
+}
+
+// batch form: concatenated bytes + offsets; returns the number of rows whose invariant broke
+extern "C" int algos_batch(int measure, int bits, int64_t n, const uint8_t* ad, const int64_t* ao,
+                           const uint8_t* bd, const int64_t* bo, int force_unicode, int* ints,
+                           double* values) {
+    int bad = 0;
+    for (int64_t r = 0; r < n; r++) {
+        int rc = algos_row(measure, bits, ad + ao[r], (int)(ao[r + 1] - ao[r]), bd + bo[r],
+                           (int)(bo[r + 1] - bo[r]), force_unicode, ints + 6 * r, values + r);
+        if (rc != 0) bad++;
+    }
+    return bad;
+}

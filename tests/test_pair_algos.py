@@ -1,0 +1,96 @@
+"""Host-side check of the product's per-pair templates (csrc/pair_algos.cuh, csrc/row_short.cuh).
+
+The same templates the CUDA kernels instantiate are compiled for the host by
+tests/host_harness/pair_algos_host.cpp and compared with the oracle: integer intermediates and f64
+bits must be identical.  CPU only -- this validates the bit-parallel arithmetic before any GPU time.
+"""
+import ctypes
+import random
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from test_oracle import load_fixture, rand_pair
+
+ROOT = Path(__file__).resolve().parent.parent
+HARNESS = ROOT / "tests" / "host_harness"
+
+
+@pytest.fixture(scope="module")
+def algos():
+    so = HARNESS / "libpair_algos_host.so"
+    srcs = [HARNESS / "pair_algos_host.cpp", ROOT / "polars-strsim_b200/csrc/row_short.cuh",
+            ROOT / "polars-strsim_b200/csrc/pair_algos.cuh"]
+    if not so.exists() or so.stat().st_mtime < max(s.stat().st_mtime for s in srcs):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++",
+                        f"-I{ROOT / 'polars-strsim_b200/csrc'}", "-o", str(so), str(srcs[0])], check=True)
+    L = ctypes.CDLL(str(so))
+    L.algos_batch.restype = ctypes.c_int
+    L.algos_batch.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int64] + [ctypes.c_void_p] * 4 + \
+        [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    return L
+
+
+def run_batch(L, oracle, measure, bits, a, b, force_unicode=False):
+    from oracle.oracle import _pack, MEASURE_ID
+
+    ad, ao, _ = _pack(a)
+    bd, bo, _ = _pack(b)
+    n = len(a)
+    ints = np.zeros((n, 6), dtype=np.int32)
+    vals = np.zeros(n, dtype=np.float64)
+    bad = L.algos_batch(MEASURE_ID[measure], bits, n, ad.ctypes.data, ao.ctypes.data, bd.ctypes.data,
+                        bo.ctypes.data, int(force_unicode), ints.ctypes.data, vals.ctypes.data)
+    assert bad == 0, "PM table not restored to zero / length over capacity"
+    ref, _, ref_ints = oracle.batch(measure, a, b)
+    mism = np.nonzero(vals.view(np.uint64) != ref.view(np.uint64))[0]
+    assert mism.size == 0, (measure, bits, a[mism[0]], b[mism[0]], vals[mism[0]], ref[mism[0]])
+    imism = np.nonzero((ints != ref_ints).any(axis=1))[0]
+    assert imism.size == 0, (measure, bits, a[imism[0]], b[imism[0]], ints[imism[0]], ref_ints[imism[0]])
+
+
+@pytest.mark.parametrize("bits", [32, 64])
+@pytest.mark.parametrize("force_unicode", [False, True])
+def test_reference_vectors(algos, oracle, bits, force_unicode):
+    fx = load_fixture()
+    for measure in oracle.MEASURES:
+        rows = [r for r in fx if r[0] == measure]
+        run_batch(algos, oracle, measure, bits, [r[1] for r in rows], [r[2] for r in rows], force_unicode)
+
+
+@pytest.mark.parametrize("bits", [32, 64])
+def test_random_pairs(algos, oracle, bits):
+    rng = random.Random(99 + bits)
+    a, b = [], []
+    while len(a) < 40000:
+        x, y = rand_pair(rng, bits)
+        if len(x.encode()) <= bits and len(y.encode()) <= bits:
+            a.append(x)
+            b.append(y)
+    for measure in oracle.MEASURES:
+        run_batch(algos, oracle, measure, bits, a, b)
+        run_batch(algos, oracle, measure, bits, a[:8000], b[:8000], force_unicode=True)
+
+
+@pytest.mark.parametrize("bits", [32, 64])
+def test_boundary_lengths(algos, oracle, bits):
+    """exactly-full words, empty sides, single characters, 1-4 byte UTF-8"""
+    rng = random.Random(5)
+    a, b = [], []
+    for la in (0, 1, 2, bits - 1, bits):
+        for lb in (0, 1, 2, bits - 1, bits):
+            for _ in range(40):
+                a.append("".join(rng.choice("abc") for _ in range(la)))
+                b.append("".join(rng.choice("abc") for _ in range(lb)))
+    for ch in ("é", "日", "\U0001f600"):
+        w = len(ch.encode())
+        for la in (1, 2, bits // w):
+            for lb in (1, 2, bits // w):
+                a.append(ch * la)
+                b.append((ch * lb)[:-1] + "x" if lb > 1 else ch)
+                a.append(ch * la)
+                b.append("x" * lb)
+    for measure in oracle.MEASURES:
+        run_batch(algos, oracle, measure, bits, a, b)
