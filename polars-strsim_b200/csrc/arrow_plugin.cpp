@@ -1,0 +1,359 @@
+// arrow_plugin.cpp -- Arrow C Data Interface front end and the Polars plugin symbols.
+//
+// Replaces what `#[polars_expr(output_type=Float64)]` generates around the five functions of
+// /root/reference/src/expressions/mod.rs:8-31 (pyo3-polars-derive 0.11.0 on polars-ffi 0.43.1
+// `version_0`, Cargo.lock:588-589,874-875): `_polars_plugin_<name>`, `_polars_plugin_field_<name>`,
+// `_polars_plugin_get_last_error_message`, `_polars_plugin_get_version`.  Pure C++ (no CUDA here);
+// all compute goes through strsim_b200_compute_host().
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/strsim_b200.h"
+
+extern "C" void strsim_set_error(const char* fmt, ...);
+
+// ---- Arrow C Data Interface (stable ABI, https://arrow.apache.org/docs/format/CDataInterface.html)
+extern "C" {
+struct ArrowSchema {
+    const char* format;
+    const char* name;
+    const char* metadata;
+    int64_t flags;
+    int64_t n_children;
+    struct ArrowSchema** children;
+    struct ArrowSchema* dictionary;
+    void (*release)(struct ArrowSchema*);
+    void* private_data;
+};
+struct ArrowArray {
+    int64_t length;
+    int64_t null_count;
+    int64_t offset;
+    int64_t n_buffers;
+    int64_t n_children;
+    const void** buffers;
+    struct ArrowArray** children;
+    struct ArrowArray* dictionary;
+    void (*release)(struct ArrowArray*);
+    void* private_data;
+};
+}
+#define ARROW_FLAG_NULLABLE 2
+
+namespace {
+
+enum Layout { L_VIEW, L_OFFSET32, L_OFFSET64, L_BAD };
+
+Layout layout_of(const char* fmt) {
+    if (!fmt) return L_BAD;
+    if (!strcmp(fmt, "vu") || !strcmp(fmt, "vz")) return L_VIEW;
+    if (!strcmp(fmt, "u") || !strcmp(fmt, "z")) return L_OFFSET32;
+    if (!strcmp(fmt, "U") || !strcmp(fmt, "Z")) return L_OFFSET64;
+    return L_BAD;
+}
+
+// One input column as chunks of views; owns the views it had to synthesise for Utf8/LargeUtf8.
+struct Column {
+    std::vector<strsim_view_chunk> chunks;
+    std::vector<std::vector<int32_t>> synthesized;  // 4 int32 per view
+    std::vector<std::vector<const void*>> buf_ptrs;
+    std::vector<std::vector<int64_t>> buf_sizes;
+};
+
+int column_from_arrow(const char* format, const ArrowArray* const* arrays, size_t n, Column& col) {
+    const Layout lay = layout_of(format);
+    if (lay == L_BAD) {
+        strsim_set_error("invalid series dtype: expected `String`, got Arrow format `%s`",
+                         format ? format : "(null)");
+        return STRSIM_ERR_DTYPE;
+    }
+    col.chunks.resize(n);
+    col.synthesized.resize(n);
+    col.buf_ptrs.resize(n);
+    col.buf_sizes.resize(n);
+    for (size_t i = 0; i < n; i++) {
+        const ArrowArray* a = arrays[i];
+        strsim_view_chunk& ch = col.chunks[i];
+        memset(&ch, 0, sizeof ch);
+        ch.length = a->length;
+        if (lay == L_VIEW) {
+            // buffers: [validity, views, data_0 .. data_{V-1}, sizes(int64[V])]
+            if (a->n_buffers < 2) {
+                strsim_set_error("Utf8View chunk %zu has %lld buffers", i, (long long)a->n_buffers);
+                return STRSIM_ERR_ARGUMENT;
+            }
+            const int64_t V = a->n_buffers >= 3 ? a->n_buffers - 3 : 0;
+            ch.validity = static_cast<const uint8_t*>(a->buffers[0]);
+            ch.views = a->buffers[1];
+            ch.offset = a->offset;
+            ch.n_data_buffers = V;
+            ch.data_buffers = V ? reinterpret_cast<const void* const*>(a->buffers + 2) : nullptr;
+            ch.data_buffer_sizes = V ? static_cast<const int64_t*>(a->buffers[2 + V]) : nullptr;
+        } else {
+            // Utf8 / LargeUtf8: [validity, offsets, data] -> synthesise views over the data buffer
+            const uint8_t* data = static_cast<const uint8_t*>(a->buffers[2]);
+            std::vector<int32_t>& views = col.synthesized[i];
+            views.assign(4 * (size_t)a->length, 0);
+            int64_t first = 0, last = 0;
+            for (int64_t r = 0; r < a->length; r++) {
+                int64_t lo, hi;
+                if (lay == L_OFFSET32) {
+                    const int32_t* off = static_cast<const int32_t*>(a->buffers[1]) + a->offset;
+                    lo = off[r];
+                    hi = off[r + 1];
+                } else {
+                    const int64_t* off = static_cast<const int64_t*>(a->buffers[1]) + a->offset;
+                    lo = off[r];
+                    hi = off[r + 1];
+                }
+                if (r == 0) first = lo;
+                last = hi;
+                const int64_t len = hi - lo;
+                int32_t* v = &views[4 * (size_t)r];
+                v[0] = (int32_t)len;
+                if (len <= 12) {
+                    memcpy(v + 1, data + lo, (size_t)len);
+                } else {
+                    if (lo - first > 0x7FFFFFFFll || len > 0x7FFFFFFFll) {
+                        strsim_set_error("offset-based string chunk exceeds 2 GiB; rechunk the column");
+                        return STRSIM_ERR_ARGUMENT;
+                    }
+                    memcpy(v + 1, data + lo, 4);
+                    v[2] = 0;
+                    v[3] = (int32_t)(lo - first);
+                }
+            }
+            col.buf_ptrs[i].assign(1, data ? data + first : nullptr);
+            col.buf_sizes[i].assign(1, last - first);
+            ch.views = views.data();
+            ch.offset = 0;
+            // validity keeps the array offset; express it by pointing `validity` at the right byte
+            // and folding the bit remainder into a views-neutral offset is not possible, so copy
+            // the logical bits when an offset is present
+            ch.validity = static_cast<const uint8_t*>(a->buffers[0]);
+            if (ch.validity && a->offset) {
+                std::vector<int32_t>& store = col.synthesized[i];
+                const size_t base = store.size();
+                store.resize(base + (size_t)((a->length + 31) / 32) + 1, 0);
+                uint8_t* bits = reinterpret_cast<uint8_t*>(&store[base]);
+                for (int64_t r = 0; r < a->length; r++) {
+                    const int64_t s = a->offset + r;
+                    if ((ch.validity[s >> 3] >> (s & 7)) & 1) bits[r >> 3] |= (uint8_t)(1u << (r & 7));
+                }
+                ch.views = store.data();  // vector may have reallocated
+                ch.validity = bits;
+            }
+            ch.n_data_buffers = 1;
+            ch.data_buffers = col.buf_ptrs[i].data();
+            ch.data_buffer_sizes = col.buf_sizes[i].data();
+        }
+    }
+    return STRSIM_OK;
+}
+
+// ---- Float64 result array --------------------------------------------------------------------------
+struct ResultPrivate {
+    double* values;
+    uint8_t* validity;
+    const void* buffers[2];
+};
+
+void release_result(ArrowArray* a) {
+    if (!a || !a->release) return;
+    ResultPrivate* p = static_cast<ResultPrivate*>(a->private_data);
+    free(p->values);
+    free(p->validity);
+    delete p;
+    a->release = nullptr;
+}
+
+int compute_to_arrow(int measure, const Column& ca, const Column& cb, ArrowArray* out) {
+    int64_t la = 0, lb = 0;
+    for (const auto& c : ca.chunks) la += c.length;
+    for (const auto& c : cb.chunks) lb += c.length;
+    if (la != lb && la != 1 && lb != 1) {
+        strsim_set_error("Inputs must have the same length, or one of them must be a Utf8 literal.");
+        return STRSIM_ERR_SHAPE;
+    }
+    const int64_t n = la == 1 ? lb : la;
+    ResultPrivate* p = new (std::nothrow) ResultPrivate();
+    if (!p) return STRSIM_ERR_NOMEM;
+    p->values = static_cast<double*>(malloc(8 * (size_t)(n > 0 ? n : 1)));
+    p->validity = static_cast<uint8_t*>(calloc((size_t)((n + 7) / 8) + 8, 1));
+    if (!p->values || !p->validity) {
+        free(p->values);
+        free(p->validity);
+        delete p;
+        strsim_set_error("out of host memory for %lld results", (long long)n);
+        return STRSIM_ERR_NOMEM;
+    }
+    int64_t nulls = 0;
+    int rc = strsim_b200_compute_host(measure, ca.chunks.data(), ca.chunks.size(), cb.chunks.data(),
+                                      cb.chunks.size(), p->values, p->validity, &nulls, nullptr);
+    if (rc != STRSIM_OK) {
+        free(p->values);
+        free(p->validity);
+        delete p;
+        return rc;
+    }
+    if (nulls == 0) {
+        free(p->validity);
+        p->validity = nullptr;
+    }
+    p->buffers[0] = p->validity;
+    p->buffers[1] = p->values;
+    memset(out, 0, sizeof *out);
+    out->length = n;
+    out->null_count = nulls;
+    out->offset = 0;
+    out->n_buffers = 2;
+    out->n_children = 0;
+    out->buffers = p->buffers;
+    out->release = release_result;
+    out->private_data = p;
+    return STRSIM_OK;
+}
+
+// ---- Float64 field ---------------------------------------------------------------------------------
+struct SchemaPrivate {
+    std::string name;
+};
+
+void release_schema(ArrowSchema* s) {
+    if (!s || !s->release) return;
+    delete static_cast<SchemaPrivate*>(s->private_data);
+    s->release = nullptr;
+}
+
+void make_f64_schema(ArrowSchema* out, const char* name) {
+    SchemaPrivate* p = new SchemaPrivate();
+    p->name = name ? name : "";
+    memset(out, 0, sizeof *out);
+    out->format = "g";
+    out->name = p->name.c_str();
+    out->metadata = nullptr;
+    out->flags = ARROW_FLAG_NULLABLE;
+    out->release = release_schema;
+    out->private_data = p;
+}
+
+// ---- SeriesExport for the return value ----------------------------------------------------------------
+struct SeriesPrivate {
+    ArrowSchema* field;
+    ArrowArray** arrays;
+    size_t n;
+};
+
+// polars-ffi's importer moves the ArrowArray structs out (and releases their contents itself) and
+// only borrows the field, so this frees the boxes and releases the schema -- not the array contents.
+void release_series(strsim_series_export* e) {
+    if (!e || !e->private_data) return;
+    SeriesPrivate* p = static_cast<SeriesPrivate*>(e->private_data);
+    if (p->field) {
+        if (p->field->release) p->field->release(p->field);
+        delete p->field;
+    }
+    for (size_t i = 0; i < p->n; i++) delete p->arrays[i];
+    delete[] p->arrays;
+    delete p;
+    e->release = nullptr;
+    e->private_data = nullptr;
+}
+
+void plugin_call(int measure, strsim_series_export* inputs, size_t n_inputs,
+                 strsim_series_export* return_value) {
+    int rc = STRSIM_OK;
+    Column ca, cb;
+    ArrowArray* result = nullptr;
+    if (n_inputs != 2 || !inputs) {
+        strsim_set_error("expected 2 input series, got %zu", n_inputs);
+        rc = STRSIM_ERR_ARGUMENT;
+    }
+    if (rc == STRSIM_OK)
+        rc = column_from_arrow(inputs[0].field ? inputs[0].field->format : nullptr,
+                               inputs[0].arrays, inputs[0].len, ca);
+    if (rc == STRSIM_OK)
+        rc = column_from_arrow(inputs[1].field ? inputs[1].field->format : nullptr,
+                               inputs[1].arrays, inputs[1].len, cb);
+    if (rc == STRSIM_OK) {
+        result = new ArrowArray();
+        rc = compute_to_arrow(measure, ca, cb, result);
+        if (rc != STRSIM_OK) {
+            delete result;
+            result = nullptr;
+        }
+    }
+    // the callee owns the inputs (polars-ffi import_series_buffer semantics): release every chunk's
+    // contents, then the SeriesExport boxes
+    for (size_t s = 0; inputs && s < n_inputs; s++) {
+        for (size_t i = 0; i < inputs[s].len; i++) {
+            ArrowArray* a = inputs[s].arrays[i];
+            if (a && a->release) a->release(a);
+        }
+        if (inputs[s].release) inputs[s].release(&inputs[s]);
+    }
+    if (rc != STRSIM_OK) return;  // return_value untouched => Polars raises with the stored message
+    SeriesPrivate* p = new SeriesPrivate();
+    p->field = new ArrowSchema();
+    make_f64_schema(p->field, "");  // reference names the parallel-branch result "" (strsim.rs:102)
+    p->arrays = new ArrowArray*[1];
+    p->arrays[0] = result;
+    p->n = 1;
+    return_value->field = p->field;
+    return_value->arrays = p->arrays;
+    return_value->len = 1;
+    return_value->release = release_series;
+    return_value->private_data = p;
+}
+
+void plugin_field(ArrowSchema* input_fields, size_t n_fields, ArrowSchema* return_field) {
+    // output_type=Float64, named like the first input (mod.rs:8,13,18,23,28)
+    make_f64_schema(return_field, n_fields > 0 && input_fields ? input_fields[0].name : "");
+}
+
+}  // namespace
+
+extern "C" {
+
+int strsim_b200_compute_arrow(int measure, const ArrowSchema* a_schema, const ArrowArray* const* a_chunks,
+                              size_t n_a, const ArrowSchema* b_schema, const ArrowArray* const* b_chunks,
+                              size_t n_b, ArrowArray* out) {
+    if (!a_schema || !b_schema || !out || (n_a && !a_chunks) || (n_b && !b_chunks)) {
+        strsim_set_error("compute_arrow: NULL argument");
+        return STRSIM_ERR_ARGUMENT;
+    }
+    Column ca, cb;
+    int rc = column_from_arrow(a_schema->format, a_chunks, n_a, ca);
+    if (rc) return rc;
+    rc = column_from_arrow(b_schema->format, b_chunks, n_b, cb);
+    if (rc) return rc;
+    return compute_to_arrow(measure, ca, cb, out);
+}
+
+#define STRSIM_DEFINE_PLUGIN(name, id)                                                             \
+    void _polars_plugin_##name(strsim_series_export* inputs, size_t n_inputs, const uint8_t*,      \
+                               size_t, strsim_series_export* return_value, strsim_caller_context*) \
+    {                                                                                              \
+        plugin_call(id, inputs, n_inputs, return_value);                                           \
+    }                                                                                              \
+    void _polars_plugin_field_##name(ArrowSchema* input_fields, size_t n_fields,                   \
+                                     ArrowSchema* return_field) {                                  \
+        plugin_field(input_fields, n_fields, return_field);                                        \
+    }
+
+STRSIM_DEFINE_PLUGIN(levenshtein, STRSIM_LEVENSHTEIN)
+STRSIM_DEFINE_PLUGIN(jaro, STRSIM_JARO)
+STRSIM_DEFINE_PLUGIN(jaro_winkler, STRSIM_JARO_WINKLER)
+STRSIM_DEFINE_PLUGIN(jaccard, STRSIM_JACCARD)
+STRSIM_DEFINE_PLUGIN(sorensen_dice, STRSIM_SORENSEN_DICE)
+
+const char* _polars_plugin_get_last_error_message(void) { return strsim_b200_last_error(); }
+
+// polars-ffi: (MAJOR << 16) + MINOR with MAJOR = 0, MINOR = 1 (the context-passing ABI)
+uint32_t _polars_plugin_get_version(void) { return (0u << 16) + 1u; }
+
+}  // extern "C"

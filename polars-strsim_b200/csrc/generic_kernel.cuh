@@ -1,0 +1,270 @@
+// generic_kernel.cuh -- any-length, any-content fallback (one pair per thread, scratch in HBM) and
+// the validity-bitmap kernel.
+//
+// Rows that leave the fused short-string kernel (longer than 64 bytes, or no room in its stage
+// area) end up on an overflow list.  This kernel finishes them with the textbook formulations of
+// SURVEY.md section 9 (/root/reference/src/expressions/strsim.rs:125-345): two-row DP, greedy
+// windowed Jaro over flag arrays, sorted-codepoint merge for the multisets.  It is the correctness
+// net: simple, memory-bound, independent of the bit-parallel code (the GPU tests cross-check the
+// two on rows both can handle).  Long-string Levenshtein has its own fast kernel
+// (long_lev_kernel.cuh); this one keeps Jaro / Jaccard / Dice for long rows and everything when
+// forced by STRSIM_B200_FORCE_GENERIC=1.
+#pragma once
+#include "short_kernel.cuh"
+
+namespace strsim {
+
+struct GenericArgs {
+    DevCol a, b;
+    double* out;
+    int* dbg;
+    const unsigned int* list;        // segment-relative rows
+    const unsigned int* list_count;  // device-resident count
+    uint32_t* scratch;               // n_slots slabs of slab_words u32
+    long long slab_words;
+    int cap_a, cap_b;  // max bytes (>= max codepoints) of a / b among the listed rows
+    int n_slots;
+};
+
+__device__ __forceinline__ const unsigned char* view_ptr(const DevCol& c, long long row, int& len) {
+    const uint4* pv = c.views + row * c.stride;
+    const uint4 v = ld_view(pv);
+    len = (int)v.x;
+    if (len <= 12) return reinterpret_cast<const unsigned char*>(pv) + 4;
+    return reinterpret_cast<const unsigned char*>(c.bufs[v.z]) + v.w;
+}
+
+// UTF-8 -> Unicode scalar values (same clamping rules as the oracle's decoder)
+__device__ inline int decode_cps(const unsigned char* s, int n, uint32_t* out) {
+    int i = 0, k = 0;
+    while (i < n) {
+        const uint32_t c = s[i];
+        int len = c < 0xC0u ? 1 : c < 0xE0u ? 2 : c < 0xF0u ? 3 : 4;
+        if (len > n - i) len = n - i;
+        uint32_t cp = len == 1 ? c : (c & (0xFFu >> (len + 1)));
+        for (int j = 1; j < len; j++) cp = (cp << 6) | (s[i + j] & 0x3Fu);
+        out[k++] = cp;
+        i += len;
+    }
+    return k;
+}
+
+__device__ inline void heap_sort(uint32_t* v, int n) {
+    for (int start = n / 2 - 1; start >= 0; start--) {
+        int root = start;
+        for (;;) {
+            int child = 2 * root + 1;
+            if (child >= n) break;
+            if (child + 1 < n && v[child] < v[child + 1]) child++;
+            if (v[root] >= v[child]) break;
+            uint32_t t = v[root];
+            v[root] = v[child];
+            v[child] = t;
+            root = child;
+        }
+    }
+    for (int end = n - 1; end > 0; end--) {
+        uint32_t t = v[0];
+        v[0] = v[end];
+        v[end] = t;
+        int root = 0;
+        for (;;) {
+            int child = 2 * root + 1;
+            if (child >= end) break;
+            if (child + 1 < end && v[child] < v[child + 1]) child++;
+            if (v[root] >= v[child]) break;
+            uint32_t t2 = v[root];
+            v[root] = v[child];
+            v[child] = t2;
+            root = child;
+        }
+    }
+}
+
+template <int MEASURE>
+__global__ void __launch_bounds__(64) generic_kernel(const GenericArgs g) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= g.n_slots) return;
+    const unsigned int count = *g.list_count;
+    uint32_t* ua = g.scratch + (long long)slot * g.slab_words;
+    uint32_t* ub = ua + g.cap_a;
+    uint32_t* work = ub + g.cap_b;
+    for (unsigned int e = slot; e < count; e += g.n_slots) {
+        const long long row = g.list[e];
+        int na, nb;
+        const unsigned char* pa = view_ptr(g.a, row, na);
+        const unsigned char* pb = view_ptr(g.b, row, nb);
+        PairInts pi = {F_GENERAL, 0, 0, 0, 0, 0};
+        double v;
+        bool equal = na == nb;
+        for (int i = 0; equal && i < na; i++) equal = pa[i] == pb[i];
+        if (equal) {
+            pi.flag = F_EQUAL;
+            v = 1.0;
+        } else if (MEASURE != LEVENSHTEIN && (na == 0 || nb == 0)) {
+            pi.flag = F_ONE_EMPTY;
+            v = 0.0;
+        } else {
+            const int la = decode_cps(pa, na, ua);
+            const int lb = decode_cps(pb, nb, ub);
+            pi.la = la;
+            pi.lb = lb;
+            if (MEASURE == LEVENSHTEIN) {
+                uint32_t* prev = work;
+                uint32_t* cur = work + (lb + 1);
+                for (int j = 0; j <= lb; j++) prev[j] = (uint32_t)j;
+                for (int i = 0; i < la; i++) {
+                    cur[0] = (uint32_t)(i + 1);
+                    const uint32_t ai = ua[i];
+                    uint32_t left = cur[0], diag = prev[0];
+                    for (int j = 0; j < lb; j++) {
+                        const uint32_t up = prev[j + 1];
+                        uint32_t x = diag + (ai != ub[j] ? 1u : 0u);
+                        x = min(x, up + 1u);
+                        x = min(x, left + 1u);
+                        cur[j + 1] = x;
+                        left = x;
+                        diag = up;
+                    }
+                    uint32_t* t = prev;
+                    prev = cur;
+                    cur = t;
+                }
+                pi.x0 = (int)prev[lb];
+                v = lev_value(pi.x0, la, lb);
+            } else if (MEASURE == JARO || MEASURE == JARO_WINKLER) {
+                if (la == 1 && lb == 1) {
+                    pi.flag = F_SINGLE_CHAR;
+                    v = ua[0] == ub[0] ? 1.0 : 0.0;
+                } else {
+                    unsigned char* fa = reinterpret_cast<unsigned char*>(work);
+                    unsigned char* fb = fa + la;
+                    for (int i = 0; i < la; i++) fa[i] = 0;
+                    for (int j = 0; j < lb; j++) fb[j] = 0;
+                    const int mx = la > lb ? la : lb;
+                    const int bound = mx / 2 - 1;
+                    const int outer = la < lb + bound ? la : lb + bound;
+                    int m = 0;
+                    for (int i = 0; i < outer; i++) {
+                        const int lo = i > bound ? i - bound : 0;
+                        const int hi = i + bound < lb - 1 ? i + bound : lb - 1;
+                        for (int j = lo; j <= hi; j++) {
+                            if (ua[i] == ub[j] && !fb[j]) {
+                                fa[i] = 1;
+                                fb[j] = 1;
+                                m++;
+                                break;
+                            }
+                        }
+                    }
+                    int t = 0, j = 0;
+                    for (int i = 0; i < la; i++) {
+                        if (!fa[i]) continue;
+                        while (j < lb && !fb[j]) j++;
+                        if (j >= lb) break;
+                        if (ua[i] != ub[j]) t++;
+                        j++;
+                    }
+                    pi.x0 = m;
+                    pi.x1 = t;
+                    v = m == 0 ? 0.0 : jaro_value(m, t, la, lb);
+                    if (MEASURE == JARO_WINKLER && v > 0.7) {
+                        int lim = la < lb ? la : lb;
+                        if (lim > 4) lim = 4;
+                        int l = 0;
+                        while (l < lim && ua[l] == ub[l]) l++;
+                        pi.x2 = l;
+                        v = winkler_value(v, l);
+                    }
+                }
+            } else {
+                heap_sort(ua, la);
+                heap_sort(ub, lb);
+                int i = 0, j = 0, inter = 0;
+                while (i < la && j < lb) {
+                    if (ua[i] == ub[j]) {
+                        inter++;
+                        i++;
+                        j++;
+                    } else if (ua[i] < ub[j]) {
+                        i++;
+                    } else {
+                        j++;
+                    }
+                }
+                pi.x0 = inter;
+                if (MEASURE == JACCARD) {
+                    pi.x1 = la + lb - inter;
+                    v = jaccard_value(inter, la + lb - inter);
+                } else {
+                    pi.x1 = la + lb;
+                    v = dice_value(inter, la + lb);
+                }
+            }
+        }
+        g.out[row] = v;
+        if (g.dbg) {
+            int* d = g.dbg + row * 6;
+            d[0] = pi.flag;
+            d[1] = pi.la;
+            d[2] = pi.lb;
+            d[3] = pi.x0;
+            d[4] = pi.x1;
+            d[5] = pi.x2;
+        }
+    }
+}
+
+// test hook (STRSIM_B200_FORCE_GENERIC=1): list every valid row for the fallback kernel
+__global__ void list_all_kernel(const SegArgs s) {
+    const long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (row >= s.n) return;
+    const bool valid = bit_valid(s.a.validity, s.a.vbit + row * s.a.stride) &&
+                       bit_valid(s.b.validity, s.b.vbit + row * s.b.stride);
+    if (!valid) {
+        s.out[row] = 0.0;
+        if (s.dbg)
+            for (int q = 0; q < 6; q++) s.dbg[row * 6 + q] = 0;
+        return;
+    }
+    s.listlong[atomicAdd(&s.ovf->nlong, 1u)] = (unsigned int)row;
+    atomicMax(&s.ovf->max_bytes_a, ld_view(s.a.views + row * s.a.stride).x);
+    atomicMax(&s.ovf->max_bytes_b, ld_view(s.b.views + row * s.b.stride).x);
+}
+
+// ---- output validity: bit = both inputs valid (polars-core arity kernels; README.md:69-70) ---------
+struct ValidityArgs {
+    const uint8_t* va;
+    long long abit;
+    int astride;
+    const uint8_t* vb;
+    long long bbit;
+    int bstride;
+    long long n;         // rows of the segment
+    long long out_row0;  // first output row of the segment
+    uint32_t* out;       // whole output bitmap (zero-initialised), LSB-first words
+    unsigned long long* null_count;
+};
+
+__global__ void validity_kernel(const ValidityArgs v) {
+    const long long w_lo = v.out_row0 >> 5;
+    const long long w = w_lo + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long r_begin = max(w << 5, v.out_row0);
+    const long long r_end = min((w + 1) << 5, v.out_row0 + v.n);
+    if (r_begin >= r_end) return;
+    uint32_t bits = 0;
+    for (long long r = r_begin; r < r_end; r++) {
+        const long long s = r - v.out_row0;
+        const bool ok = bit_valid(v.va, v.abit + s * v.astride) && bit_valid(v.vb, v.bbit + s * v.bstride);
+        bits |= (ok ? 1u : 0u) << (int)(r & 31);
+    }
+    const int rows = (int)(r_end - r_begin);
+    if (rows == 32)
+        v.out[w] = bits;
+    else
+        atomicOr(&v.out[w], bits);
+    const int nulls = rows - __popc(bits);
+    if (nulls) atomicAdd(v.null_count, (unsigned long long)nulls);
+}
+
+}  // namespace strsim

@@ -1,0 +1,619 @@
+// host.cu -- host driver of libpolars_strsim_b200.so: column upload, segment alignment, kernel
+// launches, result download.  Replaces parallel_apply() (/root/reference/src/expressions/strsim.rs:
+// 41-107) and the polars-core arity kernels it calls (chunk alignment, validity AND).
+//
+// No CPU fallback: every path ends in the CUDA kernels of short_kernel.cuh / generic_kernel.cuh /
+// long_lev_kernel.cuh, and fails with STRSIM_ERR_CUDA when no device is usable.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/strsim_b200.h"
+#include "generic_kernel.cuh"
+#include "short_kernel.cuh"
+
+using namespace strsim;
+
+// ---- error plumbing --------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static thread_local int64_t g_last_overflow[2] = {0, 0};
+static std::atomic<uint64_t> g_launches{0};
+
+extern "C" void strsim_set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+
+#define CUDA_TRY(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            strsim_set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorString(_e), __FILE__, \
+                             __LINE__, #expr);                                                \
+            return STRSIM_ERR_CUDA;                                                           \
+        }                                                                                     \
+    } while (0)
+
+// ---- per-thread device context ---------------------------------------------------------------------
+struct Workspace {
+    void* ptr = nullptr;
+    size_t cap = 0;
+};
+
+struct ThreadCtx {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    Overflow* d_ovf = nullptr;
+    Overflow* h_ovf = nullptr;  // pinned
+    unsigned long long* d_nulls = nullptr;
+    unsigned long long* h_nulls = nullptr;  // pinned
+    Workspace lists, scratch;
+};
+
+static thread_local ThreadCtx g_ctx;
+static thread_local int g_requested_device = -2;  // -2: not chosen yet
+
+static int default_device() {
+    const char* e = getenv("STRSIM_B200_DEVICE");
+    if (e && *e) return atoi(e);
+    e = getenv("LOCAL_RANK");  // one process per GPU under torchrun
+    if (e && *e) {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) == cudaSuccess && n > 0) return atoi(e) % n;
+    }
+    return 0;
+}
+
+static int ensure_ctx(ThreadCtx** out) {
+    if (g_requested_device == -2) g_requested_device = default_device();
+    ThreadCtx& c = g_ctx;
+    if (c.device != g_requested_device) {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0) {
+            strsim_set_error(
+                "no usable CUDA device (%s): polars-strsim_b200 has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+            return STRSIM_ERR_CUDA;
+        }
+        if (g_requested_device < 0 || g_requested_device >= n) {
+            strsim_set_error("device %d out of range (0..%d)", g_requested_device, n - 1);
+            return STRSIM_ERR_ARGUMENT;
+        }
+        c = ThreadCtx();
+        c.device = g_requested_device;
+        CUDA_TRY(cudaSetDevice(c.device));
+        CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, c.device));
+        CUDA_TRY(cudaMalloc(&c.d_ovf, sizeof(Overflow)));
+        CUDA_TRY(cudaMallocHost(&c.h_ovf, sizeof(Overflow)));
+        CUDA_TRY(cudaMalloc(&c.d_nulls, sizeof(unsigned long long)));
+        CUDA_TRY(cudaMallocHost(&c.h_nulls, sizeof(unsigned long long)));
+    }
+    CUDA_TRY(cudaSetDevice(c.device));
+    *out = &c;
+    return STRSIM_OK;
+}
+
+static int ws_reserve(Workspace& w, size_t bytes) {
+    if (bytes <= w.cap) return STRSIM_OK;
+    if (w.ptr) CUDA_TRY(cudaFree(w.ptr));
+    w.ptr = nullptr;
+    w.cap = 0;
+    size_t cap = bytes + bytes / 4 + 4096;
+    cudaError_t e = cudaMalloc(&w.ptr, cap);
+    if (e != cudaSuccess) {
+        strsim_set_error("cudaMalloc(%zu) failed: %s", cap, cudaGetErrorString(e));
+        return STRSIM_ERR_NOMEM;
+    }
+    w.cap = cap;
+    return STRSIM_OK;
+}
+
+// ---- device-resident column --------------------------------------------------------------------------
+struct DevChunk {
+    const uint4* views;  // row 0 of the chunk's logical range
+    const uint8_t* validity;
+    long long vbit;
+    const unsigned long long* bufs;
+    int64_t length;
+    int64_t data_bytes;  // sum of data buffer sizes
+};
+
+struct strsim_b200_column {
+    int device = 0;
+    void* block = nullptr;  // one allocation holds everything
+    size_t block_bytes = 0;
+    std::vector<DevChunk> chunks;
+    int64_t length = 0;
+    int64_t data_bytes = 0;
+    int64_t alg_bytes = -1;
+    bool has_validity = false;
+};
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// H2D copy that never blocks on pageable memory longer than needed: pinned sources are DMA'd
+// directly, pageable sources are staged by the driver (cudaMemcpyAsync semantics).
+static int h2d(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+    if (bytes == 0) return STRSIM_OK;
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    return STRSIM_OK;
+}
+
+static int upload_column(ThreadCtx& ctx, const strsim_view_chunk* chunks, size_t n_chunks,
+                         bool want_alg_bytes, strsim_b200_column** out) {
+    auto* col = new strsim_b200_column();
+    col->device = ctx.device;
+    // plan the single device block
+    struct Plan {
+        size_t views_off, validity_off, table_off;
+        std::vector<size_t> buf_off;
+        size_t validity_bytes;
+        int64_t first_byte;
+    };
+    std::vector<Plan> plans(n_chunks);
+    size_t total = 0;
+    for (size_t i = 0; i < n_chunks; i++) {
+        const strsim_view_chunk& ch = chunks[i];
+        if (ch.length < 0 || ch.offset < 0 || (ch.length > 0 && !ch.views)) {
+            strsim_set_error("chunk %zu: bad length/offset/views", i);
+            delete col;
+            return STRSIM_ERR_ARGUMENT;
+        }
+        Plan& p = plans[i];
+        p.views_off = total;
+        total = align_up(total + 16 * (size_t)ch.length, 256);
+        p.first_byte = ch.offset >> 3;
+        p.validity_bytes =
+            ch.validity && ch.length > 0 ? (size_t)(((ch.offset + ch.length + 7) >> 3) - p.first_byte) : 0;
+        p.validity_off = total;
+        total = align_up(total + p.validity_bytes, 256);
+        p.table_off = total;
+        total = align_up(total + 8 * (size_t)(ch.n_data_buffers > 0 ? ch.n_data_buffers : 1), 256);
+        p.buf_off.resize((size_t)ch.n_data_buffers);
+        for (int64_t b = 0; b < ch.n_data_buffers; b++) {
+            p.buf_off[(size_t)b] = total;
+            // 64 spare bytes: TMA spans are rounded to 16 B and word copies read a few bytes past
+            total = align_up(total + (size_t)ch.data_buffer_sizes[b] + 64, 256);
+        }
+        col->length += ch.length;
+        if (p.validity_bytes) col->has_validity = true;
+    }
+    total += 256;
+    cudaError_t e = cudaMalloc(&col->block, total);
+    if (e != cudaSuccess) {
+        strsim_set_error("cudaMalloc(%zu) for a column failed: %s", total, cudaGetErrorString(e));
+        delete col;
+        return STRSIM_ERR_NOMEM;
+    }
+    col->block_bytes = total;
+    char* base = static_cast<char*>(col->block);
+    std::vector<unsigned long long> table;
+    for (size_t i = 0; i < n_chunks; i++) {
+        const strsim_view_chunk& ch = chunks[i];
+        const Plan& p = plans[i];
+        DevChunk dc;
+        dc.length = ch.length;
+        dc.views = reinterpret_cast<const uint4*>(base + p.views_off);
+        int rc = h2d(base + p.views_off, static_cast<const char*>(ch.views) + 16 * ch.offset,
+                     16 * (size_t)ch.length, ctx.stream);
+        if (rc) return rc;
+        if (p.validity_bytes) {
+            rc = h2d(base + p.validity_off, ch.validity + p.first_byte, p.validity_bytes, ctx.stream);
+            if (rc) return rc;
+            dc.validity = reinterpret_cast<const uint8_t*>(base + p.validity_off);
+            dc.vbit = ch.offset & 7;
+        } else {
+            dc.validity = nullptr;
+            dc.vbit = 0;
+        }
+        table.assign((size_t)(ch.n_data_buffers > 0 ? ch.n_data_buffers : 1), 0ull);
+        dc.data_bytes = 0;
+        for (int64_t b = 0; b < ch.n_data_buffers; b++) {
+            table[(size_t)b] = reinterpret_cast<unsigned long long>(base + p.buf_off[(size_t)b]);
+            rc = h2d(base + p.buf_off[(size_t)b], ch.data_buffers[b], (size_t)ch.data_buffer_sizes[b],
+                     ctx.stream);
+            if (rc) return rc;
+            dc.data_bytes += ch.data_buffer_sizes[b];
+        }
+        // the table is tiny; a synchronous copy keeps `table` reusable
+        CUDA_TRY(cudaMemcpyAsync(base + p.table_off, table.data(), 8 * table.size(),
+                                 cudaMemcpyHostToDevice, ctx.stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx.stream));
+        dc.bufs = reinterpret_cast<const unsigned long long*>(base + p.table_off);
+        col->data_bytes += dc.data_bytes;
+        col->chunks.push_back(dc);
+    }
+    if (want_alg_bytes) {
+        // 16 B of view per row + out-of-line payload (byte length > 12) + validity bits
+        int64_t bytes = 0;
+        for (size_t i = 0; i < n_chunks; i++) {
+            const strsim_view_chunk& ch = chunks[i];
+            const int32_t* v = static_cast<const int32_t*>(ch.views) + 4 * ch.offset;
+            for (int64_t r = 0; r < ch.length; r++) {
+                int32_t len = v[4 * r];
+                bytes += 16 + (len > 12 ? len : 0);
+            }
+            if (ch.validity) bytes += (ch.length + 7) / 8;
+        }
+        col->alg_bytes = bytes;
+    }
+    *out = col;
+    return STRSIM_OK;
+}
+
+// ---- kernel launch helpers -----------------------------------------------------------------------------
+template <class M, int MEASURE, int TPB, int RPT, bool GATHER>
+static int launch_short(ThreadCtx& ctx, const SegArgs& args, long long n_upper, cudaStream_t st) {
+    using L = ShortLayout<M, TPB, RPT>;
+    auto kern = short_kernel<M, MEASURE, TPB, RPT, GATHER>;
+    const size_t smem = L::bytes(args.stage_bytes);
+    static thread_local size_t configured = 0;
+    if (smem > configured) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TPB, smem));
+    if (per_sm < 1) {
+        strsim_set_error("short kernel does not fit an SM (smem %zu)", smem);
+        return STRSIM_ERR_CUDA;
+    }
+    const long long tiles = (n_upper + L::TILE - 1) / L::TILE;
+    long long grid = (long long)per_sm * ctx.sm_count;
+    if (tiles < grid) grid = tiles;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, TPB, smem, st>>>(args);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return STRSIM_OK;
+}
+
+// rows on the long list -> fallback kernel, scratch slabs sized from the device-side maxima
+template <int MEASURE>
+static int run_generic(ThreadCtx& ctx, const SegArgs& args, const Overflow& ov, cudaStream_t st) {
+    GenericArgs g{};
+    g.a = args.a;
+    g.b = args.b;
+    g.out = args.out;
+    g.dbg = args.dbg;
+    g.list = args.listlong;
+    g.list_count = &ctx.d_ovf->nlong;
+    g.cap_a = (int)ov.max_bytes_a + 1;
+    g.cap_b = (int)ov.max_bytes_b + 1;
+    long long work = 2ll * (g.cap_b + 1);
+    const long long flags = ((long long)g.cap_a + g.cap_b) / 4 + 2;
+    if (flags > work) work = flags;
+    g.slab_words = (long long)g.cap_a + g.cap_b + work;
+    long long slots = (long long)ctx.sm_count * 512;
+    if ((long long)ov.nlong < slots) slots = ov.nlong;
+    const long long budget = 2ll << 30;  // bytes of scratch at most
+    if (slots * g.slab_words * 4 > budget) slots = budget / (g.slab_words * 4);
+    if (slots < 1) {
+        strsim_set_error("a row of %u/%u bytes needs more than the 2 GiB fallback scratch",
+                         ov.max_bytes_a, ov.max_bytes_b);
+        return STRSIM_ERR_NOMEM;
+    }
+    int rc = ws_reserve(ctx.scratch, (size_t)(slots * g.slab_words * 4));
+    if (rc) return rc;
+    g.scratch = static_cast<uint32_t*>(ctx.scratch.ptr);
+    g.n_slots = (int)slots;
+    generic_kernel<MEASURE><<<(unsigned)((slots + 63) / 64), 64, 0, st>>>(g);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return STRSIM_OK;
+}
+
+template <int MEASURE>
+static int run_segment(ThreadCtx& ctx, SegArgs args, int stage32, int64_t seg_rows, cudaStream_t st) {
+    // overflow lists: worst case every row
+    int rc = ws_reserve(ctx.lists, 2 * sizeof(unsigned int) * (size_t)seg_rows + 64);
+    if (rc) return rc;
+    args.list64 = static_cast<unsigned int*>(ctx.lists.ptr);
+    args.listlong = args.list64 + seg_rows;
+    args.ovf = ctx.d_ovf;
+    CUDA_TRY(cudaMemsetAsync(ctx.d_ovf, 0, sizeof(Overflow), st));
+    static const bool force_generic = getenv("STRSIM_B200_FORCE_GENERIC") != nullptr &&
+                                      atoi(getenv("STRSIM_B200_FORCE_GENERIC")) != 0;
+    args.stage_bytes = stage32;
+    args.list = nullptr;
+    args.list_count = nullptr;
+    if (force_generic) {
+        // test hook: every valid row goes straight to the fallback kernel
+        list_all_kernel<<<(unsigned)((seg_rows + 255) / 256), 256, 0, st>>>(args);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        CUDA_TRY(cudaGetLastError());
+    } else {
+        rc = launch_short<uint32_t, MEASURE, 128, 4, false>(ctx, args, seg_rows, st);
+        if (rc) return rc;
+    }
+    CUDA_TRY(cudaMemcpyAsync(ctx.h_ovf, ctx.d_ovf, sizeof(Overflow), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    Overflow ov = *ctx.h_ovf;
+    g_last_overflow[0] += ov.n64;
+    if (ov.n64 > 0) {
+        SegArgs a64 = args;
+        a64.list = args.list64;
+        a64.list_count = &ctx.d_ovf->n64;
+        a64.n = ov.n64;
+        a64.stage_bytes = 64 * ShortLayout<uint64_t, 64, 2>::TILE;  // every listed row fits
+        rc = launch_short<uint64_t, MEASURE, 64, 2, true>(ctx, a64, ov.n64, st);
+        if (rc) return rc;
+        // rows the 64-bit kernel could not stage are appended to listlong; re-read the counters
+        CUDA_TRY(cudaMemcpyAsync(ctx.h_ovf, ctx.d_ovf, sizeof(Overflow), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        ov = *ctx.h_ovf;
+    }
+    g_last_overflow[1] += ov.nlong;
+    if (ov.nlong > 0) {
+        rc = run_generic<MEASURE>(ctx, args, ov, st);
+        if (rc) return rc;
+    }
+    return STRSIM_OK;
+}
+
+static int compute_on_device(ThreadCtx& ctx, int measure, const strsim_b200_column* a,
+                             const strsim_b200_column* b, double* d_out, uint32_t* d_validity,
+                             int32_t* d_dbg, cudaStream_t st) {
+    if (measure < 0 || measure > 4) {
+        strsim_set_error("unknown measure %d", measure);
+        return STRSIM_ERR_ARGUMENT;
+    }
+    const int64_t la = a->length, lb = b->length;
+    if (la != lb && la != 1 && lb != 1) {
+        strsim_set_error("Inputs must have the same length, or one of them must be a Utf8 literal.");
+        return STRSIM_ERR_SHAPE;
+    }
+    const int64_t n = (la == 1) ? lb : la;
+    g_last_overflow[0] = g_last_overflow[1] = 0;
+    if (n == 0) return STRSIM_OK;
+    const bool bc_a = la == 1 && n != 1, bc_b = lb == 1 && n != 1;
+    const bool any_validity = a->has_validity || b->has_validity;
+    if (d_validity && any_validity) {
+        CUDA_TRY(cudaMemsetAsync(d_validity, 0, 4 * (size_t)((n + 31) / 32), st));
+        CUDA_TRY(cudaMemsetAsync(ctx.d_nulls, 0, sizeof(unsigned long long), st));
+    } else if (d_validity) {
+        CUDA_TRY(cudaMemsetAsync(d_validity, 0xFF, 4 * (size_t)((n + 31) / 32), st));
+        CUDA_TRY(cudaMemsetAsync(ctx.d_nulls, 0, sizeof(unsigned long long), st));
+    }
+    // walk both chunk lists in lock step (polars-core align_chunks equivalent)
+    size_t ia = 0, ib = 0;
+    int64_t oa = 0, ob = 0, row = 0;
+    while (row < n) {
+        while (!bc_a && ia < a->chunks.size() && oa >= a->chunks[ia].length) {
+            ia++;
+            oa = 0;
+        }
+        while (!bc_b && ib < b->chunks.size() && ob >= b->chunks[ib].length) {
+            ib++;
+            ob = 0;
+        }
+        const DevChunk& ca = a->chunks[bc_a ? 0 : ia];
+        const DevChunk& cb = b->chunks[bc_b ? 0 : ib];
+        int64_t len = n - row;
+        if (!bc_a && ca.length - oa < len) len = ca.length - oa;
+        if (!bc_b && cb.length - ob < len) len = cb.length - ob;
+        if (len > 0x7FFFFFF0ll) len = 0x7FFFFFF0ll;  // list entries are 32-bit
+        SegArgs s{};
+        s.a.views = ca.views + (bc_a ? 0 : oa);
+        s.a.validity = ca.validity;
+        s.a.vbit = ca.vbit + (bc_a ? 0 : oa);
+        s.a.bufs = ca.bufs;
+        s.a.stride = bc_a ? 0 : 1;
+        s.b.views = cb.views + (bc_b ? 0 : ob);
+        s.b.validity = cb.validity;
+        s.b.vbit = cb.vbit + (bc_b ? 0 : ob);
+        s.b.bufs = cb.bufs;
+        s.b.stride = bc_b ? 0 : 1;
+        s.n = len;
+        s.out = d_out + row;
+        s.dbg = d_dbg ? d_dbg + 6 * row : nullptr;
+        // stage capacity: mean out-of-line bytes per row of the heavier column, +25 % and slack
+        const double avg_a = bc_a ? 0.0 : (double)ca.data_bytes / (double)(ca.length > 0 ? ca.length : 1);
+        const double avg_b = bc_b ? 0.0 : (double)cb.data_bytes / (double)(cb.length > 0 ? cb.length : 1);
+        const double avg = avg_a > avg_b ? avg_a : avg_b;
+        long long stage = (long long)(avg * 512 * 1.25) + 512;
+        if (stage < 2048) stage = 2048;
+        if (stage > 32 * 512) stage = 32 * 512;  // every row of a tile at 32 bytes
+        stage = (stage + 15) & ~15ll;
+        int rc;
+        switch (measure) {
+            case 0: rc = run_segment<0>(ctx, s, (int)stage, len, st); break;
+            case 1: rc = run_segment<1>(ctx, s, (int)stage, len, st); break;
+            case 2: rc = run_segment<2>(ctx, s, (int)stage, len, st); break;
+            case 3: rc = run_segment<3>(ctx, s, (int)stage, len, st); break;
+            default: rc = run_segment<4>(ctx, s, (int)stage, len, st); break;
+        }
+        if (rc) return rc;
+        if (d_validity && any_validity) {
+            ValidityArgs v;
+            v.va = s.a.validity;
+            v.abit = s.a.vbit;
+            v.astride = s.a.stride;
+            v.vb = s.b.validity;
+            v.bbit = s.b.vbit;
+            v.bstride = s.b.stride;
+            v.n = len;
+            v.out_row0 = row;
+            v.out = d_validity;
+            v.null_count = ctx.d_nulls;
+            const long long words = ((row + len - 1) >> 5) - (row >> 5) + 1;
+            validity_kernel<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(v);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            CUDA_TRY(cudaGetLastError());
+        }
+        row += len;
+        oa += len;
+        ob += len;
+    }
+    return STRSIM_OK;
+}
+
+// ---- exported C ABI ----------------------------------------------------------------------------------------
+extern "C" {
+
+int strsim_b200_set_device(int device) {
+    g_requested_device = device;
+    ThreadCtx* c;
+    return ensure_ctx(&c);
+}
+
+int strsim_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+const char* strsim_b200_last_error(void) { return g_last_error.c_str(); }
+uint64_t strsim_b200_kernel_launches(void) { return g_launches.load(); }
+void strsim_b200_last_overflow(int64_t out[2]) {
+    out[0] = g_last_overflow[0];
+    out[1] = g_last_overflow[1];
+}
+const char* strsim_b200_version(void) { return "polars-strsim_b200 0.1.0 (sm_100a)"; }
+
+int strsim_b200_column_upload(const strsim_view_chunk* chunks, size_t n_chunks, strsim_b200_column** out) {
+    if (!out || (n_chunks && !chunks)) {
+        strsim_set_error("column_upload: NULL argument");
+        return STRSIM_ERR_ARGUMENT;
+    }
+    ThreadCtx* ctx;
+    int rc = ensure_ctx(&ctx);
+    if (rc) return rc;
+    rc = upload_column(*ctx, chunks, n_chunks, true, out);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return STRSIM_OK;
+}
+
+void strsim_b200_column_free(strsim_b200_column* col) {
+    if (!col) return;
+    if (col->block) {
+        cudaSetDevice(col->device);
+        cudaFree(col->block);
+    }
+    delete col;
+}
+
+int64_t strsim_b200_column_length(const strsim_b200_column* col) { return col ? col->length : -1; }
+int64_t strsim_b200_column_algorithmic_bytes(const strsim_b200_column* col) {
+    return col ? col->alg_bytes : -1;
+}
+
+int strsim_b200_compute_device(int measure, const strsim_b200_column* a, const strsim_b200_column* b,
+                               double* d_out_values, uint32_t* d_out_validity, int32_t* d_dbg_ints,
+                               void* stream) {
+    if (!a || !b || !d_out_values) {
+        strsim_set_error("compute_device: NULL argument");
+        return STRSIM_ERR_ARGUMENT;
+    }
+    ThreadCtx* ctx;
+    int rc = ensure_ctx(&ctx);
+    if (rc) return rc;
+    if (a->device != ctx->device || b->device != ctx->device) {
+        strsim_set_error("columns live on device %d/%d, calling thread uses device %d", a->device,
+                         b->device, ctx->device);
+        return STRSIM_ERR_ARGUMENT;
+    }
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    return compute_on_device(*ctx, measure, a, b, d_out_values, d_out_validity, d_dbg_ints, st);
+}
+
+int strsim_b200_compute_host(int measure, const strsim_view_chunk* a, size_t n_a, const strsim_view_chunk* b,
+                             size_t n_b, double* out_values, uint8_t* out_validity, int64_t* out_null_count,
+                             int32_t* dbg_ints) {
+    if ((n_a && !a) || (n_b && !b)) {
+        strsim_set_error("compute_host: NULL chunk array");
+        return STRSIM_ERR_ARGUMENT;
+    }
+    int64_t la = 0, lb = 0;
+    for (size_t i = 0; i < n_a; i++) la += a[i].length;
+    for (size_t i = 0; i < n_b; i++) lb += b[i].length;
+    if (la != lb && la != 1 && lb != 1) {
+        strsim_set_error("Inputs must have the same length, or one of them must be a Utf8 literal.");
+        return STRSIM_ERR_SHAPE;
+    }
+    const int64_t n = la == 1 ? lb : la;
+    if (out_null_count) *out_null_count = 0;
+    if (n > 0 && !out_values) {
+        strsim_set_error("compute_host: NULL out_values");
+        return STRSIM_ERR_ARGUMENT;
+    }
+    ThreadCtx* ctx;
+    int rc = ensure_ctx(&ctx);
+    if (rc) return rc;
+    if (n == 0) return STRSIM_OK;
+    strsim_b200_column *ca = nullptr, *cb = nullptr;
+    rc = upload_column(*ctx, a, n_a, false, &ca);
+    if (rc) return rc;
+    rc = upload_column(*ctx, b, n_b, false, &cb);
+    if (rc) {
+        strsim_b200_column_free(ca);
+        return rc;
+    }
+    const size_t val_words = (size_t)((n + 31) / 32);
+    const size_t bytes = align_up(8 * (size_t)n, 256) + align_up(4 * val_words, 256) +
+                         (dbg_ints ? 24 * (size_t)n : 0);
+    void* d_block = nullptr;
+    cudaError_t e = cudaMalloc(&d_block, bytes);
+    if (e != cudaSuccess) {
+        strsim_set_error("cudaMalloc(%zu) for results failed: %s", bytes, cudaGetErrorString(e));
+        strsim_b200_column_free(ca);
+        strsim_b200_column_free(cb);
+        return STRSIM_ERR_NOMEM;
+    }
+    double* d_out = static_cast<double*>(d_block);
+    uint32_t* d_val = reinterpret_cast<uint32_t*>(static_cast<char*>(d_block) + align_up(8 * (size_t)n, 256));
+    int32_t* d_dbg = dbg_ints ? reinterpret_cast<int32_t*>(reinterpret_cast<char*>(d_val) + align_up(4 * val_words, 256))
+                              : nullptr;
+    const bool want_validity = out_validity != nullptr || out_null_count != nullptr;
+    rc = compute_on_device(*ctx, measure, ca, cb, d_out, want_validity ? d_val : nullptr, d_dbg, ctx->stream);
+    cudaError_t ce = cudaSuccess;
+    if (rc == STRSIM_OK) {
+        ce = cudaMemcpyAsync(out_values, d_out, 8 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+        if (ce == cudaSuccess && out_validity)
+            ce = cudaMemcpyAsync(out_validity, d_val, (size_t)((n + 7) / 8), cudaMemcpyDeviceToHost, ctx->stream);
+        if (ce == cudaSuccess && dbg_ints)
+            ce = cudaMemcpyAsync(dbg_ints, d_dbg, 24 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+        if (ce == cudaSuccess && want_validity)
+            ce = cudaMemcpyAsync(ctx->h_nulls, ctx->d_nulls, 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+        if (ce != cudaSuccess) {
+            strsim_set_error("CUDA error while downloading results: %s", cudaGetErrorString(ce));
+            rc = STRSIM_ERR_CUDA;
+        } else if (out_null_count) {
+            *out_null_count = (int64_t)*ctx->h_nulls;
+        }
+    }
+    cudaFree(d_block);
+    strsim_b200_column_free(ca);
+    strsim_b200_column_free(cb);
+    return rc;
+}
+
+}  // extern "C"

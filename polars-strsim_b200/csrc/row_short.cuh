@@ -174,19 +174,25 @@ SS_HD double row_short(int measure, Store& s, int na, int nb, bool equal, bool a
         out.lb = lb;
         if ((measure == JARO || measure == JARO_WINKLER) && la == 1 && lb == 1) {
             out.flag = F_SINGLE_CHAR;
-            return s.cp(0) == s.cp(CAP) ? 1.0 : 0.0;
+            v = s.cp(0) == s.cp(CAP) ? 1.0 : 0.0;
+        } else {
+            const bool table_b = measure != LEVENSHTEIN || lb <= la;
+            ScanPM<M, Store> pm(s, table_b ? CAP : 0, table_b ? lb : la);
+            CpReader<Store> ra(s, table_b ? 0 : CAP), ra2(s, table_b ? 0 : CAP);
+            v = measure_core<M>(measure, pm, ra, ra2, la, lb, table_b ? lb : la, table_b ? la : lb,
+                                out);
+            if (measure == JARO_WINKLER && v > 0.7) {
+                int lim = la < lb ? la : lb;
+                if (lim > 4) lim = 4;
+                int l = 0;
+                while (l < lim && s.cp(l) == s.cp(CAP + l)) l++;
+                out.x2 = l;
+                v = winkler_value(v, l);
+            }
         }
-        const bool table_b = measure != LEVENSHTEIN || lb <= la;
-        ScanPM<M, Store> pm(s, table_b ? CAP : 0, table_b ? lb : la);
-        CpReader<Store> ra(s, table_b ? 0 : CAP), ra2(s, table_b ? 0 : CAP);
-        v = measure_core<M>(measure, pm, ra, ra2, la, lb, table_b ? lb : la, table_b ? la : lb, out);
-        if (measure == JARO_WINKLER && v > 0.7) {
-            int lim = la < lb ? la : lb;
-            if (lim > 4) lim = 4;
-            int l = 0;
-            while (l < lim && s.cp(l) == s.cp(CAP + l)) l++;
-            out.x2 = l;
-            v = winkler_value(v, l);
+        if (Store::CPS_ALIAS_TABLE) {  // the keys live in the table's memory: restore all-zero
+            for (int k = 0; k < la; k++) s.cp(k) = 0u;
+            for (int k = 0; k < lb; k++) s.cp(CAP + k) = 0u;
         }
     }
     return v;

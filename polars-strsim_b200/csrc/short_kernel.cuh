@@ -1,0 +1,515 @@
+// short_kernel.cuh -- the fused short-string kernel (one pair per thread, strings <= bits(M) bytes).
+//
+// One persistent CTA walks tiles of TILE = TPB*RPT consecutive rows:
+//   1. load   : coalesced 16-byte loads of both columns' Arrow views (+ validity bits) -> smem
+//   2. stage  : the tile's out-of-line payload (byte length > 12) is one contiguous span of the data
+//               buffer when the column was built sequentially, so ONE TMA bulk copy
+//               (cp.async.bulk.shared.global, SASS UBLKCP) per column brings it into shared memory,
+//               completion on an mbarrier; columns whose views are scattered (gather/filter
+//               results) fall back to a cooperative word copy into the same stage area
+//   3. bucket : every row gets a cost key (Unicode?, max byte length); a shared-memory counting
+//               sort yields a permutation so that the 32 lanes of a warp work on pairs of (nearly)
+//               equal length and the same code path -- the length-bucketing pre-pass, done per tile
+//               on chip, no extra HBM traffic and no global reordering
+//   4. compute: each thread copies its pair into a private, bank-conflict-free slab
+//               ([slot][thread] layout), then runs row_short<M>() (Myers / bitmask Jaro / multiset)
+//               with its private 128-entry position-mask table, and writes the f64 result
+// Rows that do not fit (longer than bits(M) bytes, or the stage area is full) are appended to an
+// overflow list and finished by the 64-bit instantiation of this kernel (gather mode) or by
+// long_kernel.cuh.  Null rows (either input null, README.md:69-70) get 0.0 and are never
+// dereferenced beyond their view.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "row_short.cuh"
+
+namespace strsim {
+
+struct DevCol {
+    const uint4* views;       // row 0 of the segment
+    const uint8_t* validity;  // or nullptr
+    long long vbit;           // bit index of row 0 inside validity
+    const unsigned long long* bufs;  // device table of data-buffer base addresses
+    int stride;               // 1, or 0 for a broadcast scalar (strsim.rs:61-66)
+};
+
+struct Overflow {
+    unsigned int n64;    // rows for the 64-bit short kernel
+    unsigned int nlong;  // rows for the long kernel
+    unsigned int max_bytes_a, max_bytes_b;  // over the long rows
+};
+
+struct SegArgs {
+    DevCol a, b;
+    long long n;   // rows of the segment, or entries of `list` in gather mode
+    double* out;   // row 0 of the segment
+    int* dbg;      // row 0 of the segment (STRSIM_DBG_INTS per row) or nullptr
+    const unsigned int* list;  // gather mode: segment-relative row numbers
+    const unsigned int* list_count;  // gather mode: device-resident number of entries
+    Overflow* ovf;
+    unsigned int* list64;
+    unsigned int* listlong;
+    int stage_bytes;  // capacity of each column's stage area (multiple of 16)
+};
+
+// ---- small device helpers ------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ld_view(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ bool bit_valid(const uint8_t* validity, long long bit) {
+    return validity == nullptr || ((__ldg(validity + (bit >> 3)) >> (bit & 7)) & 1);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+
+// TMA bulk copy global -> shared (1-D, no tensor map): dst, src 16-byte aligned, bytes % 16 == 0
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes,
+                                             uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+template <class M, int TPB>
+struct DevStore {
+    static constexpr bool CPS_ALIAS_TABLE = true;
+    M* tab_;          // &table[tid]
+    uint32_t* cps_;   // same memory viewed as u32, &u32[tid]
+    uint32_t* wa_;    // &slab_a[tid]
+    uint32_t* wb_;    // &slab_b[tid]
+    __device__ __forceinline__ M& tab(uint32_t c) { return tab_[c * TPB]; }
+    __device__ __forceinline__ const M& tab(uint32_t c) const { return tab_[c * TPB]; }
+    __device__ __forceinline__ uint32_t& cp(int s) { return cps_[s * TPB]; }
+    __device__ __forceinline__ const uint32_t& cp(int s) const { return cps_[s * TPB]; }
+    __device__ __forceinline__ uint32_t wa(int k) const { return wa_[k * TPB]; }
+    __device__ __forceinline__ uint32_t wb(int k) const { return wb_[k * TPB]; }
+};
+
+template <class M, int TPB, int RPT>
+struct ShortLayout {
+    static constexpr int CAP = (int)sizeof(M) * 8;
+    static constexpr int WORDS = CAP / 4;
+    static constexpr int TILE = TPB * RPT;
+    static constexpr int NB = 2 * CAP + 3;  // keys 0 .. 2*CAP+2
+    static constexpr int NWARP = TPB / 32;
+    static constexpr size_t off_sva = 0;
+    static constexpr size_t off_svb = off_sva + sizeof(uint4) * TILE;
+    static constexpr size_t off_tab = off_svb + sizeof(uint4) * TILE;
+    static constexpr size_t off_slab_a = off_tab + sizeof(M) * 128 * TPB;
+    static constexpr size_t off_slab_b = off_slab_a + 4 * WORDS * TPB;
+    static constexpr size_t off_hist = off_slab_b + 4 * WORDS * TPB;
+    static constexpr size_t off_red = off_hist + 4 * ((NB + 3) & ~3);
+    static constexpr size_t off_mbar = off_red + 4 * 16 * NWARP;
+    static constexpr size_t off_perm = off_mbar + 16;
+    static constexpr size_t off_stage = (off_perm + 2 * TILE + 15) & ~(size_t)15;
+    static size_t bytes(int stage_bytes) { return off_stage + 2 * ((size_t)stage_bytes + 16); }
+};
+
+__device__ __forceinline__ uint32_t byte_mask(int nbytes) {  // low nbytes bytes set, nbytes in 0..4
+    return nbytes >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nbytes)) - 1u);
+}
+
+// Loads the bytes of one string (view v; out-of-line bytes already staged at stage + v.y) into the
+// thread's slab as zero-masked little-endian words.  Returns OR of all words (for the ASCII test).
+template <int WORDS, int TPB>
+__device__ __forceinline__ uint32_t load_string(const uint4& v, const unsigned char* stage,
+                                                uint32_t* slab /* &slab[tid] */) {
+    const int len = (int)v.x;
+    const int nw = (len + 3) >> 2;
+    uint32_t acc = 0;
+    if (len <= 12) {
+        uint32_t w0 = v.y & byte_mask(len);
+        uint32_t w1 = v.z & byte_mask(len - 4 < 0 ? 0 : len - 4);
+        uint32_t w2 = v.w & byte_mask(len - 8 < 0 ? 0 : len - 8);
+        slab[0] = w0;
+        slab[TPB] = w1;
+        slab[2 * TPB] = w2;
+        acc = w0 | w1 | w2;
+    } else {
+        const uint32_t soff = v.y;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(stage) + (soff >> 2);
+        const int sh = (int)(soff & 3) * 8;
+        uint32_t lo = src[0];
+#pragma unroll
+        for (int w = 0; w < WORDS; w++) {
+            if (w < nw) {
+                uint32_t hi = src[w + 1];
+                uint32_t word = __funnelshift_r(lo, hi, sh);
+                lo = hi;
+                if (w == nw - 1) word &= byte_mask(len - 4 * w);
+                slab[w * TPB] = word;
+                acc |= word;
+            }
+        }
+    }
+    return acc;
+}
+
+template <class M, int MEASURE, int TPB, int RPT, bool GATHER>
+__global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
+    using L = ShortLayout<M, TPB, RPT>;
+    constexpr int CAP = L::CAP;
+    constexpr int WORDS = L::WORDS;
+    constexpr int TILE = L::TILE;
+    constexpr int NB = L::NB;
+    constexpr int NWARP = L::NWARP;
+
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint4* sva = reinterpret_cast<uint4*>(smem + L::off_sva);
+    uint4* svb = reinterpret_cast<uint4*>(smem + L::off_svb);
+    M* tab = reinterpret_cast<M*>(smem + L::off_tab);
+    uint32_t* slab_a = reinterpret_cast<uint32_t*>(smem + L::off_slab_a);
+    uint32_t* slab_b = reinterpret_cast<uint32_t*>(smem + L::off_slab_b);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(smem + L::off_hist);
+    uint32_t* red = reinterpret_cast<uint32_t*>(smem + L::off_red);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + L::off_mbar);
+    uint16_t* perm = reinterpret_cast<uint16_t*>(smem + L::off_perm);
+    unsigned char* stage_a = smem + L::off_stage;
+    unsigned char* stage_b = stage_a + s.stage_bytes + 16;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const long long n = GATHER ? (long long)*s.list_count : s.n;
+    const long long n_tiles = (n + TILE - 1) / TILE;
+
+    // one-time: zero the position-mask tables (row_short keeps them zero), init the mbarrier
+    {
+        uint4* t4 = reinterpret_cast<uint4*>(tab);
+        constexpr int N4 = (int)(sizeof(M) * 128 * TPB / 16);
+        for (int i = tid; i < N4; i += TPB) t4[i] = make_uint4(0, 0, 0, 0);
+        if (tid == 0) mbar_init(mbar, 1);
+    }
+    uint32_t mbar_phase = 0;
+    DevStore<M, TPB> store;
+    store.tab_ = tab + tid;
+    store.cps_ = reinterpret_cast<uint32_t*>(tab) + tid;
+    store.wa_ = slab_a + tid;
+    store.wb_ = slab_b + tid;
+    __syncthreads();
+
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long tile0 = tile * TILE;
+        for (int i = tid; i < NB; i += TPB) hist[i] = 0;
+
+        // ---------------- 1. load views, validity; route rows that do not fit --------------------
+        unsigned active = 0;  // bit k: row k*TPB+tid goes through the sort
+        uint32_t mn_off[2] = {0xFFFFFFFFu, 0xFFFFFFFFu}, mx_end[2] = {0, 0};
+        uint32_t mn_buf[2] = {0xFFFFFFFFu, 0xFFFFFFFFu}, mx_buf[2] = {0, 0};
+        uint32_t cnt[2] = {0, 0}, pad_bytes[2] = {0, 0};
+#pragma unroll
+        for (int k = 0; k < RPT; k++) {
+            const int i = k * TPB + tid;
+            const long long idx = tile0 + i;
+            uint4 va = make_uint4(0, 0, 0, 0), vb = make_uint4(0, 0, 0, 0);
+            if (idx < n) {
+                const long long row = GATHER ? (long long)s.list[idx] : idx;
+                va = ld_view(s.a.views + row * s.a.stride);
+                vb = ld_view(s.b.views + row * s.b.stride);
+                const bool valid = bit_valid(s.a.validity, s.a.vbit + row * s.a.stride) &&
+                                   bit_valid(s.b.validity, s.b.vbit + row * s.b.stride);
+                const uint32_t mx = va.x > vb.x ? va.x : vb.x;
+                if (!valid) {
+                    s.out[row] = 0.0;
+                    if (s.dbg) {
+                        int* d = s.dbg + row * 6;
+#pragma unroll
+                        for (int q = 0; q < 6; q++) d[q] = 0;
+                    }
+                } else if (mx > (uint32_t)CAP) {
+                    if (CAP == 32 && mx <= 64u) {
+                        s.list64[atomicAdd(&s.ovf->n64, 1u)] = (unsigned int)row;
+                    } else {
+                        s.listlong[atomicAdd(&s.ovf->nlong, 1u)] = (unsigned int)row;
+                        atomicMax(&s.ovf->max_bytes_a, va.x);
+                        atomicMax(&s.ovf->max_bytes_b, vb.x);
+                    }
+                } else {
+                    active |= 1u << k;
+                    if (va.x > 12u) {
+                        mn_off[0] = min(mn_off[0], va.w);
+                        mx_end[0] = max(mx_end[0], va.w + va.x);
+                        mn_buf[0] = min(mn_buf[0], va.z);
+                        mx_buf[0] = max(mx_buf[0], va.z);
+                        cnt[0]++;
+                        pad_bytes[0] += (va.x + 3u) & ~3u;
+                    }
+                    if (vb.x > 12u) {
+                        mn_off[1] = min(mn_off[1], vb.w);
+                        mx_end[1] = max(mx_end[1], vb.w + vb.x);
+                        mn_buf[1] = min(mn_buf[1], vb.z);
+                        mx_buf[1] = max(mx_buf[1], vb.z);
+                        cnt[1]++;
+                        pad_bytes[1] += (vb.x + 3u) & ~3u;
+                    }
+                }
+            }
+            sva[i] = va;
+            svb[i] = vb;
+        }
+
+        // ---------------- 2. stage the out-of-line payload -----------------------------------------
+        // block reduction of the span descriptors (warp shuffle, then warp 0 over the partials)
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                mn_off[c] = min(mn_off[c], __shfl_xor_sync(0xFFFFFFFFu, mn_off[c], o));
+                mx_end[c] = max(mx_end[c], __shfl_xor_sync(0xFFFFFFFFu, mx_end[c], o));
+                mn_buf[c] = min(mn_buf[c], __shfl_xor_sync(0xFFFFFFFFu, mn_buf[c], o));
+                mx_buf[c] = max(mx_buf[c], __shfl_xor_sync(0xFFFFFFFFu, mx_buf[c], o));
+                cnt[c] += __shfl_xor_sync(0xFFFFFFFFu, cnt[c], o);
+            }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                red[warp * 16 + c * 5 + 0] = mn_off[c];
+                red[warp * 16 + c * 5 + 1] = mx_end[c];
+                red[warp * 16 + c * 5 + 2] = mn_buf[c];
+                red[warp * 16 + c * 5 + 3] = mx_buf[c];
+                red[warp * 16 + c * 5 + 4] = cnt[c];
+            }
+        }
+        __syncthreads();
+        int mode[2];          // 0 nothing out of line, 1 TMA bulk span, 2 cooperative gather copy
+        uint32_t base16[2];   // TMA mode: 16-aligned start offset of the span in the data buffer
+        uint32_t span[2], bufidx[2];
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            uint32_t a0 = 0xFFFFFFFFu, a1 = 0, a2 = 0xFFFFFFFFu, a3 = 0, a4 = 0;
+#pragma unroll
+            for (int w = 0; w < NWARP; w++) {
+                a0 = min(a0, red[w * 16 + c * 5 + 0]);
+                a1 = max(a1, red[w * 16 + c * 5 + 1]);
+                a2 = min(a2, red[w * 16 + c * 5 + 2]);
+                a3 = max(a3, red[w * 16 + c * 5 + 3]);
+                a4 += red[w * 16 + c * 5 + 4];
+            }
+            base16[c] = a0 & ~15u;
+            span[c] = ((a1 + 15u) & ~15u) - base16[c];
+            bufidx[c] = a2;
+            mode[c] = a4 == 0 ? 0 : (a2 == a3 && span[c] <= (uint32_t)s.stage_bytes) ? 1 : 2;
+        }
+        const bool used_tma = mode[0] == 1 || mode[1] == 1;
+        if (used_tma && tid == 0) {
+            // one arrival per phase: announce the bytes of both copies, then issue them
+            mbar_expect_tx(mbar, (mode[0] == 1 ? span[0] : 0u) + (mode[1] == 1 ? span[1] : 0u));
+            if (mode[0] == 1)
+                tma_bulk_g2s(stage_a,
+                             reinterpret_cast<const unsigned char*>(s.a.bufs[bufidx[0]]) + base16[0],
+                             span[0], mbar);
+            if (mode[1] == 1)
+                tma_bulk_g2s(stage_b,
+                             reinterpret_cast<const unsigned char*>(s.b.bufs[bufidx[1]]) + base16[1],
+                             span[1], mbar);
+        }
+
+        // gather-copy fallback: exclusive scan of padded byte counts, then each thread copies its
+        // rows' bytes global -> stage (aligned words, funnel shift on the source)
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            if (mode[c] != 2) continue;  // CTA-uniform
+            __syncthreads();             // red[] reuse
+            uint32_t incl = pad_bytes[c];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) red[warp] = incl;
+            __syncthreads();
+            uint32_t warp_base = 0;
+            for (int w = 0; w < warp; w++) warp_base += red[w];
+            uint32_t pos = warp_base + incl - pad_bytes[c];
+            uint4* sv = c == 0 ? sva : svb;
+            unsigned char* stage = c == 0 ? stage_a : stage_b;
+            const DevCol& col = c == 0 ? s.a : s.b;
+#pragma unroll
+            for (int k = 0; k < RPT; k++) {
+                const int i = k * TPB + tid;
+                if (!((active >> k) & 1u)) continue;
+                uint4 v = sv[i];
+                if (v.x <= 12u) continue;
+                const uint32_t padded = (v.x + 3u) & ~3u;
+                if (pos + padded > (uint32_t)s.stage_bytes) {
+                    // stage full: finish this row in the long kernel
+                    const long long idx = tile0 + i;
+                    const long long row = GATHER ? (long long)s.list[idx] : idx;
+                    s.listlong[atomicAdd(&s.ovf->nlong, 1u)] = (unsigned int)row;
+                    atomicMax(&s.ovf->max_bytes_a, sva[i].x);
+                    atomicMax(&s.ovf->max_bytes_b, svb[i].x);
+                    active &= ~(1u << k);
+                    continue;
+                }
+                const unsigned char* g =
+                    reinterpret_cast<const unsigned char*>(col.bufs[v.z]) + v.w;
+                const uint32_t* gw = reinterpret_cast<const uint32_t*>(
+                    reinterpret_cast<uintptr_t>(g) & ~(uintptr_t)3);
+                const int sh = (int)(reinterpret_cast<uintptr_t>(g) & 3) * 8;
+                uint32_t* dst = reinterpret_cast<uint32_t*>(stage + pos);
+                uint32_t lo = __ldg(gw);
+                const int nw = (int)(padded >> 2);
+                for (int w = 0; w < nw; w++) {
+                    // reads at most 7 bytes past the string: inside the padded device buffer
+                    const uint32_t hi = __ldg(gw + w + 1);
+                    dst[w] = __funnelshift_r(lo, hi, sh);
+                    lo = hi;
+                }
+                sv[i].y = pos;
+                pos += padded;
+            }
+        }
+        // TMA mode: rewrite the views so that .y is the offset inside the stage area
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            if (mode[c] != 1) continue;
+            uint4* sv = c == 0 ? sva : svb;
+#pragma unroll
+            for (int k = 0; k < RPT; k++) {
+                const int i = k * TPB + tid;
+                if (((active >> k) & 1u) && sv[i].x > 12u) sv[i].y = sv[i].w - base16[c];
+            }
+        }
+        if (used_tma) {
+            mbar_wait(mbar, mbar_phase);
+            mbar_phase ^= 1u;
+        }
+        __syncthreads();
+
+        // ---------------- 3. bucket: cost key per row, counting sort (descending) -----------------
+        uint32_t key[RPT], rank[RPT];
+#pragma unroll
+        for (int k = 0; k < RPT; k++) {
+            const int i = k * TPB + tid;
+            key[k] = 0;
+            rank[k] = 0;
+            if (!((active >> k) & 1u)) continue;
+            const uint4 va = sva[i], vb = svb[i];
+            uint32_t hi_bits = 0;  // conservative (unmasked) non-ASCII test; exact test in step 4
+            if (va.x <= 12u) {
+                hi_bits |= va.y | va.z | va.w;
+            } else {
+                const uint32_t* p = reinterpret_cast<const uint32_t*>(stage_a) + (va.y >> 2);
+                const int nwords = (int)(((va.y & 3u) + va.x + 3u) >> 2);
+                for (int w = 0; w < nwords; w++) hi_bits |= p[w];
+            }
+            if (vb.x <= 12u) {
+                hi_bits |= vb.y | vb.z | vb.w;
+            } else {
+                const uint32_t* p = reinterpret_cast<const uint32_t*>(stage_b) + (vb.y >> 2);
+                const int nwords = (int)(((vb.y & 3u) + vb.x + 3u) >> 2);
+                for (int w = 0; w < nwords; w++) hi_bits |= p[w];
+            }
+            const uint32_t mx = va.x > vb.x ? va.x : vb.x;
+            key[k] = 1u + mx + ((hi_bits & 0x80808080u) ? (uint32_t)(CAP + 1) : 0u);
+            rank[k] = atomicAdd(&hist[key[k]], 1u);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // start[key] = number of rows with a larger key; lane l owns bins [l*CH, (l+1)*CH)
+            constexpr int CH = (NB + 31) / 32;
+            uint32_t local[CH];
+            uint32_t sum = 0;
+#pragma unroll
+            for (int q = 0; q < CH; q++) {
+                const int bin = NB - 1 - (lane * CH + q);  // descending
+                local[q] = bin >= 1 ? hist[bin] : 0u;      // bin 0 = inactive rows
+                sum += local[q];
+            }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            uint32_t run = incl - sum;
+#pragma unroll
+            for (int q = 0; q < CH; q++) {
+                const int bin = NB - 1 - (lane * CH + q);
+                if (bin >= 1) hist[bin] = run;
+                run += local[q];
+            }
+            if (lane == 31) hist[0] = incl;  // total active rows
+        }
+        __syncthreads();
+        const int n_active = (int)hist[0];
+#pragma unroll
+        for (int k = 0; k < RPT; k++)
+            if (key[k]) perm[hist[key[k]] + rank[k]] = (uint16_t)(k * TPB + tid);
+        __syncthreads();
+
+        // ---------------- 4. compute -----------------------------------------------------------------
+#pragma unroll 1
+        for (int k = 0; k < RPT; k++) {
+            const int p = k * TPB + ((k & 1) ? (TPB - 1 - tid) : tid);  // snake order balances warps
+            if (p >= n_active) continue;
+            const int i = perm[p];
+            const uint4 va = sva[i], vb = svb[i];
+            const uint32_t or_a = load_string<WORDS, TPB>(va, stage_a, store.wa_);
+            const uint32_t or_b = load_string<WORDS, TPB>(vb, stage_b, store.wb_);
+            const int na = (int)va.x, nb = (int)vb.x;
+            bool equal = na == nb;
+            if (equal) {
+                const int nw = (na + 3) >> 2;
+                uint32_t diff = 0;
+#pragma unroll
+                for (int w = 0; w < WORDS; w++)
+                    if (w < nw) diff |= store.wa(w) ^ store.wb(w);
+                equal = diff == 0;
+            }
+            const bool ascii = ((or_a | or_b) & 0x80808080u) == 0;
+            PairInts ints;
+            const double v = row_short<M>(MEASURE, store, na, nb, equal, ascii, ints);
+            const long long idx = tile0 + i;
+            const long long row = GATHER ? (long long)s.list[idx] : idx;
+            s.out[row] = v;
+            if (s.dbg) {
+                int* d = s.dbg + row * 6;
+                d[0] = ints.flag;
+                d[1] = ints.la;
+                d[2] = ints.lb;
+                d[3] = ints.x0;
+                d[4] = ints.x1;
+                d[5] = ints.x2;
+            }
+        }
+        __syncthreads();  // smem is reused by the next tile
+    }
+}
+
+}  // namespace strsim

@@ -10,6 +10,7 @@ using namespace strsim;
 template <class M>
 struct HostStore {
     static constexpr int CAP = (int)sizeof(M) * 8;
+    static constexpr bool CPS_ALIAS_TABLE = false;
     M table[128];
     uint32_t cps[2 * CAP];
     uint32_t a_words[CAP / 4], b_words[CAP / 4];

@@ -1,0 +1,246 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle.  Run with `-m gpu` on a B200.
+
+Bar (BASELINE.json north_star): integer intermediates bit-exact, f64 results bit-identical
+(target 0 ulp; the contract allows 1 ulp), identical null masks.
+"""
+import json
+import os
+import random
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from test_oracle import GOLDEN, load_fixture, rand_pair
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def native():
+    from polars_strsim import _native
+
+    assert _native.lib().strsim_b200_device_count() > 0, "no CUDA device: these tests need the B200"
+    return _native
+
+
+def sv(values):
+    import pyarrow as pa
+
+    return pa.array(values, type=pa.string_view())
+
+
+def ulp_diff(x, y):
+    xi = x.view(np.int64)
+    yi = y.view(np.int64)
+    return np.abs(xi - yi)
+
+
+def check(native, oracle, measure, a, b, A=None, B=None, ref_a=None, ref_b=None):
+    """a, b: python lists (the logical rows); A, B: arrow inputs if they differ from sv(a), sv(b)."""
+    A = sv(a) if A is None else A
+    B = sv(b) if B is None else B
+    ra = a if ref_a is None else ref_a
+    rb = b if ref_b is None else ref_b
+    ref, ref_valid, ref_ints = oracle.batch(measure, ra, rb)
+    vals, valid, nulls, ints = native.compute_host(measure, A, B, debug=True)
+    assert len(vals) == len(ref)
+    assert (valid == ref_valid).all(), "null masks differ"
+    assert nulls == int((~ref_valid).sum())
+    bad = np.nonzero(valid & (vals.view(np.uint64) != ref.view(np.uint64)))[0]
+    assert bad.size == 0, (measure, ra[bad[0]], rb[bad[0]], vals[bad[0]], ref[bad[0]], ints[bad[0]], ref_ints[bad[0]])
+    ibad = np.nonzero(valid & (ints != ref_ints).any(axis=1))[0]
+    assert ibad.size == 0, (measure, ra[ibad[0]], rb[ibad[0]], ints[ibad[0]], ref_ints[ibad[0]])
+    return vals, valid
+
+
+def test_reference_golden_vectors(native, oracle):
+    """All 1115 known-answer vectors of the reference's own tests (strsim.rs:371-1534)."""
+    fx = load_fixture()
+    for measure in oracle.MEASURES:
+        rows = [r for r in fx if r[0] == measure]
+        vals, valid = check(native, oracle, measure, [r[1] for r in rows], [r[2] for r in rows])
+        exp = np.array([r[3] for r in rows])
+        exact = np.array([r[4] for r in rows])
+        assert valid.all()
+        assert (np.abs(vals - exp) < 1e-8).all()          # the reference's own tolerance, strsim.rs:349
+        assert (vals.view(np.uint64) == exact.view(np.uint64)).all()  # and bit-exact vs the fixture
+
+
+def test_readme_table(native, oracle):
+    table = json.loads((GOLDEN / "readme_table.json").read_text())
+    for measure in oracle.MEASURES:
+        vals, valid, nulls = native.compute_host(measure, sv(table["name_a"]), sv(table["name_b"]))
+        assert nulls == 2
+        for v, ok, printed, hx in zip(vals, valid, table["printed"][measure], table["oracle_hex"][measure]):
+            assert ok == (printed is not None)
+            if ok:
+                assert abs(v - printed) < 5e-7 and v == float.fromhex(hx)
+
+
+def test_random_short_mixed_scripts(native, oracle):
+    rng = random.Random(2024)
+    pairs = [rand_pair(rng, 24) for _ in range(30000)]
+    a, b = [p[0] for p in pairs], [p[1] for p in pairs]
+    for measure in oracle.MEASURES:
+        check(native, oracle, measure, a, b)
+
+
+def test_length_boundaries(native, oracle):
+    """12/13 bytes (inline vs out-of-line view), 32/33 and 64/65 (mask word boundaries), 1-4 byte UTF-8."""
+    rng = random.Random(77)
+    a, b = [], []
+    lens = [0, 1, 2, 3, 4, 11, 12, 13, 14, 15, 16, 17, 31, 32, 33, 34, 63, 64, 65, 66, 100]
+    for la in lens:
+        for lb in lens:
+            for alpha in ("ab", "abcdefghijklmnopqrstuvwxyz"):
+                x = "".join(rng.choice(alpha) for _ in range(la))
+                y = "".join(rng.choice(alpha) for _ in range(lb))
+                a += [x, x]
+                b += [y, x[: lb] if lb <= la else x + y[la:]]
+    for ch in ("é", "ß", "日", "\U0001f600"):
+        w = len(ch.encode())
+        for la in (1, 2, 3, 12 // w, 12 // w + 1, 32 // w, 32 // w + 1, 64 // w, 64 // w + 1):
+            for lb in (1, 2, 12 // w, 32 // w, 64 // w + 1):
+                a += [ch * la, ch * la, "x" + ch * la]
+                b += [ch * lb, ("z" * lb), ch * lb + "y"]
+    for measure in oracle.MEASURES:
+        check(native, oracle, measure, a, b)
+
+
+def test_medium_and_long_strings(native, oracle):
+    rng = random.Random(31337)
+    pairs = [rand_pair(rng, 64) for _ in range(4000)] + [rand_pair(rng, 200) for _ in range(600)]
+    pairs += [rand_pair(rng, 900) for _ in range(40)]
+    a, b = [p[0] for p in pairs], [p[1] for p in pairs]
+    for measure in oracle.MEASURES:
+        check(native, oracle, measure, a, b)
+    assert sum(native.last_overflow()) > 0  # the overflow kernels really ran
+
+
+def test_nulls_slices_chunks_broadcast(native, oracle):
+    import pyarrow as pa
+
+    rng = random.Random(5)
+    n = 7001
+    a, b = [], []
+    for _ in range(n):
+        x, y = rand_pair(rng, 30)
+        a.append(None if rng.random() < 0.05 else x)
+        b.append(None if rng.random() < 0.05 else y)
+    for measure in oracle.MEASURES:
+        check(native, oracle, measure, a, b)
+    # sliced arrays: non-zero ArrowArray.offset on views AND validity
+    A, B = sv(a), sv(b)
+    check(native, oracle, "jaro_winkler", a[13:5013], b[101:5101], A=A.slice(13, 5000), B=B.slice(101, 5000))
+    # different chunkings on the two sides
+    cuts_a, cuts_b = [0, 1, 64, 1000, 4097, n], [0, 333, 2048, 2049, n]
+    CA = pa.chunked_array([A.slice(lo, hi - lo) for lo, hi in zip(cuts_a, cuts_a[1:])])
+    CB = pa.chunked_array([B.slice(lo, hi - lo) for lo, hi in zip(cuts_b, cuts_b[1:])])
+    for measure in ("levenshtein", "sorensen_dice"):
+        check(native, oracle, measure, a, b, A=CA, B=CB)
+    # scalar broadcast, both orientations (the left-literal case returns n rows, not the
+    # reference's 1-row quirk of strsim.rs:73)
+    for measure in oracle.MEASURES:
+        check(native, oracle, measure, a, ["smith"] * n, B=sv(["smith"]))
+        check(native, oracle, measure, ["josé maría"] * n, b, A=sv(["josé maría"]))
+    check(native, oracle, "jaro", a, [None] * n, B=sv([None]))
+    # all null, single row, zero rows
+    check(native, oracle, "jaccard", [None] * 100, b[:100])
+    check(native, oracle, "levenshtein", ["x"], ["y"])
+    vals, valid, nulls = native.compute_host("jaro", sv([]), sv([]))
+    assert len(vals) == 0 and nulls == 0
+    with pytest.raises(native.StrsimError, match="same length"):
+        native.compute_host("jaro", sv(a[:10]), sv(b[:11]))
+
+
+def test_scattered_views_take_the_gather_path(native, oracle):
+    """Views that do not reference one contiguous span (a take() result) and several data buffers."""
+    import pyarrow as pa
+
+    rng = random.Random(11)
+    base = ["".join(rng.choice("abcdefghij") for _ in range(rng.randint(13, 30))) for _ in range(20000)]
+    idx = [rng.randrange(len(base)) for _ in range(6000)]
+    A = sv(base).take(pa.array(idx))
+    a = [base[i] for i in idx]
+    b = ["".join(rng.choice("abcdefghij") for _ in range(rng.randint(0, 30))) for _ in idx]
+    for measure in oracle.MEASURES:
+        check(native, oracle, measure, a, b, A=A)
+    big = pa.concat_arrays([sv(base[:10000]), sv(base[10000:])])  # >= 2 variadic buffers
+    check(native, oracle, "levenshtein", base, list(reversed(base)), A=big)
+
+
+def test_arrow_c_data_interface_and_offset_layouts(native, oracle):
+    import pyarrow as pa
+    from polars_strsim import arrow
+
+    rng = random.Random(3)
+    pairs = [rand_pair(rng, 40) for _ in range(3000)]
+    a = [None if rng.random() < 0.1 else p[0] for p in pairs]
+    b = [p[1] for p in pairs]
+    for measure in oracle.MEASURES:
+        ref, ref_valid, _ = oracle.batch(measure, a, b)
+        for typ in (pa.string_view(), pa.string(), pa.large_string()):
+            out = getattr(arrow, measure)(pa.array(a, type=typ), pa.array(b, type=typ))
+            assert out.type == pa.float64() and len(out) == len(a)
+            got_valid = np.array([v is not None for v in out.to_pylist()])
+            assert (got_valid == ref_valid).all()
+            got = np.array([0.0 if v is None else v for v in out.to_pylist()])
+            assert (got[ref_valid] == ref[ref_valid]).all()
+    out = arrow.jaro_winkler(pa.chunked_array([pa.array(a[:100]), pa.array(a[100:])]).slice(7), pa.array(b[7:]))
+    ref, ref_valid, _ = oracle.batch("jaro_winkler", a[7:], b[7:])
+    got = np.array([0.0 if v is None else v for v in out.to_pylist()])
+    assert (got[ref_valid] == ref[ref_valid]).all()
+    with pytest.raises(native.StrsimError, match="expected `String`"):
+        arrow.jaro(pa.array([1, 2]), pa.array(["a", "b"]))
+
+
+def test_fallback_kernel_cross_check(oracle):
+    """STRSIM_B200_FORCE_GENERIC=1 sends every row through the independent textbook kernel."""
+    code = r"""
+import sys, random, numpy as np
+sys.path[:0] = [%r, %r, %r]
+import pyarrow as pa
+from polars_strsim import _native
+from oracle import oracle
+from test_oracle import rand_pair
+rng = random.Random(8)
+pairs = [rand_pair(rng, 50) for _ in range(5000)]
+a = [None if rng.random() < 0.03 else p[0] for p in pairs]; b = [p[1] for p in pairs]
+for m in oracle.MEASURES:
+    ref, rv, ri = oracle.batch(m, a, b)
+    v, valid, nulls, ints = _native.compute_host(m, pa.array(a, type=pa.string_view()), pa.array(b, type=pa.string_view()), debug=True)
+    assert (valid == rv).all() and (v[rv].view(np.uint64) == ref[rv].view(np.uint64)).all() and (ints[rv] == ri[rv]).all(), m
+    assert _native.last_overflow()[1] == int(rv.sum())
+print("ok")
+""" % (str(ROOT), str(ROOT / "polars-strsim_b200"), str(ROOT / "tests"))
+    env = dict(os.environ, STRSIM_B200_FORCE_GENERIC="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_device_resident_api(native, oracle):
+    torch = pytest.importorskip("torch")
+    rng = random.Random(17)
+    pairs = [rand_pair(rng, 24) for _ in range(50000)]
+    a = [None if rng.random() < 0.02 else p[0] for p in pairs]
+    b = [p[1] for p in pairs]
+    ca, cb = native.DeviceColumn(sv(a)), native.DeviceColumn(sv(b))
+    assert len(ca) == len(a) and ca.algorithmic_bytes > 16 * len(a)
+    n = len(a)
+    out = torch.empty(n, dtype=torch.float64, device="cuda")
+    val = torch.zeros((n + 31) // 32, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for measure in oracle.MEASURES:
+        before = native.kernel_launches()
+        native.compute_device(measure, ca, cb, out.data_ptr(), val.data_ptr(), 0, st)
+        torch.cuda.synchronize()
+        assert native.kernel_launches() > before
+        ref, ref_valid, _ = oracle.batch(measure, a, b)
+        got = out.cpu().numpy()
+        bits = np.unpackbits(val.cpu().numpy().view(np.uint8), bitorder="little")[:n].astype(bool)
+        assert (bits == ref_valid).all()
+        assert (got[ref_valid].view(np.uint64) == ref[ref_valid].view(np.uint64)).all()
