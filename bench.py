@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- string pairs/sec of the row-wise similarity hot path on B200 (BASELINE.json metric).
+
+A step = one pass of ALL FIVE measures (levenshtein, jaro, jaro_winkler, jaccard, sorensen_dice)
+over one batch of synthetic pairs (default: BASELINE config C2, 10M ASCII name pairs of length
+4..24 per GPU, seeds in SURVEY.md 8(d)).  `value` counts pair evaluations (rows x 5) per second
+with the two columns already resident in HBM; `e2e` is the same work through the host-buffer C ABI
+call (`strsim_b200_compute_host`), pinned host memory in, H2D + kernels + D2H inside the timed
+region, five calls per step exactly as Polars would call the plugin five times.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2|C3|C4] [--rows R]
+    python bench.py --impl reference ...     # the reference's CPU algorithm (oracle port) on host cores
+    torchrun --nproc-per-node N bench.py --gpus N ...   # one process per GPU, rows sharded by range
+
+Multi-GPU is row-range sharding with no data-path collective: every rank owns
+`rows` rows (weak scaling); NCCL is used only for the barrier and the max-over-ranks of the time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+for p in (ROOT, ROOT / "polars-strsim_b200"):
+    if str(p) not in sys.path:
+        sys.path.insert(0, str(p))
+
+MEASURES = ("levenshtein", "jaro", "jaro_winkler", "jaccard", "sorensen_dice")
+WORKLOADS = {
+    "C2": dict(config=2, rows=10_000_000, measures=MEASURES,
+               desc="C2: 10M synthetic ASCII name pairs, lengths 4-24, all five measures"),
+    "C3": dict(config=3, rows=100_000_000, measures=MEASURES,
+               desc="C3: mixed-Unicode name pairs (Latin-1 diacritics + CJK), 5% nulls, uneven chunks"),
+    "C4": dict(config=4, rows=1_000_000, measures=("levenshtein",),
+               desc="C4: long-text pairs, 200-4000 codepoints, Levenshtein"),
+    "C5": dict(config=5, rows=125_000_000, measures=("jaro_winkler", "sorensen_dice"),
+               desc="C5: record-linkage pairs (C2 generator, seed 0xC5), Jaro-Winkler + Sorensen-Dice"),
+}
+UNIT = "pairs/s"
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, val in zip(names, r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(n_gpus: int):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return world, rank, local
+
+
+def cpu_baseline(A, B, measures, budget_s: float = 15.0):
+    """The oracle (a port of the reference's algorithms with its static row-range threading,
+    strsim.rs:21-39,72-100) on this box's host cores, on a bounded sample of the same workload."""
+    import pyarrow as pa
+    from oracle import oracle
+
+    threads = oracle.n_host_threads()
+    n = len(A)
+    flatA = A.combine_chunks() if isinstance(A, pa.ChunkedArray) else A
+    flatB = B.combine_chunks() if isinstance(B, pa.ChunkedArray) else B
+    probe = min(n, 50_000)
+    t0 = time.perf_counter()
+    for m in measures:
+        oracle.batch_views(m, flatA.slice(0, probe), flatB.slice(0, probe), n_threads=threads)
+    rate = probe * len(measures) / max(time.perf_counter() - t0, 1e-6)
+    sample = int(min(n, max(probe, rate * budget_s / len(measures))))
+    per = {}
+    t_all = 0.0
+    for m in measures:
+        t0 = time.perf_counter()
+        oracle.batch_views(m, flatA.slice(0, sample), flatB.slice(0, sample), n_threads=threads)
+        dt = time.perf_counter() - t0
+        per[m] = sample / dt
+        t_all += dt
+    return {"value": sample * len(measures) / t_all, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"first {sample} rows of the workload x {len(measures)} measures, "
+                      f"C restatement of polars-strsim's rayon path, {threads} threads",
+            "per_measure": per}
+
+
+def run_reference(args, wl, world, rank):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference is Rust and
+    cannot be built in this image (no cargo), so this times the oracle port (kind "port") with all
+    host threads.  Each step is a bounded sample of the workload."""
+    if rank != 0:
+        return
+    from bench_support import workloads
+    from oracle import oracle
+
+    measures = wl["measures"]
+    threads = oracle.n_host_threads()
+    sample = min(args.rows, 2_000_000 if wl["config"] != 4 else 2_000)
+    A, B = workloads.make_pairs(wl["config"], sample)
+    import pyarrow as pa
+
+    if isinstance(A, pa.ChunkedArray):
+        A, B = A.combine_chunks(), B.combine_chunks()
+    for _ in range(args.warmup):
+        for m in measures:
+            oracle.batch_views(m, A, B, n_threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for m in measures:
+            oracle.batch_views(m, A, B, n_threads=threads)
+    dt = time.perf_counter() - t0
+    value = sample * len(measures) * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "string pairs/sec (mean over the measures of the workload)",
+        "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8/u32 codepoints, f64 results", "data": "synthetic",
+        "config": {"workload": wl["desc"], "rows_per_step": sample, "measures": list(measures)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{sample} rows x {len(measures)} measures per step"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--rows", type=int, default=None, help="rows per GPU (default: the workload's size)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.rows is None:
+        args.rows = wl["rows"]
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    world, rank, local = dist_setup(args.gpus)
+
+    if args.impl == "reference":
+        run_reference(args, wl, world, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from bench_support import workloads
+    from polars_strsim import _native
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: polars-strsim_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    _native.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    measures = wl["measures"]
+    n = args.rows
+    # ---- data: this rank's row range [rank*n, (rank+1)*n), generated into pinned host memory --------
+    A, B = workloads.make_pairs(wl["config"], n, row_base=rank * n, pinned=not args.no_e2e,
+                                uneven_b=(wl["config"] == 3))
+    alg_bytes = workloads.algorithmic_bytes(A, B)  # per launch of one measure
+    colA, colB = _native.DeviceColumn(A), _native.DeviceColumn(B)
+    has_nulls = A.null_count + B.null_count > 0
+    out = torch.empty(n, dtype=torch.float64, device="cuda")
+    val = torch.zeros((n + 31) // 32, dtype=torch.int32, device="cuda") if has_nulls else None
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+
+    def step(events=None):
+        for i, m in enumerate(measures):
+            if events is not None:
+                events[i][0].record(stream)
+            _native.compute_device(m, colA, colB, out.data_ptr(), val.data_ptr() if val is not None else 0, 0, sptr)
+            if events is not None:
+                events[i][1].record(stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _native.kernel_launches()
+    per_events = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                   for _ in measures] for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for k in range(args.steps):
+        step(per_events[k])
+    e1.record(stream)
+    barrier()
+    launches = _native.kernel_launches() - launches0
+    overflow = _native.last_overflow()
+    elapsed_ms = e0.elapsed_time(e1)
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    checksum = float(out.sum().item())
+
+    per_measure_ms = {m: float(np.mean([per_events[k][i][0].elapsed_time(per_events[k][i][1])
+                                        for k in range(args.steps)])) for i, m in enumerate(measures)}
+
+    # ---- end to end through the host-buffer C ABI (pinned in, pinned out) -------------------------------
+    e2e = None
+    if not args.no_e2e:
+        prepared = _native.prepare(A, B)
+        host_out = torch.empty(n, dtype=torch.float64, pin_memory=True)
+        host_val = torch.zeros((n + 7) // 8 + 8, dtype=torch.uint8, pin_memory=True)
+        ov, ob = host_out.numpy(), host_val.numpy()
+
+        def e2e_step():
+            for m in measures:
+                _native.compute_host(m, None, None, out_values=ov, out_validity=ob, prepared=prepared)
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps = max(1, min(args.steps, 3))
+        for _ in range(e2e_steps):
+            e2e_step()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        in_bytes = sum(b.size for col in (A, B)
+                       for ch in (col.chunks if hasattr(col, "chunks") else [col])
+                       for b in ch.buffers() if b is not None)
+        e2e = {"value": n * len(measures) * world * e2e_steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": in_bytes * len(measures),
+               "d2h_bytes_per_step": (8 * n + ((n + 7) // 8 if has_nulls else 0)) * len(measures),
+               "ms_per_step": dt / e2e_steps * 1e3,
+               "api": "strsim_b200_compute_host (one call per measure, pinned host buffers)",
+               "checksum_matches_device": bool(abs(float(host_out.sum().item()) - checksum) < 1e-6 * max(1.0, abs(checksum)))}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    dominant = max(per_measure_ms, key=per_measure_ms.get)
+    dom_s = per_measure_ms[dominant] * 1e-3
+    traffic = None
+    tp = ROOT / "profiles" / "traffic.json"
+    if tp.exists():
+        traffic = json.loads(tp.read_text()).get(args.workload, {}).get(dominant)
+    roofline = {"bound": "hbm", "kernel": f"short_kernel<{dominant}>", "achieved": alg_bytes / dom_s / 1e9,
+                "peak": peak, "unit": "GB/s", "frac": alg_bytes / dom_s / 1e9 / peak, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                "algorithmic_bytes_per_pair": alg_bytes / n, "launch_ms": per_measure_ms[dominant]}
+    per_measure = {m: {"ms": ms, "pairs_per_s": n / (ms * 1e-3), "gbps": alg_bytes / (ms * 1e-3) / 1e9,
+                       "hbm_frac": alg_bytes / (ms * 1e-3) / 1e9 / peak} for m, ms in per_measure_ms.items()}
+    line = {
+        "metric": "string pairs/sec (pair evaluations = rows x measures; per-measure rates in per_measure)",
+        "value": n * len(measures) * world * args.steps / (elapsed_ms * 1e-3),
+        "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8/u32 codepoints, u32/u64 bit-vectors, f64 results", "data": "synthetic",
+        "config": {"workload": wl["desc"], "rows_per_gpu": n, "measures": list(measures),
+                   "parallelism": f"row-range x{world}, no collective",
+                   "l2": "inputs per launch (views+payload %.0f MB) exceed the 126 MB L2; no flush needed" % (alg_bytes / 1e6)},
+        "per_measure": per_measure, "roofline": roofline, "clocks": clocks, "gpu_launches": launches,
+        "overflow_rows_last_call": {"to_64bit_kernel": overflow[0], "to_long_kernel": overflow[1]},
+        "checksum": checksum,
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline(A, B, measures)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

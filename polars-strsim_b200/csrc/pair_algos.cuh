@@ -196,4 +196,133 @@ SS_HD int multiset_intersection(const PM& pmb, TextA& a, int la) {
     return inter;
 }
 
+// =====================================================================================================
+// ASCII fast path: characters are bytes packed four per word; the position masks live in a table
+// indexed by the byte.  Same arithmetic as the generic templates above, organised around whole words
+// so that the inner loops carry no per-character bookkeeping.
+// =====================================================================================================
+
+// Applies f to the first n bytes of a string given as little-endian words (src(w) -> word w).
+template <class Src, class F>
+SS_HD void for_each_byte(const Src& src, int n, F& f) {
+    int w = 0;
+    for (; 4 * (w + 1) <= n; w++) {
+        const uint32_t word = src(w);
+        f(word & 0xFFu);
+        f((word >> 8) & 0xFFu);
+        f((word >> 16) & 0xFFu);
+        f(word >> 24);
+    }
+    const int rem = n - 4 * w;
+    if (rem > 0) {
+        const uint32_t word = src(w);
+        f(word & 0xFFu);
+        if (rem > 1) f((word >> 8) & 0xFFu);
+        if (rem > 2) f((word >> 16) & 0xFFu);
+    }
+}
+
+// table[c] |= 1 << position, for the n characters of the tabled string.  Runs over whole words: the
+// zero padding after the string sets bits >= n in table[0], which no consumer looks at (Myers reads
+// bits < m only, Jaro masks with the window, the multiset marks them used).
+template <class M, class Tab>
+struct BuildTable {
+    Tab& tab;
+    M bit;
+    SS_HD explicit BuildTable(Tab& t) : tab(t), bit(M(1)) {}
+    SS_HD void operator()(uint32_t c) {
+        tab(c) = tab(c) | bit;
+        bit = bit << 1;
+    }
+};
+template <class M, class Tab>
+struct ClearTable {
+    Tab& tab;
+    SS_HD explicit ClearTable(Tab& t) : tab(t) {}
+    SS_HD void operator()(uint32_t c) { tab(c) = M(0); }
+};
+
+// One Myers / Hyyro column per text character.  The distance is read off the final vertical delta
+// vectors: D[m][n] = D[0][n] + sum_{i<m} (Pv_i - Mv_i) with D[0][n] = n, so no per-step score update.
+template <class M, class Tab>
+struct MyersStep {
+    const Tab& tab;
+    M Pv, Mv;
+    SS_HD explicit MyersStep(const Tab& t) : tab(t), Pv(~M(0)), Mv(M(0)) {}
+    SS_HD void operator()(uint32_t c) {
+        const M Eq = tab(c);
+        const M Xv = Eq | Mv;
+        const M Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+        M Ph = Mv | ~(Xh | Pv);
+        M Mh = Pv & Xh;
+        Ph = (Ph << 1) | M(1);
+        Mh = Mh << 1;
+        Pv = Mh | ~(Xv | Ph);
+        Mv = Ph & Xv;
+    }
+    SS_HD int distance(int m, int n) const {
+        const M mask = m >= (int)(sizeof(M) * 8) ? ~M(0) : ((M(1) << m) - M(1));
+        return n + popc(Pv & mask) - popc(Mv & mask);
+    }
+};
+
+// Jaro match pass (strsim.rs:208-219).  The window [i-bound, i+bound] slides one bit per character:
+// it grows at the top every step and starts dropping bit `lo` once i > bound.
+template <class M, class Tab>
+struct JaroMatchStep {
+    const Tab& tab;
+    M win, lbmask, flag_a, flag_b, abit;
+    int m, i, bound;
+    SS_HD JaroMatchStep(const Tab& t, int lb, int bound_)
+        : tab(t), flag_a(M(0)), flag_b(M(0)), abit(M(1)), m(0), i(0), bound(bound_) {
+        win = (M(2) << bound_) - M(1);  // bits 0..bound
+        lbmask = lb >= (int)(sizeof(M) * 8) ? ~M(0) : ((M(1) << lb) - M(1));
+    }
+    SS_HD void operator()(uint32_t c) {
+        const M cand = tab(c) & win & lbmask & ~flag_b;
+        if (cand) {
+            flag_b |= cand & (M(0) - cand);
+            flag_a |= abit;
+            m++;
+        }
+        abit = abit << 1;
+        i++;
+        win = (win << 1) | M(i <= bound ? 1 : 0);
+    }
+};
+
+// Jaro transposition pass (strsim.rs:220-237)
+template <class M, class Tab>
+struct JaroTransStep {
+    const Tab& tab;
+    M flag_a, fb;
+    int t;
+    SS_HD JaroTransStep(const Tab& tb, M fa, M fbb) : tab(tb), flag_a(fa), fb(fbb), t(0) {}
+    SS_HD void operator()(uint32_t c) {
+        if (flag_a & M(1)) {
+            const M low = fb & (M(0) - fb);
+            fb ^= low;
+            if (!(tab(c) & low)) t++;
+        }
+        flag_a = flag_a >> 1;
+    }
+};
+
+// multiset intersection (strsim.rs:297-305); `used` starts with the padding positions >= lb set
+template <class M, class Tab>
+struct MultisetStep {
+    const Tab& tab;
+    M used;
+    int inter;
+    SS_HD MultisetStep(const Tab& t, int lb)
+        : tab(t), used(lb >= (int)(sizeof(M) * 8) ? M(0) : ~((M(1) << lb) - M(1))), inter(0) {}
+    SS_HD void operator()(uint32_t c) {
+        const M cand = tab(c) & ~used;
+        if (cand) {
+            used |= cand & (M(0) - cand);
+            inter++;
+        }
+    }
+};
+
 }  // namespace strsim

@@ -64,6 +64,22 @@ struct ScanPM {
     }
 };
 
+// adapters for the ASCII fast path of pair_algos.cuh
+template <class Store>
+struct StoreWords {
+    const Store& s;
+    bool second;
+    SS_HD StoreWords(const Store& s_, bool second_) : s(s_), second(second_) {}
+    SS_HD uint32_t operator()(int w) const { return second ? s.wb(w) : s.wa(w); }
+};
+template <class M, class Store>
+struct StoreTable {
+    Store& s;
+    SS_HD explicit StoreTable(Store& s_) : s(s_) {}
+    SS_HD M& operator()(uint32_t c) { return s.tab(c); }
+    SS_HD const M& operator()(uint32_t c) const { return s.tab(c); }
+};
+
 // UTF-8 bytes -> packed-byte character keys; returns the number of characters
 template <class Store>
 SS_HD int decode_keys(Store& s, bool second, int nbytes, int base) {
@@ -144,19 +160,56 @@ SS_HD double row_short(int measure, Store& s, int na, int nb, bool equal, bool a
         // Levenshtein tables the shorter string (fewer table writes, more text steps are cheap)
         const bool table_b = measure != LEVENSHTEIN || lb <= la;
         const int n_tab = table_b ? lb : la;
+        const int n_str = table_b ? la : lb;
+        StoreWords<Store> tabled(s, table_b), streamed(s, !table_b);
+        StoreTable<M, Store> tab(s);
         {
-            ByteReader<Store> r(s, table_b);
-            for (int j = 0; j < n_tab; j++) {
-                uint32_t c = r.next();
-                s.tab(c) = s.tab(c) | (M(1) << j);
+            BuildTable<M, StoreTable<M, Store>> build(tab);
+            for_each_byte(tabled, (n_tab + 3) & ~3, build);
+        }
+        switch (measure) {
+            case LEVENSHTEIN: {
+                int d = n_str;
+                if (n_tab > 0) {
+                    MyersStep<M, StoreTable<M, Store>> step(tab);
+                    for_each_byte(streamed, n_str, step);
+                    d = step.distance(n_tab, n_str);
+                }
+                out.x0 = d;
+                v = lev_value(d, la, lb);
+                break;
+            }
+            case JARO:
+            case JARO_WINKLER: {
+                const int mx = la > lb ? la : lb;
+                const int bound = mx / 2 - 1;  // strsim.rs:200
+                const int outer = la < lb + bound ? la : lb + bound;
+                JaroMatchStep<M, StoreTable<M, Store>> match(tab, lb, bound);
+                for_each_byte(streamed, outer, match);
+                JaroTransStep<M, StoreTable<M, Store>> trans(tab, match.flag_a, match.flag_b);
+                if (match.m > 0) for_each_byte(streamed, outer, trans);
+                out.x0 = match.m;
+                out.x1 = trans.t;
+                v = match.m == 0 ? 0.0 : jaro_value(match.m, trans.t, la, lb);
+                break;
+            }
+            default: {
+                MultisetStep<M, StoreTable<M, Store>> ms(tab, lb);
+                for_each_byte(streamed, la, ms);
+                out.x0 = ms.inter;
+                if (measure == JACCARD) {
+                    out.x1 = la + lb - ms.inter;  // sum_c max = la + lb - sum_c min
+                    v = jaccard_value(ms.inter, la + lb - ms.inter);
+                } else {
+                    out.x1 = la + lb;
+                    v = dice_value(ms.inter, la + lb);
+                }
+                break;
             }
         }
-        TablePM<M, Store> pm(s);
-        ByteReader<Store> ra(s, !table_b), ra2(s, !table_b);
-        v = measure_core<M>(measure, pm, ra, ra2, la, lb, n_tab, table_b ? la : lb, out);
         {
-            ByteReader<Store> r(s, table_b);
-            for (int j = 0; j < n_tab; j++) s.tab(r.next()) = M(0);
+            ClearTable<M, StoreTable<M, Store>> clear(tab);
+            for_each_byte(tabled, (n_tab + 3) & ~3, clear);
         }
         if (measure == JARO_WINKLER && v > 0.7) {  // strsim.rs:260-267
             uint32_t x = s.wa(0) ^ s.wb(0);

@@ -105,17 +105,26 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
         : "memory");
 }
 
+#ifndef STRSIM_EXP_TAB
+#define STRSIM_EXP_TAB 128  // experiment knob: entries of the per-thread table (128 = exact for ASCII)
+#endif
+
 template <class M, int TPB>
 struct DevStore {
     static constexpr bool CPS_ALIAS_TABLE = true;
     M* tab_;          // &table[tid]
-    uint32_t* cps_;   // same memory viewed as u32, &u32[tid]
     uint32_t* wa_;    // &slab_a[tid]
     uint32_t* wb_;    // &slab_b[tid]
-    __device__ __forceinline__ M& tab(uint32_t c) { return tab_[c * TPB]; }
-    __device__ __forceinline__ const M& tab(uint32_t c) const { return tab_[c * TPB]; }
-    __device__ __forceinline__ uint32_t& cp(int s) { return cps_[s * TPB]; }
-    __device__ __forceinline__ const uint32_t& cp(int s) const { return cps_[s * TPB]; }
+    __device__ __forceinline__ M& tab(uint32_t c) { return tab_[(c & (STRSIM_EXP_TAB - 1)) * TPB]; }
+    __device__ __forceinline__ const M& tab(uint32_t c) const { return tab_[(c & (STRSIM_EXP_TAB - 1)) * TPB]; }
+    // codepoint keys alias the thread's OWN table entries (slot s -> 32-bit part s % R of entry s / R)
+    static constexpr int R = (int)(sizeof(M) / 4);
+    __device__ __forceinline__ uint32_t& cp(int s) {
+        return reinterpret_cast<uint32_t*>(&tab_[(s / R) * TPB])[s % R];
+    }
+    __device__ __forceinline__ const uint32_t& cp(int s) const {
+        return reinterpret_cast<const uint32_t*>(&tab_[(s / R) * TPB])[s % R];
+    }
     __device__ __forceinline__ uint32_t wa(int k) const { return wa_[k * TPB]; }
     __device__ __forceinline__ uint32_t wb(int k) const { return wb_[k * TPB]; }
 };
@@ -130,7 +139,7 @@ struct ShortLayout {
     static constexpr size_t off_sva = 0;
     static constexpr size_t off_svb = off_sva + sizeof(uint4) * TILE;
     static constexpr size_t off_tab = off_svb + sizeof(uint4) * TILE;
-    static constexpr size_t off_slab_a = off_tab + sizeof(M) * 128 * TPB;
+    static constexpr size_t off_slab_a = off_tab + sizeof(M) * STRSIM_EXP_TAB * TPB;
     static constexpr size_t off_slab_b = off_slab_a + 4 * WORDS * TPB;
     static constexpr size_t off_hist = off_slab_b + 4 * WORDS * TPB;
     static constexpr size_t off_red = off_hist + 4 * ((NB + 3) & ~3);
@@ -210,14 +219,13 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
     // one-time: zero the position-mask tables (row_short keeps them zero), init the mbarrier
     {
         uint4* t4 = reinterpret_cast<uint4*>(tab);
-        constexpr int N4 = (int)(sizeof(M) * 128 * TPB / 16);
+        constexpr int N4 = (int)(sizeof(M) * STRSIM_EXP_TAB * TPB / 16);
         for (int i = tid; i < N4; i += TPB) t4[i] = make_uint4(0, 0, 0, 0);
         if (tid == 0) mbar_init(mbar, 1);
     }
     uint32_t mbar_phase = 0;
     DevStore<M, TPB> store;
     store.tab_ = tab + tid;
-    store.cps_ = reinterpret_cast<uint32_t*>(tab) + tid;
     store.wa_ = slab_a + tid;
     store.wb_ = slab_b + tid;
     __syncthreads();

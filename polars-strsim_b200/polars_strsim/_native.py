@@ -7,7 +7,9 @@ from pathlib import Path
 import numpy as np
 
 LIB_NAME = "libpolars_strsim_b200.so"
-LIB_PATH = Path(__file__).parent / LIB_NAME
+import os as _os
+
+LIB_PATH = Path(_os.environ.get("STRSIM_B200_LIB") or (Path(__file__).parent / LIB_NAME))
 
 MEASURES = ("levenshtein", "jaro", "jaro_winkler", "jaccard", "sorensen_dice")
 MEASURE_ID = {m: i for i, m in enumerate(MEASURES)}
@@ -143,27 +145,40 @@ def total_length(col) -> int:
     return 1 if isinstance(col, (str, bytes)) or col is None else len(col)
 
 
-def compute_host(measure, a, b, debug: bool = False):
-    """End-to-end call with host buffers: returns (values f64[n], valid bool[n], null_count[, ints])."""
+def compute_host(measure, a, b, debug: bool = False, out_values=None, out_validity=None, prepared=None):
+    """End-to-end call with host buffers: returns (values f64[n], valid bool[n], null_count[, ints]).
+
+    out_values / out_validity: optional preallocated numpy arrays (e.g. views of pinned memory) of
+    n float64 / ceil(n/8)+8 uint8; with out_validity given, the packed bitmap is returned instead of
+    a bool array.  prepared: result of prepare(a, b) to keep chunk marshalling out of a timed loop."""
     L = lib()
+    ca, na, cb, nb, n, _keep = prepared if prepared is not None else prepare(a, b)
+    values = out_values if out_values is not None else np.zeros(max(n, 1), dtype=np.float64)
+    vbytes = out_validity if out_validity is not None else np.zeros((max(n, 1) + 7) // 8 + 8, dtype=np.uint8)
+    ints = np.zeros((max(n, 1), DBG_INTS), dtype=np.int32) if debug else None
+    nulls = ctypes.c_int64(0)
+    rc = L.strsim_b200_compute_host(measure_id(measure), ca, na, cb, nb, values.ctypes.data, vbytes.ctypes.data,
+                                    ctypes.byref(nulls), ints.ctypes.data if debug else None)
+    _check(rc)
+    if out_validity is not None:
+        valid = vbytes
+    else:
+        valid = np.unpackbits(vbytes, bitorder="little")[:n].astype(bool)
+    values = values[:n]
+    if debug:
+        return values, valid, nulls.value, ints[:n]
+    return values, valid, nulls.value
+
+
+def prepare(a, b):
+    """Marshal two Arrow columns into ViewChunk arrays once (reusable across calls)."""
     ca, na, keep_a = as_chunks(a)
     cb, nb, keep_b = as_chunks(b)
     la, lb = total_length(a), total_length(b)
     n = lb if la == 1 else la
     if la != lb and la != 1 and lb != 1:
         n = 0  # the library reports the shape error
-    values = np.zeros(max(n, 1), dtype=np.float64)
-    vbytes = np.zeros((max(n, 1) + 7) // 8 + 8, dtype=np.uint8)
-    ints = np.zeros((max(n, 1), DBG_INTS), dtype=np.int32) if debug else None
-    nulls = ctypes.c_int64(0)
-    rc = L.strsim_b200_compute_host(measure_id(measure), ca, na, cb, nb, values.ctypes.data, vbytes.ctypes.data,
-                                    ctypes.byref(nulls), ints.ctypes.data if debug else None)
-    _check(rc)
-    valid = np.unpackbits(vbytes, bitorder="little")[:n].astype(bool)
-    values = values[:n]
-    if debug:
-        return values, valid, nulls.value, ints[:n]
-    return values, valid, nulls.value
+    return ca, na, cb, nb, n, (keep_a, keep_b)
 
 
 class DeviceColumn:
