@@ -232,6 +232,65 @@ __global__ void list_all_kernel(const SegArgs s) {
     atomicMax(&s.ovf->max_bytes_b, ld_view(s.b.views + row * s.b.stride).x);
 }
 
+// ---- column statistics: OR and AND of every string byte (views' inline bytes + data buffers) --------
+// Decides, per pair of columns, whether the whole alphabet is ASCII and whether it fits one aligned
+// block of 32 / 64 code points (=> smaller position-mask tables, see DevStore).  Supersets are fine:
+// unreferenced bytes in a data buffer can only make the answer more conservative.
+struct ColumnStats {
+    unsigned int or_bits;   // OR of all bytes, replicated over the four byte lanes
+    unsigned int and_bits;  // AND of all bytes (padding treated as 0xFF)
+};
+
+__device__ __forceinline__ void stats_commit(ColumnStats* out, uint32_t o, uint32_t a) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        o |= __shfl_xor_sync(0xFFFFFFFFu, o, d);
+        a &= __shfl_xor_sync(0xFFFFFFFFu, a, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicOr(&out->or_bits, o);
+        atomicAnd(&out->and_bits, a);
+    }
+}
+
+__global__ void stats_views_kernel(const uint4* views, long long n, ColumnStats* out) {
+    uint32_t o = 0, a = 0xFFFFFFFFu;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const uint4 v = ld_view(views + i);
+        const int len = (int)v.x;
+        if (len > 12) {  // prefix; the rest is in the data buffer
+            o |= v.y;
+            a &= v.y;
+        } else {
+            const uint32_t m0 = byte_mask(len), m1 = byte_mask(len - 4 < 0 ? 0 : len - 4),
+                           m2 = byte_mask(len - 8 < 0 ? 0 : len - 8);
+            o |= (v.y & m0) | (v.z & m1) | (v.w & m2);
+            a &= (v.y | ~m0) & (v.z | ~m1) & (v.w | ~m2);
+        }
+    }
+    stats_commit(out, o, a);
+}
+
+// data: 16-byte aligned device buffer, `bytes` valid bytes
+__global__ void stats_bytes_kernel(const unsigned char* data, long long bytes, ColumnStats* out) {
+    uint32_t o = 0, a = 0xFFFFFFFFu;
+    const long long n16 = bytes >> 4;
+    const uint4* d4 = reinterpret_cast<const uint4*>(data);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16;
+         i += (long long)gridDim.x * blockDim.x) {
+        const uint4 v = ld_view(d4 + i);
+        o |= v.x | v.y | v.z | v.w;
+        a &= v.x & v.y & v.z & v.w;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (bytes & 15)) {
+        const uint32_t c = data[(n16 << 4) + threadIdx.x];
+        o |= c * 0x01010101u;
+        a &= c * 0x01010101u;
+    }
+    stats_commit(out, o, a);
+}
+
 // ---- output validity: bit = both inputs valid (polars-core arity kernels; README.md:69-70) ---------
 struct ValidityArgs {
     const uint8_t* va;

@@ -59,6 +59,8 @@ struct ThreadCtx {
     Overflow* h_ovf = nullptr;  // pinned
     unsigned long long* d_nulls = nullptr;
     unsigned long long* h_nulls = nullptr;  // pinned
+    ColumnStats* d_stats = nullptr;
+    ColumnStats* h_stats = nullptr;  // pinned
     Workspace lists, scratch;
 };
 
@@ -101,6 +103,8 @@ static int ensure_ctx(ThreadCtx** out) {
         CUDA_TRY(cudaMallocHost(&c.h_ovf, sizeof(Overflow)));
         CUDA_TRY(cudaMalloc(&c.d_nulls, sizeof(unsigned long long)));
         CUDA_TRY(cudaMallocHost(&c.h_nulls, sizeof(unsigned long long)));
+        CUDA_TRY(cudaMalloc(&c.d_stats, sizeof(ColumnStats)));
+        CUDA_TRY(cudaMallocHost(&c.h_stats, sizeof(ColumnStats)));
     }
     CUDA_TRY(cudaSetDevice(c.device));
     *out = &c;
@@ -141,6 +145,7 @@ struct strsim_b200_column {
     int64_t data_bytes = 0;
     int64_t alg_bytes = -1;
     bool has_validity = false;
+    unsigned or_byte = 0, and_byte = 0xFF;  // OR / AND over every string byte of the column
 };
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -246,6 +251,37 @@ static int upload_column(ThreadCtx& ctx, const strsim_view_chunk* chunks, size_t
         col->data_bytes += dc.data_bytes;
         col->chunks.push_back(dc);
     }
+    // column statistics (alphabet block, ASCII-ness) for the kernel choice in run_segment()
+    {
+        ColumnStats init = {0u, 0xFFFFFFFFu};
+        *ctx.h_stats = init;
+        CUDA_TRY(cudaMemcpyAsync(ctx.d_stats, ctx.h_stats, sizeof init, cudaMemcpyHostToDevice, ctx.stream));
+        for (size_t i = 0; i < n_chunks; i++) {
+            const DevChunk& dc = col->chunks[i];
+            if (dc.length > 0) {
+                long long blocks = (dc.length + 255) / 256;
+                if (blocks > 148 * 16) blocks = 148 * 16;
+                stats_views_kernel<<<(unsigned)blocks, 256, 0, ctx.stream>>>(dc.views, dc.length, ctx.d_stats);
+                g_launches.fetch_add(1, std::memory_order_relaxed);
+            }
+            for (int64_t b = 0; b < chunks[i].n_data_buffers; b++) {
+                const long long bytes = chunks[i].data_buffer_sizes[b];
+                if (bytes <= 0) continue;
+                long long blocks = ((bytes >> 4) + 255) / 256;
+                if (blocks > 148 * 16) blocks = 148 * 16;
+                if (blocks < 1) blocks = 1;
+                stats_bytes_kernel<<<(unsigned)blocks, 256, 0, ctx.stream>>>(
+                    reinterpret_cast<const unsigned char*>(base + plans[i].buf_off[(size_t)b]), bytes, ctx.d_stats);
+                g_launches.fetch_add(1, std::memory_order_relaxed);
+            }
+        }
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(ctx.h_stats, ctx.d_stats, sizeof init, cudaMemcpyDeviceToHost, ctx.stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx.stream));
+        unsigned o = ctx.h_stats->or_bits, a = ctx.h_stats->and_bits;
+        col->or_byte = (o | (o >> 8) | (o >> 16) | (o >> 24)) & 0xFFu;
+        col->and_byte = (a & (a >> 8) & (a >> 16) & (a >> 24)) & 0xFFu;
+    }
     if (want_alg_bytes) {
         // 16 B of view per row + out-of-line payload (byte length > 12) + validity bits
         int64_t bytes = 0;
@@ -265,17 +301,25 @@ static int upload_column(ThreadCtx& ctx, const strsim_view_chunk* chunks, size_t
 }
 
 // ---- kernel launch helpers -----------------------------------------------------------------------------
-template <class M, int MEASURE, int TPB, int RPT, bool GATHER>
-static int launch_short(ThreadCtx& ctx, const SegArgs& args, long long n_upper, cudaStream_t st) {
-    using L = ShortLayout<M, TPB, RPT>;
-    auto kern = short_kernel<M, MEASURE, TPB, RPT, GATHER>;
+template <class M, int MEASURE, int TPB, int RPT, bool GATHER, int T, bool ASCII_ONLY>
+static int launch_short(ThreadCtx& ctx, SegArgs args, long long n_upper, cudaStream_t st) {
+    using L = ShortLayout<M, TPB, RPT, T>;
+    auto kern = short_kernel<M, MEASURE, TPB, RPT, GATHER, T, ASCII_ONLY>;
+    if (args.stage_bytes < 0) {
+        // -stage_bytes = mean out-of-line bytes per row (x16) of the heavier column: size the stage
+        // area for this tile shape with 25 % headroom (rows that still do not fit take the long path)
+        long long stage = (long long)(-args.stage_bytes) * L::TILE * 5 / (16 * 4) + 256;
+        if (stage < 1024) stage = 1024;
+        if (stage > (long long)L::CAP * L::TILE) stage = (long long)L::CAP * L::TILE;
+        args.stage_bytes = (int)((stage + 15) & ~15ll);
+    }
     const size_t smem = L::bytes(args.stage_bytes);
     static thread_local size_t configured = 0;
-    if (smem > configured) {
+    static thread_local int per_sm = 0;
+    if (smem > configured || per_sm == 0) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    int per_sm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TPB, smem));
     if (per_sm < 1) {
         strsim_set_error("short kernel does not fit an SM (smem %zu)", smem);
@@ -289,6 +333,50 @@ static int launch_short(ThreadCtx& ctx, const SegArgs& args, long long n_upper, 
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CUDA_TRY(cudaGetLastError());
     return STRSIM_OK;
+}
+
+// Which instantiation of the fused kernel serves a segment (see DevStore): decided from the union of
+// the two columns' byte statistics.
+enum Alphabet { ALPHA_GENERAL = 0, ALPHA_ASCII128 = 1, ALPHA_ASCII64 = 2, ALPHA_ASCII32 = 3 };
+
+static Alphabet classify_alphabet(const strsim_b200_column* a, const strsim_b200_column* b) {
+    static const char* force = getenv("STRSIM_B200_ALPHABET");  // test / tuning knob: 0..3 caps the choice
+    const unsigned o = a->or_byte | b->or_byte, n = a->and_byte & b->and_byte;
+    Alphabet al;
+    if (o & 0x80u)
+        al = ALPHA_GENERAL;
+    else if (((o ^ n) & 0x60u) == 0)
+        al = ALPHA_ASCII32;  // every byte in one aligned block of 32 code points
+    else if (((o ^ n) & 0x40u) == 0)
+        al = ALPHA_ASCII64;
+    else
+        al = ALPHA_ASCII128;
+    if (force && *force) {
+        const int cap = atoi(force);
+        if (al != ALPHA_GENERAL && (int)al > cap) al = (Alphabet)cap;
+    }
+    return al;
+}
+
+template <int MEASURE>
+static int launch_fused(ThreadCtx& ctx, Alphabet al, const SegArgs& args, long long rows, cudaStream_t st) {
+    static const char* cfg_env = getenv("STRSIM_B200_TILE");  // tuning knob
+    const int cfg = cfg_env && *cfg_env ? atoi(cfg_env) : 0;
+    switch (al) {
+        case ALPHA_ASCII32:
+            if (cfg == 1) return launch_short<uint32_t, MEASURE, 128, 2, false, 32, true>(ctx, args, rows, st);
+            if (cfg == 2) return launch_short<uint32_t, MEASURE, 256, 4, false, 32, true>(ctx, args, rows, st);
+            if (cfg == 3) return launch_short<uint32_t, MEASURE, 128, 8, false, 32, true>(ctx, args, rows, st);
+            if (cfg == 4) return launch_short<uint32_t, MEASURE, 192, 4, false, 32, true>(ctx, args, rows, st);
+            if (cfg == 5) return launch_short<uint32_t, MEASURE, 128, 3, false, 32, true>(ctx, args, rows, st);
+            return launch_short<uint32_t, MEASURE, 128, 4, false, 32, true>(ctx, args, rows, st);
+        case ALPHA_ASCII64:
+            return launch_short<uint32_t, MEASURE, 128, 4, false, 64, true>(ctx, args, rows, st);
+        case ALPHA_ASCII128:
+            return launch_short<uint32_t, MEASURE, 128, 4, false, 128, true>(ctx, args, rows, st);
+        default:
+            return launch_short<uint32_t, MEASURE, 128, 4, false, 128, false>(ctx, args, rows, st);
+    }
 }
 
 // rows on the long list -> fallback kernel, scratch slabs sized from the device-side maxima
@@ -327,7 +415,7 @@ static int run_generic(ThreadCtx& ctx, const SegArgs& args, const Overflow& ov, 
 }
 
 template <int MEASURE>
-static int run_segment(ThreadCtx& ctx, SegArgs args, int stage32, int64_t seg_rows, cudaStream_t st) {
+static int run_segment(ThreadCtx& ctx, SegArgs args, Alphabet al, int stage32, int64_t seg_rows, cudaStream_t st) {
     // overflow lists: worst case every row
     int rc = ws_reserve(ctx.lists, 2 * sizeof(unsigned int) * (size_t)seg_rows + 64);
     if (rc) return rc;
@@ -346,7 +434,7 @@ static int run_segment(ThreadCtx& ctx, SegArgs args, int stage32, int64_t seg_ro
         g_launches.fetch_add(1, std::memory_order_relaxed);
         CUDA_TRY(cudaGetLastError());
     } else {
-        rc = launch_short<uint32_t, MEASURE, 128, 4, false>(ctx, args, seg_rows, st);
+        rc = launch_fused<MEASURE>(ctx, al, args, seg_rows, st);
         if (rc) return rc;
     }
     CUDA_TRY(cudaMemcpyAsync(ctx.h_ovf, ctx.d_ovf, sizeof(Overflow), cudaMemcpyDeviceToHost, st));
@@ -358,8 +446,8 @@ static int run_segment(ThreadCtx& ctx, SegArgs args, int stage32, int64_t seg_ro
         a64.list = args.list64;
         a64.list_count = &ctx.d_ovf->n64;
         a64.n = ov.n64;
-        a64.stage_bytes = 64 * ShortLayout<uint64_t, 64, 2>::TILE;  // every listed row fits
-        rc = launch_short<uint64_t, MEASURE, 64, 2, true>(ctx, a64, ov.n64, st);
+        a64.stage_bytes = 64 * ShortLayout<uint64_t, 64, 2, 128>::TILE;  // every listed row fits
+        rc = launch_short<uint64_t, MEASURE, 64, 2, true, 128, false>(ctx, a64, ov.n64, st);
         if (rc) return rc;
         // rows the 64-bit kernel could not stage are appended to listlong; re-read the counters
         CUDA_TRY(cudaMemcpyAsync(ctx.h_ovf, ctx.d_ovf, sizeof(Overflow), cudaMemcpyDeviceToHost, st));
@@ -398,6 +486,7 @@ static int compute_on_device(ThreadCtx& ctx, int measure, const strsim_b200_colu
         CUDA_TRY(cudaMemsetAsync(d_validity, 0xFF, 4 * (size_t)((n + 31) / 32), st));
         CUDA_TRY(cudaMemsetAsync(ctx.d_nulls, 0, sizeof(unsigned long long), st));
     }
+    const Alphabet al = classify_alphabet(a, b);
     // walk both chunk lists in lock step (polars-core align_chunks equivalent)
     size_t ia = 0, ib = 0;
     int64_t oa = 0, ob = 0, row = 0;
@@ -430,21 +519,20 @@ static int compute_on_device(ThreadCtx& ctx, int measure, const strsim_b200_colu
         s.n = len;
         s.out = d_out + row;
         s.dbg = d_dbg ? d_dbg + 6 * row : nullptr;
-        // stage capacity: mean out-of-line bytes per row of the heavier column, +25 % and slack
+        // stage capacity is derived per tile shape in launch_short() from the mean out-of-line bytes
+        // per row of the heavier column (passed as a negative fixed-point number)
         const double avg_a = bc_a ? 0.0 : (double)ca.data_bytes / (double)(ca.length > 0 ? ca.length : 1);
         const double avg_b = bc_b ? 0.0 : (double)cb.data_bytes / (double)(cb.length > 0 ? cb.length : 1);
         const double avg = avg_a > avg_b ? avg_a : avg_b;
-        long long stage = (long long)(avg * 512 * 1.25) + 512;
-        if (stage < 2048) stage = 2048;
-        if (stage > 32 * 512) stage = 32 * 512;  // every row of a tile at 32 bytes
-        stage = (stage + 15) & ~15ll;
+        long long stage = -(long long)(avg * 16.0 + 1.0);
+        if (stage < -64 * 16) stage = -64 * 16;
         int rc;
         switch (measure) {
-            case 0: rc = run_segment<0>(ctx, s, (int)stage, len, st); break;
-            case 1: rc = run_segment<1>(ctx, s, (int)stage, len, st); break;
-            case 2: rc = run_segment<2>(ctx, s, (int)stage, len, st); break;
-            case 3: rc = run_segment<3>(ctx, s, (int)stage, len, st); break;
-            default: rc = run_segment<4>(ctx, s, (int)stage, len, st); break;
+            case 0: rc = run_segment<0>(ctx, s, al, (int)stage, len, st); break;
+            case 1: rc = run_segment<1>(ctx, s, al, (int)stage, len, st); break;
+            case 2: rc = run_segment<2>(ctx, s, al, (int)stage, len, st); break;
+            case 3: rc = run_segment<3>(ctx, s, al, (int)stage, len, st); break;
+            default: rc = run_segment<4>(ctx, s, al, (int)stage, len, st); break;
         }
         if (rc) return rc;
         if (d_validity && any_validity) {

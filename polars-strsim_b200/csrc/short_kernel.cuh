@@ -105,18 +105,18 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
         : "memory");
 }
 
-#ifndef STRSIM_EXP_TAB
-#define STRSIM_EXP_TAB 128  // experiment knob: entries of the per-thread table (128 = exact for ASCII)
-#endif
-
-template <class M, int TPB>
+// T = entries of the per-thread position-mask table.  128 is exact for any ASCII string; when the
+// column statistics (host.cu: column_stats) prove that every byte of both columns lies in one aligned
+// block of 32 or 64 code points (e.g. lower-case names: 0x60..0x7F), c & (T-1) is injective on the
+// alphabet and the smaller table quadruples / doubles the resident warps per SM.
+template <class M, int TPB, int T>
 struct DevStore {
     static constexpr bool CPS_ALIAS_TABLE = true;
     M* tab_;          // &table[tid]
     uint32_t* wa_;    // &slab_a[tid]
     uint32_t* wb_;    // &slab_b[tid]
-    __device__ __forceinline__ M& tab(uint32_t c) { return tab_[(c & (STRSIM_EXP_TAB - 1)) * TPB]; }
-    __device__ __forceinline__ const M& tab(uint32_t c) const { return tab_[(c & (STRSIM_EXP_TAB - 1)) * TPB]; }
+    __device__ __forceinline__ M& tab(uint32_t c) { return tab_[(c & (T - 1)) * TPB]; }
+    __device__ __forceinline__ const M& tab(uint32_t c) const { return tab_[(c & (T - 1)) * TPB]; }
     // codepoint keys alias the thread's OWN table entries (slot s -> 32-bit part s % R of entry s / R)
     static constexpr int R = (int)(sizeof(M) / 4);
     __device__ __forceinline__ uint32_t& cp(int s) {
@@ -129,7 +129,7 @@ struct DevStore {
     __device__ __forceinline__ uint32_t wb(int k) const { return wb_[k * TPB]; }
 };
 
-template <class M, int TPB, int RPT>
+template <class M, int TPB, int RPT, int T>
 struct ShortLayout {
     static constexpr int CAP = (int)sizeof(M) * 8;
     static constexpr int WORDS = CAP / 4;
@@ -139,7 +139,7 @@ struct ShortLayout {
     static constexpr size_t off_sva = 0;
     static constexpr size_t off_svb = off_sva + sizeof(uint4) * TILE;
     static constexpr size_t off_tab = off_svb + sizeof(uint4) * TILE;
-    static constexpr size_t off_slab_a = off_tab + sizeof(M) * STRSIM_EXP_TAB * TPB;
+    static constexpr size_t off_slab_a = off_tab + sizeof(M) * T * TPB;
     static constexpr size_t off_slab_b = off_slab_a + 4 * WORDS * TPB;
     static constexpr size_t off_hist = off_slab_b + 4 * WORDS * TPB;
     static constexpr size_t off_red = off_hist + 4 * ((NB + 3) & ~3);
@@ -189,9 +189,10 @@ __device__ __forceinline__ uint32_t load_string(const uint4& v, const unsigned c
     return acc;
 }
 
-template <class M, int MEASURE, int TPB, int RPT, bool GATHER>
+template <class M, int MEASURE, int TPB, int RPT, bool GATHER, int T, bool ASCII_ONLY>
 __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
-    using L = ShortLayout<M, TPB, RPT>;
+    static_assert(ASCII_ONLY || T >= 64, "the Unicode path keeps 2*bits(M) 32-bit keys in the table memory");
+    using L = ShortLayout<M, TPB, RPT, T>;
     constexpr int CAP = L::CAP;
     constexpr int WORDS = L::WORDS;
     constexpr int TILE = L::TILE;
@@ -219,12 +220,12 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
     // one-time: zero the position-mask tables (row_short keeps them zero), init the mbarrier
     {
         uint4* t4 = reinterpret_cast<uint4*>(tab);
-        constexpr int N4 = (int)(sizeof(M) * STRSIM_EXP_TAB * TPB / 16);
+        constexpr int N4 = (int)(sizeof(M) * T * TPB / 16);
         for (int i = tid; i < N4; i += TPB) t4[i] = make_uint4(0, 0, 0, 0);
         if (tid == 0) mbar_init(mbar, 1);
     }
     uint32_t mbar_phase = 0;
-    DevStore<M, TPB> store;
+    DevStore<M, TPB, T> store;
     store.tab_ = tab + tid;
     store.wa_ = slab_a + tid;
     store.wb_ = slab_b + tid;
@@ -429,19 +430,21 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
             if (!((active >> k) & 1u)) continue;
             const uint4 va = sva[i], vb = svb[i];
             uint32_t hi_bits = 0;  // conservative (unmasked) non-ASCII test; exact test in step 4
-            if (va.x <= 12u) {
-                hi_bits |= va.y | va.z | va.w;
-            } else {
-                const uint32_t* p = reinterpret_cast<const uint32_t*>(stage_a) + (va.y >> 2);
-                const int nwords = (int)(((va.y & 3u) + va.x + 3u) >> 2);
-                for (int w = 0; w < nwords; w++) hi_bits |= p[w];
-            }
-            if (vb.x <= 12u) {
-                hi_bits |= vb.y | vb.z | vb.w;
-            } else {
-                const uint32_t* p = reinterpret_cast<const uint32_t*>(stage_b) + (vb.y >> 2);
-                const int nwords = (int)(((vb.y & 3u) + vb.x + 3u) >> 2);
-                for (int w = 0; w < nwords; w++) hi_bits |= p[w];
+            if (!ASCII_ONLY) {
+                if (va.x <= 12u) {
+                    hi_bits |= va.y | va.z | va.w;
+                } else {
+                    const uint32_t* p = reinterpret_cast<const uint32_t*>(stage_a) + (va.y >> 2);
+                    const int nwords = (int)(((va.y & 3u) + va.x + 3u) >> 2);
+                    for (int w = 0; w < nwords; w++) hi_bits |= p[w];
+                }
+                if (vb.x <= 12u) {
+                    hi_bits |= vb.y | vb.z | vb.w;
+                } else {
+                    const uint32_t* p = reinterpret_cast<const uint32_t*>(stage_b) + (vb.y >> 2);
+                    const int nwords = (int)(((vb.y & 3u) + vb.x + 3u) >> 2);
+                    for (int w = 0; w < nwords; w++) hi_bits |= p[w];
+                }
             }
             const uint32_t mx = va.x > vb.x ? va.x : vb.x;
             key[k] = 1u + mx + ((hi_bits & 0x80808080u) ? (uint32_t)(CAP + 1) : 0u);
@@ -500,7 +503,7 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
                     if (w < nw) diff |= store.wa(w) ^ store.wb(w);
                 equal = diff == 0;
             }
-            const bool ascii = ((or_a | or_b) & 0x80808080u) == 0;
+            const bool ascii = ASCII_ONLY || ((or_a | or_b) & 0x80808080u) == 0;
             PairInts ints;
             const double v = row_short<M>(MEASURE, store, na, nb, equal, ascii, ints);
             const long long idx = tile0 + i;
