@@ -98,6 +98,17 @@ STRSIM_API int strsim_b200_compute_host(int measure, const strsim_view_chunk *a,
                                         double *out_values, uint8_t *out_validity,
                                         int64_t *out_null_count, int32_t *dbg_ints);
 
+/* Same, for several measures over ONE upload of the two columns (the five README expressions,
+ * README.md:47-51, evaluate the same pair of columns five times; the PCIe transfer dominates the
+ * end-to-end cost).  out_values[m] / dbg_ints[m] receive measure measures[m];
+ * out_validity / out_null_count are shared (the null mask does not depend on the measure).
+ * n_measures <= 8.  Downloads of finished measures overlap the kernels of the next one. */
+STRSIM_API int strsim_b200_compute_host_multi(const int *measures, size_t n_measures,
+                                              const strsim_view_chunk *a, size_t n_a_chunks,
+                                              const strsim_view_chunk *b, size_t n_b_chunks,
+                                              double *const *out_values, uint8_t *out_validity,
+                                              int64_t *out_null_count, int32_t *const *dbg_ints);
+
 /* ---- Arrow C Data Interface entry point -----------------------------------------------------------
  * Inputs are BORROWED (not released).  Accepted formats: "vu"/"vz" (Utf8View/BinaryView); "u"/"U"
  * (Utf8/LargeUtf8) are converted to views on the host first.  `out` receives a Float64 array

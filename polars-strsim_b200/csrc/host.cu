@@ -17,6 +17,7 @@
 
 #include "../../include/strsim_b200.h"
 #include "generic_kernel.cuh"
+#include "long_lev_kernel.cuh"
 #include "short_kernel.cuh"
 
 using namespace strsim;
@@ -54,12 +55,16 @@ struct Workspace {
 struct ThreadCtx {
     int device = -1;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // D2H of finished measures overlaps the next kernel
+    cudaEvent_t done_event[8] = {};
     int sm_count = 0;
     Overflow* d_ovf = nullptr;
     Overflow* h_ovf = nullptr;  // pinned
     unsigned long long* d_nulls = nullptr;
     unsigned long long* h_nulls = nullptr;  // pinned
     ColumnStats* d_stats = nullptr;
+    unsigned int* d_counters = nullptr;  // [0] long-kernel cursor, [1] huge-row count
+    unsigned int* h_counters = nullptr;  // pinned
     ColumnStats* h_stats = nullptr;  // pinned
     Workspace lists, scratch;
 };
@@ -98,12 +103,16 @@ static int ensure_ctx(ThreadCtx** out) {
         c.device = g_requested_device;
         CUDA_TRY(cudaSetDevice(c.device));
         CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+        for (auto& ev : c.done_event) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         CUDA_TRY(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, c.device));
         CUDA_TRY(cudaMalloc(&c.d_ovf, sizeof(Overflow)));
         CUDA_TRY(cudaMallocHost(&c.h_ovf, sizeof(Overflow)));
         CUDA_TRY(cudaMalloc(&c.d_nulls, sizeof(unsigned long long)));
         CUDA_TRY(cudaMallocHost(&c.h_nulls, sizeof(unsigned long long)));
         CUDA_TRY(cudaMalloc(&c.d_stats, sizeof(ColumnStats)));
+        CUDA_TRY(cudaMalloc(&c.d_counters, 4 * sizeof(unsigned int)));
+        CUDA_TRY(cudaMallocHost(&c.h_counters, 4 * sizeof(unsigned int)));
         CUDA_TRY(cudaMallocHost(&c.h_stats, sizeof(ColumnStats)));
     }
     CUDA_TRY(cudaSetDevice(c.device));
@@ -124,6 +133,73 @@ static int ws_reserve(Workspace& w, size_t bytes) {
     }
     w.cap = cap;
     return STRSIM_OK;
+}
+
+// ---- device block pool: cudaMalloc / cudaFree cost milliseconds (and cudaFree synchronises), so the
+//      per-call blocks (uploaded columns, results) are recycled ------------------------------------------
+struct PoolBlock {
+    int device;
+    void* ptr;
+    size_t bytes;
+};
+static std::mutex g_pool_mutex;
+static std::vector<PoolBlock> g_pool;
+static size_t pool_limit() {
+    static const size_t lim = [] {
+        const char* e = getenv("STRSIM_B200_POOL_BYTES");
+        return e && *e ? (size_t)strtoull(e, nullptr, 10) : ((size_t)16 << 30);
+    }();
+    return lim;
+}
+
+static int pool_alloc(int device, size_t bytes, void** out) {
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        size_t best = g_pool.size();
+        for (size_t i = 0; i < g_pool.size(); i++) {
+            const PoolBlock& b = g_pool[i];
+            if (b.device == device && b.bytes >= bytes && b.bytes <= bytes + bytes / 2 + (1 << 20) &&
+                (best == g_pool.size() || b.bytes < g_pool[best].bytes))
+                best = i;
+        }
+        if (best != g_pool.size()) {
+            *out = g_pool[best].ptr;
+            g_pool.erase(g_pool.begin() + (long)best);
+            return STRSIM_OK;
+        }
+    }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e != cudaSuccess) {
+        // make room: drop every cached block of this device and retry once
+        {
+            std::lock_guard<std::mutex> lock(g_pool_mutex);
+            for (size_t i = g_pool.size(); i-- > 0;)
+                if (g_pool[i].device == device) {
+                    cudaFree(g_pool[i].ptr);
+                    g_pool.erase(g_pool.begin() + (long)i);
+                }
+        }
+        cudaGetLastError();
+        e = cudaMalloc(out, bytes);
+    }
+    if (e != cudaSuccess) {
+        strsim_set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        return STRSIM_ERR_NOMEM;
+    }
+    return STRSIM_OK;
+}
+
+// the block must no longer be in use by any stream (callers synchronise first)
+static void pool_free(int device, void* ptr, size_t bytes) {
+    if (!ptr) return;
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    size_t total = bytes;
+    for (const PoolBlock& b : g_pool) total += b.bytes;
+    if (total > pool_limit() || g_pool.size() >= 16) {
+        cudaFree(ptr);
+        return;
+    }
+    g_pool.push_back({device, ptr, bytes});
 }
 
 // ---- device-resident column --------------------------------------------------------------------------
@@ -207,11 +283,12 @@ static int upload_column(ThreadCtx& ctx, const strsim_view_chunk* chunks, size_t
         if (p.validity_bytes) col->has_validity = true;
     }
     total += 256;
-    cudaError_t e = cudaMalloc(&col->block, total);
-    if (e != cudaSuccess) {
-        strsim_set_error("cudaMalloc(%zu) for a column failed: %s", total, cudaGetErrorString(e));
-        delete col;
-        return STRSIM_ERR_NOMEM;
+    {
+        int rc = pool_alloc(ctx.device, total, &col->block);
+        if (rc) {
+            delete col;
+            return rc;
+        }
     }
     col->block_bytes = total;
     char* base = static_cast<char*>(col->block);
@@ -381,14 +458,17 @@ static int launch_fused(ThreadCtx& ctx, Alphabet al, const SegArgs& args, long l
 
 // rows on the long list -> fallback kernel, scratch slabs sized from the device-side maxima
 template <int MEASURE>
-static int run_generic(ThreadCtx& ctx, const SegArgs& args, const Overflow& ov, cudaStream_t st) {
+static int run_generic(ThreadCtx& ctx, const SegArgs& args, const Overflow& ov, cudaStream_t st,
+                       const unsigned int* list = nullptr, const unsigned int* list_count = nullptr,
+                       unsigned int n_rows = 0) {
     GenericArgs g{};
     g.a = args.a;
     g.b = args.b;
     g.out = args.out;
     g.dbg = args.dbg;
-    g.list = args.listlong;
-    g.list_count = &ctx.d_ovf->nlong;
+    g.list = list ? list : args.listlong;
+    g.list_count = list_count ? list_count : &ctx.d_ovf->nlong;
+    if (!list) n_rows = ov.nlong;
     g.cap_a = (int)ov.max_bytes_a + 1;
     g.cap_b = (int)ov.max_bytes_b + 1;
     long long work = 2ll * (g.cap_b + 1);
@@ -396,7 +476,7 @@ static int run_generic(ThreadCtx& ctx, const SegArgs& args, const Overflow& ov, 
     if (flags > work) work = flags;
     g.slab_words = (long long)g.cap_a + g.cap_b + work;
     long long slots = (long long)ctx.sm_count * 512;
-    if ((long long)ov.nlong < slots) slots = ov.nlong;
+    if ((long long)n_rows < slots) slots = n_rows;
     const long long budget = 2ll << 30;  // bytes of scratch at most
     if (slots * g.slab_words * 4 > budget) slots = budget / (g.slab_words * 4);
     if (slots < 1) {
@@ -411,6 +491,54 @@ static int run_generic(ThreadCtx& ctx, const SegArgs& args, const Overflow& ov, 
     generic_kernel<MEASURE><<<(unsigned)((slots + 63) / 64), 64, 0, st>>>(g);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CUDA_TRY(cudaGetLastError());
+    return STRSIM_OK;
+}
+
+// long Levenshtein rows -> warp-cooperative multi-word Myers; rows whose pattern exceeds LONG_PAT_MAX
+// come back on `huge_list` and are finished by the generic kernel
+static int run_long_lev(ThreadCtx& ctx, const SegArgs& args, const Overflow& ov, unsigned int* huge_list,
+                        unsigned int* n_huge, cudaStream_t st) {
+    LongLevArgs g{};
+    g.a = args.a;
+    g.b = args.b;
+    g.out = args.out;
+    g.dbg = args.dbg;
+    g.list = args.listlong;
+    g.list_count = &ctx.d_ovf->nlong;
+    g.cursor = ctx.d_counters;
+    g.huge_list = huge_list;
+    g.huge_count = ctx.d_counters + 1;
+    g.cap_a = (int)ov.max_bytes_a + 4;
+    g.cap_b = (int)ov.max_bytes_b + 4;
+    int cap_pat = g.cap_a < g.cap_b ? g.cap_a : g.cap_b;
+    if (cap_pat > LONG_PAT_MAX) cap_pat = LONG_PAT_MAX;
+    g.cap_pat = cap_pat;
+    int hs = 64;
+    while (hs < 2 * cap_pat) hs <<= 1;
+    g.hash_size = hs;
+    g.w_max = (cap_pat + 63) / 64;
+    g.slab_bytes = long_lev_slab_bytes(g.cap_a, g.cap_b, g.cap_pat, g.hash_size, g.w_max);
+    long long warps = (long long)ctx.sm_count * 8;
+    if ((long long)ov.nlong < warps) warps = ov.nlong;
+    const long long budget = 6ll << 30;
+    if (warps * g.slab_bytes > budget) warps = budget / g.slab_bytes;
+    *n_huge = 0;
+    if (warps < 1) {  // a single slab exceeds the budget: everything goes to the generic kernel
+        *n_huge = ov.nlong;
+        CUDA_TRY(cudaMemcpyAsync(huge_list, args.listlong, 4 * (size_t)ov.nlong, cudaMemcpyDeviceToDevice, st));
+        return STRSIM_OK;
+    }
+    int rc = ws_reserve(ctx.scratch, (size_t)(warps * g.slab_bytes));
+    if (rc) return rc;
+    g.scratch = static_cast<unsigned char*>(ctx.scratch.ptr);
+    g.n_warps = (int)warps;
+    CUDA_TRY(cudaMemsetAsync(ctx.d_counters, 0, 4 * sizeof(unsigned int), st));
+    long_lev_kernel<<<(unsigned)((warps + LONG_WPB - 1) / LONG_WPB), 32 * LONG_WPB, 0, st>>>(g);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(ctx.h_counters, ctx.d_counters, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *n_huge = ctx.h_counters[1];
     return STRSIM_OK;
 }
 
@@ -456,7 +584,14 @@ static int run_segment(ThreadCtx& ctx, SegArgs args, Alphabet al, int stage32, i
     }
     g_last_overflow[1] += ov.nlong;
     if (ov.nlong > 0) {
-        rc = run_generic<MEASURE>(ctx, args, ov, st);
+        if (MEASURE == LEVENSHTEIN && !force_generic) {
+            unsigned int n_huge = 0;
+            rc = run_long_lev(ctx, args, ov, args.list64, &n_huge, st);  // list64 is free again here
+            if (rc) return rc;
+            if (n_huge > 0) rc = run_generic<MEASURE>(ctx, args, ov, st, args.list64, ctx.d_counters + 1, n_huge);
+        } else {
+            rc = run_generic<MEASURE>(ctx, args, ov, st);
+        }
         if (rc) return rc;
     }
     return STRSIM_OK;
@@ -603,7 +738,7 @@ void strsim_b200_column_free(strsim_b200_column* col) {
     if (!col) return;
     if (col->block) {
         cudaSetDevice(col->device);
-        cudaFree(col->block);
+        pool_free(col->device, col->block, col->block_bytes);
     }
     delete col;
 }
@@ -632,13 +767,18 @@ int strsim_b200_compute_device(int measure, const strsim_b200_column* a, const s
     return compute_on_device(*ctx, measure, a, b, d_out_values, d_out_validity, d_dbg_ints, st);
 }
 
-int strsim_b200_compute_host(int measure, const strsim_view_chunk* a, size_t n_a, const strsim_view_chunk* b,
-                             size_t n_b, double* out_values, uint8_t* out_validity, int64_t* out_null_count,
-                             int32_t* dbg_ints) {
-    if ((n_a && !a) || (n_b && !b)) {
-        strsim_set_error("compute_host: NULL chunk array");
+int strsim_b200_compute_host_multi(const int* measures, size_t n_measures, const strsim_view_chunk* a, size_t n_a,
+                                   const strsim_view_chunk* b, size_t n_b, double* const* out_values,
+                                   uint8_t* out_validity, int64_t* out_null_count, int32_t* const* dbg_ints) {
+    if ((n_a && !a) || (n_b && !b) || !measures || n_measures == 0 || n_measures > 8 || !out_values) {
+        strsim_set_error("compute_host: NULL / out-of-range argument");
         return STRSIM_ERR_ARGUMENT;
     }
+    for (size_t m = 0; m < n_measures; m++)
+        if (measures[m] < 0 || measures[m] > 4) {
+            strsim_set_error("unknown measure %d", measures[m]);
+            return STRSIM_ERR_ARGUMENT;
+        }
     int64_t la = 0, lb = 0;
     for (size_t i = 0; i < n_a; i++) la += a[i].length;
     for (size_t i = 0; i < n_b; i++) lb += b[i].length;
@@ -648,14 +788,16 @@ int strsim_b200_compute_host(int measure, const strsim_view_chunk* a, size_t n_a
     }
     const int64_t n = la == 1 ? lb : la;
     if (out_null_count) *out_null_count = 0;
-    if (n > 0 && !out_values) {
-        strsim_set_error("compute_host: NULL out_values");
-        return STRSIM_ERR_ARGUMENT;
-    }
+    for (size_t m = 0; n > 0 && m < n_measures; m++)
+        if (!out_values[m]) {
+            strsim_set_error("compute_host: NULL out_values[%zu]", m);
+            return STRSIM_ERR_ARGUMENT;
+        }
     ThreadCtx* ctx;
     int rc = ensure_ctx(&ctx);
     if (rc) return rc;
     if (n == 0) return STRSIM_OK;
+    // one upload of the two columns serves every requested measure
     strsim_b200_column *ca = nullptr, *cb = nullptr;
     rc = upload_column(*ctx, a, n_a, false, &ca);
     if (rc) return rc;
@@ -665,43 +807,62 @@ int strsim_b200_compute_host(int measure, const strsim_view_chunk* a, size_t n_a
         return rc;
     }
     const size_t val_words = (size_t)((n + 31) / 32);
-    const size_t bytes = align_up(8 * (size_t)n, 256) + align_up(4 * val_words, 256) +
-                         (dbg_ints ? 24 * (size_t)n : 0);
+    const size_t out_stride = align_up(8 * (size_t)n, 256);
+    const size_t dbg_stride = align_up(24 * (size_t)n, 256);
+    bool any_dbg = false;
+    for (size_t m = 0; dbg_ints && m < n_measures; m++) any_dbg = any_dbg || dbg_ints[m] != nullptr;
+    const size_t bytes = n_measures * out_stride + align_up(4 * val_words, 256) + (any_dbg ? n_measures * dbg_stride : 0);
     void* d_block = nullptr;
-    cudaError_t e = cudaMalloc(&d_block, bytes);
-    if (e != cudaSuccess) {
-        strsim_set_error("cudaMalloc(%zu) for results failed: %s", bytes, cudaGetErrorString(e));
+    rc = pool_alloc(ctx->device, bytes, &d_block);
+    if (rc) {
         strsim_b200_column_free(ca);
         strsim_b200_column_free(cb);
-        return STRSIM_ERR_NOMEM;
+        return rc;
     }
-    double* d_out = static_cast<double*>(d_block);
-    uint32_t* d_val = reinterpret_cast<uint32_t*>(static_cast<char*>(d_block) + align_up(8 * (size_t)n, 256));
-    int32_t* d_dbg = dbg_ints ? reinterpret_cast<int32_t*>(reinterpret_cast<char*>(d_val) + align_up(4 * val_words, 256))
-                              : nullptr;
+    char* base = static_cast<char*>(d_block);
+    uint32_t* d_val = reinterpret_cast<uint32_t*>(base + n_measures * out_stride);
+    char* d_dbg_base = reinterpret_cast<char*>(d_val) + align_up(4 * val_words, 256);
     const bool want_validity = out_validity != nullptr || out_null_count != nullptr;
-    rc = compute_on_device(*ctx, measure, ca, cb, d_out, want_validity ? d_val : nullptr, d_dbg, ctx->stream);
     cudaError_t ce = cudaSuccess;
-    if (rc == STRSIM_OK) {
-        ce = cudaMemcpyAsync(out_values, d_out, 8 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
-        if (ce == cudaSuccess && out_validity)
-            ce = cudaMemcpyAsync(out_validity, d_val, (size_t)((n + 7) / 8), cudaMemcpyDeviceToHost, ctx->stream);
-        if (ce == cudaSuccess && dbg_ints)
-            ce = cudaMemcpyAsync(dbg_ints, d_dbg, 24 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
-        if (ce == cudaSuccess && want_validity)
-            ce = cudaMemcpyAsync(ctx->h_nulls, ctx->d_nulls, 8, cudaMemcpyDeviceToHost, ctx->stream);
-        if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
-        if (ce != cudaSuccess) {
-            strsim_set_error("CUDA error while downloading results: %s", cudaGetErrorString(ce));
-            rc = STRSIM_ERR_CUDA;
-        } else if (out_null_count) {
-            *out_null_count = (int64_t)*ctx->h_nulls;
-        }
+    for (size_t m = 0; rc == STRSIM_OK && m < n_measures; m++) {
+        double* d_out = reinterpret_cast<double*>(base + m * out_stride);
+        int32_t* d_dbg = (any_dbg && dbg_ints[m]) ? reinterpret_cast<int32_t*>(d_dbg_base + m * dbg_stride) : nullptr;
+        rc = compute_on_device(*ctx, measures[m], ca, cb, d_out, (want_validity && m == 0) ? d_val : nullptr, d_dbg,
+                               ctx->stream);
+        if (rc) break;
+        // download this measure on the copy stream while the next one computes
+        ce = cudaEventRecord(ctx->done_event[m], ctx->stream);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->copy_stream, ctx->done_event[m], 0);
+        if (ce == cudaSuccess)
+            ce = cudaMemcpyAsync(out_values[m], d_out, 8 * (size_t)n, cudaMemcpyDeviceToHost, ctx->copy_stream);
+        if (ce == cudaSuccess && d_dbg)
+            ce = cudaMemcpyAsync(dbg_ints[m], d_dbg, 24 * (size_t)n, cudaMemcpyDeviceToHost, ctx->copy_stream);
+        if (ce == cudaSuccess && m == 0 && out_validity)
+            ce = cudaMemcpyAsync(out_validity, d_val, (size_t)((n + 7) / 8), cudaMemcpyDeviceToHost, ctx->copy_stream);
+        if (ce == cudaSuccess && m == 0 && want_validity)
+            ce = cudaMemcpyAsync(ctx->h_nulls, ctx->d_nulls, 8, cudaMemcpyDeviceToHost, ctx->copy_stream);
+        if (ce != cudaSuccess) break;
     }
-    cudaFree(d_block);
+    cudaError_t s1 = cudaStreamSynchronize(ctx->stream);
+    cudaError_t s2 = cudaStreamSynchronize(ctx->copy_stream);
+    if (rc == STRSIM_OK && (ce != cudaSuccess || s1 != cudaSuccess || s2 != cudaSuccess)) {
+        strsim_set_error("CUDA error while computing / downloading results: %s",
+                         cudaGetErrorString(ce != cudaSuccess ? ce : (s1 != cudaSuccess ? s1 : s2)));
+        rc = STRSIM_ERR_CUDA;
+    }
+    if (rc == STRSIM_OK && out_null_count) *out_null_count = (int64_t)*ctx->h_nulls;
+    pool_free(ctx->device, d_block, bytes);
     strsim_b200_column_free(ca);
     strsim_b200_column_free(cb);
     return rc;
+}
+
+int strsim_b200_compute_host(int measure, const strsim_view_chunk* a, size_t n_a, const strsim_view_chunk* b,
+                             size_t n_b, double* out_values, uint8_t* out_validity, int64_t* out_null_count,
+                             int32_t* dbg_ints) {
+    double* outs[1] = {out_values};
+    int32_t* dbgs[1] = {dbg_ints};
+    return strsim_b200_compute_host_multi(&measure, 1, a, n_a, b, n_b, outs, out_validity, out_null_count, dbgs);
 }
 
 }  // extern "C"

@@ -1,0 +1,291 @@
+// long_lev_kernel.cuh -- Levenshtein for long strings: warp-cooperative multi-word Myers / Hyyro.
+//
+// One warp per pair (pairs are pulled from the overflow list through an atomic cursor, so long and
+// short pairs balance dynamically).  The shorter string is the pattern (m codepoints, W = ceil(m/64)
+// 64-cell blocks), the longer one the text (n codepoints).  Lane l owns K = ceil(W/32) consecutive
+// blocks, with their vertical delta vectors Pv/Mv in registers.  The blocks of one DP column depend
+// on each other top to bottom through the horizontal delta (hp, hm) that leaves a block at its last
+// row, so the warp runs a WAVEFRONT: at step s lane l works on text column s - l and receives the
+// carry of the lane above -- produced one step earlier for the same column -- with __shfl_up.  A pair
+// takes n + L - 1 steps (L = lanes in use) instead of n * W sequential block updates.
+//
+// Pattern-match vectors: per pair, the pattern's distinct codepoints get dense ids through an
+// open-addressing hash table (any Unicode scalar value), the text is translated to ids once, and
+// Peq[id][block] (64-bit words) is built with atomicOr.  All of it lives in a per-warp scratch slab in
+// HBM that stays L2-resident while the pair is processed; the Eq words of the next column are
+// prefetched into registers while the current column is computed.
+//
+// Result: D[m][n] = n + sum over blocks of popc(Pv) - popc(Mv) (the final vertical deltas), then
+// 1 - d / max(la, lb) exactly as /root/reference/src/expressions/strsim.rs:160.
+// Patterns longer than LONG_PAT_MAX codepoints go to the generic kernel (their Peq would not fit the
+// slab budget); nothing is approximated.
+#pragma once
+#include "generic_kernel.cuh"
+
+namespace strsim {
+
+constexpr int LONG_PAT_MAX = 8192;  // codepoints; 128 blocks = 4 per lane
+constexpr int LONG_WPB = 4;         // warps per block
+
+struct LongLevArgs {
+    DevCol a, b;
+    double* out;
+    int* dbg;
+    const unsigned int* list;
+    const unsigned int* list_count;
+    unsigned int* cursor;      // zero-initialised work counter
+    unsigned int* huge_list;   // rows whose pattern exceeds LONG_PAT_MAX
+    unsigned int* huge_count;
+    unsigned char* scratch;
+    long long slab_bytes;
+    int n_warps;
+    int cap_a, cap_b;  // max bytes of a / b over the listed rows (>= codepoints)
+    int cap_pat;       // min(cap_a, cap_b, LONG_PAT_MAX)
+    int hash_size;     // power of two >= 2 * cap_pat (slab capacity; each pair uses what it needs)
+    int w_max;         // ceil(cap_pat / 64)
+};
+
+struct LongLevSlab {
+    uint32_t* cps_a;
+    uint32_t* cps_b;
+    uint16_t* tid;
+    uint32_t* hkeys;
+    uint16_t* hvals;
+    unsigned long long* peq;
+};
+
+__host__ __device__ inline long long long_lev_slab_bytes(int cap_a, int cap_b, int cap_pat, int hash_size,
+                                                         int w_max) {
+    long long b = 0;
+    b += 4ll * cap_a;
+    b += 4ll * cap_b;
+    b += 2ll * ((cap_a > cap_b ? cap_a : cap_b) + 8);
+    b = (b + 15) & ~15ll;
+    b += 4ll * hash_size;
+    b += 2ll * hash_size;
+    b = (b + 15) & ~15ll;
+    b += 8ll * (cap_pat + 1) * w_max;
+    return (b + 255) & ~255ll;
+}
+
+__device__ inline LongLevSlab long_lev_carve(unsigned char* base, const LongLevArgs& g) {
+    LongLevSlab s;
+    long long o = 0;
+    s.cps_a = reinterpret_cast<uint32_t*>(base + o);
+    o += 4ll * g.cap_a;
+    s.cps_b = reinterpret_cast<uint32_t*>(base + o);
+    o += 4ll * g.cap_b;
+    s.tid = reinterpret_cast<uint16_t*>(base + o);
+    o += 2ll * ((g.cap_a > g.cap_b ? g.cap_a : g.cap_b) + 8);
+    o = (o + 15) & ~15ll;
+    s.hkeys = reinterpret_cast<uint32_t*>(base + o);
+    o += 4ll * g.hash_size;
+    s.hvals = reinterpret_cast<uint16_t*>(base + o);
+    o += 2ll * g.hash_size;
+    o = (o + 15) & ~15ll;
+    s.peq = reinterpret_cast<unsigned long long*>(base + o);
+    return s;
+}
+
+// UTF-8 -> Unicode scalar values, 32 bytes per iteration (valid UTF-8, as Polars guarantees)
+__device__ inline int warp_decode(const unsigned char* p, int nbytes, uint32_t* out, int lane) {
+    int count = 0;
+    for (int base = 0; base < nbytes; base += 32) {
+        const int i = base + lane;
+        const uint32_t c = i < nbytes ? p[i] : 0x80u;
+        const bool lead = i < nbytes && (c & 0xC0u) != 0x80u;
+        const unsigned mask = __ballot_sync(0xFFFFFFFFu, lead);
+        if (lead) {
+            int len = c < 0x80u ? 1 : c < 0xE0u ? 2 : c < 0xF0u ? 3 : 4;
+            if (len > nbytes - i) len = nbytes - i;
+            uint32_t cp = len == 1 ? c : (c & (0xFFu >> (len + 1)));
+            for (int e = 1; e < len; e++) cp = (cp << 6) | (p[i + e] & 0x3Fu);
+            out[count + __popc(mask & ((1u << lane) - 1u))] = cp;
+        }
+        count += __popc(mask);
+    }
+    __syncwarp();
+    return count;
+}
+
+__device__ __forceinline__ uint32_t long_hash(uint32_t cp, int shift) { return (cp * 2654435761u) >> shift; }
+
+// id of codepoint cp, or `absent` when the pattern does not contain it
+__device__ __forceinline__ uint32_t long_lookup(const LongLevSlab& s, uint32_t hmask, int hshift, uint32_t cp,
+                                                uint32_t absent) {
+    const uint32_t key = cp + 1u;
+    uint32_t slot = long_hash(cp, hshift);
+    for (;;) {
+        const uint32_t k = __ldcg(&s.hkeys[slot]);  // written with atomicCAS (L2): do not trust L1
+        if (k == key) return s.hvals[slot];
+        if (k == 0u) return absent;
+        slot = (slot + 1u) & hmask;
+    }
+}
+
+template <int K>
+__device__ inline int long_wavefront(const LongLevSlab& s, int m, int n, int W, int L, int lane) {
+    uint64_t Pv[K], Mv[K], eq_cur[K], eq_nxt[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        Pv[k] = ~0ull;
+        Mv[k] = 0ull;
+        eq_cur[k] = 0ull;
+        eq_nxt[k] = 0ull;
+    }
+    const int blk0 = lane * K;
+    const bool lane_on = lane < L;
+    uint32_t hp_prev = 0, hm_prev = 0;
+    // prime the pipeline: Eq words of this lane's first column (j = 0, reached at step s = lane)
+    if (lane_on) {
+        const unsigned long long* row = s.peq + (size_t)s.tid[0] * W + blk0;
+#pragma unroll
+        for (int k = 0; k < K; k++)
+            if (blk0 + k < W) eq_cur[k] = row[k];
+    }
+    const int steps = n + L - 1;
+    for (int st = 0; st < steps; st++) {
+        uint32_t hp = __shfl_up_sync(0xFFFFFFFFu, hp_prev, 1);
+        uint32_t hm = __shfl_up_sync(0xFFFFFFFFu, hm_prev, 1);
+        if (lane == 0) {
+            hp = 1u;
+            hm = 0u;
+        }
+        const int j = st - lane;
+        if (lane_on && j >= 0 && j < n) {
+            if (j + 1 < n) {  // prefetch the next column's Eq words
+                const unsigned long long* row = s.peq + (size_t)s.tid[j + 1] * W + blk0;
+#pragma unroll
+                for (int k = 0; k < K; k++)
+                    if (blk0 + k < W) eq_nxt[k] = row[k];
+            }
+#pragma unroll
+            for (int k = 0; k < K; k++)
+                if (blk0 + k < W) myers_block(Pv[k], Mv[k], eq_cur[k], hp, hm);
+            hp_prev = hp;
+            hm_prev = hm;
+#pragma unroll
+            for (int k = 0; k < K; k++) eq_cur[k] = eq_nxt[k];
+        }
+    }
+    int score = 0;
+#pragma unroll
+    for (int k = 0; k < K; k++)
+        if (lane_on && blk0 + k < W) score += myers_block_score(Pv[k], Mv[k], m - 64 * (blk0 + k));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) score += __shfl_xor_sync(0xFFFFFFFFu, score, o);
+    return n + score;
+}
+
+__global__ void __launch_bounds__(32 * LONG_WPB) long_lev_kernel(const LongLevArgs g) {
+    const int lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * LONG_WPB + (threadIdx.x >> 5);
+    if (warp >= g.n_warps) return;
+    const LongLevSlab s = long_lev_carve(g.scratch + (long long)warp * g.slab_bytes, g);
+    const unsigned int count = *g.list_count;
+    for (;;) {
+        unsigned int e = 0;
+        if (lane == 0) e = atomicAdd(g.cursor, 1u);
+        e = __shfl_sync(0xFFFFFFFFu, e, 0);
+        if (e >= count) break;
+        const long long row = g.list[e];
+        int na, nb;
+        const unsigned char* pa = view_ptr(g.a, row, na);
+        const unsigned char* pb = view_ptr(g.b, row, nb);
+        PairInts pi = {F_GENERAL, 0, 0, 0, 0, 0};
+        double v;
+        bool differ = na != nb;
+        if (!differ) {
+            bool d = false;
+            for (int i = lane; i < na; i += 32) d = d || pa[i] != pb[i];
+            differ = __any_sync(0xFFFFFFFFu, d);
+        }
+        if (!differ) {
+            pi.flag = F_EQUAL;
+            v = 1.0;
+        } else {
+            const int la = warp_decode(pa, na, s.cps_a, lane);
+            const int lb = warp_decode(pb, nb, s.cps_b, lane);
+            pi.la = la;
+            pi.lb = lb;
+            const bool pat_is_b = lb <= la;
+            const uint32_t* P = pat_is_b ? s.cps_b : s.cps_a;
+            const uint32_t* T = pat_is_b ? s.cps_a : s.cps_b;
+            const int m = pat_is_b ? lb : la, n = pat_is_b ? la : lb;
+            if (m > g.cap_pat) {  // Peq would not fit the slab: the generic kernel finishes this row
+                if (lane == 0) g.huge_list[atomicAdd(g.huge_count, 1u)] = (unsigned int)row;
+                continue;
+            }
+            int d;
+            if (m == 0) {
+                d = n;
+            } else {
+                const int W = (m + 63) >> 6;
+                // 1. hash set of the pattern's codepoints (table sized for this pattern, load <= 1/2)
+                int hbits = 6;
+                while ((1 << hbits) < 2 * m) hbits++;
+                const int hsize = 1 << hbits, hshift = 32 - hbits;
+                const uint32_t hmask = (uint32_t)hsize - 1u;
+                for (int i = lane; i < hsize; i += 32) s.hkeys[i] = 0u;
+                __syncwarp();
+                for (int i = lane; i < m; i += 32) {
+                    const uint32_t key = P[i] + 1u;
+                    uint32_t slot = long_hash(P[i], hshift);
+                    for (;;) {
+                        const uint32_t old = atomicCAS(&s.hkeys[slot], 0u, key);
+                        if (old == 0u || old == key) break;
+                        slot = (slot + 1u) & hmask;
+                    }
+                }
+                __syncwarp();
+                // 2. dense ids in slot order
+                uint32_t distinct = 0;
+                for (int base = 0; base < hsize; base += 32) {
+                    const bool occ = __ldcg(&s.hkeys[base + lane]) != 0u;
+                    const unsigned mask = __ballot_sync(0xFFFFFFFFu, occ);
+                    if (occ) s.hvals[base + lane] = (uint16_t)(distinct + __popc(mask & ((1u << lane) - 1u)));
+                    distinct += __popc(mask);
+                }
+                __syncwarp();
+                // 3. text -> ids (id `distinct` = a codepoint the pattern does not contain: zero row)
+                for (int j = lane; j < n; j += 32) s.tid[j] = (uint16_t)long_lookup(s, hmask, hshift, T[j], distinct);
+                // 4. Peq[id][block]
+                const size_t words = (size_t)(distinct + 1u) * W;
+                for (size_t i = lane; i < words; i += 32) s.peq[i] = 0ull;
+                __syncwarp();
+                for (int i = lane; i < m; i += 32) {
+                    const uint32_t id = long_lookup(s, hmask, hshift, P[i], distinct);
+                    atomicOr(&s.peq[(size_t)id * W + (i >> 6)], 1ull << (i & 63));
+                }
+                __syncwarp();
+                __threadfence();  // the atomics landed in L2; drop possibly stale L1 lines before reading Peq
+                // 5. wavefront over the blocks
+                const int K = (W + 31) >> 5;
+                const int L = (W + K - 1) / K;
+                switch (K) {
+                    case 1: d = long_wavefront<1>(s, m, n, W, L, lane); break;
+                    case 2: d = long_wavefront<2>(s, m, n, W, L, lane); break;
+                    case 3: d = long_wavefront<3>(s, m, n, W, L, lane); break;
+                    default: d = long_wavefront<4>(s, m, n, W, L, lane); break;
+                }
+            }
+            pi.x0 = d;
+            v = lev_value(d, la, lb);
+        }
+        if (lane == 0) {
+            g.out[row] = v;
+            if (g.dbg) {
+                int* o = g.dbg + row * 6;
+                o[0] = pi.flag;
+                o[1] = pi.la;
+                o[2] = pi.lb;
+                o[3] = pi.x0;
+                o[4] = pi.x1;
+                o[5] = pi.x2;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace strsim

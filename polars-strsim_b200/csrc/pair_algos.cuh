@@ -325,4 +325,32 @@ struct MultisetStep {
     }
 };
 
+// =====================================================================================================
+// Multi-word Myers / Hyyro: one 64-cell block of one DP column.  (hp, hm) carry the horizontal delta
+// (+1 / -1) entering the block from the block above on input and leaving it at the bottom on output;
+// the top block of a column is entered with (1, 0) because D[0][j] = j.  long_lev_kernel.cuh runs the
+// blocks of one pair as a wavefront across the lanes of a warp, handing (hp, hm) to the next lane
+// with __shfl_up; the host tests chain the blocks sequentially.
+// =====================================================================================================
+SS_HD void myers_block(uint64_t& Pv, uint64_t& Mv, uint64_t Eq, uint32_t& hp, uint32_t& hm) {
+    const uint64_t Xv = Eq | Mv;
+    Eq |= (uint64_t)hm;
+    const uint64_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+    uint64_t Ph = Mv | ~(Xh | Pv);
+    uint64_t Mh = Pv & Xh;
+    const uint32_t hp_out = (uint32_t)(Ph >> 63), hm_out = (uint32_t)(Mh >> 63);
+    Ph = (Ph << 1) | (uint64_t)hp;
+    Mh = (Mh << 1) | (uint64_t)hm;
+    Pv = Mh | ~(Xv | Ph);
+    Mv = Ph & Xv;
+    hp = hp_out;
+    hm = hm_out;
+}
+
+// contribution of one block's final vertical deltas to D[m][n] - n; `bits` = pattern cells in the block
+SS_HD int myers_block_score(uint64_t Pv, uint64_t Mv, int bits) {
+    const uint64_t mask = bits >= 64 ? ~0ull : ((1ull << bits) - 1ull);
+    return popc(Pv & mask) - popc(Mv & mask);
+}
+
 }  // namespace strsim

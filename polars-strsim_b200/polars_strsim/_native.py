@@ -75,6 +75,10 @@ def lib():
     L.strsim_b200_compute_host.restype = ctypes.c_int
     L.strsim_b200_compute_host.argtypes = [ctypes.c_int, ctypes.POINTER(ViewChunk), SZ,
                                            ctypes.POINTER(ViewChunk), SZ, P, P, ctypes.POINTER(I64), P]
+    L.strsim_b200_compute_host_multi.restype = ctypes.c_int
+    L.strsim_b200_compute_host_multi.argtypes = [ctypes.POINTER(ctypes.c_int), SZ, ctypes.POINTER(ViewChunk), SZ,
+                                                 ctypes.POINTER(ViewChunk), SZ, ctypes.POINTER(P), P,
+                                                 ctypes.POINTER(I64), ctypes.POINTER(P)]
     L.strsim_b200_compute_arrow.restype = ctypes.c_int
     L.strsim_b200_compute_arrow.argtypes = [ctypes.c_int, P, P, SZ, P, P, SZ, P]
     L.strsim_b200_column_upload.restype = ctypes.c_int
@@ -168,6 +172,24 @@ def compute_host(measure, a, b, debug: bool = False, out_values=None, out_validi
     if debug:
         return values, valid, nulls.value, ints[:n]
     return values, valid, nulls.value
+
+
+def compute_host_multi(measures, a, b, out_values=None, out_validity=None, prepared=None):
+    """Several measures over ONE upload of the two columns (strsim_b200_compute_host_multi).
+
+    Returns (list of float64 arrays, validity, null_count); validity is a bool array unless a
+    preallocated packed bitmap `out_validity` was passed."""
+    L = lib()
+    ca, na, cb, nb, n, _keep = prepared if prepared is not None else prepare(a, b)
+    k = len(measures)
+    ids = (ctypes.c_int * k)(*[measure_id(m) for m in measures])
+    outs = out_values if out_values is not None else [np.zeros(max(n, 1), dtype=np.float64) for _ in range(k)]
+    vbytes = out_validity if out_validity is not None else np.zeros((max(n, 1) + 7) // 8 + 8, dtype=np.uint8)
+    ptrs = (ctypes.c_void_p * k)(*[o.ctypes.data for o in outs])
+    nulls = ctypes.c_int64(0)
+    _check(L.strsim_b200_compute_host_multi(ids, k, ca, na, cb, nb, ptrs, vbytes.ctypes.data, ctypes.byref(nulls), None))
+    valid = vbytes if out_validity is not None else np.unpackbits(vbytes, bitorder="little")[:n].astype(bool)
+    return [o[:n] for o in outs], valid, nulls.value
 
 
 def prepare(a, b):

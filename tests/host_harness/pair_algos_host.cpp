@@ -61,3 +61,30 @@ extern "C" int algos_batch(int measure, int bits, int64_t n, const uint8_t* ad, 
     }
     return bad;
 }
+
+// multi-word Myers with the product's block step, blocks chained sequentially per column
+#include <unordered_map>
+#include <vector>
+extern "C" int algos_myers_multiword(const uint32_t* a, int la, const uint32_t* b, int lb) {
+    const uint32_t* pat = la <= lb ? a : b;
+    const uint32_t* txt = la <= lb ? b : a;
+    const int m = la <= lb ? la : lb, n = la <= lb ? lb : la;
+    if (m == 0) return n;
+    const int W = (m + 63) / 64;
+    std::unordered_map<uint32_t, std::vector<uint64_t>> peq;
+    for (int i = 0; i < m; i++) {
+        auto& row = peq[pat[i]];
+        if (row.empty()) row.assign(W, 0);
+        row[i / 64] |= 1ull << (i % 64);
+    }
+    std::vector<uint64_t> Pv(W, ~0ull), Mv(W, 0), zero(W, 0);
+    for (int j = 0; j < n; j++) {
+        auto it = peq.find(txt[j]);
+        const std::vector<uint64_t>& eq = it == peq.end() ? zero : it->second;
+        uint32_t hp = 1, hm = 0;
+        for (int w = 0; w < W; w++) myers_block(Pv[w], Mv[w], eq[w], hp, hm);
+    }
+    int d = n;
+    for (int w = 0; w < W; w++) d += myers_block_score(Pv[w], Mv[w], m - 64 * w);
+    return d;
+}

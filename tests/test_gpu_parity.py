@@ -249,3 +249,47 @@ def test_device_resident_api(native, oracle):
         bits = np.unpackbits(val.cpu().numpy().view(np.uint8), bitorder="little")[:n].astype(bool)
         assert (bits == ref_valid).all()
         assert (got[ref_valid].view(np.uint64) == ref[ref_valid].view(np.uint64)).all()
+
+
+def test_multi_measure_single_upload(native, oracle):
+    rng = random.Random(23)
+    pairs = [rand_pair(rng, 40) for _ in range(20000)]
+    a = [None if rng.random() < 0.04 else p[0] for p in pairs]
+    b = [None if rng.random() < 0.04 else p[1] for p in pairs]
+    outs, valid, nulls = native.compute_host_multi(list(oracle.MEASURES), sv(a), sv(b))
+    for m, got in zip(oracle.MEASURES, outs):
+        ref, ref_valid, _ = oracle.batch(m, a, b)
+        assert (valid == ref_valid).all() and nulls == int((~ref_valid).sum())
+        assert (got[ref_valid].view(np.uint64) == ref[ref_valid].view(np.uint64)).all(), m
+
+
+def test_long_levenshtein_multiword(native, oracle):
+    """Warp-cooperative multi-word Myers: block boundaries (64/128/2048 codepoints), 1-4 lanes'
+    worth of blocks per lane, Unicode patterns, very unequal lengths."""
+    rng = random.Random(99)
+    a, b = [], []
+    for la in (65, 127, 128, 129, 500, 2047, 2048, 2049, 4100, 6200):
+        for lb in (0, 1, 64, 65, 300, 2048, 4099):
+            alpha = rng.choice(["ab", "abcdefghijklmnopqrstuvwxyz ", "aé日\U0001f600z", "一二三四五六日本語"])
+            x = "".join(rng.choice(alpha) for _ in range(la))
+            y = "".join(rng.choice(alpha) for _ in range(lb))
+            a += [x, x]
+            b += [y, (x[: lb] + y[lb // 2:])[: max(lb, 1)]]
+    # near-identical long pairs (edits sprinkled in)
+    for _ in range(30):
+        n = rng.randint(200, 4000)
+        x = [rng.choice("abcdefghij ") for _ in range(n)]
+        y = list(x)
+        for _ in range(n // 10):
+            p = rng.randrange(len(y))
+            op = rng.randint(0, 2)
+            if op == 0:
+                y[p] = rng.choice("xyz")
+            elif op == 1:
+                y.insert(p, "q")
+            elif len(y) > 1:
+                del y[p]
+        a.append("".join(x))
+        b.append("".join(y))
+    check(native, oracle, "levenshtein", a, b)
+    assert native.last_overflow()[1] > 0

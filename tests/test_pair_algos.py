@@ -94,3 +94,20 @@ def test_boundary_lengths(algos, oracle, bits):
                 b.append("x" * lb)
     for measure in oracle.MEASURES:
         run_batch(algos, oracle, measure, bits, a, b)
+
+
+def test_multiword_myers_block(algos, oracle):
+    """The 64-cell block step of the long-string kernel, chained over blocks on the host."""
+    algos.algos_myers_multiword.restype = ctypes.c_int
+    algos.algos_myers_multiword.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+    rng = random.Random(4242)
+    cases = [rand_pair(rng, L) for L in (5, 63, 64, 65, 127, 128, 129, 300, 700) for _ in range(25)]
+    cases += [("a" * 200, "a" * 199 + "b"), ("", "x" * 100), ("ab" * 100, "ba" * 100)]
+    for x, y in cases:
+        ax = np.array([ord(c) for c in x], dtype=np.uint32)
+        ay = np.array([ord(c) for c in y], dtype=np.uint32)
+        d = algos.algos_myers_multiword(ax.ctypes.data, len(x), ay.ctypes.data, len(y))
+        if x == y:
+            assert d == 0
+        else:
+            assert d == oracle.pair("levenshtein", x, y)[1][3], (len(x), len(y))
