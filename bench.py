@@ -5,8 +5,9 @@ A step = one pass of ALL FIVE measures (levenshtein, jaro, jaro_winkler, jaccard
 over one batch of synthetic pairs (default: BASELINE config C2, 10M ASCII name pairs of length
 4..24 per GPU, seeds in SURVEY.md 8(d)).  `value` counts pair evaluations (rows x 5) per second
 with the two columns already resident in HBM; `e2e` is the same work through the host-buffer C ABI
-call (`strsim_b200_compute_host`), pinned host memory in, H2D + kernels + D2H inside the timed
-region, five calls per step exactly as Polars would call the plugin five times.
+call (`strsim_b200_compute_host_multi`): pinned host memory in, ONE H2D upload of the step's two
+columns, the kernels of every measure, and the D2H of every measure's results inside the timed
+region.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2|C3|C4] [--rows R]
     python bench.py --impl reference ...     # the reference's CPU algorithm (oracle port) on host cores
@@ -264,6 +265,16 @@ def main():
     elapsed_ms = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
     checksum = float(out.sum().item())
+    cells = None
+    if wl["config"] == 4:
+        # long-string Levenshtein work unit: DP cells = sum la*lb over pairs with a != b,
+        # codepoint lengths taken from the kernel's own debug record
+        dbg = torch.zeros((n, 6), dtype=torch.int32, device="cuda")
+        _native.compute_device("levenshtein", colA, colB, out.data_ptr(), 0, dbg.data_ptr(), sptr)
+        torch.cuda.synchronize()
+        d64 = dbg.to(torch.int64)
+        cells = int((d64[:, 1] * d64[:, 2] * (d64[:, 0] == 0)).sum().item())
+        del dbg, d64
 
     per_measure_ms = {m: float(np.mean([per_events[k][i][0].elapsed_time(per_events[k][i][1])
                                         for k in range(args.steps)])) for i, m in enumerate(measures)}
@@ -335,6 +346,10 @@ def main():
         "overflow_rows_last_call": {"to_64bit_kernel": overflow[0], "to_long_kernel": overflow[1]},
         "checksum": checksum,
     }
+    if cells is not None:
+        ms = per_measure_ms["levenshtein"]
+        line["long_levenshtein"] = {"cells_per_launch": cells, "gcups": cells / (ms * 1e-3) / 1e9,
+                                    "note": "cells = sum la*lb (codepoints) over pairs with a != b"}
     if e2e:
         line["e2e"] = e2e
     if not args.no_cpu_baseline and world == 1:

@@ -574,8 +574,8 @@ static int run_segment(ThreadCtx& ctx, SegArgs args, Alphabet al, int stage32, i
         a64.list = args.list64;
         a64.list_count = &ctx.d_ovf->n64;
         a64.n = ov.n64;
-        a64.stage_bytes = 64 * ShortLayout<uint64_t, 64, 2, 128>::TILE;  // every listed row fits
-        rc = launch_short<uint64_t, MEASURE, 64, 2, true, 128, false>(ctx, a64, ov.n64, st);
+        a64.stage_bytes = 64 * ShortLayout<uint64_t, 64, 2, 192>::TILE;  // every listed row fits
+        rc = launch_short<uint64_t, MEASURE, 64, 2, true, 192, false>(ctx, a64, ov.n64, st);
         if (rc) return rc;
         // rows the 64-bit kernel could not stage are appended to listlong; re-read the counters
         CUDA_TRY(cudaMemcpyAsync(ctx.h_ovf, ctx.d_ovf, sizeof(Overflow), cudaMemcpyDeviceToHost, st));

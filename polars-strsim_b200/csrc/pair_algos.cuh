@@ -81,6 +81,13 @@ SS_HD int popc(uint64_t x) {
     return __builtin_popcountll(x);
 #endif
 }
+SS_HD int ctz64(uint64_t x) {  // x != 0
+#if defined(__CUDA_ARCH__)
+    return __ffsll((long long)x) - 1;
+#else
+    return __builtin_ctzll(x);
+#endif
+}
 
 // bits lo..hi inclusive (0 <= lo, hi < bits(M)); empty when lo > hi
 template <class M>
@@ -115,91 +122,11 @@ SS_HD double dice_value(int inter, int total) {
     return f_div(f_mul(2.0, (double)inter), (double)total);
 }
 
-// ---- Levenshtein: Myers / Hyyro bit-parallel, single word ---------------------------------------
-// Unit-cost edit distance between a pattern of m <= bits(M) codepoints (described by `pm`) and a
-// text of n codepoints streamed from `text`.  Equals the two-row DP of strsim.rs:141-159.
-template <class M, class PM, class Text>
-SS_HD int myers_single_word(const PM& pm, int m, Text& text, int n) {
-    if (m == 0) return n;
-    M Pv = ~M(0), Mv = M(0);
-    int score = m;
-    const int top = m - 1;
-    for (int j = 0; j < n; j++) {
-        M Eq = pm(text.next());
-        M Xv = Eq | Mv;
-        M Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
-        M Ph = Mv | ~(Xh | Pv);
-        M Mh = Pv & Xh;
-        score += (int)((Ph >> top) & M(1)) - (int)((Mh >> top) & M(1));
-        Ph = (Ph << 1) | M(1);
-        Mh = Mh << 1;
-        Pv = Mh | ~(Xv | Ph);
-        Mv = Ph & Xv;
-    }
-    return score;
-}
-
-// ---- Jaro: greedy windowed matching on bitmasks --------------------------------------------------
-// `pmb` describes b (lb <= bits(M)); a (la <= bits(M)) is streamed twice (match pass, then the
-// transposition pass).  Reproduces strsim.rs:200-237 exactly: a is the outer sequence, the first
-// unflagged equal position of b inside [i-bound, min(i+bound, lb-1)] is taken.
-template <class M, class PM, class TextA>
-SS_HD void jaro_match(const PM& pmb, TextA& a_first, TextA& a_second, int la, int lb, int& m_out,
-                      int& t_out) {
-    int mx = la > lb ? la : lb;
-    int bound = mx / 2 - 1;  // strsim.rs:200 (mx >= 2 here)
-    int outer = la < lb + bound ? la : lb + bound;
-    M flag_a = M(0), flag_b = M(0);
-    int m = 0;
-    for (int i = 0; i < outer; i++) {
-        uint32_t c = a_first.next();
-        int lo = i - bound;
-        if (lo < 0) lo = 0;
-        int hi = i + bound;
-        if (hi > lb - 1) hi = lb - 1;
-        M cand = pmb(c) & mask_range<M>(lo, hi) & ~flag_b;
-        if (cand) {
-            flag_b |= cand & (M(0) - cand);  // lowest candidate
-            flag_a |= M(1) << i;
-            m++;
-        }
-    }
-    // strsim.rs:220-237: k-th flagged char of a vs k-th flagged char of b
-    int t = 0;
-    M fb = flag_b;
-    for (int i = 0; i < outer && fb; i++) {
-        uint32_t c = a_second.next();
-        if ((flag_a >> i) & M(1)) {
-            M low = fb & (M(0) - fb);
-            fb ^= low;
-            if (!(pmb(c) & low)) t++;
-        }
-    }
-    m_out = m;
-    t_out = t;
-}
-
-// ---- character multiset intersection --------------------------------------------------------------
-// inter = sum_c min(count_a(c), count_b(c)) (strsim.rs:297-305): each character of a consumes one
-// not-yet-consumed equal character of b.
-template <class M, class PM, class TextA>
-SS_HD int multiset_intersection(const PM& pmb, TextA& a, int la) {
-    M used = M(0);
-    int inter = 0;
-    for (int i = 0; i < la; i++) {
-        M cand = pmb(a.next()) & ~used;
-        if (cand) {
-            used |= cand & (M(0) - cand);
-            inter++;
-        }
-    }
-    return inter;
-}
-
 // =====================================================================================================
-// ASCII fast path: characters are bytes packed four per word; the position masks live in a table
-// indexed by the byte.  Same arithmetic as the generic templates above, organised around whole words
-// so that the inner loops carry no per-character bookkeeping.
+// Step functors.  `Tab` maps a character to the bitmask of the positions where it occurs in the
+// tabled string: a direct table indexed by the byte on the ASCII path (characters are bytes packed
+// four per word, loops run over whole words), a per-pair hash table on the Unicode path
+// (row_short.cuh).  Each functor consumes one character of the streamed string per call.
 // =====================================================================================================
 
 // Applies f to the first n bytes of a string given as little-endian words (src(w) -> word w).

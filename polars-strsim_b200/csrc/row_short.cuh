@@ -2,18 +2,20 @@
 //
 // "Short" = both strings at most bits(M) BYTES (hence at most bits(M) codepoints), M = uint32_t or
 // uint64_t.  The pair's bytes arrive zero-padded in 4-byte words through a `Store`, which also
-// provides the scratch the algorithms need:
-//     tab(c)  c in [0,128)   position-mask table for ASCII strings (all-zero between rows)
-//     cp(s)   s in [0,2*bits(M))  codepoint keys of a (first half) and b (second half)
-//     wa(k), wb(k)  k in [0,bits(M)/4)  the bytes of a and b, little-endian words
+// provides the scratch the algorithms need (all-zero between rows):
+//     wa(k), wb(k)   k in [0,bits(M)/4)   the bytes of a and b, little-endian words
+//     tab(c)                              position-mask table indexed by an ASCII byte
+//     hkey(s), hmask(s)  s in [0,2*bits(M))  open-addressing hash slots (key+1, position mask) for
+//                                         non-ASCII pairs; they may alias the table's memory
 // short_kernel.cuh backs Store with per-thread shared-memory slabs laid out [slot][thread] so that a
 // warp's accesses never bank-conflict; tests back it with plain arrays on the host.
 //
-// Two code paths, chosen per pair:
-//   * ASCII (every byte < 0x80): characters are bytes, PM lookups are one table load.
-//   * Unicode: each character is keyed by its packed UTF-8 bytes (injective for valid UTF-8, so
-//     equality of keys == equality of Unicode scalar values, which is all the measures use;
-//     strsim.rs:133,189,261,297 iterate `chars()`), PM lookups scan the stored keys.
+// Two code paths, chosen per pair, sharing the step functors of pair_algos.cuh:
+//   * ASCII (every byte < 0x80): characters are bytes, a position mask is one table load.
+//   * Unicode: characters are decoded on the fly and keyed by their packed UTF-8 bytes (injective for
+//     valid UTF-8, so key equality == equality of Unicode scalar values, which is all the measures
+//     use; strsim.rs:133,189,261,297 iterate `chars()`); position masks live in a small per-pair hash
+//     table; codepoint counts come from a SWAR count of continuation bytes.
 //
 // Row rules follow /root/reference/src/expressions/strsim.rs:128,182-186,197-199,260-270,288-292.
 #pragma once
@@ -21,57 +23,15 @@
 
 namespace strsim {
 
-template <class Store>
-struct ByteReader {
-    const Store& s;
-    bool second;  // false: a, true: b
-    int j;
-    uint32_t cur;
-    SS_HD ByteReader(const Store& s_, bool second_) : s(s_), second(second_), j(0), cur(0) {}
-    SS_HD uint32_t next() {
-        if ((j & 3) == 0) cur = second ? s.wb(j >> 2) : s.wa(j >> 2);
-        uint32_t c = cur & 0xFFu;
-        cur >>= 8;
-        j++;
-        return c;
-    }
-};
-
-template <class Store>
-struct CpReader {
-    const Store& s;
-    int pos;
-    SS_HD CpReader(const Store& s_, int base) : s(s_), pos(base) {}
-    SS_HD uint32_t next() { return s.cp(pos++); }
-};
-
-template <class M, class Store>
-struct TablePM {
-    const Store& s;
-    SS_HD explicit TablePM(const Store& s_) : s(s_) {}
-    SS_HD M operator()(uint32_t c) const { return s.tab(c); }
-};
-
-template <class M, class Store>
-struct ScanPM {
-    const Store& s;
-    int base, len;
-    SS_HD ScanPM(const Store& s_, int base_, int len_) : s(s_), base(base_), len(len_) {}
-    SS_HD M operator()(uint32_t c) const {
-        M r = M(0);
-        for (int k = 0; k < len; k++) r |= M(s.cp(base + k) == c) << k;
-        return r;
-    }
-};
-
-// adapters for the ASCII fast path of pair_algos.cuh
+// ---- adapters ---------------------------------------------------------------------------------------
 template <class Store>
 struct StoreWords {
     const Store& s;
-    bool second;
+    bool second;  // false: a, true: b
     SS_HD StoreWords(const Store& s_, bool second_) : s(s_), second(second_) {}
     SS_HD uint32_t operator()(int w) const { return second ? s.wb(w) : s.wa(w); }
 };
+
 template <class M, class Store>
 struct StoreTable {
     Store& s;
@@ -80,59 +40,187 @@ struct StoreTable {
     SS_HD const M& operator()(uint32_t c) const { return s.tab(c); }
 };
 
-// UTF-8 bytes -> packed-byte character keys; returns the number of characters
-template <class Store>
-SS_HD int decode_keys(Store& s, bool second, int nbytes, int base) {
-    ByteReader<Store> r(s, second);
-    int k = 0, j = 0;
-    while (j < nbytes) {
-        uint32_t c = r.next();
-        int len = c < 0xC0u ? 1 : c < 0xE0u ? 2 : c < 0xF0u ? 3 : 4;
-        if (len > nbytes - j) len = nbytes - j;
-        uint32_t key = c;
-        for (int e = 1; e < len; e++) key = (key << 8) | r.next();
-        s.cp(base + k) = key;
-        k++;
-        j += len;
+// ---- UTF-8 helpers ------------------------------------------------------------------------------------
+// number of characters = bytes that are not continuation bytes (10xxxxxx); padding bytes are zero
+template <class Src>
+SS_HD int count_chars(const Src& src, int nbytes) {
+    int cont = 0;
+    for (int w = 0; 4 * w < nbytes; w++) {
+        const uint32_t x = src(w);
+        cont += popc(((x >> 7) & ~(x >> 6)) & 0x01010101u);
     }
-    return k;
+    return nbytes - cont;
 }
 
-// The measure-specific part once characters and a PM provider over the "tabled" string exist.
-//   Levenshtein: tabled string = pattern (either side, the distance is symmetric), RT streams the
-//                other one (n_text characters).
-//   other measures: tabled string = b, RA/RA2 stream a.
-template <class M, class PM, class RA>
-SS_HD double measure_core(int measure, const PM& pm, RA& ra, RA& ra2, int la, int lb, int n_tabled,
-                          int n_stream, PairInts& out) {
+// Calls f(key) for the first max_chars characters of a UTF-8 string of nbytes bytes; key = the
+// character's bytes packed big-endian (1-4 bytes).  Sequences are clamped to the string.
+template <class Src, class F>
+SS_HD void for_each_char(const Src& src, int nbytes, int max_chars, F& f) {
+    int j = 0, done = 0;
+    uint32_t word = 0;
+    while (j < nbytes && done < max_chars) {
+        if ((j & 3) == 0) word = src(j >> 2);
+        uint32_t key = word & 0xFFu;
+        word >>= 8;
+        j++;
+        if (key >= 0xC0u) {
+            int extra = 1 + (key >= 0xE0u) + (key >= 0xF0u);
+            if (extra > nbytes - j) extra = nbytes - j;
+            for (int e = 0; e < extra; e++) {
+                if ((j & 3) == 0) word = src(j >> 2);
+                key = (key << 8) | (word & 0xFFu);
+                word >>= 8;
+                j++;
+            }
+        }
+        f(key);
+        done++;
+    }
+}
+
+// ---- per-pair hash table of position masks (Unicode path) ------------------------------------------
+// 2*bits(M) slots, linear probing, at most bits(M) distinct keys => load <= 1/2.  `used` remembers
+// the occupied slots so that clearing touches only those.
+template <class M, class Store>
+struct HashTab {
+    static constexpr int CAP = (int)sizeof(M) * 8;
+    static constexpr int SLOTS = 2 * CAP;
+    static constexpr int SHIFT = CAP == 32 ? 26 : 25;  // 32 - log2(SLOTS)
+    Store& s;
+    uint64_t used_lo, used_hi;  // bitmap of occupied slots (used_hi only for 128 slots)
+    SS_HD explicit HashTab(Store& s_) : s(s_), used_lo(0), used_hi(0) {}
+    SS_HD static uint32_t home(uint32_t key) { return (key * 0x9E3779B1u) >> SHIFT; }
+    SS_HD M operator()(uint32_t key) const {  // position mask of `key` (0 when absent)
+        uint32_t slot = home(key);
+        for (;;) {
+            const uint32_t k = s.hkey(slot);
+            if (k == key + 1u) return s.hmask(slot);
+            if (k == 0u) return M(0);
+            slot = (slot + 1u) & (uint32_t)(SLOTS - 1);
+        }
+    }
+    SS_HD void add(uint32_t key, M bit) {
+        uint32_t slot = home(key);
+        for (;;) {
+            const uint32_t k = s.hkey(slot);
+            if (k == key + 1u) {
+                s.hmask(slot) = s.hmask(slot) | bit;
+                return;
+            }
+            if (k == 0u) {
+                s.hkey(slot) = key + 1u;
+                s.hmask(slot) = bit;
+                if (slot < 64u)
+                    used_lo |= 1ull << slot;
+                else
+                    used_hi |= 1ull << (slot - 64u);
+                return;
+            }
+            slot = (slot + 1u) & (uint32_t)(SLOTS - 1);
+        }
+    }
+    SS_HD void clear() {
+        while (used_lo) {
+            const int slot = ctz64(used_lo);
+            used_lo &= used_lo - 1ull;
+            s.hkey(slot) = 0u;
+            s.hmask(slot) = M(0);
+        }
+        while (used_hi) {
+            const int slot = 64 + ctz64(used_hi);
+            used_hi &= used_hi - 1ull;
+            s.hkey(slot) = 0u;
+            s.hmask(slot) = M(0);
+        }
+    }
+};
+
+template <class M, class Tab>
+struct HashBuild {
+    Tab& tab;
+    M bit;
+    SS_HD explicit HashBuild(Tab& t) : tab(t), bit(M(1)) {}
+    SS_HD void operator()(uint32_t key) {
+        tab.add(key, bit);
+        bit = bit << 1;
+    }
+};
+
+struct PrefixKeys {  // first (up to) four character keys of a string
+    uint32_t k[4];
+    int n;
+    SS_HD PrefixKeys() : n(0) { k[0] = k[1] = k[2] = k[3] = 0; }
+    SS_HD void operator()(uint32_t key) {
+        if (n < 4) k[n] = key;
+        n++;
+    }
+};
+
+// ---- the measure-specific part, shared by both paths -----------------------------------------------------
+// each_streamed(n, f): applies f to the first n characters of the streamed string (ASCII: bytes;
+// Unicode: decoded keys).  `tab`: position masks of the tabled string (Levenshtein: the shorter
+// one; the other measures: b, with a streamed as in strsim.rs:208).
+template <class M, class Tab, class Each>
+SS_HD double measure_body(int measure, const Tab& tab, const Each& each_streamed, int la, int lb, int n_tab,
+                          int n_str, PairInts& out) {
     switch (measure) {
         case LEVENSHTEIN: {
-            int d = myers_single_word<M>(pm, n_tabled, ra, n_stream);
+            int d = n_str;
+            if (n_tab > 0) {
+                MyersStep<M, Tab> step(tab);
+                each_streamed(n_str, step);
+                d = step.distance(n_tab, n_str);
+            }
             out.x0 = d;
             return lev_value(d, la, lb);
         }
         case JARO:
         case JARO_WINKLER: {
-            int m, t;
-            jaro_match<M>(pm, ra, ra2, la, lb, m, t);
-            out.x0 = m;
-            out.x1 = t;
-            return m == 0 ? 0.0 : jaro_value(m, t, la, lb);
-        }
-        case JACCARD: {
-            int inter = multiset_intersection<M>(pm, ra, la);
-            out.x0 = inter;
-            out.x1 = la + lb - inter;  // sum_c max = la + lb - sum_c min
-            return jaccard_value(inter, la + lb - inter);
+            const int mx = la > lb ? la : lb;
+            const int bound = mx / 2 - 1;  // strsim.rs:200
+            const int outer = la < lb + bound ? la : lb + bound;
+            JaroMatchStep<M, Tab> match(tab, lb, bound);
+            each_streamed(outer, match);
+            JaroTransStep<M, Tab> trans(tab, match.flag_a, match.flag_b);
+            if (match.m > 0) each_streamed(outer, trans);
+            out.x0 = match.m;
+            out.x1 = trans.t;
+            return match.m == 0 ? 0.0 : jaro_value(match.m, trans.t, la, lb);
         }
         default: {
-            int inter = multiset_intersection<M>(pm, ra, la);
-            out.x0 = inter;
+            MultisetStep<M, Tab> ms(tab, lb);
+            each_streamed(la, ms);
+            out.x0 = ms.inter;
+            if (measure == JACCARD) {
+                out.x1 = la + lb - ms.inter;  // sum_c max = la + lb - sum_c min
+                return jaccard_value(ms.inter, la + lb - ms.inter);
+            }
             out.x1 = la + lb;
-            return dice_value(inter, la + lb);
+            return dice_value(ms.inter, la + lb);
         }
     }
 }
+
+template <class Store>
+struct EachByte {
+    StoreWords<Store> src;
+    SS_HD EachByte(const Store& s, bool second) : src(s, second) {}
+    template <class F>
+    SS_HD void operator()(int n, F& f) const {
+        for_each_byte(src, n, f);
+    }
+};
+
+template <class Store>
+struct EachChar {
+    StoreWords<Store> src;
+    int nbytes;
+    SS_HD EachChar(const Store& s, bool second, int nbytes_) : src(s, second), nbytes(nbytes_) {}
+    template <class F>
+    SS_HD void operator()(int n, F& f) const {
+        for_each_char(src, nbytes, n, f);
+    }
+};
 
 // na, nb: byte lengths (<= bits(M)); equal: bytes identical; ascii: no byte >= 0x80 in either.
 template <class M, class Store>
@@ -147,72 +235,33 @@ SS_HD double row_short(int measure, Store& s, int na, int nb, bool equal, bool a
         out.flag = F_ONE_EMPTY;
         return 0.0;
     }
-    constexpr int CAP = (int)sizeof(M) * 8;
+    const bool is_jaro = measure == JARO || measure == JARO_WINKLER;
     double v;
     if (ascii) {
         const int la = na, lb = nb;
         out.la = la;
         out.lb = lb;
-        if ((measure == JARO || measure == JARO_WINKLER) && la == 1 && lb == 1) {  // strsim.rs:197
+        if (is_jaro && la == 1 && lb == 1) {  // strsim.rs:197
             out.flag = F_SINGLE_CHAR;
-            return 0.0;  // bytes differ here
+            return 0.0;  // the bytes differ here
         }
-        // Levenshtein tables the shorter string (fewer table writes, more text steps are cheap)
+        // Levenshtein tables the shorter string (fewer table writes; extra text steps are cheap)
         const bool table_b = measure != LEVENSHTEIN || lb <= la;
         const int n_tab = table_b ? lb : la;
-        const int n_str = table_b ? la : lb;
-        StoreWords<Store> tabled(s, table_b), streamed(s, !table_b);
+        StoreWords<Store> tabled(s, table_b);
         StoreTable<M, Store> tab(s);
         {
             BuildTable<M, StoreTable<M, Store>> build(tab);
             for_each_byte(tabled, (n_tab + 3) & ~3, build);
         }
-        switch (measure) {
-            case LEVENSHTEIN: {
-                int d = n_str;
-                if (n_tab > 0) {
-                    MyersStep<M, StoreTable<M, Store>> step(tab);
-                    for_each_byte(streamed, n_str, step);
-                    d = step.distance(n_tab, n_str);
-                }
-                out.x0 = d;
-                v = lev_value(d, la, lb);
-                break;
-            }
-            case JARO:
-            case JARO_WINKLER: {
-                const int mx = la > lb ? la : lb;
-                const int bound = mx / 2 - 1;  // strsim.rs:200
-                const int outer = la < lb + bound ? la : lb + bound;
-                JaroMatchStep<M, StoreTable<M, Store>> match(tab, lb, bound);
-                for_each_byte(streamed, outer, match);
-                JaroTransStep<M, StoreTable<M, Store>> trans(tab, match.flag_a, match.flag_b);
-                if (match.m > 0) for_each_byte(streamed, outer, trans);
-                out.x0 = match.m;
-                out.x1 = trans.t;
-                v = match.m == 0 ? 0.0 : jaro_value(match.m, trans.t, la, lb);
-                break;
-            }
-            default: {
-                MultisetStep<M, StoreTable<M, Store>> ms(tab, lb);
-                for_each_byte(streamed, la, ms);
-                out.x0 = ms.inter;
-                if (measure == JACCARD) {
-                    out.x1 = la + lb - ms.inter;  // sum_c max = la + lb - sum_c min
-                    v = jaccard_value(ms.inter, la + lb - ms.inter);
-                } else {
-                    out.x1 = la + lb;
-                    v = dice_value(ms.inter, la + lb);
-                }
-                break;
-            }
-        }
+        EachByte<Store> streamed(s, !table_b);
+        v = measure_body<M>(measure, tab, streamed, la, lb, n_tab, table_b ? la : lb, out);
         {
             ClearTable<M, StoreTable<M, Store>> clear(tab);
             for_each_byte(tabled, (n_tab + 3) & ~3, clear);
         }
         if (measure == JARO_WINKLER && v > 0.7) {  // strsim.rs:260-267
-            uint32_t x = s.wa(0) ^ s.wb(0);
+            const uint32_t x = s.wa(0) ^ s.wb(0);
             int lim = la < lb ? la : lb;
             if (lim > 4) lim = 4;
             int l = 0;
@@ -221,31 +270,33 @@ SS_HD double row_short(int measure, Store& s, int na, int nb, bool equal, bool a
             v = winkler_value(v, l);
         }
     } else {
-        const int la = decode_keys(s, false, na, 0);
-        const int lb = decode_keys(s, true, nb, CAP);
+        StoreWords<Store> wa(s, false), wb(s, true);
+        const int la = count_chars(wa, na), lb = count_chars(wb, nb);
         out.la = la;
         out.lb = lb;
-        if ((measure == JARO || measure == JARO_WINKLER) && la == 1 && lb == 1) {
+        if (is_jaro && la == 1 && lb == 1) {
             out.flag = F_SINGLE_CHAR;
-            v = s.cp(0) == s.cp(CAP) ? 1.0 : 0.0;
-        } else {
-            const bool table_b = measure != LEVENSHTEIN || lb <= la;
-            ScanPM<M, Store> pm(s, table_b ? CAP : 0, table_b ? lb : la);
-            CpReader<Store> ra(s, table_b ? 0 : CAP), ra2(s, table_b ? 0 : CAP);
-            v = measure_core<M>(measure, pm, ra, ra2, la, lb, table_b ? lb : la, table_b ? la : lb,
-                                out);
-            if (measure == JARO_WINKLER && v > 0.7) {
-                int lim = la < lb ? la : lb;
-                if (lim > 4) lim = 4;
-                int l = 0;
-                while (l < lim && s.cp(l) == s.cp(CAP + l)) l++;
-                out.x2 = l;
-                v = winkler_value(v, l);
-            }
+            return 0.0;  // one character each and the bytes differ
         }
-        if (Store::CPS_ALIAS_TABLE) {  // the keys live in the table's memory: restore all-zero
-            for (int k = 0; k < la; k++) s.cp(k) = 0u;
-            for (int k = 0; k < lb; k++) s.cp(CAP + k) = 0u;
+        const bool table_b = measure != LEVENSHTEIN || lb <= la;
+        const int n_tab = table_b ? lb : la;
+        HashTab<M, Store> tab(s);
+        {
+            HashBuild<M, HashTab<M, Store>> build(tab);
+            for_each_char(table_b ? wb : wa, table_b ? nb : na, n_tab, build);
+        }
+        EachChar<Store> streamed(s, !table_b, table_b ? na : nb);
+        v = measure_body<M>(measure, tab, streamed, la, lb, n_tab, table_b ? la : lb, out);
+        tab.clear();
+        if (measure == JARO_WINKLER && v > 0.7) {
+            PrefixKeys pa, pb;
+            for_each_char(wa, na, 4, pa);
+            for_each_char(wb, nb, 4, pb);
+            int lim = pa.n < pb.n ? pa.n : pb.n;
+            int l = 0;
+            while (l < lim && pa.k[l] == pb.k[l]) l++;
+            out.x2 = l;
+            v = winkler_value(v, l);
         }
     }
     return v;

@@ -115,16 +115,22 @@ struct DevStore {
     M* tab_;          // &table[tid]
     uint32_t* wa_;    // &slab_a[tid]
     uint32_t* wb_;    // &slab_b[tid]
-    __device__ __forceinline__ M& tab(uint32_t c) { return tab_[(c & (T - 1)) * TPB]; }
-    __device__ __forceinline__ const M& tab(uint32_t c) const { return tab_[(c & (T - 1)) * TPB]; }
-    // codepoint keys alias the thread's OWN table entries (slot s -> 32-bit part s % R of entry s / R)
+    static constexpr uint32_t CMASK = (T >= 128 ? 128u : (uint32_t)T) - 1u;  // ASCII byte -> table entry
+    __device__ __forceinline__ M& tab(uint32_t c) { return tab_[(c & CMASK) * TPB]; }
+    __device__ __forceinline__ const M& tab(uint32_t c) const { return tab_[(c & CMASK) * TPB]; }
+    // Unicode path: 2*bits(M) hash slots alias the thread's OWN table entries -- the keys (32 bit)
+    // sit in entries [0, 2*bits(M)/R), R keys per entry, the masks in the 2*bits(M) entries after them
     static constexpr int R = (int)(sizeof(M) / 4);
-    __device__ __forceinline__ uint32_t& cp(int s) {
+    static constexpr int SLOTS = 2 * 8 * (int)sizeof(M);
+    static constexpr int HASH_ENTRIES = SLOTS / R + SLOTS;  // table entries the hash needs
+    __device__ __forceinline__ uint32_t& hkey(int s) {
         return reinterpret_cast<uint32_t*>(&tab_[(s / R) * TPB])[s % R];
     }
-    __device__ __forceinline__ const uint32_t& cp(int s) const {
+    __device__ __forceinline__ const uint32_t& hkey(int s) const {
         return reinterpret_cast<const uint32_t*>(&tab_[(s / R) * TPB])[s % R];
     }
+    __device__ __forceinline__ M& hmask(int s) { return tab_[(SLOTS / R + s) * TPB]; }
+    __device__ __forceinline__ const M& hmask(int s) const { return tab_[(SLOTS / R + s) * TPB]; }
     __device__ __forceinline__ uint32_t wa(int k) const { return wa_[k * TPB]; }
     __device__ __forceinline__ uint32_t wb(int k) const { return wb_[k * TPB]; }
 };
@@ -191,7 +197,8 @@ __device__ __forceinline__ uint32_t load_string(const uint4& v, const unsigned c
 
 template <class M, int MEASURE, int TPB, int RPT, bool GATHER, int T, bool ASCII_ONLY>
 __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
-    static_assert(ASCII_ONLY || T >= 64, "the Unicode path keeps 2*bits(M) 32-bit keys in the table memory");
+    static_assert(ASCII_ONLY || T >= DevStore<M, TPB, T>::HASH_ENTRIES,
+                  "the Unicode path keeps its hash slots in the table memory");
     using L = ShortLayout<M, TPB, RPT, T>;
     constexpr int CAP = L::CAP;
     constexpr int WORDS = L::WORDS;

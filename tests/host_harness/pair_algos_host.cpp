@@ -10,14 +10,16 @@ using namespace strsim;
 template <class M>
 struct HostStore {
     static constexpr int CAP = (int)sizeof(M) * 8;
-    static constexpr bool CPS_ALIAS_TABLE = false;
     M table[128];
-    uint32_t cps[2 * CAP];
+    uint32_t keys[2 * CAP];
+    M masks[2 * CAP];
     uint32_t a_words[CAP / 4], b_words[CAP / 4];
     M& tab(uint32_t c) { return table[c]; }
     const M& tab(uint32_t c) const { return table[c]; }
-    uint32_t& cp(int s) { return cps[s]; }
-    const uint32_t& cp(int s) const { return cps[s]; }
+    uint32_t& hkey(int s) { return keys[s]; }
+    const uint32_t& hkey(int s) const { return keys[s]; }
+    M& hmask(int s) { return masks[s]; }
+    const M& hmask(int s) const { return masks[s]; }
     uint32_t wa(int k) const { return a_words[k]; }
     uint32_t wb(int k) const { return b_words[k]; }
 };
@@ -40,6 +42,8 @@ static int run(int measure, const uint8_t* a, int na, const uint8_t* b, int nb, 
     ints[0] = pi.flag; ints[1] = pi.la; ints[2] = pi.lb; ints[3] = pi.x0; ints[4] = pi.x1; ints[5] = pi.x2;
     for (int c = 0; c < 128; c++)
         if (s.table[c] != 0) return -1;  // invariant broken
+    for (int c = 0; c < 2 * HostStore<M>::CAP; c++)
+        if (s.keys[c] != 0 || s.masks[c] != 0) return -1;
     return 0;
 }
 
