@@ -251,10 +251,17 @@ static int upload_column(ThreadCtx& ctx, const strsim_view_chunk* chunks, size_t
     struct Plan {
         size_t views_off, validity_off, table_off;
         std::vector<size_t> buf_off;
+        std::vector<char> buf_dup;  // buffer already planned for an earlier chunk (slices share buffers)
         size_t validity_bytes;
         int64_t first_byte;
     };
     std::vector<Plan> plans(n_chunks);
+    struct Seen {
+        const void* ptr;
+        int64_t size;
+        size_t off;
+    };
+    std::vector<Seen> seen;
     size_t total = 0;
     for (size_t i = 0; i < n_chunks; i++) {
         const strsim_view_chunk& ch = chunks[i];
@@ -274,8 +281,20 @@ static int upload_column(ThreadCtx& ctx, const strsim_view_chunk* chunks, size_t
         p.table_off = total;
         total = align_up(total + 8 * (size_t)(ch.n_data_buffers > 0 ? ch.n_data_buffers : 1), 256);
         p.buf_off.resize((size_t)ch.n_data_buffers);
+        p.buf_dup.assign((size_t)ch.n_data_buffers, 0);
         for (int64_t b = 0; b < ch.n_data_buffers; b++) {
+            // chunks produced by slicing share their data buffers: upload each distinct buffer once
+            bool dup = false;
+            for (const Seen& sn : seen)
+                if (sn.ptr == ch.data_buffers[b] && sn.size == ch.data_buffer_sizes[b]) {
+                    p.buf_off[(size_t)b] = sn.off;
+                    p.buf_dup[(size_t)b] = 1;
+                    dup = true;
+                    break;
+                }
+            if (dup) continue;
             p.buf_off[(size_t)b] = total;
+            if (seen.size() < 4096) seen.push_back({ch.data_buffers[b], ch.data_buffer_sizes[b], total});
             // 64 spare bytes: TMA spans are rounded to 16 B and word copies read a few bytes past
             total = align_up(total + (size_t)ch.data_buffer_sizes[b] + 64, 256);
         }
@@ -315,6 +334,7 @@ static int upload_column(ThreadCtx& ctx, const strsim_view_chunk* chunks, size_t
         dc.data_bytes = 0;
         for (int64_t b = 0; b < ch.n_data_buffers; b++) {
             table[(size_t)b] = reinterpret_cast<unsigned long long>(base + p.buf_off[(size_t)b]);
+            if (p.buf_dup[(size_t)b]) continue;
             rc = h2d(base + p.buf_off[(size_t)b], ch.data_buffers[b], (size_t)ch.data_buffer_sizes[b],
                      ctx.stream);
             if (rc) return rc;
@@ -343,7 +363,7 @@ static int upload_column(ThreadCtx& ctx, const strsim_view_chunk* chunks, size_t
             }
             for (int64_t b = 0; b < chunks[i].n_data_buffers; b++) {
                 const long long bytes = chunks[i].data_buffer_sizes[b];
-                if (bytes <= 0) continue;
+                if (bytes <= 0 || plans[i].buf_dup[(size_t)b]) continue;
                 long long blocks = ((bytes >> 4) + 255) / 256;
                 if (blocks > 148 * 16) blocks = 148 * 16;
                 if (blocks < 1) blocks = 1;
@@ -656,8 +676,8 @@ static int compute_on_device(ThreadCtx& ctx, int measure, const strsim_b200_colu
         s.dbg = d_dbg ? d_dbg + 6 * row : nullptr;
         // stage capacity is derived per tile shape in launch_short() from the mean out-of-line bytes
         // per row of the heavier column (passed as a negative fixed-point number)
-        const double avg_a = bc_a ? 0.0 : (double)ca.data_bytes / (double)(ca.length > 0 ? ca.length : 1);
-        const double avg_b = bc_b ? 0.0 : (double)cb.data_bytes / (double)(cb.length > 0 ? cb.length : 1);
+        const double avg_a = bc_a ? 0.0 : (double)a->data_bytes / (double)(a->length > 0 ? a->length : 1);
+        const double avg_b = bc_b ? 0.0 : (double)b->data_bytes / (double)(b->length > 0 ? b->length : 1);
         const double avg = avg_a > avg_b ? avg_a : avg_b;
         long long stage = -(long long)(avg * 16.0 + 1.0);
         if (stage < -64 * 16) stage = -64 * 16;
