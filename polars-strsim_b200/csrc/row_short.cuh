@@ -53,26 +53,29 @@ SS_HD int count_chars(const Src& src, int nbytes) {
 }
 
 // Calls f(key) for the first max_chars characters of a UTF-8 string of nbytes bytes; key = the
-// character's bytes packed big-endian (1-4 bytes).  Sequences are clamped to the string.
+// character's 1-4 bytes packed little-endian (any injective packing would do).  Branch-free per
+// character so that the 32 pairs of a warp stay converged: a 4-byte window at the current byte
+// position is funnel-shifted out of two consecutive words, the sequence length comes from a 2-bit
+// lookup on the lead byte's high nibble.  last_word: highest word index that may be read.
 template <class Src, class F>
-SS_HD void for_each_char(const Src& src, int nbytes, int max_chars, F& f) {
-    int j = 0, done = 0;
-    uint32_t word = 0;
-    while (j < nbytes && done < max_chars) {
-        if ((j & 3) == 0) word = src(j >> 2);
-        uint32_t key = word & 0xFFu;
-        word >>= 8;
-        j++;
-        if (key >= 0xC0u) {
-            int extra = 1 + (key >= 0xE0u) + (key >= 0xF0u);
-            if (extra > nbytes - j) extra = nbytes - j;
-            for (int e = 0; e < extra; e++) {
-                if ((j & 3) == 0) word = src(j >> 2);
-                key = (key << 8) | (word & 0xFFu);
-                word >>= 8;
-                j++;
-            }
-        }
+SS_HD void for_each_char(const Src& src, int nbytes, int max_chars, int last_word, F& f) {
+    int pos = 0, done = 0;
+    while (pos < nbytes && done < max_chars) {
+        const int wi = pos >> 2;
+        const uint32_t w0 = src(wi);
+        const uint32_t w1 = src(wi < last_word ? wi + 1 : last_word);
+        const int sh = (pos & 3) * 8;
+#if defined(__CUDA_ARCH__)
+        const uint32_t win = __funnelshift_r(w0, w1, sh);
+#else
+        const uint32_t win = (uint32_t)((((uint64_t)w1 << 32) | w0) >> sh);
+#endif
+        const uint32_t lead = win & 0xFFu;
+        // extra bytes: 0 for 0x00-0xBF, 1 for 0xC0-0xDF, 2 for 0xE0-0xEF, 3 for 0xF0-0xFF
+        uint32_t extra = (0xE5000000u >> ((lead >> 4) * 2)) & 3u;
+        if ((int)extra > nbytes - pos - 1) extra = (uint32_t)(nbytes - pos - 1);  // malformed tail
+        const uint32_t key = win & (0xFFFFFFFFu >> (24 - 8 * extra));
+        pos += 1 + (int)extra;
         f(key);
         done++;
     }
@@ -218,7 +221,7 @@ struct EachChar {
     SS_HD EachChar(const Store& s, bool second, int nbytes_) : src(s, second), nbytes(nbytes_) {}
     template <class F>
     SS_HD void operator()(int n, F& f) const {
-        for_each_char(src, nbytes, n, f);
+        for_each_char(src, nbytes, n, (int)sizeof(typename Store::mask_type) * 2 - 1, f);
     }
 };
 
@@ -236,6 +239,7 @@ SS_HD double row_short(int measure, Store& s, int na, int nb, bool equal, bool a
         return 0.0;
     }
     const bool is_jaro = measure == JARO || measure == JARO_WINKLER;
+    constexpr int LAST_WORD = (int)sizeof(M) * 2 - 1;  // bits(M)/4 words per string
     double v;
     if (ascii) {
         const int la = na, lb = nb;
@@ -283,15 +287,15 @@ SS_HD double row_short(int measure, Store& s, int na, int nb, bool equal, bool a
         HashTab<M, Store> tab(s);
         {
             HashBuild<M, HashTab<M, Store>> build(tab);
-            for_each_char(table_b ? wb : wa, table_b ? nb : na, n_tab, build);
+            for_each_char(table_b ? wb : wa, table_b ? nb : na, n_tab, LAST_WORD, build);
         }
         EachChar<Store> streamed(s, !table_b, table_b ? na : nb);
         v = measure_body<M>(measure, tab, streamed, la, lb, n_tab, table_b ? la : lb, out);
         tab.clear();
         if (measure == JARO_WINKLER && v > 0.7) {
             PrefixKeys pa, pb;
-            for_each_char(wa, na, 4, pa);
-            for_each_char(wb, nb, 4, pb);
+            for_each_char(wa, na, 4, LAST_WORD, pa);
+            for_each_char(wb, nb, 4, LAST_WORD, pb);
             int lim = pa.n < pb.n ? pa.n : pb.n;
             int l = 0;
             while (l < lim && pa.k[l] == pb.k[l]) l++;

@@ -111,6 +111,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
 // alphabet and the smaller table quadruples / doubles the resident warps per SM.
 template <class M, int TPB, int T>
 struct DevStore {
+    using mask_type = M;
     static constexpr bool CPS_ALIAS_TABLE = true;
     M* tab_;          // &table[tid]
     uint32_t* wa_;    // &slab_a[tid]

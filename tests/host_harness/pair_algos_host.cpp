@@ -9,6 +9,7 @@ using namespace strsim;
 
 template <class M>
 struct HostStore {
+    using mask_type = M;
     static constexpr int CAP = (int)sizeof(M) * 8;
     M table[128];
     uint32_t keys[2 * CAP];
