@@ -293,3 +293,53 @@ def test_long_levenshtein_multiword(native, oracle):
         b.append("".join(y))
     check(native, oracle, "levenshtein", a, b)
     assert native.last_overflow()[1] > 0
+
+
+def test_polars_plugin_symbols_end_to_end(native, oracle):
+    """Calls `_polars_plugin_<name>` the way polars-ffi does (fabricated SeriesExports, ownership of
+    the inputs moves to the callee) and imports the returned Float64 series."""
+    import ctypes
+
+    import pyarrow as pa
+    from polars_strsim._native import ArrowArray
+    from test_abi import SeriesExport, make_series
+
+    L = native.lib()
+    rng = random.Random(61)
+    pairs = [rand_pair(rng, 40) for _ in range(5000)]
+    a = [None if rng.random() < 0.05 else p[0] for p in pairs]
+    b = [p[1] for p in pairs]
+    A = pa.chunked_array([pa.array(a[:777], type=pa.string_view()), pa.array(a[777:], type=pa.string_view())])
+    B = pa.array(b, type=pa.string_view())
+    for measure in oracle.MEASURES:
+        released, keep = [], []
+        inputs = (SeriesExport * 2)()
+        inputs[0], arrs_a = make_series(A, released, keep)
+        inputs[1], arrs_b = make_series(B, released, keep)
+        ret = SeriesExport()
+        ctx = ctypes.c_uint64(1)
+        getattr(L, f"_polars_plugin_{measure}")(inputs, ctypes.c_size_t(2), None, ctypes.c_size_t(0),
+                                                 ctypes.byref(ret), ctypes.byref(ctx))
+        assert ret.private_data and ret.len == 1, native.lib().strsim_b200_last_error()
+        assert len(released) == 2 and all(not x.release for x in arrs_a + arrs_b)
+        # import like polars-ffi: move the ArrowArray out, borrow the field, then drop the SeriesExport
+        moved = ArrowArray.from_address(ret.arrays[0])
+        copy = ArrowArray()
+        ctypes.memmove(ctypes.addressof(copy), ctypes.addressof(moved), ctypes.sizeof(ArrowArray))
+        ret.release(ctypes.byref(ret))
+        out = pa.Array._import_from_c(ctypes.addressof(copy), pa.float64())
+        ref, ref_valid, _ = oracle.batch(measure, a, b)
+        got_valid = np.array(out.is_valid())
+        assert (got_valid == ref_valid).all()
+        got = out.fill_null(0.0).to_numpy(zero_copy_only=False)
+        assert (got[ref_valid] == ref[ref_valid]).all()
+    # error path: shape mismatch leaves return_value untouched and stores the reference's message
+    released, keep = [], []
+    inputs = (SeriesExport * 2)()
+    inputs[0], _ = make_series(pa.array(["a", "b", "c"], type=pa.string_view()), released, keep)
+    inputs[1], _ = make_series(pa.array(["a", "b"], type=pa.string_view()), released, keep)
+    ret = SeriesExport()
+    L._polars_plugin_jaro(inputs, ctypes.c_size_t(2), None, ctypes.c_size_t(0), ctypes.byref(ret), None)
+    assert not ret.private_data
+    L._polars_plugin_get_last_error_message.restype = ctypes.c_char_p
+    assert b"same length" in L._polars_plugin_get_last_error_message()
