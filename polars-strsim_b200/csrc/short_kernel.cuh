@@ -166,7 +166,6 @@ template <int WORDS, int TPB>
 __device__ __forceinline__ uint32_t load_string(const uint4& v, const unsigned char* stage,
                                                 uint32_t* slab /* &slab[tid] */) {
     const int len = (int)v.x;
-    const int nw = (len + 3) >> 2;
     uint32_t acc = 0;
     if (len <= 12) {
         uint32_t w0 = v.y & byte_mask(len);
@@ -180,20 +179,60 @@ __device__ __forceinline__ uint32_t load_string(const uint4& v, const unsigned c
         const uint32_t soff = v.y;
         const uint32_t* src = reinterpret_cast<const uint32_t*>(stage) + (soff >> 2);
         const int sh = (int)(soff & 3) * 8;
+        const int full = len >> 2;  // whole words
         uint32_t lo = src[0];
-#pragma unroll
-        for (int w = 0; w < WORDS; w++) {
-            if (w < nw) {
-                uint32_t hi = src[w + 1];
-                uint32_t word = __funnelshift_r(lo, hi, sh);
-                lo = hi;
-                if (w == nw - 1) word &= byte_mask(len - 4 * w);
-                slab[w * TPB] = word;
-                acc |= word;
-            }
+        int w = 0;
+        for (; w < full; w++) {
+            const uint32_t hi = src[w + 1];
+            const uint32_t word = __funnelshift_r(lo, hi, sh);
+            lo = hi;
+            slab[w * TPB] = word;
+            acc |= word;
+        }
+        if (len & 3) {
+            const uint32_t word = __funnelshift_r(lo, src[w + 1], sh) & byte_mask(len & 3);
+            slab[w * TPB] = word;
+            acc |= word;
         }
     }
     return acc;
+}
+
+// Settling byte-equal pairs before the sort frees their lanes but costs every row a prefix compare;
+// measured on C2 (20 % equal pairs) it LOSES 8 % because the compute phase is bound by the latency of
+// its rounds, not by the number of active lanes.  Kept for data sets dominated by equal pairs.
+constexpr bool PREFILTER_EQUAL = false;
+
+// first four bytes of an out-of-line string (its view's prefix word was replaced by the stage offset)
+__device__ __forceinline__ uint32_t sva_prefix(const uint4& v, const unsigned char* stage) {
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(stage) + (v.y >> 2);
+    return __funnelshift_r(p[0], p[1], (int)(v.y & 3) * 8);
+}
+
+// Exact byte equality of two strings of the same length `len` described by their staged views.
+__device__ __forceinline__ bool staged_equal(const uint4& va, const uint4& vb, const unsigned char* stage_a,
+                                             const unsigned char* stage_b) {
+    const int len = (int)va.x;
+    if (len <= 12) {
+        const uint32_t m0 = byte_mask(len), m1 = byte_mask(len - 4 < 0 ? 0 : len - 4),
+                       m2 = byte_mask(len - 8 < 0 ? 0 : len - 8);
+        return (((va.y ^ vb.y) & m0) | ((va.z ^ vb.z) & m1) | ((va.w ^ vb.w) & m2)) == 0u;
+    }
+    const uint32_t* pa = reinterpret_cast<const uint32_t*>(stage_a) + (va.y >> 2);
+    const uint32_t* pb = reinterpret_cast<const uint32_t*>(stage_b) + (vb.y >> 2);
+    const int sa = (int)(va.y & 3) * 8, sb = (int)(vb.y & 3) * 8;
+    uint32_t la = pa[0], lb = pb[0];
+    const int full = len >> 2;
+    int w = 0;
+    for (; w < full; w++) {
+        const uint32_t ha = pa[w + 1], hb = pb[w + 1];
+        if (__funnelshift_r(la, ha, sa) != __funnelshift_r(lb, hb, sb)) return false;
+        la = ha;
+        lb = hb;
+    }
+    if (len & 3)
+        return ((__funnelshift_r(la, pa[w + 1], sa) ^ __funnelshift_r(lb, pb[w + 1], sb)) & byte_mask(len & 3)) == 0u;
+    return true;
 }
 
 template <class M, int MEASURE, int TPB, int RPT, bool GATHER, int T, bool ASCII_ONLY>
@@ -257,6 +296,14 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
                 const long long row = GATHER ? (long long)s.list[idx] : idx;
                 va = ld_view(s.a.views + row * s.a.stride);
                 vb = ld_view(s.b.views + row * s.b.stride);
+                if (!GATHER) {
+                    // pull this CTA's NEXT tile of views into L2 while the current one is processed
+                    const long long nxt = idx + (long long)gridDim.x * TILE;
+                    if (nxt < n) {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(s.a.views + nxt * s.a.stride));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(s.b.views + nxt * s.b.stride));
+                    }
+                }
                 const bool valid = bit_valid(s.a.validity, s.a.vbit + row * s.a.stride) &&
                                    bit_valid(s.b.validity, s.b.vbit + row * s.b.stride);
                 const uint32_t mx = va.x > vb.x ? va.x : vb.x;
@@ -437,6 +484,22 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
             rank[k] = 0;
             if (!((active >> k) & 1u)) continue;
             const uint4 va = sva[i], vb = svb[i];
+            // byte-equal pairs score 1.0 (strsim.rs:128,182,288,324): settle them here so that they do
+            // not occupy lanes of the compute phase (the 4-byte prefix in the view rejects most rows)
+            if (PREFILTER_EQUAL && va.x == vb.x && (va.x == 0u || ((va.x <= 12u ? va.y : sva_prefix(va, stage_a)) ==
+                                                (vb.x <= 12u ? vb.y : sva_prefix(vb, stage_b)))) &&
+                staged_equal(va, vb, stage_a, stage_b)) {
+                const long long idx = tile0 + i;
+                const long long row = GATHER ? (long long)s.list[idx] : idx;
+                s.out[row] = 1.0;
+                if (s.dbg) {
+                    int* d = s.dbg + row * 6;
+                    d[0] = F_EQUAL;
+#pragma unroll
+                    for (int q = 1; q < 6; q++) d[q] = 0;
+                }
+                continue;
+            }
             uint32_t hi_bits = 0;  // conservative (unmasked) non-ASCII test; exact test in step 4
             if (!ASCII_ONLY) {
                 if (va.x <= 12u) {
@@ -502,13 +565,11 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
             const uint32_t or_a = load_string<WORDS, TPB>(va, stage_a, store.wa_);
             const uint32_t or_b = load_string<WORDS, TPB>(vb, stage_b, store.wb_);
             const int na = (int)va.x, nb = (int)vb.x;
-            bool equal = na == nb;
-            if (equal) {
+            bool equal = false;  // with the prefilter, byte-equal pairs were settled before the sort
+            if (!PREFILTER_EQUAL && na == nb) {
                 const int nw = (na + 3) >> 2;
                 uint32_t diff = 0;
-#pragma unroll
-                for (int w = 0; w < WORDS; w++)
-                    if (w < nw) diff |= store.wa(w) ^ store.wb(w);
+                for (int w = 0; w < nw; w++) diff |= store.wa(w) ^ store.wb(w);
                 equal = diff == 0;
             }
             const bool ascii = ASCII_ONLY || ((or_a | or_b) & 0x80808080u) == 0;
