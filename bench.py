@@ -304,9 +304,15 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
-        in_bytes = sum(b.size for col in (A, B)
-                       for ch in (col.chunks if hasattr(col, "chunks") else [col])
-                       for b in ch.buffers() if b is not None)
+        seen, in_bytes = set(), 0  # chunks made by slicing share buffers: the library uploads each once
+        for col in (A, B):
+            for ch in (col.chunks if hasattr(col, "chunks") else [col]):
+                bufs = ch.buffers()
+                in_bytes += 16 * len(ch) + ((len(ch) + 7) // 8 if bufs[0] is not None else 0)
+                for b in bufs[2:]:
+                    if b is not None and b.address not in seen:
+                        seen.add(b.address)
+                        in_bytes += b.size
         e2e = {"value": n * len(measures) * world * e2e_steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": in_bytes,
                "d2h_bytes_per_step": (8 * n + ((n + 7) // 8 if has_nulls else 0)) * len(measures),

@@ -46,6 +46,10 @@ extern "C" void strsim_set_error(const char* fmt, ...) {
         }                                                                                     \
     } while (0)
 
+// row slices of one host call (compute_host_multi): H2D of slice s+1 overlaps compute / D2H of slice s
+constexpr int MAX_SLICES = 16;
+constexpr long long SLICE_ROWS = 1ll << 21;
+
 // ---- per-thread device context ---------------------------------------------------------------------
 struct Workspace {
     void* ptr = nullptr;
@@ -55,8 +59,12 @@ struct Workspace {
 struct ThreadCtx {
     int device = -1;
     cudaStream_t stream = nullptr;
-    cudaStream_t copy_stream = nullptr;  // D2H of finished measures overlaps the next kernel
+    cudaStream_t copy_stream = nullptr;    // D2H of finished measures overlaps the next kernel
+    cudaStream_t upload_stream = nullptr;  // H2D of later row slices overlaps compute of earlier ones
     cudaEvent_t done_event[8] = {};
+    cudaEvent_t slice_event[MAX_SLICES] = {};
+    ColumnStats* d_slice_stats = nullptr;  // [0] data of a, [1] data of b, [2+s] views of slice s
+    ColumnStats* h_slice_stats = nullptr;  // pinned
     int sm_count = 0;
     Overflow* d_ovf = nullptr;
     Overflow* h_ovf = nullptr;  // pinned
@@ -104,6 +112,10 @@ static int ensure_ctx(ThreadCtx** out) {
         CUDA_TRY(cudaSetDevice(c.device));
         CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&c.upload_stream, cudaStreamNonBlocking));
+        for (auto& ev : c.slice_event) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CUDA_TRY(cudaMalloc(&c.d_slice_stats, sizeof(ColumnStats) * (2 + MAX_SLICES)));
+        CUDA_TRY(cudaMallocHost(&c.h_slice_stats, sizeof(ColumnStats) * (2 + MAX_SLICES)));
         for (auto& ev : c.done_event) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         CUDA_TRY(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, c.device));
         CUDA_TRY(cudaMalloc(&c.d_ovf, sizeof(Overflow)));
@@ -225,6 +237,7 @@ struct strsim_b200_column {
 };
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+extern "C" void strsim_b200_column_free(strsim_b200_column* col);
 
 static bool is_pinned(const void* p) {
     cudaPointerAttributes at;
@@ -243,19 +256,45 @@ static int h2d(void* dst, const void* src, size_t bytes, cudaStream_t st) {
     return STRSIM_OK;
 }
 
-static int upload_column(ThreadCtx& ctx, const strsim_view_chunk* chunks, size_t n_chunks,
-                         bool want_alg_bytes, strsim_b200_column** out) {
+// Upload of one column, split into steps so that a host call can pipeline row slices:
+//   upload_plan  : one device block for everything, DevChunks with their final device addresses
+//   upload_data  : buffer tables + every distinct data buffer (+ byte statistics of the buffers)
+//   upload_rows  : views + validity of a row range (+ byte statistics of the inline strings)
+struct ChunkPlan {
+    size_t views_off, validity_off, table_off;
+    std::vector<size_t> buf_off;
+    std::vector<char> buf_dup;  // buffer already planned for an earlier chunk (slices share buffers)
+    size_t validity_bytes;
+    int64_t first_byte;
+    int64_t row0;  // first row of the chunk in the column
+};
+
+struct Uploader {
+    strsim_b200_column* col = nullptr;
+    const strsim_view_chunk* chunks = nullptr;
+    size_t n_chunks = 0;
+    std::vector<ChunkPlan> plans;
+    std::vector<unsigned long long> tables;  // all chunks' buffer tables, alive until the copies ran
+    std::vector<size_t> table_pos;
+};
+
+static void stats_init_value(ColumnStats* s) {
+    s->or_bits = 0u;
+    s->and_bits = 0xFFFFFFFFu;
+}
+static void stats_fold(const ColumnStats& s, unsigned* or_byte, unsigned* and_byte) {
+    const unsigned o = s.or_bits, a = s.and_bits;
+    *or_byte = (o | (o >> 8) | (o >> 16) | (o >> 24)) & 0xFFu;
+    *and_byte = (a & (a >> 8) & (a >> 16) & (a >> 24)) & 0xFFu;
+}
+
+static int upload_plan(ThreadCtx& ctx, const strsim_view_chunk* chunks, size_t n_chunks, Uploader* up) {
     auto* col = new strsim_b200_column();
     col->device = ctx.device;
-    // plan the single device block
-    struct Plan {
-        size_t views_off, validity_off, table_off;
-        std::vector<size_t> buf_off;
-        std::vector<char> buf_dup;  // buffer already planned for an earlier chunk (slices share buffers)
-        size_t validity_bytes;
-        int64_t first_byte;
-    };
-    std::vector<Plan> plans(n_chunks);
+    up->col = col;
+    up->chunks = chunks;
+    up->n_chunks = n_chunks;
+    up->plans.assign(n_chunks, ChunkPlan());
     struct Seen {
         const void* ptr;
         int64_t size;
@@ -268,9 +307,11 @@ static int upload_column(ThreadCtx& ctx, const strsim_view_chunk* chunks, size_t
         if (ch.length < 0 || ch.offset < 0 || (ch.length > 0 && !ch.views)) {
             strsim_set_error("chunk %zu: bad length/offset/views", i);
             delete col;
+            up->col = nullptr;
             return STRSIM_ERR_ARGUMENT;
         }
-        Plan& p = plans[i];
+        ChunkPlan& p = up->plans[i];
+        p.row0 = col->length;
         p.views_off = total;
         total = align_up(total + 16 * (size_t)ch.length, 256);
         p.first_byte = ch.offset >> 3;
@@ -297,88 +338,121 @@ static int upload_column(ThreadCtx& ctx, const strsim_view_chunk* chunks, size_t
             if (seen.size() < 4096) seen.push_back({ch.data_buffers[b], ch.data_buffer_sizes[b], total});
             // 64 spare bytes: TMA spans are rounded to 16 B and word copies read a few bytes past
             total = align_up(total + (size_t)ch.data_buffer_sizes[b] + 64, 256);
+            col->data_bytes += ch.data_buffer_sizes[b];
         }
         col->length += ch.length;
         if (p.validity_bytes) col->has_validity = true;
     }
     total += 256;
-    {
-        int rc = pool_alloc(ctx.device, total, &col->block);
-        if (rc) {
-            delete col;
-            return rc;
-        }
+    int rc = pool_alloc(ctx.device, total, &col->block);
+    if (rc) {
+        delete col;
+        up->col = nullptr;
+        return rc;
     }
     col->block_bytes = total;
     char* base = static_cast<char*>(col->block);
-    std::vector<unsigned long long> table;
+    up->table_pos.assign(n_chunks, 0);
     for (size_t i = 0; i < n_chunks; i++) {
         const strsim_view_chunk& ch = chunks[i];
-        const Plan& p = plans[i];
+        const ChunkPlan& p = up->plans[i];
         DevChunk dc;
         dc.length = ch.length;
         dc.views = reinterpret_cast<const uint4*>(base + p.views_off);
-        int rc = h2d(base + p.views_off, static_cast<const char*>(ch.views) + 16 * ch.offset,
-                     16 * (size_t)ch.length, ctx.stream);
-        if (rc) return rc;
-        if (p.validity_bytes) {
-            rc = h2d(base + p.validity_off, ch.validity + p.first_byte, p.validity_bytes, ctx.stream);
-            if (rc) return rc;
-            dc.validity = reinterpret_cast<const uint8_t*>(base + p.validity_off);
-            dc.vbit = ch.offset & 7;
-        } else {
-            dc.validity = nullptr;
-            dc.vbit = 0;
-        }
-        table.assign((size_t)(ch.n_data_buffers > 0 ? ch.n_data_buffers : 1), 0ull);
-        dc.data_bytes = 0;
-        for (int64_t b = 0; b < ch.n_data_buffers; b++) {
-            table[(size_t)b] = reinterpret_cast<unsigned long long>(base + p.buf_off[(size_t)b]);
-            if (p.buf_dup[(size_t)b]) continue;
-            rc = h2d(base + p.buf_off[(size_t)b], ch.data_buffers[b], (size_t)ch.data_buffer_sizes[b],
-                     ctx.stream);
-            if (rc) return rc;
-            dc.data_bytes += ch.data_buffer_sizes[b];
-        }
-        // the table is tiny; a synchronous copy keeps `table` reusable
-        CUDA_TRY(cudaMemcpyAsync(base + p.table_off, table.data(), 8 * table.size(),
-                                 cudaMemcpyHostToDevice, ctx.stream));
-        CUDA_TRY(cudaStreamSynchronize(ctx.stream));
+        dc.validity = p.validity_bytes ? reinterpret_cast<const uint8_t*>(base + p.validity_off) : nullptr;
+        dc.vbit = p.validity_bytes ? (ch.offset & 7) : 0;
         dc.bufs = reinterpret_cast<const unsigned long long*>(base + p.table_off);
-        col->data_bytes += dc.data_bytes;
+        dc.data_bytes = 0;
+        up->table_pos[i] = up->tables.size();
+        if (ch.n_data_buffers == 0) up->tables.push_back(0ull);
+        for (int64_t b = 0; b < ch.n_data_buffers; b++)
+            up->tables.push_back(reinterpret_cast<unsigned long long>(base + p.buf_off[(size_t)b]));
         col->chunks.push_back(dc);
     }
-    // column statistics (alphabet block, ASCII-ness) for the kernel choice in run_segment()
-    {
-        ColumnStats init = {0u, 0xFFFFFFFFu};
-        *ctx.h_stats = init;
-        CUDA_TRY(cudaMemcpyAsync(ctx.d_stats, ctx.h_stats, sizeof init, cudaMemcpyHostToDevice, ctx.stream));
-        for (size_t i = 0; i < n_chunks; i++) {
-            const DevChunk& dc = col->chunks[i];
-            if (dc.length > 0) {
-                long long blocks = (dc.length + 255) / 256;
-                if (blocks > 148 * 16) blocks = 148 * 16;
-                stats_views_kernel<<<(unsigned)blocks, 256, 0, ctx.stream>>>(dc.views, dc.length, ctx.d_stats);
-                g_launches.fetch_add(1, std::memory_order_relaxed);
-            }
-            for (int64_t b = 0; b < chunks[i].n_data_buffers; b++) {
-                const long long bytes = chunks[i].data_buffer_sizes[b];
-                if (bytes <= 0 || plans[i].buf_dup[(size_t)b]) continue;
-                long long blocks = ((bytes >> 4) + 255) / 256;
-                if (blocks > 148 * 16) blocks = 148 * 16;
-                if (blocks < 1) blocks = 1;
-                stats_bytes_kernel<<<(unsigned)blocks, 256, 0, ctx.stream>>>(
-                    reinterpret_cast<const unsigned char*>(base + plans[i].buf_off[(size_t)b]), bytes, ctx.d_stats);
-                g_launches.fetch_add(1, std::memory_order_relaxed);
-            }
+    return STRSIM_OK;
+}
+
+static int upload_data(ThreadCtx& ctx, Uploader& up, cudaStream_t st, ColumnStats* d_stats) {
+    (void)ctx;
+    char* base = static_cast<char*>(up.col->block);
+    for (size_t i = 0; i < up.n_chunks; i++) {
+        const strsim_view_chunk& ch = up.chunks[i];
+        const ChunkPlan& p = up.plans[i];
+        const size_t n_tab = ch.n_data_buffers > 0 ? (size_t)ch.n_data_buffers : 1;
+        CUDA_TRY(cudaMemcpyAsync(base + p.table_off, up.tables.data() + up.table_pos[i], 8 * n_tab,
+                                 cudaMemcpyHostToDevice, st));
+        for (int64_t b = 0; b < ch.n_data_buffers; b++) {
+            const long long bytes = ch.data_buffer_sizes[b];
+            if (p.buf_dup[(size_t)b] || bytes <= 0) continue;
+            CUDA_TRY(cudaMemcpyAsync(base + p.buf_off[(size_t)b], ch.data_buffers[b], (size_t)bytes,
+                                     cudaMemcpyHostToDevice, st));
+            long long blocks = ((bytes >> 4) + 255) / 256;
+            if (blocks > 148 * 16) blocks = 148 * 16;
+            if (blocks < 1) blocks = 1;
+            stats_bytes_kernel<<<(unsigned)blocks, 256, 0, st>>>(
+                reinterpret_cast<const unsigned char*>(base + p.buf_off[(size_t)b]), bytes, d_stats);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
         }
-        CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaMemcpyAsync(ctx.h_stats, ctx.d_stats, sizeof init, cudaMemcpyDeviceToHost, ctx.stream));
-        CUDA_TRY(cudaStreamSynchronize(ctx.stream));
-        unsigned o = ctx.h_stats->or_bits, a = ctx.h_stats->and_bits;
-        col->or_byte = (o | (o >> 8) | (o >> 16) | (o >> 24)) & 0xFFu;
-        col->and_byte = (a & (a >> 8) & (a >> 16) & (a >> 24)) & 0xFFu;
     }
+    CUDA_TRY(cudaGetLastError());
+    return STRSIM_OK;
+}
+
+// rows [lo, hi) of the column (a scalar column of length 1 is copied whenever lo == 0)
+static int upload_rows(ThreadCtx& ctx, Uploader& up, int64_t lo, int64_t hi, cudaStream_t st, ColumnStats* d_stats) {
+    (void)ctx;
+    char* base = static_cast<char*>(up.col->block);
+    for (size_t i = 0; i < up.n_chunks; i++) {
+        const strsim_view_chunk& ch = up.chunks[i];
+        const ChunkPlan& p = up.plans[i];
+        const int64_t c_lo = lo > p.row0 ? lo - p.row0 : 0;
+        const int64_t c_hi = hi - p.row0 < ch.length ? hi - p.row0 : ch.length;
+        if (c_lo >= c_hi) continue;
+        CUDA_TRY(cudaMemcpyAsync(base + p.views_off + 16 * c_lo,
+                                 static_cast<const char*>(ch.views) + 16 * (ch.offset + c_lo),
+                                 16 * (size_t)(c_hi - c_lo), cudaMemcpyHostToDevice, st));
+        if (p.validity_bytes) {
+            const int64_t b_lo = ((ch.offset + c_lo) >> 3) - p.first_byte;
+            const int64_t b_hi = ((ch.offset + c_hi + 7) >> 3) - p.first_byte;
+            CUDA_TRY(cudaMemcpyAsync(base + p.validity_off + b_lo, ch.validity + p.first_byte + b_lo,
+                                     (size_t)(b_hi - b_lo), cudaMemcpyHostToDevice, st));
+        }
+        long long blocks = (c_hi - c_lo + 255) / 256;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        stats_views_kernel<<<(unsigned)blocks, 256, 0, st>>>(
+            reinterpret_cast<const uint4*>(base + p.views_off) + c_lo, c_hi - c_lo, d_stats);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return STRSIM_OK;
+}
+
+// whole column in one go (device-resident API): synchronises and folds the statistics
+static int upload_column(ThreadCtx& ctx, const strsim_view_chunk* chunks, size_t n_chunks,
+                         bool want_alg_bytes, strsim_b200_column** out) {
+    Uploader up;
+    int rc = upload_plan(ctx, chunks, n_chunks, &up);
+    if (rc) return rc;
+    stats_init_value(ctx.h_stats);
+    cudaError_t e = cudaMemcpyAsync(ctx.d_stats, ctx.h_stats, sizeof(ColumnStats), cudaMemcpyHostToDevice, ctx.stream);
+    if (e == cudaSuccess) {
+        rc = upload_data(ctx, up, ctx.stream, ctx.d_stats);
+        if (rc == STRSIM_OK) rc = upload_rows(ctx, up, 0, up.col->length > 0 ? up.col->length : 1, ctx.stream, ctx.d_stats);
+    }
+    if (e == cudaSuccess && rc == STRSIM_OK)
+        e = cudaMemcpyAsync(ctx.h_stats, ctx.d_stats, sizeof(ColumnStats), cudaMemcpyDeviceToHost, ctx.stream);
+    if (e == cudaSuccess && rc == STRSIM_OK) e = cudaStreamSynchronize(ctx.stream);
+    if (e != cudaSuccess || rc != STRSIM_OK) {
+        if (e != cudaSuccess) {
+            strsim_set_error("CUDA error during column upload: %s", cudaGetErrorString(e));
+            rc = STRSIM_ERR_CUDA;
+        }
+        cudaStreamSynchronize(ctx.stream);
+        strsim_b200_column_free(up.col);
+        return rc;
+    }
+    strsim_b200_column* col = up.col;
+    stats_fold(*ctx.h_stats, &col->or_byte, &col->and_byte);
     if (want_alg_bytes) {
         // 16 B of view per row + out-of-line payload (byte length > 12) + validity bits
         int64_t bytes = 0;
@@ -436,9 +510,8 @@ static int launch_short(ThreadCtx& ctx, SegArgs args, long long n_upper, cudaStr
 // the two columns' byte statistics.
 enum Alphabet { ALPHA_GENERAL = 0, ALPHA_ASCII128 = 1, ALPHA_ASCII64 = 2, ALPHA_ASCII32 = 3 };
 
-static Alphabet classify_alphabet(const strsim_b200_column* a, const strsim_b200_column* b) {
+static Alphabet classify_alphabet(unsigned o, unsigned n) {  // OR / AND over every byte of both columns
     static const char* force = getenv("STRSIM_B200_ALPHABET");  // test / tuning knob: 0..3 caps the choice
-    const unsigned o = a->or_byte | b->or_byte, n = a->and_byte & b->and_byte;
     Alphabet al;
     if (o & 0x80u)
         al = ALPHA_GENERAL;
@@ -617,9 +690,12 @@ static int run_segment(ThreadCtx& ctx, SegArgs args, Alphabet al, int stage32, i
     return STRSIM_OK;
 }
 
+// Rows [row_lo, row_lo + n_rows) of measure(a, b) -> d_out[row] / validity bits / debug records, all
+// indexed by the absolute row.  `reset`: zero the validity words of the range and (first slice only)
+// the null counter.
 static int compute_on_device(ThreadCtx& ctx, int measure, const strsim_b200_column* a,
-                             const strsim_b200_column* b, double* d_out, uint32_t* d_validity,
-                             int32_t* d_dbg, cudaStream_t st) {
+                             const strsim_b200_column* b, int64_t row_lo, int64_t n_rows, Alphabet al,
+                             double* d_out, uint32_t* d_validity, int32_t* d_dbg, cudaStream_t st) {
     if (measure < 0 || measure > 4) {
         strsim_set_error("unknown measure %d", measure);
         return STRSIM_ERR_ARGUMENT;
@@ -629,22 +705,29 @@ static int compute_on_device(ThreadCtx& ctx, int measure, const strsim_b200_colu
         strsim_set_error("Inputs must have the same length, or one of them must be a Utf8 literal.");
         return STRSIM_ERR_SHAPE;
     }
-    const int64_t n = (la == 1) ? lb : la;
-    g_last_overflow[0] = g_last_overflow[1] = 0;
-    if (n == 0) return STRSIM_OK;
-    const bool bc_a = la == 1 && n != 1, bc_b = lb == 1 && n != 1;
+    const int64_t n_total = (la == 1) ? lb : la;
+    if (n_total == 0 || n_rows <= 0) return STRSIM_OK;
+    const int64_t n = row_lo + n_rows;  // exclusive end row
+    const bool bc_a = la == 1 && n_total != 1, bc_b = lb == 1 && n_total != 1;
     const bool any_validity = a->has_validity || b->has_validity;
-    if (d_validity && any_validity) {
-        CUDA_TRY(cudaMemsetAsync(d_validity, 0, 4 * (size_t)((n + 31) / 32), st));
-        CUDA_TRY(cudaMemsetAsync(ctx.d_nulls, 0, sizeof(unsigned long long), st));
-    } else if (d_validity) {
-        CUDA_TRY(cudaMemsetAsync(d_validity, 0xFF, 4 * (size_t)((n + 31) / 32), st));
-        CUDA_TRY(cudaMemsetAsync(ctx.d_nulls, 0, sizeof(unsigned long long), st));
+    if (d_validity) {
+        // row_lo is a multiple of 32 for every slice but the caller's first (0)
+        uint32_t* w0 = d_validity + (row_lo >> 5);
+        const size_t words = (size_t)(((n + 31) >> 5) - (row_lo >> 5));
+        CUDA_TRY(cudaMemsetAsync(w0, any_validity ? 0 : 0xFF, 4 * words, st));
+        if (row_lo == 0) CUDA_TRY(cudaMemsetAsync(ctx.d_nulls, 0, sizeof(unsigned long long), st));
     }
-    const Alphabet al = classify_alphabet(a, b);
     // walk both chunk lists in lock step (polars-core align_chunks equivalent)
     size_t ia = 0, ib = 0;
-    int64_t oa = 0, ob = 0, row = 0;
+    int64_t oa = 0, ob = 0, row = row_lo;
+    if (!bc_a) {
+        oa = row_lo;
+        while (ia < a->chunks.size() && oa >= a->chunks[ia].length) oa -= a->chunks[ia++].length;
+    }
+    if (!bc_b) {
+        ob = row_lo;
+        while (ib < b->chunks.size() && ob >= b->chunks[ib].length) ob -= b->chunks[ib++].length;
+    }
     while (row < n) {
         while (!bc_a && ia < a->chunks.size() && oa >= a->chunks[ia].length) {
             ia++;
@@ -784,7 +867,10 @@ int strsim_b200_compute_device(int measure, const strsim_b200_column* a, const s
         return STRSIM_ERR_ARGUMENT;
     }
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
-    return compute_on_device(*ctx, measure, a, b, d_out_values, d_out_validity, d_dbg_ints, st);
+    g_last_overflow[0] = g_last_overflow[1] = 0;
+    const int64_t n = a->length == 1 ? b->length : a->length;
+    return compute_on_device(*ctx, measure, a, b, 0, n, classify_alphabet(a->or_byte | b->or_byte, a->and_byte & b->and_byte),
+                             d_out_values, d_out_validity, d_dbg_ints, st);
 }
 
 int strsim_b200_compute_host_multi(const int* measures, size_t n_measures, const strsim_view_chunk* a, size_t n_a,
@@ -817,15 +903,31 @@ int strsim_b200_compute_host_multi(const int* measures, size_t n_measures, const
     int rc = ensure_ctx(&ctx);
     if (rc) return rc;
     if (n == 0) return STRSIM_OK;
-    // one upload of the two columns serves every requested measure
-    strsim_b200_column *ca = nullptr, *cb = nullptr;
-    rc = upload_column(*ctx, a, n_a, false, &ca);
+
+    // One upload of the two columns serves every requested measure.  The rows are cut into slices:
+    // all H2D copies are queued up front on the upload stream (data buffers first, then the views
+    // slice by slice), slice s is computed as soon as its views have landed, and its results go back
+    // on the download stream -- so H2D, kernels and D2H of different slices overlap (PCIe is full
+    // duplex) instead of running back to back.
+    Uploader ua, ub;
+    rc = upload_plan(*ctx, a, n_a, &ua);
     if (rc) return rc;
-    rc = upload_column(*ctx, b, n_b, false, &cb);
+    rc = upload_plan(*ctx, b, n_b, &ub);
     if (rc) {
-        strsim_b200_column_free(ca);
+        strsim_b200_column_free(ua.col);
         return rc;
     }
+    strsim_b200_column *ca = ua.col, *cb = ub.col;
+    static const long long slice_target = [] {
+        const char* e = getenv("STRSIM_B200_SLICE_ROWS");
+        const long long v = e && *e ? atoll(e) : 0;
+        return v > 0 ? v : SLICE_ROWS;
+    }();
+    int n_slices = (int)((n + slice_target - 1) / slice_target);
+    if (n_slices > MAX_SLICES) n_slices = MAX_SLICES;
+    if (n_slices < 1) n_slices = 1;
+    int64_t slice_rows = ((n + n_slices - 1) / n_slices + 63) & ~63ll;
+
     const size_t val_words = (size_t)((n + 31) / 32);
     const size_t out_stride = align_up(8 * (size_t)n, 256);
     const size_t dbg_stride = align_up(24 * (size_t)n, 256);
@@ -843,31 +945,82 @@ int strsim_b200_compute_host_multi(const int* measures, size_t n_measures, const
     uint32_t* d_val = reinterpret_cast<uint32_t*>(base + n_measures * out_stride);
     char* d_dbg_base = reinterpret_cast<char*>(d_val) + align_up(4 * val_words, 256);
     const bool want_validity = out_validity != nullptr || out_null_count != nullptr;
+
+    // ---- queue every upload; statistics slots: [0] data of a, [1] data of b, [2+s] views of slice s
     cudaError_t ce = cudaSuccess;
-    for (size_t m = 0; rc == STRSIM_OK && m < n_measures; m++) {
-        double* d_out = reinterpret_cast<double*>(base + m * out_stride);
-        int32_t* d_dbg = (any_dbg && dbg_ints[m]) ? reinterpret_cast<int32_t*>(d_dbg_base + m * dbg_stride) : nullptr;
-        rc = compute_on_device(*ctx, measures[m], ca, cb, d_out, (want_validity && m == 0) ? d_val : nullptr, d_dbg,
-                               ctx->stream);
-        if (rc) break;
-        // download this measure on the copy stream while the next one computes
-        ce = cudaEventRecord(ctx->done_event[m], ctx->stream);
-        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->copy_stream, ctx->done_event[m], 0);
-        if (ce == cudaSuccess)
-            ce = cudaMemcpyAsync(out_values[m], d_out, 8 * (size_t)n, cudaMemcpyDeviceToHost, ctx->copy_stream);
-        if (ce == cudaSuccess && d_dbg)
-            ce = cudaMemcpyAsync(dbg_ints[m], d_dbg, 24 * (size_t)n, cudaMemcpyDeviceToHost, ctx->copy_stream);
-        if (ce == cudaSuccess && m == 0 && out_validity)
-            ce = cudaMemcpyAsync(out_validity, d_val, (size_t)((n + 7) / 8), cudaMemcpyDeviceToHost, ctx->copy_stream);
-        if (ce == cudaSuccess && m == 0 && want_validity)
-            ce = cudaMemcpyAsync(ctx->h_nulls, ctx->d_nulls, 8, cudaMemcpyDeviceToHost, ctx->copy_stream);
-        if (ce != cudaSuccess) break;
+    for (int i = 0; i < 2 + MAX_SLICES; i++) stats_init_value(&ctx->h_slice_stats[i]);
+    ce = cudaMemcpyAsync(ctx->d_slice_stats, ctx->h_slice_stats, sizeof(ColumnStats) * (2 + MAX_SLICES),
+                         cudaMemcpyHostToDevice, ctx->upload_stream);
+    if (ce == cudaSuccess) rc = upload_data(*ctx, ua, ctx->upload_stream, ctx->d_slice_stats + 0);
+    if (ce == cudaSuccess && rc == STRSIM_OK) rc = upload_data(*ctx, ub, ctx->upload_stream, ctx->d_slice_stats + 1);
+    for (int sidx = 0; ce == cudaSuccess && rc == STRSIM_OK && sidx < n_slices; sidx++) {
+        const int64_t lo = sidx * slice_rows, hi = lo + slice_rows < n ? lo + slice_rows : n;
+        if (lo >= hi) {
+            n_slices = sidx;
+            break;
+        }
+        // a scalar (length-1) column is uploaded with the first slice
+        rc = upload_rows(*ctx, ua, la == 1 && n != 1 ? 0 : lo, la == 1 && n != 1 ? (sidx == 0 ? 1 : 0) : hi,
+                         ctx->upload_stream, ctx->d_slice_stats + 2 + sidx);
+        if (rc == STRSIM_OK)
+            rc = upload_rows(*ctx, ub, lb == 1 && n != 1 ? 0 : lo, lb == 1 && n != 1 ? (sidx == 0 ? 1 : 0) : hi,
+                             ctx->upload_stream, ctx->d_slice_stats + 2 + sidx);
+        if (rc == STRSIM_OK)
+            ce = cudaMemcpyAsync(ctx->h_slice_stats, ctx->d_slice_stats, sizeof(ColumnStats) * (3 + sidx),
+                                 cudaMemcpyDeviceToHost, ctx->upload_stream);
+        if (rc == STRSIM_OK && ce == cudaSuccess) ce = cudaEventRecord(ctx->slice_event[sidx], ctx->upload_stream);
     }
+
+    // ---- compute + download slice by slice
+    for (int sidx = 0; ce == cudaSuccess && rc == STRSIM_OK && sidx < n_slices; sidx++) {
+        const int64_t lo = sidx * slice_rows, hi = lo + slice_rows < n ? lo + slice_rows : n;
+        ce = cudaEventSynchronize(ctx->slice_event[sidx]);  // views + statistics of this slice are here
+        if (ce != cudaSuccess) break;
+        ColumnStats acc = ctx->h_slice_stats[0];
+        acc.or_bits |= ctx->h_slice_stats[1].or_bits | ctx->h_slice_stats[2 + sidx].or_bits;
+        acc.and_bits &= ctx->h_slice_stats[1].and_bits & ctx->h_slice_stats[2 + sidx].and_bits;
+        if (la == 1 || lb == 1) {  // the scalar's inline bytes were counted with slice 0
+            acc.or_bits |= ctx->h_slice_stats[2].or_bits;
+            acc.and_bits &= ctx->h_slice_stats[2].and_bits;
+        }
+        unsigned ob, nb_;
+        stats_fold(acc, &ob, &nb_);
+        const Alphabet al = classify_alphabet(ob, nb_);
+        ce = cudaStreamWaitEvent(ctx->stream, ctx->slice_event[sidx], 0);
+        for (size_t m = 0; ce == cudaSuccess && rc == STRSIM_OK && m < n_measures; m++) {
+            if (sidx == 0) g_last_overflow[0] = g_last_overflow[1] = 0;
+            double* d_out = reinterpret_cast<double*>(base + m * out_stride);
+            int32_t* d_dbg = (any_dbg && dbg_ints[m]) ? reinterpret_cast<int32_t*>(d_dbg_base + m * dbg_stride) : nullptr;
+            rc = compute_on_device(*ctx, measures[m], ca, cb, lo, hi - lo, al, d_out,
+                                   (want_validity && m == 0) ? d_val : nullptr, d_dbg, ctx->stream);
+            if (rc) break;
+            // download this measure's slice on the copy stream while the next kernel runs
+            cudaEvent_t ev = ctx->done_event[m];
+            ce = cudaEventRecord(ev, ctx->stream);
+            if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->copy_stream, ev, 0);
+            if (ce == cudaSuccess)
+                ce = cudaMemcpyAsync(out_values[m] + lo, d_out + lo, 8 * (size_t)(hi - lo), cudaMemcpyDeviceToHost,
+                                     ctx->copy_stream);
+            if (ce == cudaSuccess && d_dbg)
+                ce = cudaMemcpyAsync(dbg_ints[m] + 6 * lo, d_dbg + 6 * lo, 24 * (size_t)(hi - lo),
+                                     cudaMemcpyDeviceToHost, ctx->copy_stream);
+            if (ce == cudaSuccess && m == 0 && out_validity)
+                ce = cudaMemcpyAsync(out_validity + lo / 8, reinterpret_cast<const uint8_t*>(d_val) + lo / 8,
+                                     (size_t)((hi - lo + 7) / 8), cudaMemcpyDeviceToHost, ctx->copy_stream);
+        }
+    }
+    if (ce == cudaSuccess && rc == STRSIM_OK && want_validity) {
+        ce = cudaEventRecord(ctx->done_event[0], ctx->stream);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->copy_stream, ctx->done_event[0], 0);
+        if (ce == cudaSuccess)
+            ce = cudaMemcpyAsync(ctx->h_nulls, ctx->d_nulls, 8, cudaMemcpyDeviceToHost, ctx->copy_stream);
+    }
+    cudaError_t s0 = cudaStreamSynchronize(ctx->upload_stream);
     cudaError_t s1 = cudaStreamSynchronize(ctx->stream);
     cudaError_t s2 = cudaStreamSynchronize(ctx->copy_stream);
-    if (rc == STRSIM_OK && (ce != cudaSuccess || s1 != cudaSuccess || s2 != cudaSuccess)) {
-        strsim_set_error("CUDA error while computing / downloading results: %s",
-                         cudaGetErrorString(ce != cudaSuccess ? ce : (s1 != cudaSuccess ? s1 : s2)));
+    if (rc == STRSIM_OK && (ce != cudaSuccess || s0 != cudaSuccess || s1 != cudaSuccess || s2 != cudaSuccess)) {
+        const cudaError_t first = ce != cudaSuccess ? ce : s0 != cudaSuccess ? s0 : s1 != cudaSuccess ? s1 : s2;
+        strsim_set_error("CUDA error while uploading / computing / downloading: %s", cudaGetErrorString(first));
         rc = STRSIM_ERR_CUDA;
     }
     if (rc == STRSIM_OK && out_null_count) *out_null_count = (int64_t)*ctx->h_nulls;
