@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../include/strsim_b200.h"
+#include "direct_kernel.cuh"
 #include "generic_kernel.cuh"
 #include "long_lev_kernel.cuh"
 #include "short_kernel.cuh"
@@ -506,6 +507,31 @@ static int launch_short(ThreadCtx& ctx, SegArgs args, long long n_upper, cudaStr
     return STRSIM_OK;
 }
 
+template <class M, int MEASURE, int TPB, int RPT, bool GATHER, int T, bool ASCII_ONLY>
+static int launch_direct(ThreadCtx& ctx, const SegArgs& args, long long n_upper, cudaStream_t st) {
+    using L = DirectLayout<M, TPB, RPT, T>;
+    auto kern = direct_kernel<M, MEASURE, TPB, RPT, GATHER, T, ASCII_ONLY>;
+    const size_t smem = L::bytes;
+    static thread_local int per_sm = 0;
+    if (per_sm == 0) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TPB, smem));
+        if (per_sm < 1) {
+            per_sm = 0;
+            strsim_set_error("direct kernel does not fit an SM (smem %zu)", smem);
+            return STRSIM_ERR_CUDA;
+        }
+    }
+    const long long tiles = (n_upper + L::TILE - 1) / L::TILE;
+    long long grid = (long long)per_sm * ctx.sm_count;
+    if (tiles < grid) grid = tiles;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, TPB, smem, st>>>(args);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return STRSIM_OK;
+}
+
 // Which instantiation of the fused kernel serves a segment (see DevStore): decided from the union of
 // the two columns' byte statistics.
 enum Alphabet { ALPHA_GENERAL = 0, ALPHA_ASCII128 = 1, ALPHA_ASCII64 = 2, ALPHA_ASCII32 = 3 };
@@ -532,13 +558,28 @@ template <int MEASURE>
 static int launch_fused(ThreadCtx& ctx, Alphabet al, const SegArgs& args, long long rows, cudaStream_t st) {
     static const char* cfg_env = getenv("STRSIM_B200_TILE");  // tuning knob
     const int cfg = cfg_env && *cfg_env ? atoi(cfg_env) : 0;
+    // "direct" = direct_kernel.cuh (no shared-memory staging).  Measured on C2 (profiles/README.md): it
+    // doubles the resident warps but is SLOWER (levenshtein 0.70 ms vs 0.58 ms per 10M pairs) because the
+    // sorted threads' scattered global loads cost 32 L1TEX wavefronts per warp instruction, where the
+    // staged kernel reads shared memory conflict-free.  Kept as an experiment knob and for the gather
+    // (overflow-list) launches, whose rows are scattered anyway.
+    static const char* kern_env = getenv("STRSIM_B200_KERNEL");
+    const bool direct = kern_env && !strcmp(kern_env, "direct");
+    (void)cfg;
+    if (direct) {
+        switch (al) {
+            case ALPHA_ASCII32:
+                return launch_direct<uint32_t, MEASURE, 128, 2, false, 32, true>(ctx, args, rows, st);
+            case ALPHA_ASCII64:
+                return launch_direct<uint32_t, MEASURE, 128, 4, false, 64, true>(ctx, args, rows, st);
+            case ALPHA_ASCII128:
+                return launch_direct<uint32_t, MEASURE, 128, 4, false, 128, true>(ctx, args, rows, st);
+            default:
+                return launch_direct<uint32_t, MEASURE, 128, 4, false, 128, false>(ctx, args, rows, st);
+        }
+    }
     switch (al) {
         case ALPHA_ASCII32:
-            if (cfg == 1) return launch_short<uint32_t, MEASURE, 128, 2, false, 32, true>(ctx, args, rows, st);
-            if (cfg == 2) return launch_short<uint32_t, MEASURE, 256, 4, false, 32, true>(ctx, args, rows, st);
-            if (cfg == 3) return launch_short<uint32_t, MEASURE, 128, 8, false, 32, true>(ctx, args, rows, st);
-            if (cfg == 4) return launch_short<uint32_t, MEASURE, 192, 4, false, 32, true>(ctx, args, rows, st);
-            if (cfg == 5) return launch_short<uint32_t, MEASURE, 128, 3, false, 32, true>(ctx, args, rows, st);
             return launch_short<uint32_t, MEASURE, 128, 4, false, 32, true>(ctx, args, rows, st);
         case ALPHA_ASCII64:
             return launch_short<uint32_t, MEASURE, 128, 4, false, 64, true>(ctx, args, rows, st);
@@ -667,8 +708,7 @@ static int run_segment(ThreadCtx& ctx, SegArgs args, Alphabet al, int stage32, i
         a64.list = args.list64;
         a64.list_count = &ctx.d_ovf->n64;
         a64.n = ov.n64;
-        a64.stage_bytes = 64 * ShortLayout<uint64_t, 64, 2, 192>::TILE;  // every listed row fits
-        rc = launch_short<uint64_t, MEASURE, 64, 2, true, 192, false>(ctx, a64, ov.n64, st);
+        rc = launch_direct<uint64_t, MEASURE, 64, 4, true, 192, false>(ctx, a64, ov.n64, st);
         if (rc) return rc;
         // rows the 64-bit kernel could not stage are appended to listlong; re-read the counters
         CUDA_TRY(cudaMemcpyAsync(ctx.h_ovf, ctx.d_ovf, sizeof(Overflow), cudaMemcpyDeviceToHost, st));
