@@ -473,10 +473,10 @@ static int upload_column(ThreadCtx& ctx, const strsim_view_chunk* chunks, size_t
 }
 
 // ---- kernel launch helpers -----------------------------------------------------------------------------
-template <class M, int MEASURE, int TPB, int RPT, bool GATHER, int T, bool ASCII_ONLY>
+template <class M, int MEASURE, int TPB, int RPT, bool GATHER, int T, bool ASCII_ONLY, bool REG = false>
 static int launch_short(ThreadCtx& ctx, SegArgs args, long long n_upper, cudaStream_t st) {
-    using L = ShortLayout<M, TPB, RPT, T>;
-    auto kern = short_kernel<M, MEASURE, TPB, RPT, GATHER, T, ASCII_ONLY>;
+    using L = ShortLayout<M, TPB, RPT, T, REG>;
+    auto kern = short_kernel<M, MEASURE, TPB, RPT, GATHER, T, ASCII_ONLY, REG>;
     if (args.stage_bytes < 0) {
         // -stage_bytes = mean out-of-line bytes per row (x16) of the heavier column: size the stage
         // area for this tile shape with 25 % headroom (rows that still do not fit take the long path)
@@ -576,6 +576,21 @@ static int launch_fused(ThreadCtx& ctx, Alphabet al, const SegArgs& args, long l
                 return launch_direct<uint32_t, MEASURE, 128, 4, false, 128, true>(ctx, args, rows, st);
             default:
                 return launch_direct<uint32_t, MEASURE, 128, 4, false, 128, false>(ctx, args, rows, st);
+        }
+    }
+    static const char* reg_env = getenv("STRSIM_B200_REG");  // "0": table-driven ASCII path instead
+    const bool reg = !(reg_env && !strcmp(reg_env, "0"));
+    if (reg) {
+        switch (al) {
+            case ALPHA_ASCII32:
+                if (cfg == 1) return launch_short<uint32_t, MEASURE, 128, 4, false, 32, true, true>(ctx, args, rows, st);
+                return launch_short<uint32_t, MEASURE, 256, 4, false, 32, true, true>(ctx, args, rows, st);
+            case ALPHA_ASCII64:
+                return launch_short<uint32_t, MEASURE, 256, 4, false, 64, true, true>(ctx, args, rows, st);
+            case ALPHA_ASCII128:
+                return launch_short<uint32_t, MEASURE, 256, 4, false, 128, true, true>(ctx, args, rows, st);
+            default:
+                break;
         }
     }
     switch (al) {

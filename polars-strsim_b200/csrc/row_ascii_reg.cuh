@@ -1,0 +1,175 @@
+// row_ascii_reg.cuh -- one ASCII pair, strings and position masks entirely in REGISTERS.
+//
+// The table-driven path of row_short.cuh keeps a 32..128-entry position-mask table and a copy of the
+// pair per thread in shared memory; profiles show that this shared memory is what limits the resident
+// warps and that its load/store traffic keeps the LSU half busy.  For ASCII pairs of at most 32 bytes
+// this variant needs neither:
+//   * the two strings live in 2 x 8 registers (all loops are fully unrolled, indices are static);
+//   * instead of table[c], the position mask of a character is computed from BIT PLANES of the
+//     tabled string: plane k holds bit k of every character (bit i of B[k] = bit k of char i), and
+//         Eq(c) = valid & ~( OR_k ( B[k] ^ S_k(c) ) ),   S_k(c) = all-ones if bit k of c is set.
+//     The seven S_k come from two multiplies that park bit k in the sign bit of some byte, and one
+//     byte-permute with sign replication each (PRMT); with the column statistics proving a 32- or
+//     64-code-point alphabet block only 5 or 6 planes are needed.
+// Arithmetic and row rules are those of row_short.cuh (same step functors, same f64 formulas).
+#pragma once
+#include "pair_algos.cuh"
+
+namespace strsim {
+
+constexpr int REG_WORDS = 8;  // 32 bytes per string
+
+SS_HD uint32_t sign_fill_byte(uint32_t x, int byte) {  // all-ones if bit 7 of byte `byte` of x is set
+#if defined(__CUDA_ARCH__)
+    // prmt with the msb of a selector nibble set replicates the SIGN of the selected byte over the
+    // target byte (the __byte_perm intrinsic is documented to ignore that bit, so use PTX directly)
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(0u), "r"(0x8888u + 0x1111u * (uint32_t)byte));
+    return r;
+#else
+    return 0u - ((x >> (8 * byte + 7)) & 1u);
+#endif
+}
+
+template <int NBITS>
+struct PlaneTab {
+    uint32_t B[NBITS];
+    uint32_t valid;  // bits < m
+    SS_HD uint32_t operator()(uint32_t c) const {
+        // u: bits 6,5,4,3 of c in the sign bits of bytes 0..3; v: bits 2,1,0 in bytes 0..2
+        const uint32_t u = c * 0x10080402u, v = c * 0x00804020u;
+        uint32_t X = B[0] ^ sign_fill_byte(v, 2);
+        if (NBITS > 1) X |= B[1] ^ sign_fill_byte(v, 1);
+        if (NBITS > 2) X |= B[2] ^ sign_fill_byte(v, 0);
+        if (NBITS > 3) X |= B[3] ^ sign_fill_byte(u, 3);
+        if (NBITS > 4) X |= B[4] ^ sign_fill_byte(u, 2);
+        if (NBITS > 5) X |= B[5] ^ sign_fill_byte(u, 1);
+        if (NBITS > 6) X |= B[6] ^ sign_fill_byte(u, 0);
+        return ~X & valid;
+    }
+};
+
+// bit planes of the first m characters of P (zero padded words)
+template <int NBITS>
+SS_HD void build_planes(const uint32_t (&P)[REG_WORDS], int m, PlaneTab<NBITS>& tab) {
+#pragma unroll
+    for (int k = 0; k < NBITS; k++) tab.B[k] = 0u;
+#pragma unroll
+    for (int w = 0; w < REG_WORDS; w++) {
+        if (4 * w >= m) break;
+        const uint32_t word = P[w];
+#pragma unroll
+        for (int k = 0; k < NBITS; k++) {
+            // bit k of the four bytes -> four adjacent bits (character order) at nibble w
+            const uint32_t prod = ((word >> k) & 0x01010101u) * 0x10204080u;
+            tab.B[k] |= w == 7 ? (prod & 0xF0000000u) : ((prod >> (28 - 4 * w)) & (0xFu << (4 * w)));
+        }
+    }
+    tab.valid = m >= 32 ? 0xFFFFFFFFu : ((1u << m) - 1u);
+}
+
+// applies f to the first n bytes of a register-resident string
+template <class F>
+SS_HD void for_each_byte_reg(const uint32_t (&W)[REG_WORDS], int n, F& f) {
+#pragma unroll
+    for (int w = 0; w < REG_WORDS; w++) {
+        if (4 * w >= n) break;
+        const uint32_t word = W[w];
+        f(word & 0xFFu);
+        if (4 * w + 1 < n) f((word >> 8) & 0xFFu);
+        if (4 * w + 2 < n) f((word >> 16) & 0xFFu);
+        if (4 * w + 3 < n) f(word >> 24);
+    }
+}
+
+// a, b: zero-padded little-endian words; na, nb <= 32 bytes, every byte < 0x80 and (for NBITS < 7)
+// inside one aligned block of 2^NBITS code points.
+template <int MEASURE, int NBITS>
+SS_HD double row_ascii_reg(const uint32_t (&a)[REG_WORDS], const uint32_t (&b)[REG_WORDS], int na, int nb,
+                           PairInts& out) {
+    out.flag = F_GENERAL;
+    out.la = out.lb = out.x0 = out.x1 = out.x2 = 0;
+    bool equal = na == nb;
+    if (equal) {
+        uint32_t diff = 0;
+#pragma unroll
+        for (int w = 0; w < REG_WORDS; w++) diff |= a[w] ^ b[w];
+        equal = diff == 0u;
+    }
+    if (equal) {  // strsim.rs:128,182,288,324
+        out.flag = F_EQUAL;
+        return 1.0;
+    }
+    if (MEASURE != LEVENSHTEIN && (na == 0 || nb == 0)) {  // strsim.rs:184,290,326
+        out.flag = F_ONE_EMPTY;
+        return 0.0;
+    }
+    const int la = na, lb = nb;
+    out.la = la;
+    out.lb = lb;
+    constexpr bool IS_JARO = MEASURE == JARO || MEASURE == JARO_WINKLER;
+    if (IS_JARO && la == 1 && lb == 1) {  // strsim.rs:197
+        out.flag = F_SINGLE_CHAR;
+        return 0.0;
+    }
+    typedef PlaneTab<NBITS> Tab;
+    Tab tab;
+    double v;
+    if (MEASURE == LEVENSHTEIN) {
+        // the shorter string is tabled; the longer one is streamed (the distance is symmetric)
+        const bool table_b = lb <= la;
+        uint32_t P[REG_WORDS], X[REG_WORDS];
+#pragma unroll
+        for (int w = 0; w < REG_WORDS; w++) {
+            P[w] = table_b ? b[w] : a[w];
+            X[w] = table_b ? a[w] : b[w];
+        }
+        const int m = table_b ? lb : la, n = table_b ? la : lb;
+        int d = n;
+        if (m > 0) {
+            build_planes<NBITS>(P, m, tab);
+            MyersStep<uint32_t, Tab> step(tab);
+            for_each_byte_reg(X, n, step);
+            d = step.distance(m, n);
+        }
+        out.x0 = d;
+        v = lev_value(d, la, lb);
+    } else {
+        build_planes<NBITS>(b, lb, tab);
+        if (IS_JARO) {
+            const int mx = la > lb ? la : lb;
+            const int bound = mx / 2 - 1;  // strsim.rs:200
+            const int outer = la < lb + bound ? la : lb + bound;
+            JaroMatchStep<uint32_t, Tab> match(tab, lb, bound);
+            for_each_byte_reg(a, outer, match);
+            JaroTransStep<uint32_t, Tab> trans(tab, match.flag_a, match.flag_b);
+            if (match.m > 0) for_each_byte_reg(a, outer, trans);
+            out.x0 = match.m;
+            out.x1 = trans.t;
+            v = match.m == 0 ? 0.0 : jaro_value(match.m, trans.t, la, lb);
+            if (MEASURE == JARO_WINKLER && v > 0.7) {  // strsim.rs:260-267
+                const uint32_t x = a[0] ^ b[0];
+                int lim = la < lb ? la : lb;
+                if (lim > 4) lim = 4;
+                int l = 0;
+                while (l < lim && ((x >> (8 * l)) & 0xFFu) == 0) l++;
+                out.x2 = l;
+                v = winkler_value(v, l);
+            }
+        } else {
+            MultisetStep<uint32_t, Tab> ms(tab, lb);
+            for_each_byte_reg(a, la, ms);
+            out.x0 = ms.inter;
+            if (MEASURE == JACCARD) {
+                out.x1 = la + lb - ms.inter;
+                v = jaccard_value(ms.inter, la + lb - ms.inter);
+            } else {
+                out.x1 = la + lb;
+                v = dice_value(ms.inter, la + lb);
+            }
+        }
+    }
+    return v;
+}
+
+}  // namespace strsim

@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "row_ascii_reg.cuh"
 #include "row_short.cuh"
 
 namespace strsim {
@@ -136,7 +137,8 @@ struct DevStore {
     __device__ __forceinline__ uint32_t wb(int k) const { return wb_[k * TPB]; }
 };
 
-template <class M, int TPB, int RPT, int T>
+// REG: register-resident ASCII path (row_ascii_reg.cuh) -- no table, no slabs in shared memory
+template <class M, int TPB, int RPT, int T, bool REG = false>
 struct ShortLayout {
     static constexpr int CAP = (int)sizeof(M) * 8;
     static constexpr int WORDS = CAP / 4;
@@ -146,9 +148,9 @@ struct ShortLayout {
     static constexpr size_t off_sva = 0;
     static constexpr size_t off_svb = off_sva + sizeof(uint4) * TILE;
     static constexpr size_t off_tab = off_svb + sizeof(uint4) * TILE;
-    static constexpr size_t off_slab_a = off_tab + sizeof(M) * T * TPB;
-    static constexpr size_t off_slab_b = off_slab_a + 4 * WORDS * TPB;
-    static constexpr size_t off_hist = off_slab_b + 4 * WORDS * TPB;
+    static constexpr size_t off_slab_a = off_tab + (REG ? 0 : sizeof(M) * T * TPB);
+    static constexpr size_t off_slab_b = off_slab_a + (REG ? 0 : 4 * WORDS * TPB);
+    static constexpr size_t off_hist = off_slab_b + (REG ? 0 : 4 * WORDS * TPB);
     static constexpr size_t off_red = off_hist + 4 * ((NB + 3) & ~3);
     static constexpr size_t off_mbar = off_red + 4 * 16 * NWARP;
     static constexpr size_t off_perm = off_mbar + 16;
@@ -198,6 +200,34 @@ __device__ __forceinline__ uint32_t load_string(const uint4& v, const unsigned c
     return acc;
 }
 
+// Same as load_string, but into registers (static indices: the loop is fully unrolled).
+__device__ __forceinline__ void load_string_reg(const uint4& v, const unsigned char* stage,
+                                                uint32_t (&r)[REG_WORDS]) {
+    const int len = (int)v.x;
+#pragma unroll
+    for (int w = 0; w < REG_WORDS; w++) r[w] = 0u;
+    if (len <= 12) {
+        r[0] = v.y & byte_mask(len);
+        r[1] = v.z & byte_mask(len - 4 < 0 ? 0 : len - 4);
+        r[2] = v.w & byte_mask(len - 8 < 0 ? 0 : len - 8);
+    } else {
+        const uint32_t soff = v.y;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(stage) + (soff >> 2);
+        const int sh = (int)(soff & 3) * 8;
+        uint32_t lo = src[0];
+#pragma unroll
+        for (int w = 0; w < REG_WORDS; w++) {
+            if (4 * w < len) {
+                const uint32_t hi = src[w + 1];
+                uint32_t word = __funnelshift_r(lo, hi, sh);
+                lo = hi;
+                if (4 * w + 4 > len) word &= byte_mask(len - 4 * w);
+                r[w] = word;
+            }
+        }
+    }
+}
+
 // Settling byte-equal pairs before the sort frees their lanes but costs every row a prefix compare;
 // measured on C2 (20 % equal pairs) it LOSES 8 % because the compute phase is bound by the latency of
 // its rounds, not by the number of active lanes.  Kept for data sets dominated by equal pairs.
@@ -235,11 +265,14 @@ __device__ __forceinline__ bool staged_equal(const uint4& va, const uint4& vb, c
     return true;
 }
 
-template <class M, int MEASURE, int TPB, int RPT, bool GATHER, int T, bool ASCII_ONLY>
+template <class M, int MEASURE, int TPB, int RPT, bool GATHER, int T, bool ASCII_ONLY, bool REG = false>
 __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
     static_assert(ASCII_ONLY || T >= DevStore<M, TPB, T>::HASH_ENTRIES,
                   "the Unicode path keeps its hash slots in the table memory");
-    using L = ShortLayout<M, TPB, RPT, T>;
+    static_assert(!REG || (ASCII_ONLY && sizeof(M) == 4 && (T == 32 || T == 64 || T == 128)),
+                  "the register path serves ASCII-only columns with strings of at most 32 bytes");
+    constexpr int NBITS = T == 32 ? 5 : T == 64 ? 6 : 7;
+    using L = ShortLayout<M, TPB, RPT, T, REG>;
     constexpr int CAP = L::CAP;
     constexpr int WORDS = L::WORDS;
     constexpr int TILE = L::TILE;
@@ -266,9 +299,11 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
 
     // one-time: zero the position-mask tables (row_short keeps them zero), init the mbarrier
     {
-        uint4* t4 = reinterpret_cast<uint4*>(tab);
-        constexpr int N4 = (int)(sizeof(M) * T * TPB / 16);
-        for (int i = tid; i < N4; i += TPB) t4[i] = make_uint4(0, 0, 0, 0);
+        if (!REG) {
+            uint4* t4 = reinterpret_cast<uint4*>(tab);
+            constexpr int N4 = (int)(sizeof(M) * T * TPB / 16);
+            for (int i = tid; i < N4; i += TPB) t4[i] = make_uint4(0, 0, 0, 0);
+        }
         if (tid == 0) mbar_init(mbar, 1);
     }
     uint32_t mbar_phase = 0;
@@ -562,19 +597,27 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
             if (p >= n_active) continue;
             const int i = perm[p];
             const uint4 va = sva[i], vb = svb[i];
-            const uint32_t or_a = load_string<WORDS, TPB>(va, stage_a, store.wa_);
-            const uint32_t or_b = load_string<WORDS, TPB>(vb, stage_b, store.wb_);
             const int na = (int)va.x, nb = (int)vb.x;
-            bool equal = false;  // with the prefilter, byte-equal pairs were settled before the sort
-            if (!PREFILTER_EQUAL && na == nb) {
-                const int nw = (na + 3) >> 2;
-                uint32_t diff = 0;
-                for (int w = 0; w < nw; w++) diff |= store.wa(w) ^ store.wb(w);
-                equal = diff == 0;
-            }
-            const bool ascii = ASCII_ONLY || ((or_a | or_b) & 0x80808080u) == 0;
             PairInts ints;
-            const double v = row_short<M>(MEASURE, store, na, nb, equal, ascii, ints);
+            double v;
+            if (REG) {
+                uint32_t ra[REG_WORDS], rb[REG_WORDS];
+                load_string_reg(va, stage_a, ra);
+                load_string_reg(vb, stage_b, rb);
+                v = row_ascii_reg<MEASURE, NBITS>(ra, rb, na, nb, ints);
+            } else {
+                const uint32_t or_a = load_string<WORDS, TPB>(va, stage_a, store.wa_);
+                const uint32_t or_b = load_string<WORDS, TPB>(vb, stage_b, store.wb_);
+                bool equal = false;  // with the prefilter, byte-equal pairs were settled before the sort
+                if (!PREFILTER_EQUAL && na == nb) {
+                    const int nw = (na + 3) >> 2;
+                    uint32_t diff = 0;
+                    for (int w = 0; w < nw; w++) diff |= store.wa(w) ^ store.wb(w);
+                    equal = diff == 0;
+                }
+                const bool ascii = ASCII_ONLY || ((or_a | or_b) & 0x80808080u) == 0;
+                v = row_short<M>(MEASURE, store, na, nb, equal, ascii, ints);
+            }
             const long long idx = tile0 + i;
             const long long row = GATHER ? (long long)s.list[idx] : idx;
             s.out[row] = v;

@@ -93,3 +93,38 @@ extern "C" int algos_myers_multiword(const uint32_t* a, int la, const uint32_t* 
     for (int w = 0; w < W; w++) d += myers_block_score(Pv[w], Mv[w], m - 64 * w);
     return d;
 }
+
+// register-resident ASCII path (row_ascii_reg.cuh): planes instead of tables
+#include "row_ascii_reg.cuh"
+template <int MEASURE>
+static double reg_dispatch(int nbits, const uint32_t (&a)[REG_WORDS], const uint32_t (&b)[REG_WORDS], int na, int nb,
+                           PairInts& pi) {
+    switch (nbits) {
+        case 5: return row_ascii_reg<MEASURE, 5>(a, b, na, nb, pi);
+        case 6: return row_ascii_reg<MEASURE, 6>(a, b, na, nb, pi);
+        default: return row_ascii_reg<MEASURE, 7>(a, b, na, nb, pi);
+    }
+}
+extern "C" int algos_batch_reg(int measure, int nbits, int64_t n, const uint8_t* ad, const int64_t* ao,
+                               const uint8_t* bd, const int64_t* bo, int* ints, double* values) {
+    for (int64_t r = 0; r < n; r++) {
+        const int na = (int)(ao[r + 1] - ao[r]), nb = (int)(bo[r + 1] - bo[r]);
+        if (na > 32 || nb > 32) return -2;
+        uint32_t a[REG_WORDS] = {0}, b[REG_WORDS] = {0};
+        std::memcpy(a, ad + ao[r], na);
+        std::memcpy(b, bd + bo[r], nb);
+        PairInts pi;
+        double v;
+        switch (measure) {
+            case 0: v = reg_dispatch<0>(nbits, a, b, na, nb, pi); break;
+            case 1: v = reg_dispatch<1>(nbits, a, b, na, nb, pi); break;
+            case 2: v = reg_dispatch<2>(nbits, a, b, na, nb, pi); break;
+            case 3: v = reg_dispatch<3>(nbits, a, b, na, nb, pi); break;
+            default: v = reg_dispatch<4>(nbits, a, b, na, nb, pi); break;
+        }
+        values[r] = v;
+        int* o = ints + 6 * r;
+        o[0] = pi.flag; o[1] = pi.la; o[2] = pi.lb; o[3] = pi.x0; o[4] = pi.x1; o[5] = pi.x2;
+    }
+    return 0;
+}

@@ -111,3 +111,53 @@ def test_multiword_myers_block(algos, oracle):
             assert d == 0
         else:
             assert d == oracle.pair("levenshtein", x, y)[1][3], (len(x), len(y))
+
+
+@pytest.mark.parametrize("nbits,alphabet", [(5, "abcdefghijklmnopqrstuvwxyz"), (5, "ABCXYZ@["),
+                                            (6, "abcxyzABCXYZ_`{"), (7, "ab yz-'09AZ~\x01\x7f!")])
+def test_register_resident_ascii_path(algos, oracle, nbits, alphabet):
+    """row_ascii_reg.cuh: strings in registers, position masks from bit planes (no table)."""
+    from oracle.oracle import _pack, MEASURE_ID
+
+    algos.algos_batch_reg.restype = ctypes.c_int
+    algos.algos_batch_reg.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int64] + [ctypes.c_void_p] * 6
+    rng = random.Random(1000 + nbits)
+    a, b = [], []
+    for _ in range(20000):
+        x = "".join(rng.choice(alphabet) for _ in range(rng.randint(0, 32)))
+        if rng.random() < 0.6:
+            y = list(x)
+            for _ in range(rng.randint(0, 3)):
+                op, pos = rng.randint(0, 3), rng.randint(0, len(y))
+                if op == 0 and y:
+                    y[min(pos, len(y) - 1)] = rng.choice(alphabet)
+                elif op == 1 and len(y) < 32:
+                    y.insert(pos, rng.choice(alphabet))
+                elif op == 2 and y:
+                    del y[min(pos, len(y) - 1)]
+                elif op == 3 and len(y) > 1:
+                    p = min(pos, len(y) - 2)
+                    y[p], y[p + 1] = y[p + 1], y[p]
+            y = "".join(y)
+        else:
+            y = "".join(rng.choice(alphabet) for _ in range(rng.randint(0, 32)))
+        a.append(x)
+        b.append(y)
+    for la in (0, 1, 2, 31, 32):
+        for lb in (0, 1, 2, 31, 32):
+            a.append(alphabet[0] * la)
+            b.append((alphabet[1] * lb))
+            a.append("".join(rng.choice(alphabet) for _ in range(la)))
+            b.append("".join(rng.choice(alphabet) for _ in range(lb)))
+    ad, ao, _ = _pack(a)
+    bd, bo, _ = _pack(b)
+    for measure in oracle.MEASURES:
+        ints = np.zeros((len(a), 6), dtype=np.int32)
+        vals = np.zeros(len(a), dtype=np.float64)
+        rc = algos.algos_batch_reg(MEASURE_ID[measure], nbits, len(a), ad.ctypes.data, ao.ctypes.data,
+                                   bd.ctypes.data, bo.ctypes.data, ints.ctypes.data, vals.ctypes.data)
+        assert rc == 0
+        ref, _, ref_ints = oracle.batch(measure, a, b)
+        bad = np.nonzero(vals.view(np.uint64) != ref.view(np.uint64))[0]
+        assert bad.size == 0, (measure, a[bad[0]], b[bad[0]], vals[bad[0]], ref[bad[0]])
+        assert (ints == ref_ints).all(), measure
