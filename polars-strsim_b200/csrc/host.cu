@@ -643,20 +643,24 @@ static int run_generic(ThreadCtx& ctx, const SegArgs& args, const Overflow& ov, 
     return STRSIM_OK;
 }
 
-// long Levenshtein rows -> warp-cooperative multi-word Myers; rows whose pattern exceeds LONG_PAT_MAX
-// come back on `huge_list` and are finished by the generic kernel
-static int run_long_lev(ThreadCtx& ctx, const SegArgs& args, const Overflow& ov, unsigned int* huge_list,
-                        unsigned int* n_huge, cudaStream_t st) {
+// long Levenshtein rows -> warp-cooperative multi-word Myers.  Two tiers: first many warps with
+// modest Peq slabs (typical pairs need (distinct+1) x W words, far below the worst case), then the
+// pairs that did not fit with worst-case slabs and fewer warps.  Rows whose pattern exceeds
+// LONG_PAT_MAX come back on `huge_list` and are finished by the generic kernel.
+struct Leftover {  // rows the long kernel could not take: finished by the generic kernel
+    const unsigned int* list = nullptr;
+    const unsigned int* count = nullptr;  // device-resident
+    unsigned int n = 0;
+};
+
+static int run_long_lev(ThreadCtx& ctx, const SegArgs& args, const Overflow& ov, unsigned int* spare_list,
+                        Leftover* left, cudaStream_t st) {
     LongLevArgs g{};
     g.a = args.a;
     g.b = args.b;
     g.out = args.out;
     g.dbg = args.dbg;
-    g.list = args.listlong;
-    g.list_count = &ctx.d_ovf->nlong;
     g.cursor = ctx.d_counters;
-    g.huge_list = huge_list;
-    g.huge_count = ctx.d_counters + 1;
     g.cap_a = (int)ov.max_bytes_a + 4;
     g.cap_b = (int)ov.max_bytes_b + 4;
     int cap_pat = g.cap_a < g.cap_b ? g.cap_a : g.cap_b;
@@ -666,28 +670,43 @@ static int run_long_lev(ThreadCtx& ctx, const SegArgs& args, const Overflow& ov,
     while (hs < 2 * cap_pat) hs <<= 1;
     g.hash_size = hs;
     g.w_max = (cap_pat + 63) / 64;
-    g.slab_bytes = long_lev_slab_bytes(g.cap_a, g.cap_b, g.cap_pat, g.hash_size, g.w_max);
-    long long warps = (long long)ctx.sm_count * 8;
-    if ((long long)ov.nlong < warps) warps = ov.nlong;
-    const long long budget = 6ll << 30;
-    if (warps * g.slab_bytes > budget) warps = budget / g.slab_bytes;
-    *n_huge = 0;
-    if (warps < 1) {  // a single slab exceeds the budget: everything goes to the generic kernel
-        *n_huge = ov.nlong;
-        CUDA_TRY(cudaMemcpyAsync(huge_list, args.listlong, 4 * (size_t)ov.nlong, cudaMemcpyDeviceToDevice, st));
-        return STRSIM_OK;
-    }
-    int rc = ws_reserve(ctx.scratch, (size_t)(warps * g.slab_bytes));
-    if (rc) return rc;
-    g.scratch = static_cast<unsigned char*>(ctx.scratch.ptr);
-    g.n_warps = (int)warps;
+    const long long worst_words = (long long)(cap_pat + 1) * g.w_max;
+    const long long budget = 8ll << 30;
+    // tier 0 reads listlong and defers into spare_list (count d_counters[1]);
+    // tier 1 reads spare_list and defers into listlong, free again by then (count d_counters[2])
+    Leftover src;
+    src.list = args.listlong;
+    src.count = &ctx.d_ovf->nlong;
+    src.n = ov.nlong;
     CUDA_TRY(cudaMemsetAsync(ctx.d_counters, 0, 4 * sizeof(unsigned int), st));
-    long_lev_kernel<<<(unsigned)((warps + LONG_WPB - 1) / LONG_WPB), 32 * LONG_WPB, 0, st>>>(g);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(ctx.h_counters, ctx.d_counters, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    *n_huge = ctx.h_counters[1];
+    for (int tier = 0; tier < 2 && src.n > 0; tier++) {
+        long long peq_words = tier == 0 ? (128ll << 10) : worst_words;  // tier 0: 1 MiB of Peq per warp
+        if (peq_words > worst_words) peq_words = worst_words;
+        g.peq_words = peq_words;
+        g.slab_bytes = long_lev_slab_bytes(g.cap_a, g.cap_b, g.hash_size, peq_words);
+        long long warps = (long long)ctx.sm_count * (tier == 0 ? 24 : 8);
+        if ((long long)src.n < warps) warps = src.n;
+        if (warps * g.slab_bytes > budget) warps = budget / g.slab_bytes;
+        if (warps < 1) break;  // not even one slab fits the budget: the generic kernel takes `src`
+        int rc = ws_reserve(ctx.scratch, (size_t)(warps * g.slab_bytes));
+        if (rc) return rc;
+        g.scratch = static_cast<unsigned char*>(ctx.scratch.ptr);
+        g.n_warps = (int)warps;
+        g.list = src.list;
+        g.list_count = src.count;
+        g.huge_list = tier == 0 ? spare_list : args.listlong;
+        g.huge_count = ctx.d_counters + 1 + tier;
+        CUDA_TRY(cudaMemsetAsync(ctx.d_counters, 0, sizeof(unsigned int), st));  // the cursor
+        long_lev_kernel<<<(unsigned)((warps + LONG_WPB - 1) / LONG_WPB), 32 * LONG_WPB, 0, st>>>(g);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(ctx.h_counters, ctx.d_counters, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        src.list = g.huge_list;
+        src.count = g.huge_count;
+        src.n = ctx.h_counters[1 + tier];
+    }
+    *left = src;
     return STRSIM_OK;
 }
 
@@ -733,10 +752,10 @@ static int run_segment(ThreadCtx& ctx, SegArgs args, Alphabet al, int stage32, i
     g_last_overflow[1] += ov.nlong;
     if (ov.nlong > 0) {
         if (MEASURE == LEVENSHTEIN && !force_generic) {
-            unsigned int n_huge = 0;
-            rc = run_long_lev(ctx, args, ov, args.list64, &n_huge, st);  // list64 is free again here
+            Leftover left;
+            rc = run_long_lev(ctx, args, ov, args.list64, &left, st);  // list64 is free again here
             if (rc) return rc;
-            if (n_huge > 0) rc = run_generic<MEASURE>(ctx, args, ov, st, args.list64, ctx.d_counters + 1, n_huge);
+            if (left.n > 0) rc = run_generic<MEASURE>(ctx, args, ov, st, left.list, left.count, left.n);
         } else {
             rc = run_generic<MEASURE>(ctx, args, ov, st);
         }

@@ -43,6 +43,8 @@ struct LongLevArgs {
     int cap_pat;       // min(cap_a, cap_b, LONG_PAT_MAX)
     int hash_size;     // power of two >= 2 * cap_pat (slab capacity; each pair uses what it needs)
     int w_max;         // ceil(cap_pat / 64)
+    long long peq_words;  // capacity of one slab's Peq area in 64-bit words; a pair that needs more is
+                          // deferred to `huge_list` (the host relaunches it with worst-case slabs)
 };
 
 struct LongLevSlab {
@@ -54,8 +56,7 @@ struct LongLevSlab {
     unsigned long long* peq;
 };
 
-__host__ __device__ inline long long long_lev_slab_bytes(int cap_a, int cap_b, int cap_pat, int hash_size,
-                                                         int w_max) {
+__host__ __device__ inline long long long_lev_slab_bytes(int cap_a, int cap_b, int hash_size, long long peq_words) {
     long long b = 0;
     b += 4ll * cap_a;
     b += 4ll * cap_b;
@@ -64,7 +65,7 @@ __host__ __device__ inline long long long_lev_slab_bytes(int cap_a, int cap_b, i
     b += 4ll * hash_size;
     b += 2ll * hash_size;
     b = (b + 15) & ~15ll;
-    b += 8ll * (cap_pat + 1) * w_max;
+    b += 8ll * peq_words;
     return (b + 255) & ~255ll;
 }
 
@@ -125,47 +126,54 @@ __device__ __forceinline__ uint32_t long_lookup(const LongLevSlab& s, uint32_t h
 
 template <int K>
 __device__ inline int long_wavefront(const LongLevSlab& s, int m, int n, int W, int L, int lane) {
-    uint64_t Pv[K], Mv[K], eq_cur[K], eq_nxt[K];
+    uint64_t Pv[K], Mv[K], eq0[K], eq1[K], eq2[K];
 #pragma unroll
     for (int k = 0; k < K; k++) {
         Pv[k] = ~0ull;
         Mv[k] = 0ull;
-        eq_cur[k] = 0ull;
-        eq_nxt[k] = 0ull;
+        eq0[k] = eq1[k] = eq2[k] = 0ull;
     }
     const int blk0 = lane * K;
     const bool lane_on = lane < L;
-    uint32_t hp_prev = 0, hm_prev = 0;
-    // prime the pipeline: Eq words of this lane's first column (j = 0, reached at step s = lane)
+    // Software pipeline, two columns deep: while column j is computed, the Eq words of column j+2 are
+    // in flight (their row index tid[j+2] was fetched one step earlier) and those of j+1 have landed.
+    uint32_t t2 = 0, t3 = 0;
     if (lane_on) {
-        const unsigned long long* row = s.peq + (size_t)s.tid[0] * W + blk0;
+        const unsigned long long* r0 = s.peq + (size_t)s.tid[0] * W + blk0;
+        const unsigned long long* r1 = s.peq + (size_t)s.tid[n > 1 ? 1 : 0] * W + blk0;
 #pragma unroll
         for (int k = 0; k < K; k++)
-            if (blk0 + k < W) eq_cur[k] = row[k];
+            if (blk0 + k < W) {
+                eq0[k] = r0[k];
+                eq1[k] = r1[k];
+            }
+        t2 = s.tid[n > 2 ? 2 : 0];
     }
+    uint32_t carry_prev = 0;  // bit 0: hp, bit 1: hm of this lane's last block in the previous step
     const int steps = n + L - 1;
     for (int st = 0; st < steps; st++) {
-        uint32_t hp = __shfl_up_sync(0xFFFFFFFFu, hp_prev, 1);
-        uint32_t hm = __shfl_up_sync(0xFFFFFFFFu, hm_prev, 1);
-        if (lane == 0) {
-            hp = 1u;
-            hm = 0u;
-        }
+        uint32_t carry = __shfl_up_sync(0xFFFFFFFFu, carry_prev, 1);
+        if (lane == 0) carry = 1u;  // D[0][j] - D[0][j-1] = +1
         const int j = st - lane;
         if (lane_on && j >= 0 && j < n) {
-            if (j + 1 < n) {  // prefetch the next column's Eq words
-                const unsigned long long* row = s.peq + (size_t)s.tid[j + 1] * W + blk0;
+            if (j + 3 < n) t3 = s.tid[j + 3];
+            if (j + 2 < n) {
+                const unsigned long long* row = s.peq + (size_t)t2 * W + blk0;
 #pragma unroll
                 for (int k = 0; k < K; k++)
-                    if (blk0 + k < W) eq_nxt[k] = row[k];
+                    if (blk0 + k < W) eq2[k] = row[k];
             }
+            uint32_t hp = carry & 1u, hm = carry >> 1;
 #pragma unroll
             for (int k = 0; k < K; k++)
-                if (blk0 + k < W) myers_block(Pv[k], Mv[k], eq_cur[k], hp, hm);
-            hp_prev = hp;
-            hm_prev = hm;
+                if (blk0 + k < W) myers_block(Pv[k], Mv[k], eq0[k], hp, hm);
+            carry_prev = hp | (hm << 1);
 #pragma unroll
-            for (int k = 0; k < K; k++) eq_cur[k] = eq_nxt[k];
+            for (int k = 0; k < K; k++) {
+                eq0[k] = eq1[k];
+                eq1[k] = eq2[k];
+            }
+            t2 = t3;
         }
     }
     int score = 0;
@@ -251,6 +259,10 @@ __global__ void __launch_bounds__(32 * LONG_WPB) long_lev_kernel(const LongLevAr
                 for (int j = lane; j < n; j += 32) s.tid[j] = (uint16_t)long_lookup(s, hmask, hshift, T[j], distinct);
                 // 4. Peq[id][block]
                 const size_t words = (size_t)(distinct + 1u) * W;
+                if ((long long)words > g.peq_words) {  // needs a bigger slab: second launch
+                    if (lane == 0) g.huge_list[atomicAdd(g.huge_count, 1u)] = (unsigned int)row;
+                    continue;
+                }
                 for (size_t i = lane; i < words; i += 32) s.peq[i] = 0ull;
                 __syncwarp();
                 for (int i = lane; i < m; i += 32) {

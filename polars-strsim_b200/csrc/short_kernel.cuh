@@ -229,8 +229,9 @@ __device__ __forceinline__ void load_string_reg(const uint4& v, const unsigned c
 }
 
 // Settling byte-equal pairs before the sort frees their lanes but costs every row a prefix compare;
-// measured on C2 (20 % equal pairs) it LOSES 8 % because the compute phase is bound by the latency of
-// its rounds, not by the number of active lanes.  Kept for data sets dominated by equal pairs.
+// measured on C2 (20 % equal pairs) it LOSES 5-8 % (table path: latency-bound rounds; register path:
+// the extra prefix reads and compares cost more ALU work than the freed lanes give back).  Kept for
+// data sets dominated by equal pairs.
 constexpr bool PREFILTER_EQUAL = false;
 
 // first four bytes of an out-of-line string (its view's prefix word was replaced by the stage offset)

@@ -343,3 +343,48 @@ def test_polars_plugin_symbols_end_to_end(native, oracle):
     assert not ret.private_data
     L._polars_plugin_get_last_error_message.restype = ctypes.c_char_p
     assert b"same length" in L._polars_plugin_get_last_error_message()
+
+
+@pytest.mark.parametrize("alphabet", ["abcdefghijklmnopqrstuvwxyz", "ABCDEFxyz_`{|", "aB-c'D 0129.~\x01\x7f", "MiXeD case"])
+def test_ascii_alphabet_blocks(native, oracle, alphabet):
+    """ASCII columns whose bytes fit one 32- or 64-code-point block, or need all 7 bits: the
+    5/6/7-plane instantiations of the register-resident path (row_ascii_reg.cuh)."""
+    rng = random.Random(hash(alphabet) & 0xFFFF)
+    a, b = [], []
+    for _ in range(20000):
+        x = "".join(rng.choice(alphabet) for _ in range(rng.randint(0, 32)))
+        y = "".join(rng.choice(alphabet) for _ in range(rng.randint(0, 32))) if rng.random() < 0.4 else x
+        if y is x and x:
+            y = list(x)
+            for _ in range(rng.randint(0, 3)):
+                p = rng.randrange(len(y))
+                y[p] = rng.choice(alphabet)
+            if rng.random() < 0.5:
+                y = y[1:]
+            y = "".join(y)
+        a.append(x)
+        b.append(y)
+    for measure in oracle.MEASURES:
+        check(native, oracle, measure, a, b)
+
+
+def test_long_levenshtein_tiers(native, oracle):
+    """Pairs whose Peq does not fit the first-tier slab (many distinct codepoints x many blocks) and a
+    pattern above 8192 codepoints (generic kernel) still give the exact distance."""
+    rng = random.Random(2718)
+    cjk = [chr(c) for c in range(0x4E00, 0x4E00 + 3000)]
+    a, b = [], []
+    for n in (3000, 5000):  # ~n distinct codepoints x n/64 blocks  >> 128 Ki words
+        x = [rng.choice(cjk) for _ in range(n)]
+        y = list(x)
+        for _ in range(n // 20):
+            y[rng.randrange(n)] = rng.choice(cjk)
+        a.append("".join(x))
+        b.append("".join(y[: n - 7]))
+    x = "".join(rng.choice("abcdefgh") for _ in range(9000))
+    y = "".join(rng.choice("abcdefgh") for _ in range(8500))
+    a.append(x)
+    b.append(y)
+    a += ["short", "x" * 70]
+    b += ["y" * 100, "x" * 69 + "z"]
+    check(native, oracle, "levenshtein", a, b)
