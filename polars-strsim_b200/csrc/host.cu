@@ -684,7 +684,12 @@ static int run_long_lev(ThreadCtx& ctx, const SegArgs& args, const Overflow& ov,
         if (peq_words > worst_words) peq_words = worst_words;
         g.peq_words = peq_words;
         g.slab_bytes = long_lev_slab_bytes(g.cap_a, g.cap_b, g.hash_size, peq_words);
-        long long warps = (long long)ctx.sm_count * (tier == 0 ? 24 : 8);
+        static const int tier0_warps = [] {
+            const char* e = getenv("STRSIM_B200_LONG_WARPS");  // tuning knob: resident warps per SM
+            const int v = e && *e ? atoi(e) : 0;
+            return v > 0 ? v : 32;
+        }();
+        long long warps = (long long)ctx.sm_count * (tier == 0 ? tier0_warps : 8);
         if ((long long)src.n < warps) warps = src.n;
         if (warps * g.slab_bytes > budget) warps = budget / g.slab_bytes;
         if (warps < 1) break;  // not even one slab fits the budget: the generic kernel takes `src`

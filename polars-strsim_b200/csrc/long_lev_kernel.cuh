@@ -185,7 +185,7 @@ __device__ inline int long_wavefront(const LongLevSlab& s, int m, int n, int W, 
     return n + score;
 }
 
-__global__ void __launch_bounds__(32 * LONG_WPB) long_lev_kernel(const LongLevArgs g) {
+__global__ void __launch_bounds__(32 * LONG_WPB, 8) long_lev_kernel(const LongLevArgs g) {
     const int lane = threadIdx.x & 31;
     const int warp = blockIdx.x * LONG_WPB + (threadIdx.x >> 5);
     if (warp >= g.n_warps) return;
