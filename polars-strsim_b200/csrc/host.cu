@@ -473,10 +473,11 @@ static int upload_column(ThreadCtx& ctx, const strsim_view_chunk* chunks, size_t
 }
 
 // ---- kernel launch helpers -----------------------------------------------------------------------------
-template <class M, int MEASURE, int TPB, int RPT, bool GATHER, int T, bool ASCII_ONLY, bool REG = false>
+template <class M, int MEASURE, int TPB, int RPT, bool GATHER, int T, bool ASCII_ONLY, bool REG = false,
+          bool UREG = false>
 static int launch_short(ThreadCtx& ctx, SegArgs args, long long n_upper, cudaStream_t st) {
-    using L = ShortLayout<M, TPB, RPT, T, REG>;
-    auto kern = short_kernel<M, MEASURE, TPB, RPT, GATHER, T, ASCII_ONLY, REG>;
+    using L = ShortLayout<M, TPB, RPT, T, REG, UREG>;
+    auto kern = short_kernel<M, MEASURE, TPB, RPT, GATHER, T, ASCII_ONLY, REG, UREG>;
     if (args.stage_bytes < 0) {
         // -stage_bytes = mean out-of-line bytes per row (x16) of the heavier column: size the stage
         // area for this tile shape with 25 % headroom (rows that still do not fit take the long path)
@@ -590,7 +591,10 @@ static int launch_fused(ThreadCtx& ctx, Alphabet al, const SegArgs& args, long l
             case ALPHA_ASCII128:
                 return launch_short<uint32_t, MEASURE, 256, 4, false, 128, true, true>(ctx, args, rows, st);
             default:
-                break;
+                // any script: register-compare path (row_unicode_reg.cuh), no table in shared memory
+                if (cfg == 1) return launch_short<uint32_t, MEASURE, 128, 4, false, 128, false, false, true>(ctx, args, rows, st);
+                if (cfg == 2) return launch_short<uint32_t, MEASURE, 128, 2, false, 128, false, false, true>(ctx, args, rows, st);
+                return launch_short<uint32_t, MEASURE, 256, 4, false, 128, false, false, true>(ctx, args, rows, st);
         }
     }
     switch (al) {

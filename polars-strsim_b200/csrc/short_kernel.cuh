@@ -24,6 +24,7 @@
 
 #include "row_ascii_reg.cuh"
 #include "row_short.cuh"
+#include "row_unicode_reg.cuh"
 
 namespace strsim {
 
@@ -138,7 +139,8 @@ struct DevStore {
 };
 
 // REG: register-resident ASCII path (row_ascii_reg.cuh) -- no table, no slabs in shared memory
-template <class M, int TPB, int RPT, int T, bool REG = false>
+// UREG: register-compare path for any script (row_unicode_reg.cuh) -- no table, slabs only
+template <class M, int TPB, int RPT, int T, bool REG = false, bool UREG = false>
 struct ShortLayout {
     static constexpr int CAP = (int)sizeof(M) * 8;
     static constexpr int WORDS = CAP / 4;
@@ -148,7 +150,7 @@ struct ShortLayout {
     static constexpr size_t off_sva = 0;
     static constexpr size_t off_svb = off_sva + sizeof(uint4) * TILE;
     static constexpr size_t off_tab = off_svb + sizeof(uint4) * TILE;
-    static constexpr size_t off_slab_a = off_tab + (REG ? 0 : sizeof(M) * T * TPB);
+    static constexpr size_t off_slab_a = off_tab + ((REG || UREG) ? 0 : sizeof(M) * T * TPB);
     static constexpr size_t off_slab_b = off_slab_a + (REG ? 0 : 4 * WORDS * TPB);
     static constexpr size_t off_hist = off_slab_b + (REG ? 0 : 4 * WORDS * TPB);
     static constexpr size_t off_red = off_hist + 4 * ((NB + 3) & ~3);
@@ -266,14 +268,20 @@ __device__ __forceinline__ bool staged_equal(const uint4& va, const uint4& vb, c
     return true;
 }
 
-template <class M, int MEASURE, int TPB, int RPT, bool GATHER, int T, bool ASCII_ONLY, bool REG = false>
+struct WarpMaxDev {  // maximum over the 32 lanes of the warp (all lanes must call it)
+    __device__ __forceinline__ int operator()(int v) const { return __reduce_max_sync(0xFFFFFFFFu, v); }
+};
+
+template <class M, int MEASURE, int TPB, int RPT, bool GATHER, int T, bool ASCII_ONLY, bool REG = false,
+          bool UREG = false>
 __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
-    static_assert(ASCII_ONLY || T >= DevStore<M, TPB, T>::HASH_ENTRIES,
+    static_assert(ASCII_ONLY || UREG || T >= DevStore<M, TPB, T>::HASH_ENTRIES,
                   "the Unicode path keeps its hash slots in the table memory");
+    static_assert(!UREG || (!ASCII_ONLY && !REG && sizeof(M) == 4), "register-compare path: general u32 kernel");
     static_assert(!REG || (ASCII_ONLY && sizeof(M) == 4 && (T == 32 || T == 64 || T == 128)),
                   "the register path serves ASCII-only columns with strings of at most 32 bytes");
     constexpr int NBITS = T == 32 ? 5 : T == 64 ? 6 : 7;
-    using L = ShortLayout<M, TPB, RPT, T, REG>;
+    using L = ShortLayout<M, TPB, RPT, T, REG, UREG>;
     constexpr int CAP = L::CAP;
     constexpr int WORDS = L::WORDS;
     constexpr int TILE = L::TILE;
@@ -300,7 +308,7 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
 
     // one-time: zero the position-mask tables (row_short keeps them zero), init the mbarrier
     {
-        if (!REG) {
+        if (!REG && !UREG) {
             uint4* t4 = reinterpret_cast<uint4*>(tab);
             constexpr int N4 = (int)(sizeof(M) * T * TPB / 16);
             for (int i = tid; i < N4; i += TPB) t4[i] = make_uint4(0, 0, 0, 0);
@@ -537,7 +545,7 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
                 continue;
             }
             uint32_t hi_bits = 0;  // conservative (unmasked) non-ASCII test; exact test in step 4
-            if (!ASCII_ONLY) {
+            if (!ASCII_ONLY && !UREG) {
                 if (va.x <= 12u) {
                     hi_bits |= va.y | va.z | va.w;
                 } else {
@@ -595,6 +603,46 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
 #pragma unroll 1
         for (int k = 0; k < RPT; k++) {
             const int p = k * TPB + ((k & 1) ? (TPB - 1 - tid) : tid);  // snake order balances warps
+            if (UREG) {
+                // every lane of the warp runs the row function (idle lanes on an empty, "equal" pair):
+                // the compare loops are bounded by a warp-wide maximum
+                const bool has = p < n_active;
+                const int i = has ? (int)perm[p] : 0;
+                int na = 0, nb = 0;
+                bool equal = true;
+                if (has) {
+                    const uint4 va = sva[i], vb = svb[i];
+                    na = (int)va.x;
+                    nb = (int)vb.x;
+                    load_string<WORDS, TPB>(va, stage_a, store.wa_);
+                    load_string<WORDS, TPB>(vb, stage_b, store.wb_);
+                    equal = na == nb;
+                    if (equal) {
+                        const int nw = (na + 3) >> 2;
+                        uint32_t diff = 0;
+                        for (int w = 0; w < nw; w++) diff |= store.wa(w) ^ store.wb(w);
+                        equal = diff == 0;
+                    }
+                }
+                PairInts ints;
+                WarpMaxDev wm;
+                const double v = row_unicode_reg<MEASURE>(store, na, nb, equal, wm, ints);
+                if (has) {
+                    const long long idx = tile0 + i;
+                    const long long row = GATHER ? (long long)s.list[idx] : idx;
+                    s.out[row] = v;
+                    if (s.dbg) {
+                        int* d = s.dbg + row * 6;
+                        d[0] = ints.flag;
+                        d[1] = ints.la;
+                        d[2] = ints.lb;
+                        d[3] = ints.x0;
+                        d[4] = ints.x1;
+                        d[5] = ints.x2;
+                    }
+                }
+                continue;
+            }
             if (p >= n_active) continue;
             const int i = perm[p];
             const uint4 va = sva[i], vb = svb[i];

@@ -128,3 +128,33 @@ extern "C" int algos_batch_reg(int measure, int nbits, int64_t n, const uint8_t*
     }
     return 0;
 }
+
+// register-compare path for any script (row_unicode_reg.cuh)
+#include "row_unicode_reg.cuh"
+extern "C" int algos_batch_ureg(int measure, int64_t n, const uint8_t* ad, const int64_t* ao, const uint8_t* bd,
+                                const int64_t* bo, int* ints, double* values) {
+    static thread_local HostStore<uint32_t> s;
+    for (int64_t r = 0; r < n; r++) {
+        const int na = (int)(ao[r + 1] - ao[r]), nb = (int)(bo[r + 1] - bo[r]);
+        if (na > 32 || nb > 32) return -2;
+        std::memset(s.a_words, 0, sizeof s.a_words);
+        std::memset(s.b_words, 0, sizeof s.b_words);
+        std::memcpy(s.a_words, ad + ao[r], na);
+        std::memcpy(s.b_words, bd + bo[r], nb);
+        const bool equal = na == nb && std::memcmp(ad + ao[r], bd + bo[r], na) == 0;
+        PairInts pi;
+        HostWarpMax wm;
+        double v;
+        switch (measure) {
+            case 0: v = row_unicode_reg<0>(s, na, nb, equal, wm, pi); break;
+            case 1: v = row_unicode_reg<1>(s, na, nb, equal, wm, pi); break;
+            case 2: v = row_unicode_reg<2>(s, na, nb, equal, wm, pi); break;
+            case 3: v = row_unicode_reg<3>(s, na, nb, equal, wm, pi); break;
+            default: v = row_unicode_reg<4>(s, na, nb, equal, wm, pi); break;
+        }
+        values[r] = v;
+        int* o = ints + 6 * r;
+        o[0] = pi.flag; o[1] = pi.la; o[2] = pi.lb; o[3] = pi.x0; o[4] = pi.x1; o[5] = pi.x2;
+    }
+    return 0;
+}

@@ -161,3 +161,37 @@ def test_register_resident_ascii_path(algos, oracle, nbits, alphabet):
         bad = np.nonzero(vals.view(np.uint64) != ref.view(np.uint64))[0]
         assert bad.size == 0, (measure, a[bad[0]], b[bad[0]], vals[bad[0]], ref[bad[0]])
         assert (ints == ref_ints).all(), measure
+
+
+def test_register_compare_unicode_path(algos, oracle):
+    """row_unicode_reg.cuh: tabled string decoded into registers, position masks by compares."""
+    from oracle.oracle import _pack, MEASURE_ID
+
+    algos.algos_batch_ureg.restype = ctypes.c_int
+    algos.algos_batch_ureg.argtypes = [ctypes.c_int, ctypes.c_int64] + [ctypes.c_void_p] * 6
+    rng = random.Random(777)
+    a, b = [], []
+    while len(a) < 40000:
+        x, y = rand_pair(rng, 32)
+        if len(x.encode()) <= 32 and len(y.encode()) <= 32:
+            a.append(x)
+            b.append(y)
+    for ch in ("é", "日", "\U0001f600", "a"):
+        w = len(ch.encode())
+        for la in (0, 1, 2, 32 // w):
+            for lb in (0, 1, 32 // w):
+                a += [ch * la, ch * la]
+                b += [ch * lb, ("z" * lb)]
+    ad, ao, _ = _pack(a)
+    bd, bo, _ = _pack(b)
+    for measure in oracle.MEASURES:
+        ints = np.zeros((len(a), 6), dtype=np.int32)
+        vals = np.zeros(len(a), dtype=np.float64)
+        rc = algos.algos_batch_ureg(MEASURE_ID[measure], len(a), ad.ctypes.data, ao.ctypes.data, bd.ctypes.data,
+                                    bo.ctypes.data, ints.ctypes.data, vals.ctypes.data)
+        assert rc == 0
+        ref, _, ref_ints = oracle.batch(measure, a, b)
+        bad = np.nonzero(vals.view(np.uint64) != ref.view(np.uint64))[0]
+        assert bad.size == 0, (measure, a[bad[0]], b[bad[0]], vals[bad[0]], ref[bad[0]])
+        ib = np.nonzero((ints != ref_ints).any(axis=1))[0]
+        assert ib.size == 0, (measure, a[ib[0]], b[ib[0]], ints[ib[0]], ref_ints[ib[0]])
