@@ -18,15 +18,28 @@ namespace strsim {
 constexpr int UREG_MAX = 32;
 constexpr uint32_t UREG_NONE = 0xFFFFFFFFu;  // no UTF-8 byte is 0xFF: never equals a key
 
+// eq |= bit when x == c: one compare and one predicated OR (the compiler's SEL + add tree costs three)
+SS_HD void or_if_equal(uint32_t& eq, uint32_t x, uint32_t c, uint32_t bit) {
+#if defined(__CUDA_ARCH__)
+    asm("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(eq) : "r"(x), "r"(c), "r"(bit));
+#else
+    if (x == c) eq |= bit;
+#endif
+}
+
 struct CmpTab {
     uint32_t P[UREG_MAX];
     int bound;  // compares run over [0, bound): >= the pattern length, uniform across the warp
     SS_HD uint32_t operator()(uint32_t c) const {
         uint32_t eq = 0u;
+        // groups of four positions; entries past the pattern hold UREG_NONE, so a group may overrun it
 #pragma unroll
-        for (int i = 0; i < UREG_MAX; i++) {
-            if (i >= bound) break;
-            eq |= (uint32_t)(P[i] == c) << i;
+        for (int g = 0; g < UREG_MAX; g += 4) {
+            if (g >= bound) break;
+            or_if_equal(eq, P[g], c, 1u << g);
+            or_if_equal(eq, P[g + 1], c, 2u << g);
+            or_if_equal(eq, P[g + 2], c, 4u << g);
+            or_if_equal(eq, P[g + 3], c, 8u << g);
         }
         return eq;
     }

@@ -230,6 +230,29 @@ __device__ __forceinline__ void load_string_reg(const uint4& v, const unsigned c
     }
 }
 
+// number of characters (bytes that are not UTF-8 continuation bytes) of a staged string
+__device__ __forceinline__ int staged_char_count(const uint4& v, const unsigned char* stage) {
+    const int len = (int)v.x;
+    int cont = 0;
+    if (len <= 12) {
+        const uint32_t w0 = v.y & byte_mask(len), w1 = v.z & byte_mask(len - 4 < 0 ? 0 : len - 4),
+                       w2 = v.w & byte_mask(len - 8 < 0 ? 0 : len - 8);
+        cont = __popc(((w0 >> 7) & ~(w0 >> 6)) & 0x01010101u) + __popc(((w1 >> 7) & ~(w1 >> 6)) & 0x01010101u) +
+               __popc(((w2 >> 7) & ~(w2 >> 6)) & 0x01010101u);
+    } else {
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(stage) + (v.y >> 2);
+        const int head = (int)(v.y & 3u);               // bytes of the first word before the string
+        const int nwords = (head + len + 3) >> 2;
+        for (int w = 0; w < nwords; w++) {
+            uint32_t x = p[w];
+            if (w == 0) x &= ~byte_mask(head);
+            if (w == nwords - 1) x &= byte_mask(head + len - 4 * w);
+            cont += __popc(((x >> 7) & ~(x >> 6)) & 0x01010101u);
+        }
+    }
+    return len - cont;
+}
+
 // Settling byte-equal pairs before the sort frees their lanes but costs every row a prefix compare;
 // measured on C2 (20 % equal pairs) it LOSES 5-8 % (table path: latency-bound rounds; register path:
 // the extra prefix reads and compares cost more ALU work than the freed lanes give back).  Kept for
@@ -561,7 +584,14 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
                     for (int w = 0; w < nwords; w++) hi_bits |= p[w];
                 }
             }
-            const uint32_t mx = va.x > vb.x ? va.x : vb.x;
+            uint32_t mx = va.x > vb.x ? va.x : vb.x;
+            if (UREG) {
+                // the register-compare path costs (streamed characters) x (tabled characters): bucket by
+                // CHARACTER counts so that e.g. 6-character CJK rows do not share a warp with 18-character
+                // Latin rows of the same byte length
+                const int ca = staged_char_count(va, stage_a), cb = staged_char_count(vb, stage_b);
+                mx = (uint32_t)(ca > cb ? ca : cb);
+            }
             key[k] = 1u + mx + ((hi_bits & 0x80808080u) ? (uint32_t)(CAP + 1) : 0u);
             rank[k] = atomicAdd(&hist[key[k]], 1u);
         }
