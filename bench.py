@@ -329,14 +329,22 @@ def main():
     peak, peak_src = peaks()
     dominant = max(per_measure_ms, key=per_measure_ms.get)
     dom_s = per_measure_ms[dominant] * 1e-3
-    traffic = None
+    traffic = warp_inst = None
     tp = ROOT / "profiles" / "traffic.json"
-    if tp.exists():
-        traffic = json.loads(tp.read_text()).get(args.workload, {}).get(dominant)
+    if tp.exists() and n == wl["rows"]:  # the ncu capture was taken at the workload's full size
+        prof = json.loads(tp.read_text())
+        traffic = prof.get(args.workload, {}).get(dominant)
+        warp_inst = prof.get(args.workload + "_warp_instructions", {}).get(dominant)
     roofline = {"bound": "hbm", "kernel": f"short_kernel<{dominant}>", "achieved": alg_bytes / dom_s / 1e9,
                 "peak": peak, "unit": "GB/s", "frac": alg_bytes / dom_s / 1e9 / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "algorithmic_bytes_per_pair": alg_bytes / n, "launch_ms": per_measure_ms[dominant]}
+    if warp_inst and clocks and clocks.get("sm_mhz"):
+        # what actually bounds the kernel (ncu: math-pipe throttle): issue rate against 4 warp
+        # instructions / cycle / SM, of which the integer ALU pipe sustains about 2
+        ipc = warp_inst / (148 * dom_s * clocks["sm_mhz"] * 1e6)
+        roofline["issue"] = {"warp_instructions_per_launch": warp_inst, "ipc_per_sm": ipc, "ipc_peak": 4.0,
+                             "note": "SM integer/ALU pipe bound (LOP3/PRMT/SHF at 2 per cycle per SM), not HBM"}
     per_measure = {m: {"ms": ms, "pairs_per_s": n / (ms * 1e-3), "gbps": alg_bytes / (ms * 1e-3) / 1e9,
                        "hbm_frac": alg_bytes / (ms * 1e-3) / 1e9 / peak} for m, ms in per_measure_ms.items()}
     line = {

@@ -49,6 +49,7 @@ def main():
              "Numbers under the profiler are cold-cache and serialised: use them for shares and counters,",
              "not as bench values (bench.py times with CUDA events outside the profiler).", ""]
     traffic = {}
+    insts = {}
     for r in rows[2:]:
         name = r[ix["Kernel Name"]]
         lines.append(f"## `{name}`")
@@ -64,10 +65,12 @@ def main():
             t = to_bytes(r[ix["dram__bytes_read.sum"]], units[ix["dram__bytes_read.sum"]]) + \
                 to_bytes(r[ix["dram__bytes_write.sum"]], units[ix["dram__bytes_write.sum"]])
             traffic[MEASURES[int(m.group(1))]] = t
+            insts[MEASURES[int(m.group(1))]] = float(r[ix["smsp__inst_executed.sum"]].replace(",", ""))
     Path(out_md).write_text("\n".join(lines) + "\n")
     if traffic_path and traffic:
         cur = json.loads(traffic_path.read_text()) if traffic_path.exists() else {}
         cur.setdefault(workload, {}).update(traffic)
+        cur.setdefault(workload + "_warp_instructions", {}).update(insts)
         cur["_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch of short_kernel<measure>, "
                         "from one ncu --set full capture of `python bench.py --workload <W> --steps 1 --warmup 3`")
         traffic_path.write_text(json.dumps(cur, indent=1) + "\n")
