@@ -3,11 +3,13 @@
 
 A step = one pass of ALL FIVE measures (levenshtein, jaro, jaro_winkler, jaccard, sorensen_dice)
 over one batch of synthetic pairs (default: BASELINE config C2, 10M ASCII name pairs of length
-4..24 per GPU, seeds in SURVEY.md 8(d)).  `value` counts pair evaluations (rows x 5) per second
-with the two columns already resident in HBM; `e2e` is the same work through the host-buffer C ABI
-call (`strsim_b200_compute_host_multi`): pinned host memory in, ONE H2D upload of the step's two
-columns, the kernels of every measure, and the D2H of every measure's results inside the timed
-region.
+4..24 per GPU, seeds in SURVEY.md 8(d)), evaluated by ONE fused kernel launch
+(`strsim_b200_compute_device_multi`: views and bytes read once, one position mask per character
+feeding all measures).  `value` counts pair evaluations (rows x 5) per second with the two columns
+already resident in HBM; `per_measure` times each measure's own single-measure kernel the same way
+(the BASELINE metric is quoted per measure); `e2e` is the step through the host-buffer C ABI call
+(`strsim_b200_compute_host_multi`): pinned host memory in, ONE H2D upload of the step's two
+columns, the fused kernel, and the D2H of every measure's results inside the timed region.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2|C3|C4] [--rows R]
     python bench.py --impl reference ...     # the reference's CPU algorithm (oracle port) on host cores
@@ -189,6 +191,7 @@ def main():
     ap.add_argument("--rows", type=int, default=None, help="rows per GPU (default: the workload's size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fuse", action="store_true", help="step = one single-measure launch per measure")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.rows is None:
@@ -222,18 +225,23 @@ def main():
     alg_bytes = workloads.algorithmic_bytes(A, B)  # per launch of one measure
     colA, colB = _native.DeviceColumn(A), _native.DeviceColumn(B)
     has_nulls = A.null_count + B.null_count > 0
-    out = torch.empty(n, dtype=torch.float64, device="cuda")
+    fused = len(measures) > 1 and not args.no_fuse
+    if args.no_fuse:
+        os.environ["STRSIM_B200_NO_FUSE"] = "1"  # read once by the library: the e2e call follows suit
+    outs = [torch.empty(n, dtype=torch.float64, device="cuda") for _ in measures]
+    out = outs[-1]
+    out_ptrs = [o.data_ptr() for o in outs]
     val = torch.zeros((n + 31) // 32, dtype=torch.int32, device="cuda") if has_nulls else None
+    vptr = val.data_ptr() if val is not None else 0
     stream = torch.cuda.current_stream()
     sptr = stream.cuda_stream
 
-    def step(events=None):
-        for i, m in enumerate(measures):
-            if events is not None:
-                events[i][0].record(stream)
-            _native.compute_device(m, colA, colB, out.data_ptr(), val.data_ptr() if val is not None else 0, 0, sptr)
-            if events is not None:
-                events[i][1].record(stream)
+    def step():
+        if fused:
+            _native.compute_device_multi(measures, colA, colB, out_ptrs, vptr, None, sptr)
+        else:
+            for i, m in enumerate(measures):
+                _native.compute_device(m, colA, colB, out_ptrs[i], vptr, 0, sptr)
 
     def barrier():
         torch.cuda.synchronize()
@@ -248,12 +256,10 @@ def main():
     if rank == 0:
         sampler.start()
     launches0 = _native.kernel_launches()
-    per_events = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-                   for _ in measures] for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for k in range(args.steps):
-        step(per_events[k])
+        step()
     e1.record(stream)
     barrier()
     launches = _native.kernel_launches() - launches0
@@ -263,8 +269,25 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms = float(t.item())
-    clocks = sampler.stop() if rank == 0 else None
     checksum = float(out.sum().item())
+    checksums = {m: float(o.sum().item()) for m, o in zip(measures, outs)}
+
+    # ---- each measure's own kernel (single-measure launches), same rules: CUDA events on the launching
+    # stream, averaged over the steps; the clock sampler keeps running
+    per_events = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                   for _ in measures] for _ in range(args.steps)]
+    scratch = torch.empty(n, dtype=torch.float64, device="cuda")
+    for i, m in enumerate(measures):
+        _native.compute_device(m, colA, colB, scratch.data_ptr(), vptr, 0, sptr)
+    for k in range(args.steps):
+        for i, m in enumerate(measures):
+            per_events[k][i][0].record(stream)
+            _native.compute_device(m, colA, colB, scratch.data_ptr(), vptr, 0, sptr)
+            per_events[k][i][1].record(stream)
+    barrier()
+    fused_matches_single = bool(abs(float(scratch.sum().item()) - checksum) == 0.0)
+    del scratch
+    clocks = sampler.stop() if rank == 0 else None
     cells = None
     if wl["config"] == 4:
         # long-string Levenshtein work unit: DP cells = sum la*lb over pairs with a != b,
@@ -318,7 +341,7 @@ def main():
                "d2h_bytes_per_step": (8 * n + ((n + 7) // 8 if has_nulls else 0)) * len(measures),
                "ms_per_step": dt / e2e_steps * 1e3,
                "api": "strsim_b200_compute_host_multi: one upload of the step's two columns, all measures of the "
-                      "step, results downloaded (pinned host buffers)",
+                      "step (one fused pass per row slice), results downloaded (pinned host buffers)",
                "checksum_matches_device": bool(abs(float(host_out.sum().item()) - checksum) < 1e-6 * max(1.0, abs(checksum)))}
 
     if rank != 0:
@@ -327,18 +350,25 @@ def main():
         return
 
     peak, peak_src = peaks()
-    dominant = max(per_measure_ms, key=per_measure_ms.get)
-    dom_s = per_measure_ms[dominant] * 1e-3
+    if fused:
+        # the step IS one launch of the fused kernel: views + payload read once, one f64 per measure written
+        dominant, dom_key = "fused:" + "+".join(measures), "fused"
+        dom_s = elapsed_ms / args.steps * 1e-3
+        dom_bytes = alg_bytes + 8 * n * (len(measures) - 1)
+    else:
+        dominant = dom_key = max(per_measure_ms, key=per_measure_ms.get)
+        dom_s = per_measure_ms[dominant] * 1e-3
+        dom_bytes = alg_bytes
     traffic = warp_inst = None
     tp = ROOT / "profiles" / "traffic.json"
     if tp.exists() and n == wl["rows"]:  # the ncu capture was taken at the workload's full size
         prof = json.loads(tp.read_text())
-        traffic = prof.get(args.workload, {}).get(dominant)
-        warp_inst = prof.get(args.workload + "_warp_instructions", {}).get(dominant)
-    roofline = {"bound": "hbm", "kernel": f"short_kernel<{dominant}>", "achieved": alg_bytes / dom_s / 1e9,
-                "peak": peak, "unit": "GB/s", "frac": alg_bytes / dom_s / 1e9 / peak, "traffic": traffic,
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                "algorithmic_bytes_per_pair": alg_bytes / n, "launch_ms": per_measure_ms[dominant]}
+        traffic = prof.get(args.workload, {}).get(dom_key)
+        warp_inst = prof.get(args.workload + "_warp_instructions", {}).get(dom_key)
+    roofline = {"bound": "hbm", "kernel": f"short_kernel<{dominant}>", "achieved": dom_bytes / dom_s / 1e9,
+                "peak": peak, "unit": "GB/s", "frac": dom_bytes / dom_s / 1e9 / peak, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
+                "algorithmic_bytes_per_pair": dom_bytes / n, "launch_ms": dom_s * 1e3}
     if warp_inst and clocks and clocks.get("sm_mhz"):
         # what actually bounds the kernel (ncu: math-pipe throttle): issue rate against 4 warp
         # instructions / cycle / SM, of which the integer ALU pipe sustains about 2
@@ -358,7 +388,11 @@ def main():
                    "l2": "inputs per launch (views+payload %.0f MB) exceed the 126 MB L2; no flush needed" % (alg_bytes / 1e6)},
         "per_measure": per_measure, "roofline": roofline, "clocks": clocks, "gpu_launches": launches,
         "overflow_rows_last_call": {"to_64bit_kernel": overflow[0], "to_long_kernel": overflow[1]},
-        "checksum": checksum,
+        "checksum": checksum, "checksums": checksums,
+        "step": ("one fused launch for all measures (strsim_b200_compute_device_multi)" if fused
+                 else "one single-measure launch per measure"),
+        "fused_matches_single_measure_kernel": fused_matches_single,
+        "per_measure_note": "each measure's own single-measure kernel, timed separately after the step loop",
     }
     if cells is not None:
         ms = per_measure_ms["levenshtein"]

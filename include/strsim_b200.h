@@ -140,6 +140,20 @@ STRSIM_API int strsim_b200_compute_device(int measure, const strsim_b200_column 
                                           const strsim_b200_column *b, double *d_out_values,
                                           uint32_t *d_out_validity, int32_t *d_dbg_ints, void *stream);
 
+/* Several DISTINCT measures (n_measures <= 5) over the same resident columns in ONE fused pass
+ * (the five README expressions, README.md:47-51, evaluate the same two columns):
+ * views and bytes are read once, the position mask of every character is computed once and feeds
+ * the Myers column, the Jaro match step and the multiset step together; Jaro / Jaro-Winkler share
+ * the match and transposition counts, Jaccard / Sorensen-Dice the intersection.  d_out_values[k] and
+ * d_dbg_ints[k] (array or entries may be NULL) belong to measures[k]; results are bit-identical to
+ * the single-measure calls. */
+STRSIM_API int strsim_b200_compute_device_multi(const int *measures, size_t n_measures,
+                                                const strsim_b200_column *a,
+                                                const strsim_b200_column *b,
+                                                double *const *d_out_values,
+                                                uint32_t *d_out_validity,
+                                                int32_t *const *d_dbg_ints, void *stream);
+
 /* ---- housekeeping -------------------------------------------------------------------------------- */
 /* device used by the calling thread's subsequent calls (default: STRSIM_B200_DEVICE env or 0) */
 STRSIM_API int strsim_b200_set_device(int device);

@@ -222,9 +222,18 @@ __global__ void list_all_kernel(const SegArgs s) {
     const bool valid = bit_valid(s.a.validity, s.a.vbit + row * s.a.stride) &&
                        bit_valid(s.b.validity, s.b.vbit + row * s.b.stride);
     if (!valid) {
-        s.out[row] = 0.0;
-        if (s.dbg)
-            for (int q = 0; q < 6; q++) s.dbg[row * 6 + q] = 0;
+        if (s.out) {
+            s.out[row] = 0.0;
+            if (s.dbg)
+                for (int q = 0; q < 6; q++) s.dbg[row * 6 + q] = 0;
+        } else {  // fused call: every wanted measure
+            for (int m = 0; m < 5; m++) {
+                if (!s.outs[m]) continue;
+                s.outs[m][row] = 0.0;
+                if (s.dbgs[m])
+                    for (int q = 0; q < 6; q++) s.dbgs[m][row * 6 + q] = 0;
+            }
+        }
         return;
     }
     s.listlong[atomicAdd(&s.ovf->nlong, 1u)] = (unsigned int)row;

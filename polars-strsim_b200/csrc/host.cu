@@ -609,6 +609,22 @@ static int launch_fused(ThreadCtx& ctx, Alphabet al, const SegArgs& args, long l
     }
 }
 
+// fused evaluation of several measures in one pass (pair_algos.cuh: FusedStep): register paths only
+template <int GROUPS>
+static int launch_multi(ThreadCtx& ctx, Alphabet al, const SegArgs& args, long long rows, cudaStream_t st) {
+    constexpr int ME = MULTI_BASE + GROUPS;
+    switch (al) {
+        case ALPHA_ASCII32:
+            return launch_short<uint32_t, ME, 256, 4, false, 32, true, true>(ctx, args, rows, st);
+        case ALPHA_ASCII64:
+            return launch_short<uint32_t, ME, 256, 4, false, 64, true, true>(ctx, args, rows, st);
+        case ALPHA_ASCII128:
+            return launch_short<uint32_t, ME, 256, 4, false, 128, true, true>(ctx, args, rows, st);
+        default:
+            return launch_short<uint32_t, ME, 256, 4, false, 128, false, false, true>(ctx, args, rows, st);
+    }
+}
+
 // rows on the long list -> fallback kernel, scratch slabs sized from the device-side maxima
 template <int MEASURE>
 static int run_generic(ThreadCtx& ctx, const SegArgs& args, const Overflow& ov, cudaStream_t st,
@@ -719,21 +735,62 @@ static int run_long_lev(ThreadCtx& ctx, const SegArgs& args, const Overflow& ov,
     return STRSIM_OK;
 }
 
-template <int MEASURE>
-static int run_segment(ThreadCtx& ctx, SegArgs args, Alphabet al, int stage32, int64_t seg_rows, cudaStream_t st) {
-    // overflow lists: worst case every row
+static bool force_generic_rows() {
+    static const bool v = getenv("STRSIM_B200_FORCE_GENERIC") != nullptr && atoi(getenv("STRSIM_B200_FORCE_GENERIC")) != 0;
+    return v;
+}
+
+// overflow lists (worst case every row) and counters for one segment
+static int prepare_segment(ThreadCtx& ctx, SegArgs& args, int stage32, int64_t seg_rows, cudaStream_t st) {
     int rc = ws_reserve(ctx.lists, 2 * sizeof(unsigned int) * (size_t)seg_rows + 64);
     if (rc) return rc;
     args.list64 = static_cast<unsigned int*>(ctx.lists.ptr);
     args.listlong = args.list64 + seg_rows;
     args.ovf = ctx.d_ovf;
     CUDA_TRY(cudaMemsetAsync(ctx.d_ovf, 0, sizeof(Overflow), st));
-    static const bool force_generic = getenv("STRSIM_B200_FORCE_GENERIC") != nullptr &&
-                                      atoi(getenv("STRSIM_B200_FORCE_GENERIC")) != 0;
     args.stage_bytes = stage32;
     args.list = nullptr;
     args.list_count = nullptr;
-    if (force_generic) {
+    return STRSIM_OK;
+}
+
+static int read_overflow(ThreadCtx& ctx, Overflow* ov, cudaStream_t st) {
+    CUDA_TRY(cudaMemcpyAsync(ctx.h_ovf, ctx.d_ovf, sizeof(Overflow), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *ov = *ctx.h_ovf;
+    return STRSIM_OK;
+}
+
+// rows of 33..64 bytes -> 64-bit instantiation in gather mode
+template <int MEASURE>
+static int finish_64(ThreadCtx& ctx, const SegArgs& args, const Overflow& ov, cudaStream_t st) {
+    SegArgs a64 = args;
+    a64.list = args.list64;
+    a64.list_count = &ctx.d_ovf->n64;
+    a64.n = ov.n64;
+    return launch_direct<uint64_t, MEASURE, 64, 4, true, 192, false>(ctx, a64, ov.n64, st);
+}
+
+// rows on the long list -> multi-word Myers (Levenshtein; consumes list64 and listlong) or the generic kernel
+template <int MEASURE>
+static int finish_long(ThreadCtx& ctx, const SegArgs& args, const Overflow& ov, cudaStream_t st) {
+    int rc;
+    if (MEASURE == LEVENSHTEIN && !force_generic_rows()) {
+        Leftover left;
+        rc = run_long_lev(ctx, args, ov, args.list64, &left, st);  // list64 is free again here
+        if (rc) return rc;
+        if (left.n > 0) rc = run_generic<MEASURE>(ctx, args, ov, st, left.list, left.count, left.n);
+    } else {
+        rc = run_generic<MEASURE>(ctx, args, ov, st);
+    }
+    return rc;
+}
+
+template <int MEASURE>
+static int run_segment(ThreadCtx& ctx, SegArgs args, Alphabet al, int stage32, int64_t seg_rows, cudaStream_t st) {
+    int rc = prepare_segment(ctx, args, stage32, seg_rows, st);
+    if (rc) return rc;
+    if (force_generic_rows()) {
         // test hook: every valid row goes straight to the fallback kernel
         list_all_kernel<<<(unsigned)((seg_rows + 255) / 256), 256, 0, st>>>(args);
         g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -742,33 +799,96 @@ static int run_segment(ThreadCtx& ctx, SegArgs args, Alphabet al, int stage32, i
         rc = launch_fused<MEASURE>(ctx, al, args, seg_rows, st);
         if (rc) return rc;
     }
-    CUDA_TRY(cudaMemcpyAsync(ctx.h_ovf, ctx.d_ovf, sizeof(Overflow), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    Overflow ov = *ctx.h_ovf;
+    Overflow ov;
+    rc = read_overflow(ctx, &ov, st);
+    if (rc) return rc;
     g_last_overflow[0] += ov.n64;
     if (ov.n64 > 0) {
-        SegArgs a64 = args;
-        a64.list = args.list64;
-        a64.list_count = &ctx.d_ovf->n64;
-        a64.n = ov.n64;
-        rc = launch_direct<uint64_t, MEASURE, 64, 4, true, 192, false>(ctx, a64, ov.n64, st);
+        rc = finish_64<MEASURE>(ctx, args, ov, st);
         if (rc) return rc;
-        // rows the 64-bit kernel could not stage are appended to listlong; re-read the counters
-        CUDA_TRY(cudaMemcpyAsync(ctx.h_ovf, ctx.d_ovf, sizeof(Overflow), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-        ov = *ctx.h_ovf;
+        // rows the 64-bit kernel could not take are appended to listlong; re-read the counters
+        rc = read_overflow(ctx, &ov, st);
+        if (rc) return rc;
+    }
+    g_last_overflow[1] += ov.nlong;
+    if (ov.nlong > 0) rc = finish_long<MEASURE>(ctx, args, ov, st);
+    return rc;
+}
+
+static int finish_64_any(int measure, ThreadCtx& ctx, const SegArgs& args, const Overflow& ov, cudaStream_t st) {
+    switch (measure) {
+        case 0: return finish_64<0>(ctx, args, ov, st);
+        case 1: return finish_64<1>(ctx, args, ov, st);
+        case 2: return finish_64<2>(ctx, args, ov, st);
+        case 3: return finish_64<3>(ctx, args, ov, st);
+        default: return finish_64<4>(ctx, args, ov, st);
+    }
+}
+static int finish_long_any(int measure, ThreadCtx& ctx, const SegArgs& args, const Overflow& ov, cudaStream_t st) {
+    switch (measure) {
+        case 0: return finish_long<0>(ctx, args, ov, st);
+        case 1: return finish_long<1>(ctx, args, ov, st);
+        case 2: return finish_long<2>(ctx, args, ov, st);
+        case 3: return finish_long<3>(ctx, args, ov, st);
+        default: return finish_long<4>(ctx, args, ov, st);
+    }
+}
+
+// Several measures over one segment: ONE fused launch settles every row of at most 32 bytes for all
+// wanted measures (args.outs / args.dbgs); the overflow lists it leaves are then finished measure by
+// measure with the single-measure follow-up kernels.  Levenshtein goes last: its long-row kernel
+// reuses both lists as scratch.
+static int run_segment_multi(ThreadCtx& ctx, SegArgs args, int groups, Alphabet al, int stage32, int64_t seg_rows,
+                             cudaStream_t st) {
+    int rc = prepare_segment(ctx, args, stage32, seg_rows, st);
+    if (rc) return rc;
+    args.out = nullptr;
+    args.dbg = nullptr;
+    if (force_generic_rows()) {
+        list_all_kernel<<<(unsigned)((seg_rows + 255) / 256), 256, 0, st>>>(args);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        CUDA_TRY(cudaGetLastError());
+    } else {
+        switch (groups) {
+            case 2: rc = launch_multi<2>(ctx, al, args, seg_rows, st); break;
+            case 3: rc = launch_multi<3>(ctx, al, args, seg_rows, st); break;
+            case 4: rc = launch_multi<4>(ctx, al, args, seg_rows, st); break;
+            case 5: rc = launch_multi<5>(ctx, al, args, seg_rows, st); break;
+            case 6: rc = launch_multi<6>(ctx, al, args, seg_rows, st); break;
+            case 7: rc = launch_multi<7>(ctx, al, args, seg_rows, st); break;
+            default:
+                strsim_set_error("fused evaluation: bad group mask %d", groups);
+                rc = STRSIM_ERR_ARGUMENT;
+        }
+        if (rc) return rc;
+    }
+    Overflow ov;
+    rc = read_overflow(ctx, &ov, st);
+    if (rc) return rc;
+    g_last_overflow[0] += ov.n64;
+    if (ov.n64 > 0) {
+        for (int m = 0; m < 5; m++) {
+            if (!args.outs[m]) continue;
+            SegArgs am = args;
+            am.out = args.outs[m];
+            am.dbg = args.dbgs[m];
+            rc = finish_64_any(m, ctx, am, ov, st);
+            if (rc) return rc;
+        }
+        rc = read_overflow(ctx, &ov, st);
+        if (rc) return rc;
     }
     g_last_overflow[1] += ov.nlong;
     if (ov.nlong > 0) {
-        if (MEASURE == LEVENSHTEIN && !force_generic) {
-            Leftover left;
-            rc = run_long_lev(ctx, args, ov, args.list64, &left, st);  // list64 is free again here
+        for (int k = 0; k < 5; k++) {
+            const int m = (k + 1) % 5;  // 1, 2, 3, 4, then Levenshtein
+            if (!args.outs[m]) continue;
+            SegArgs am = args;
+            am.out = args.outs[m];
+            am.dbg = args.dbgs[m];
+            rc = finish_long_any(m, ctx, am, ov, st);
             if (rc) return rc;
-            if (left.n > 0) rc = run_generic<MEASURE>(ctx, args, ov, st, left.list, left.count, left.n);
-        } else {
-            rc = run_generic<MEASURE>(ctx, args, ov, st);
         }
-        if (rc) return rc;
     }
     return STRSIM_OK;
 }
@@ -776,13 +896,31 @@ static int run_segment(ThreadCtx& ctx, SegArgs args, Alphabet al, int stage32, i
 // Rows [row_lo, row_lo + n_rows) of measure(a, b) -> d_out[row] / validity bits / debug records, all
 // indexed by the absolute row.  `reset`: zero the validity words of the range and (first slice only)
 // the null counter.
-static int compute_on_device(ThreadCtx& ctx, int measure, const strsim_b200_column* a,
+//
+// Several distinct measures (n_measures > 1) are evaluated by ONE fused launch per segment
+// (run_segment_multi); d_outs[k] / d_dbgs[k] belong to measures[k].
+static int compute_on_device(ThreadCtx& ctx, const int* measures, size_t n_measures, const strsim_b200_column* a,
                              const strsim_b200_column* b, int64_t row_lo, int64_t n_rows, Alphabet al,
-                             double* d_out, uint32_t* d_validity, int32_t* d_dbg, cudaStream_t st) {
-    if (measure < 0 || measure > 4) {
-        strsim_set_error("unknown measure %d", measure);
-        return STRSIM_ERR_ARGUMENT;
+                             double* const* d_outs, uint32_t* d_validity, int32_t* const* d_dbgs, cudaStream_t st) {
+    int groups = 0;
+    unsigned seen = 0;
+    for (size_t k = 0; k < n_measures; k++) {
+        const int m = measures[k];
+        if (m < 0 || m > 4) {
+            strsim_set_error("unknown measure %d", m);
+            return STRSIM_ERR_ARGUMENT;
+        }
+        if (seen & (1u << m)) {
+            strsim_set_error("measure %d requested twice in one fused call", m);
+            return STRSIM_ERR_ARGUMENT;
+        }
+        seen |= 1u << m;
+        groups |= group_of(m);
     }
+    if (n_measures == 0) return STRSIM_OK;
+    const int measure = measures[0];
+    double* const d_out = d_outs[0];
+    int32_t* const d_dbg = d_dbgs ? d_dbgs[0] : nullptr;
     const int64_t la = a->length, lb = b->length;
     if (la != lb && la != 1 && lb != 1) {
         strsim_set_error("Inputs must have the same length, or one of them must be a Utf8 literal.");
@@ -848,12 +986,20 @@ static int compute_on_device(ThreadCtx& ctx, int measure, const strsim_b200_colu
         long long stage = -(long long)(avg * 16.0 + 1.0);
         if (stage < -64 * 16) stage = -64 * 16;
         int rc;
-        switch (measure) {
-            case 0: rc = run_segment<0>(ctx, s, al, (int)stage, len, st); break;
-            case 1: rc = run_segment<1>(ctx, s, al, (int)stage, len, st); break;
-            case 2: rc = run_segment<2>(ctx, s, al, (int)stage, len, st); break;
-            case 3: rc = run_segment<3>(ctx, s, al, (int)stage, len, st); break;
-            default: rc = run_segment<4>(ctx, s, al, (int)stage, len, st); break;
+        if (n_measures > 1) {
+            for (size_t k = 0; k < n_measures; k++) {
+                s.outs[measures[k]] = d_outs[k] + row;
+                s.dbgs[measures[k]] = (d_dbgs && d_dbgs[k]) ? d_dbgs[k] + 6 * row : nullptr;
+            }
+            rc = run_segment_multi(ctx, s, groups, al, (int)stage, len, st);
+        } else {
+            switch (measure) {
+                case 0: rc = run_segment<0>(ctx, s, al, (int)stage, len, st); break;
+                case 1: rc = run_segment<1>(ctx, s, al, (int)stage, len, st); break;
+                case 2: rc = run_segment<2>(ctx, s, al, (int)stage, len, st); break;
+                case 3: rc = run_segment<3>(ctx, s, al, (int)stage, len, st); break;
+                default: rc = run_segment<4>(ctx, s, al, (int)stage, len, st); break;
+            }
         }
         if (rc) return rc;
         if (d_validity && any_validity) {
@@ -952,8 +1098,38 @@ int strsim_b200_compute_device(int measure, const strsim_b200_column* a, const s
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
     g_last_overflow[0] = g_last_overflow[1] = 0;
     const int64_t n = a->length == 1 ? b->length : a->length;
-    return compute_on_device(*ctx, measure, a, b, 0, n, classify_alphabet(a->or_byte | b->or_byte, a->and_byte & b->and_byte),
-                             d_out_values, d_out_validity, d_dbg_ints, st);
+    double* outs[1] = {d_out_values};
+    int32_t* dbgs[1] = {d_dbg_ints};
+    return compute_on_device(*ctx, &measure, 1, a, b, 0, n, classify_alphabet(a->or_byte | b->or_byte, a->and_byte & b->and_byte),
+                             outs, d_out_validity, dbgs, st);
+}
+
+int strsim_b200_compute_device_multi(const int* measures, size_t n_measures, const strsim_b200_column* a,
+                                     const strsim_b200_column* b, double* const* d_out_values,
+                                     uint32_t* d_out_validity, int32_t* const* d_dbg_ints, void* stream) {
+    if (!a || !b || !measures || !d_out_values || n_measures == 0 || n_measures > 5) {
+        strsim_set_error("compute_device_multi: NULL / out-of-range argument");
+        return STRSIM_ERR_ARGUMENT;
+    }
+    for (size_t k = 0; k < n_measures; k++)
+        if (!d_out_values[k]) {
+            strsim_set_error("compute_device_multi: NULL d_out_values[%zu]", k);
+            return STRSIM_ERR_ARGUMENT;
+        }
+    ThreadCtx* ctx;
+    int rc = ensure_ctx(&ctx);
+    if (rc) return rc;
+    if (a->device != ctx->device || b->device != ctx->device) {
+        strsim_set_error("columns live on device %d/%d, calling thread uses device %d", a->device,
+                         b->device, ctx->device);
+        return STRSIM_ERR_ARGUMENT;
+    }
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    g_last_overflow[0] = g_last_overflow[1] = 0;
+    const int64_t n = a->length == 1 ? b->length : a->length;
+    return compute_on_device(*ctx, measures, n_measures, a, b, 0, n,
+                             classify_alphabet(a->or_byte | b->or_byte, a->and_byte & b->and_byte), d_out_values,
+                             d_out_validity, d_dbg_ints, st);
 }
 
 int strsim_b200_compute_host_multi(const int* measures, size_t n_measures, const strsim_view_chunk* a, size_t n_a,
@@ -986,6 +1162,14 @@ int strsim_b200_compute_host_multi(const int* measures, size_t n_measures, const
     int rc = ensure_ctx(&ctx);
     if (rc) return rc;
     if (n == 0) return STRSIM_OK;
+    unsigned seen_measures = 0;
+    bool distinct = true;
+    for (size_t m = 0; m < n_measures; m++) {
+        distinct = distinct && !(seen_measures & (1u << measures[m]));
+        seen_measures |= 1u << measures[m];
+    }
+    static const bool no_fuse = getenv("STRSIM_B200_NO_FUSE") != nullptr && atoi(getenv("STRSIM_B200_NO_FUSE")) != 0;
+    const bool fuse = n_measures > 1 && n_measures <= 5 && distinct && !no_fuse;
 
     // One upload of the two columns serves every requested measure.  The rows are cut into slices:
     // all H2D copies are queued up front on the upload stream (data buffers first, then the views
@@ -1070,24 +1254,35 @@ int strsim_b200_compute_host_multi(const int* measures, size_t n_measures, const
         stats_fold(acc, &ob, &nb_);
         const Alphabet al = classify_alphabet(ob, nb_);
         ce = cudaStreamWaitEvent(ctx->stream, ctx->slice_event[sidx], 0);
-        for (size_t m = 0; ce == cudaSuccess && rc == STRSIM_OK && m < n_measures; m++) {
-            if (sidx == 0) g_last_overflow[0] = g_last_overflow[1] = 0;
-            double* d_out = reinterpret_cast<double*>(base + m * out_stride);
-            int32_t* d_dbg = (any_dbg && dbg_ints[m]) ? reinterpret_cast<int32_t*>(d_dbg_base + m * dbg_stride) : nullptr;
-            rc = compute_on_device(*ctx, measures[m], ca, cb, lo, hi - lo, al, d_out,
-                                   (want_validity && m == 0) ? d_val : nullptr, d_dbg, ctx->stream);
+        if (sidx == 0) g_last_overflow[0] = g_last_overflow[1] = 0;
+        // fused: ONE launch per segment evaluates every requested measure (run_segment_multi); otherwise
+        // (a single measure, or the same measure requested twice) one pass per measure
+        const size_t n_pass = fuse ? 1 : n_measures;
+        for (size_t p = 0; ce == cudaSuccess && rc == STRSIM_OK && p < n_pass; p++) {
+            const size_t m0 = p, m1 = fuse ? n_measures : p + 1;
+            double* d_outs[8];
+            int32_t* d_dbgs[8];
+            for (size_t m = m0; m < m1; m++) {
+                d_outs[m - m0] = reinterpret_cast<double*>(base + m * out_stride);
+                d_dbgs[m - m0] = (any_dbg && dbg_ints[m]) ? reinterpret_cast<int32_t*>(d_dbg_base + m * dbg_stride) : nullptr;
+            }
+            rc = compute_on_device(*ctx, measures + m0, m1 - m0, ca, cb, lo, hi - lo, al, d_outs,
+                                   (want_validity && p == 0) ? d_val : nullptr, d_dbgs, ctx->stream);
             if (rc) break;
-            // download this measure's slice on the copy stream while the next kernel runs
-            cudaEvent_t ev = ctx->done_event[m];
+            // download the finished slice on the copy stream while the next kernel runs
+            cudaEvent_t ev = ctx->done_event[p];
             ce = cudaEventRecord(ev, ctx->stream);
             if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->copy_stream, ev, 0);
-            if (ce == cudaSuccess)
+            for (size_t m = m0; ce == cudaSuccess && m < m1; m++) {
+                double* d_out = d_outs[m - m0];
+                int32_t* d_dbg = d_dbgs[m - m0];
                 ce = cudaMemcpyAsync(out_values[m] + lo, d_out + lo, 8 * (size_t)(hi - lo), cudaMemcpyDeviceToHost,
                                      ctx->copy_stream);
-            if (ce == cudaSuccess && d_dbg)
-                ce = cudaMemcpyAsync(dbg_ints[m] + 6 * lo, d_dbg + 6 * lo, 24 * (size_t)(hi - lo),
-                                     cudaMemcpyDeviceToHost, ctx->copy_stream);
-            if (ce == cudaSuccess && m == 0 && out_validity)
+                if (ce == cudaSuccess && d_dbg)
+                    ce = cudaMemcpyAsync(dbg_ints[m] + 6 * lo, d_dbg + 6 * lo, 24 * (size_t)(hi - lo),
+                                         cudaMemcpyDeviceToHost, ctx->copy_stream);
+            }
+            if (ce == cudaSuccess && p == 0 && out_validity)
                 ce = cudaMemcpyAsync(out_validity + lo / 8, reinterpret_cast<const uint8_t*>(d_val) + lo / 8,
                                      (size_t)((hi - lo + 7) / 8), cudaMemcpyDeviceToHost, ctx->copy_stream);
         }

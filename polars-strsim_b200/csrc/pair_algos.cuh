@@ -176,8 +176,8 @@ struct MyersStep {
     const Tab& tab;
     M Pv, Mv;
     SS_HD explicit MyersStep(const Tab& t) : tab(t), Pv(~M(0)), Mv(M(0)) {}
-    SS_HD void operator()(uint32_t c) {
-        const M Eq = tab(c);
+    SS_HD void operator()(uint32_t c) { step(tab(c)); }
+    SS_HD void step(const M Eq) {
         const M Xv = Eq | Mv;
         const M Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
         M Ph = Mv | ~(Xh | Pv);
@@ -205,8 +205,9 @@ struct JaroMatchStep {
         win = (M(2) << bound_) - M(1);  // bits 0..bound
         lbmask = lb >= (int)(sizeof(M) * 8) ? ~M(0) : ((M(1) << lb) - M(1));
     }
-    SS_HD void operator()(uint32_t c) {
-        const M cand = tab(c) & win & lbmask & ~flag_b;
+    SS_HD void operator()(uint32_t c) { step(tab(c)); }
+    SS_HD void step(const M Eq) {
+        const M cand = Eq & win & lbmask & ~flag_b;
         if (cand) {
             flag_b |= cand & (M(0) - cand);
             flag_a |= abit;
@@ -243,12 +244,42 @@ struct MultisetStep {
     int inter;
     SS_HD MultisetStep(const Tab& t, int lb)
         : tab(t), used(lb >= (int)(sizeof(M) * 8) ? M(0) : ~((M(1) << lb) - M(1))), inter(0) {}
-    SS_HD void operator()(uint32_t c) {
-        const M cand = tab(c) & ~used;
+    SS_HD void operator()(uint32_t c) { step(tab(c)); }
+    SS_HD void step(const M Eq) {
+        const M cand = Eq & ~used;
         if (cand) {
             used |= cand & (M(0) - cand);
             inter++;
         }
+    }
+};
+
+// ---- fused evaluation of several measures over ONE pass ----------------------------
+// The README evaluates all five expressions over the same two columns (README.md:47-51).  With b
+// tabled and a streamed -- the orientation Jaro and the multisets need anyway (strsim.rs:208,297) and
+// one Levenshtein accepts because the distance is symmetric -- the position mask Eq(c) of every
+// character of a is computed ONCE and feeds the Myers column, the Jaro match step and the multiset
+// step together.  Groups: Jaro and Jaro-Winkler share the match/transposition counts, Jaccard and
+// Sorensen-Dice share the intersection.
+enum Group : int { G_LEV = 1, G_JARO = 2, G_SET = 4 };
+constexpr int MULTI_BASE = 8;  // kernel template values MULTI_BASE + groups (9..15) = fused evaluation
+SS_HD constexpr bool is_multi(int measure) { return measure >= MULTI_BASE; }
+SS_HD constexpr int group_of(int measure) {
+    return measure == LEVENSHTEIN ? G_LEV : (measure == JARO || measure == JARO_WINKLER) ? G_JARO : G_SET;
+}
+
+template <int GROUPS, class M, class Tab>
+struct FusedStep {
+    const Tab& tab;
+    MyersStep<M, Tab> my;
+    JaroMatchStep<M, Tab> jm;
+    MultisetStep<M, Tab> ms;
+    SS_HD FusedStep(const Tab& t, int lb, int bound) : tab(t), my(t), jm(t, lb, bound), ms(t, lb) {}
+    SS_HD void operator()(uint32_t c) {
+        const M Eq = tab(c);
+        if (GROUPS & G_LEV) my.step(Eq);
+        if (GROUPS & G_JARO) jm.step(Eq);
+        if (GROUPS & G_SET) ms.step(Eq);
     }
 };
 

@@ -13,7 +13,7 @@
 //     64-code-point alphabet block only 5 or 6 planes are needed.
 // Arithmetic and row rules are those of row_short.cuh (same step functors, same f64 formulas).
 #pragma once
-#include "pair_algos.cuh"
+#include "row_short.cuh"
 
 namespace strsim {
 
@@ -170,6 +170,53 @@ SS_HD double row_ascii_reg(const uint32_t (&a)[REG_WORDS], const uint32_t (&b)[R
         }
     }
     return v;
+}
+
+// ---- fused evaluation of several measures (row_short.cuh: multi_body) ---------------------------------
+struct EachByteReg {
+    const uint32_t (&W)[REG_WORDS];
+    SS_HD explicit EachByteReg(const uint32_t (&w)[REG_WORDS]) : W(w) {}
+    template <class F>
+    SS_HD void operator()(int n, F& f) const {
+        for_each_byte_reg(W, n, f);
+    }
+};
+
+struct PrefixReg {  // common prefix of two ASCII strings, capped at 4 (strsim.rs:261-266)
+    uint32_t x;
+    int lim;
+    SS_HD int operator()() const {
+        int l = 0;
+        while (l < lim && ((x >> (8 * l)) & 0xFFu) == 0) l++;
+        return l;
+    }
+};
+
+template <int GROUPS, int NBITS, class Emit>
+SS_HD void row_ascii_reg_multi(const uint32_t (&a)[REG_WORDS], const uint32_t (&b)[REG_WORDS], int na, int nb,
+                               Emit& emit) {
+    bool equal = na == nb;
+    if (equal) {
+        uint32_t diff = 0;
+#pragma unroll
+        for (int w = 0; w < REG_WORDS; w++) diff |= a[w] ^ b[w];
+        equal = diff == 0u;
+    }
+    if (equal) {  // strsim.rs:128,182,288,324
+        PairInts o;
+        o.flag = F_EQUAL;
+        o.la = o.lb = o.x0 = o.x1 = o.x2 = 0;
+        emit_groups<GROUPS>(emit, 1.0, o);
+        return;
+    }
+    PlaneTab<NBITS> tab;
+    build_planes<NBITS>(b, nb, tab);
+    EachByteReg each_a(a);
+    PrefixReg prefix;
+    prefix.x = a[0] ^ b[0];
+    prefix.lim = na < nb ? na : nb;
+    if (prefix.lim > 4) prefix.lim = 4;
+    multi_body<GROUPS, uint32_t>(tab, each_a, na, nb, na == 0 || nb == 0, prefix, emit);
 }
 
 }  // namespace strsim

@@ -204,6 +204,94 @@ SS_HD double measure_body(int measure, const Tab& tab, const Each& each_streamed
     }
 }
 
+// ---- fused evaluation (pair_algos.cuh: FusedStep) ----------------------------------------------------------
+// emit(measure, value, ints) is called once for every measure of GROUPS; the caller decides which of
+// them it keeps (short_kernel.cuh stores those whose output pointer is set).
+template <int GROUPS, class Emit>
+SS_HD void emit_groups(Emit& emit, double v, const PairInts& o) {
+    if (GROUPS & G_LEV) emit(LEVENSHTEIN, v, o);
+    if (GROUPS & G_JARO) {
+        emit(JARO, v, o);
+        emit(JARO_WINKLER, v, o);
+    }
+    if (GROUPS & G_SET) {
+        emit(JACCARD, v, o);
+        emit(SORENSEN_DICE, v, o);
+    }
+}
+
+// The pair is NOT byte-equal.  tab: position masks of b (lb characters); each_a(n, f) applies f to the
+// first n characters of a; prefix() = length of the common character prefix, capped at 4
+// (strsim.rs:261-266); one_empty: either string is empty (strsim.rs:184,290,326).  The integer records
+// and values are those of measure_body() / row_short() for each single measure.
+template <int GROUPS, class M, class Tab, class Each, class Prefix, class Emit>
+SS_HD void multi_body(const Tab& tab, const Each& each_a, int la, int lb, bool one_empty, const Prefix& prefix,
+                      Emit& emit) {
+    const int mx = la > lb ? la : lb;
+    int bound = mx / 2 - 1;  // strsim.rs:200
+    if (bound < 0) bound = 0;  // both strings of at most one character: settled by the row rules below
+    FusedStep<GROUPS, M, Tab> f(tab, lb, bound);
+    each_a(la, f);  // Jaro's outer limit min(la, lb+bound) needs no cut: later windows lie beyond b
+    PairInts o;
+    o.flag = F_GENERAL;
+    o.la = la;
+    o.lb = lb;
+    o.x0 = o.x1 = o.x2 = 0;
+    if (GROUPS & G_LEV) {
+        // b tabled whatever the lengths; an empty side needs no special case: no column (la = 0) leaves
+        // Pv all ones -> d = lb, an empty pattern (lb = 0) scores no vertical delta -> d = la
+        const int d = f.my.distance(lb, la);
+        o.x0 = d;
+        emit(LEVENSHTEIN, lev_value(d, la, lb), o);
+    }
+    PairInts z;
+    z.flag = F_ONE_EMPTY;
+    z.la = z.lb = z.x0 = z.x1 = z.x2 = 0;
+    if (GROUPS & G_JARO) {
+        if (one_empty) {
+            emit(JARO, 0.0, z);
+            emit(JARO_WINKLER, 0.0, z);
+        } else if (la == 1 && lb == 1) {  // strsim.rs:197; the bytes differ here
+            o.flag = F_SINGLE_CHAR;
+            o.x0 = 0;
+            emit(JARO, 0.0, o);
+            emit(JARO_WINKLER, 0.0, o);
+            o.flag = F_GENERAL;
+        } else {
+            int t = 0;
+            if (f.jm.m > 0) {
+                JaroTransStep<M, Tab> trans(tab, f.jm.flag_a, f.jm.flag_b);
+                each_a(la, trans);
+                t = trans.t;
+            }
+            o.x0 = f.jm.m;
+            o.x1 = t;
+            double v = f.jm.m == 0 ? 0.0 : jaro_value(f.jm.m, t, la, lb);
+            emit(JARO, v, o);
+            if (v > 0.7) {  // strsim.rs:260-267
+                const int l = prefix();
+                o.x2 = l;
+                v = winkler_value(v, l);
+            }
+            emit(JARO_WINKLER, v, o);
+            o.x2 = 0;
+        }
+    }
+    if (GROUPS & G_SET) {
+        if (one_empty) {
+            emit(JACCARD, 0.0, z);
+            emit(SORENSEN_DICE, 0.0, z);
+        } else {
+            const int inter = f.ms.inter;
+            o.x0 = inter;
+            o.x1 = la + lb - inter;
+            emit(JACCARD, jaccard_value(inter, la + lb - inter), o);
+            o.x1 = la + lb;
+            emit(SORENSEN_DICE, dice_value(inter, la + lb), o);
+        }
+    }
+}
+
 template <class Store>
 struct EachByte {
     StoreWords<Store> src;

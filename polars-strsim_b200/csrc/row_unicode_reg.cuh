@@ -125,6 +125,42 @@ SS_HD double row_unicode_reg(Store& s, int na, int nb, bool equal, const WarpMax
     return v;
 }
 
+// ---- fused evaluation of several measures (row_short.cuh: multi_body) ---------------------------------
+template <class Words>
+struct PrefixChars {  // common prefix in characters, capped at 4 (strsim.rs:261-266)
+    const Words &wa, &wb;
+    int na, nb;
+    SS_HD PrefixChars(const Words& a, const Words& b, int na_, int nb_) : wa(a), wb(b), na(na_), nb(nb_) {}
+    SS_HD int operator()() const {
+        PrefixKeys pa, pb;
+        for_each_char(wa, na, 4, 7, pa);
+        for_each_char(wb, nb, 4, 7, pb);
+        const int lim = pa.n < pb.n ? pa.n : pb.n;
+        int l = 0;
+        while (l < lim && pa.k[l] == pb.k[l]) l++;
+        return l;
+    }
+};
+
+template <int GROUPS, class Store, class WarpMax, class Emit>
+SS_HD void row_unicode_reg_multi(Store& s, int na, int nb, bool equal, const WarpMax& warp_max, Emit& emit) {
+    StoreWords<Store> wa(s, false), wb(s, true);
+    const int la = count_chars(wa, na), lb = count_chars(wb, nb);
+    CmpTab tab;
+    tab.bound = warp_max(equal ? 0 : lb);  // every lane of the warp reaches this point
+    if (equal) {  // strsim.rs:128,182,288,324
+        PairInts o;
+        o.flag = F_EQUAL;
+        o.la = o.lb = o.x0 = o.x1 = o.x2 = 0;
+        emit_groups<GROUPS>(emit, 1.0, o);
+        return;
+    }
+    decode_to_regs(wb, nb, 7, tab);
+    EachChar<Store> each_a(s, false, na);
+    PrefixChars<StoreWords<Store>> prefix(wa, wb, na, nb);
+    multi_body<GROUPS, uint32_t>(tab, each_a, la, lb, na == 0 || nb == 0, prefix, emit);
+}
+
 struct HostWarpMax {  // host tests: one "lane"
     SS_HD int operator()(int v) const { return v; }
 };

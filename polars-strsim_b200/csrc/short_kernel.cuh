@@ -47,6 +47,10 @@ struct SegArgs {
     long long n;   // rows of the segment, or entries of `list` in gather mode
     double* out;   // row 0 of the segment
     int* dbg;      // row 0 of the segment (STRSIM_DBG_INTS per row) or nullptr
+    // fused evaluation (MEASURE >= MULTI_BASE): one output per measure, row 0 of the segment; nullptr =
+    // this measure is not wanted (its group may still be computed for the group's other member)
+    double* outs[5];
+    int* dbgs[5];
     const unsigned int* list;  // gather mode: segment-relative row numbers
     const unsigned int* list_count;  // gather mode: device-resident number of entries
     Overflow* ovf;
@@ -291,6 +295,50 @@ __device__ __forceinline__ bool staged_equal(const uint4& va, const uint4& vb, c
     return true;
 }
 
+__device__ __forceinline__ void store_dbg(int* d, const PairInts& o) {
+    d[0] = o.flag;
+    d[1] = o.la;
+    d[2] = o.lb;
+    d[3] = o.x0;
+    d[4] = o.x1;
+    d[5] = o.x2;
+}
+
+// result of a row settled without looking at its characters (null row: 0.0 / zero record; byte-equal
+// row: 1.0 / F_EQUAL), written to the single output or to every wanted output of a fused launch
+template <int MEASURE>
+__device__ __forceinline__ void store_settled(const SegArgs& s, long long row, double v, int flag) {
+    PairInts o;
+    o.flag = flag;
+    o.la = o.lb = o.x0 = o.x1 = o.x2 = 0;
+    if (is_multi(MEASURE)) {
+#pragma unroll
+        for (int m = 0; m < 5; m++) {
+            if (!s.outs[m]) continue;
+            s.outs[m][row] = v;
+            if (s.dbgs[m]) store_dbg(s.dbgs[m] + row * 6, o);
+        }
+    } else {
+        s.out[row] = v;
+        if (s.dbg) store_dbg(s.dbg + row * 6, o);
+    }
+}
+
+// sink of the fused row functions: keeps the measures whose output pointer is set
+struct RowEmit {
+    const SegArgs& s;
+    long long row;
+    bool has;
+    __device__ __forceinline__ void operator()(int measure, double v, const PairInts& o) const {
+        double* out = s.outs[measure];
+        if (has && out) {
+            out[row] = v;
+            int* d = s.dbgs[measure];
+            if (d) store_dbg(d + row * 6, o);
+        }
+    }
+};
+
 struct WarpMaxDev {  // maximum over the 32 lanes of the warp (all lanes must call it)
     __device__ __forceinline__ int operator()(int v) const { return __reduce_max_sync(0xFFFFFFFFu, v); }
 };
@@ -303,6 +351,8 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
     static_assert(!UREG || (!ASCII_ONLY && !REG && sizeof(M) == 4), "register-compare path: general u32 kernel");
     static_assert(!REG || (ASCII_ONLY && sizeof(M) == 4 && (T == 32 || T == 64 || T == 128)),
                   "the register path serves ASCII-only columns with strings of at most 32 bytes");
+    static_assert(!is_multi(MEASURE) || REG || UREG, "fused evaluation: register paths only");
+    constexpr int GROUPS = is_multi(MEASURE) ? MEASURE - MULTI_BASE : 0;
     constexpr int NBITS = T == 32 ? 5 : T == 64 ? 6 : 7;
     using L = ShortLayout<M, TPB, RPT, T, REG, UREG>;
     constexpr int CAP = L::CAP;
@@ -375,12 +425,7 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
                                    bit_valid(s.b.validity, s.b.vbit + row * s.b.stride);
                 const uint32_t mx = va.x > vb.x ? va.x : vb.x;
                 if (!valid) {
-                    s.out[row] = 0.0;
-                    if (s.dbg) {
-                        int* d = s.dbg + row * 6;
-#pragma unroll
-                        for (int q = 0; q < 6; q++) d[q] = 0;
-                    }
+                    store_settled<MEASURE>(s, row, 0.0, 0);
                 } else if (mx > (uint32_t)CAP) {
                     if (CAP == 32 && mx <= 64u) {
                         s.list64[atomicAdd(&s.ovf->n64, 1u)] = (unsigned int)row;
@@ -558,13 +603,7 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
                 staged_equal(va, vb, stage_a, stage_b)) {
                 const long long idx = tile0 + i;
                 const long long row = GATHER ? (long long)s.list[idx] : idx;
-                s.out[row] = 1.0;
-                if (s.dbg) {
-                    int* d = s.dbg + row * 6;
-                    d[0] = F_EQUAL;
-#pragma unroll
-                    for (int q = 1; q < 6; q++) d[q] = 0;
-                }
+                store_settled<MEASURE>(s, row, 1.0, F_EQUAL);
                 continue;
             }
             uint32_t hi_bits = 0;  // conservative (unmasked) non-ASCII test; exact test in step 4
@@ -585,6 +624,8 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
                 }
             }
             uint32_t mx = va.x > vb.x ? va.x : vb.x;
+            // fused evaluation streams a against the tabled b for every group: the loops run la times
+            if (is_multi(MEASURE) && REG) mx = va.x;
             if (UREG) {
                 // the register-compare path costs (streamed characters) x (tabled characters): bucket by
                 // CHARACTER counts so that e.g. 6-character CJK rows do not share a warp with 18-character
@@ -654,9 +695,15 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
                         equal = diff == 0;
                     }
                 }
-                PairInts ints;
                 WarpMaxDev wm;
-                const double v = row_unicode_reg<MEASURE>(store, na, nb, equal, wm, ints);
+                if constexpr (is_multi(MEASURE)) {
+                    const long long idx = tile0 + i;
+                    RowEmit emit{s, has ? (GATHER ? (long long)s.list[idx] : idx) : 0ll, has};
+                    row_unicode_reg_multi<GROUPS>(store, na, nb, equal, wm, emit);
+                    continue;
+                }
+                PairInts ints;
+                const double v = row_unicode_reg<is_multi(MEASURE) ? 0 : MEASURE>(store, na, nb, equal, wm, ints);
                 if (has) {
                     const long long idx = tile0 + i;
                     const long long row = GATHER ? (long long)s.list[idx] : idx;
@@ -683,7 +730,13 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
                 uint32_t ra[REG_WORDS], rb[REG_WORDS];
                 load_string_reg(va, stage_a, ra);
                 load_string_reg(vb, stage_b, rb);
-                v = row_ascii_reg<MEASURE, NBITS>(ra, rb, na, nb, ints);
+                if constexpr (is_multi(MEASURE)) {
+                    const long long idx = tile0 + i;
+                    RowEmit emit{s, GATHER ? (long long)s.list[idx] : idx, true};
+                    row_ascii_reg_multi<GROUPS, NBITS>(ra, rb, na, nb, emit);
+                    continue;
+                }
+                v = row_ascii_reg<is_multi(MEASURE) ? 0 : MEASURE, NBITS>(ra, rb, na, nb, ints);
             } else {
                 const uint32_t or_a = load_string<WORDS, TPB>(va, stage_a, store.wa_);
                 const uint32_t or_b = load_string<WORDS, TPB>(vb, stage_b, store.wb_);
@@ -695,7 +748,7 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
                     equal = diff == 0;
                 }
                 const bool ascii = ASCII_ONLY || ((or_a | or_b) & 0x80808080u) == 0;
-                v = row_short<M>(MEASURE, store, na, nb, equal, ascii, ints);
+                v = row_short<M>(is_multi(MEASURE) ? 0 : MEASURE, store, na, nb, equal, ascii, ints);
             }
             const long long idx = tile0 + i;
             const long long row = GATHER ? (long long)s.list[idx] : idx;

@@ -91,6 +91,9 @@ def lib():
     L.strsim_b200_column_algorithmic_bytes.argtypes = [P]
     L.strsim_b200_compute_device.restype = ctypes.c_int
     L.strsim_b200_compute_device.argtypes = [ctypes.c_int, P, P, P, P, P, P]
+    L.strsim_b200_compute_device_multi.restype = ctypes.c_int
+    L.strsim_b200_compute_device_multi.argtypes = [ctypes.POINTER(ctypes.c_int), SZ, P, P, ctypes.POINTER(P), P,
+                                                   ctypes.POINTER(P), P]
     L.strsim_b200_set_device.restype = ctypes.c_int
     L.strsim_b200_set_device.argtypes = [ctypes.c_int]
     L.strsim_b200_device_count.restype = ctypes.c_int
@@ -174,11 +177,12 @@ def compute_host(measure, a, b, debug: bool = False, out_values=None, out_validi
     return values, valid, nulls.value
 
 
-def compute_host_multi(measures, a, b, out_values=None, out_validity=None, prepared=None):
-    """Several measures over ONE upload of the two columns (strsim_b200_compute_host_multi).
+def compute_host_multi(measures, a, b, out_values=None, out_validity=None, prepared=None, debug: bool = False):
+    """Several measures over ONE upload of the two columns and (for distinct measures) ONE fused
+    kernel pass (strsim_b200_compute_host_multi).
 
-    Returns (list of float64 arrays, validity, null_count); validity is a bool array unless a
-    preallocated packed bitmap `out_validity` was passed."""
+    Returns (list of float64 arrays, validity, null_count[, list of int32[n,6] records]); validity is a
+    bool array unless a preallocated packed bitmap `out_validity` was passed."""
     L = lib()
     ca, na, cb, nb, n, _keep = prepared if prepared is not None else prepare(a, b)
     k = len(measures)
@@ -186,9 +190,13 @@ def compute_host_multi(measures, a, b, out_values=None, out_validity=None, prepa
     outs = out_values if out_values is not None else [np.zeros(max(n, 1), dtype=np.float64) for _ in range(k)]
     vbytes = out_validity if out_validity is not None else np.zeros((max(n, 1) + 7) // 8 + 8, dtype=np.uint8)
     ptrs = (ctypes.c_void_p * k)(*[o.ctypes.data for o in outs])
+    ints = [np.zeros((max(n, 1), DBG_INTS), dtype=np.int32) for _ in range(k)] if debug else None
+    iptrs = (ctypes.c_void_p * k)(*[i.ctypes.data for i in ints]) if debug else None
     nulls = ctypes.c_int64(0)
-    _check(L.strsim_b200_compute_host_multi(ids, k, ca, na, cb, nb, ptrs, vbytes.ctypes.data, ctypes.byref(nulls), None))
+    _check(L.strsim_b200_compute_host_multi(ids, k, ca, na, cb, nb, ptrs, vbytes.ctypes.data, ctypes.byref(nulls), iptrs))
     valid = vbytes if out_validity is not None else np.unpackbits(vbytes, bitorder="little")[:n].astype(bool)
+    if debug:
+        return [o[:n] for o in outs], valid, nulls.value, [i[:n] for i in ints]
     return [o[:n] for o in outs], valid, nulls.value
 
 
@@ -241,6 +249,18 @@ def compute_device(measure, a: DeviceColumn, b: DeviceColumn, out_ptr: int, vali
     """Launch on device-resident columns; pointers are raw device addresses (e.g. tensor.data_ptr())."""
     _check(lib().strsim_b200_compute_device(measure_id(measure), a.handle, b.handle, out_ptr,
                                             validity_ptr or None, dbg_ptr or None, stream or None))
+
+
+def compute_device_multi(measures, a: DeviceColumn, b: DeviceColumn, out_ptrs, validity_ptr: int = 0, dbg_ptrs=None,
+                         stream: int = 0):
+    """Several distinct measures over resident columns in ONE fused pass; out_ptrs[k] (raw device
+    addresses of n float64) receives measures[k]."""
+    k = len(measures)
+    ids = (ctypes.c_int * k)(*[measure_id(m) for m in measures])
+    outs = (ctypes.c_void_p * k)(*out_ptrs)
+    dbgs = (ctypes.c_void_p * k)(*[(p or None) for p in dbg_ptrs]) if dbg_ptrs else None
+    _check(lib().strsim_b200_compute_device_multi(ids, k, a.handle, b.handle, outs, validity_ptr or None, dbgs,
+                                                  stream or None))
 
 
 def set_device(device: int):

@@ -158,3 +158,76 @@ extern "C" int algos_batch_ureg(int measure, int64_t n, const uint8_t* ad, const
     }
     return 0;
 }
+
+// fused evaluation of several measures (row_*_multi): values / ints are [5][n] / [5][n][6], measures
+// outside `groups` are left untouched
+struct HostEmit {
+    int64_t r, n;
+    int* ints;
+    double* values;
+    void operator()(int measure, double v, const PairInts& pi) {
+        values[measure * n + r] = v;
+        int* o = ints + (measure * n + r) * 6;
+        o[0] = pi.flag; o[1] = pi.la; o[2] = pi.lb; o[3] = pi.x0; o[4] = pi.x1; o[5] = pi.x2;
+    }
+};
+
+template <int GROUPS>
+static void reg_multi_dispatch(int nbits, const uint32_t (&a)[REG_WORDS], const uint32_t (&b)[REG_WORDS], int na,
+                               int nb, HostEmit& e) {
+    switch (nbits) {
+        case 5: row_ascii_reg_multi<GROUPS, 5>(a, b, na, nb, e); break;
+        case 6: row_ascii_reg_multi<GROUPS, 6>(a, b, na, nb, e); break;
+        default: row_ascii_reg_multi<GROUPS, 7>(a, b, na, nb, e); break;
+    }
+}
+
+extern "C" int algos_batch_reg_multi(int groups, int nbits, int64_t n, const uint8_t* ad, const int64_t* ao,
+                                     const uint8_t* bd, const int64_t* bo, int* ints, double* values) {
+    for (int64_t r = 0; r < n; r++) {
+        const int na = (int)(ao[r + 1] - ao[r]), nb = (int)(bo[r + 1] - bo[r]);
+        if (na > 32 || nb > 32) return -2;
+        uint32_t a[REG_WORDS] = {0}, b[REG_WORDS] = {0};
+        std::memcpy(a, ad + ao[r], na);
+        std::memcpy(b, bd + bo[r], nb);
+        HostEmit e{r, n, ints, values};
+        switch (groups) {
+            case 1: reg_multi_dispatch<1>(nbits, a, b, na, nb, e); break;
+            case 2: reg_multi_dispatch<2>(nbits, a, b, na, nb, e); break;
+            case 3: reg_multi_dispatch<3>(nbits, a, b, na, nb, e); break;
+            case 4: reg_multi_dispatch<4>(nbits, a, b, na, nb, e); break;
+            case 5: reg_multi_dispatch<5>(nbits, a, b, na, nb, e); break;
+            case 6: reg_multi_dispatch<6>(nbits, a, b, na, nb, e); break;
+            case 7: reg_multi_dispatch<7>(nbits, a, b, na, nb, e); break;
+            default: return -3;
+        }
+    }
+    return 0;
+}
+
+extern "C" int algos_batch_ureg_multi(int groups, int64_t n, const uint8_t* ad, const int64_t* ao, const uint8_t* bd,
+                                      const int64_t* bo, int* ints, double* values) {
+    static thread_local HostStore<uint32_t> s;
+    for (int64_t r = 0; r < n; r++) {
+        const int na = (int)(ao[r + 1] - ao[r]), nb = (int)(bo[r + 1] - bo[r]);
+        if (na > 32 || nb > 32) return -2;
+        std::memset(s.a_words, 0, sizeof s.a_words);
+        std::memset(s.b_words, 0, sizeof s.b_words);
+        std::memcpy(s.a_words, ad + ao[r], na);
+        std::memcpy(s.b_words, bd + bo[r], nb);
+        const bool equal = na == nb && std::memcmp(ad + ao[r], bd + bo[r], na) == 0;
+        HostWarpMax wm;
+        HostEmit e{r, n, ints, values};
+        switch (groups) {
+            case 1: row_unicode_reg_multi<1>(s, na, nb, equal, wm, e); break;
+            case 2: row_unicode_reg_multi<2>(s, na, nb, equal, wm, e); break;
+            case 3: row_unicode_reg_multi<3>(s, na, nb, equal, wm, e); break;
+            case 4: row_unicode_reg_multi<4>(s, na, nb, equal, wm, e); break;
+            case 5: row_unicode_reg_multi<5>(s, na, nb, equal, wm, e); break;
+            case 6: row_unicode_reg_multi<6>(s, na, nb, equal, wm, e); break;
+            case 7: row_unicode_reg_multi<7>(s, na, nb, equal, wm, e); break;
+            default: return -3;
+        }
+    }
+    return 0;
+}

@@ -388,3 +388,134 @@ def test_long_levenshtein_tiers(native, oracle):
     a += ["short", "x" * 70]
     b += ["y" * 100, "x" * 69 + "z"]
     check(native, oracle, "levenshtein", a, b)
+
+
+FUSED_SETS = [list(range(5)), [2, 4], [0, 1], [3, 4], [1, 2], [0, 3], [4, 2, 0], [1, 2, 3, 4]]
+
+
+def check_multi(native, oracle, measure_ids, a, b, A=None, B=None):
+    names = [oracle.MEASURES[i] for i in measure_ids]
+    A = sv(a) if A is None else A
+    B = sv(b) if B is None else B
+    outs, valid, nulls, ints = native.compute_host_multi(names, A, B, debug=True)
+    for m, got, gi in zip(names, outs, ints):
+        ref, ref_valid, ref_ints = oracle.batch(m, a, b)
+        assert (valid == ref_valid).all() and nulls == int((~ref_valid).sum()), (m, "null masks differ")
+        bad = np.nonzero(valid & (got.view(np.uint64) != ref.view(np.uint64)))[0]
+        assert bad.size == 0, (names, m, a[bad[0]], b[bad[0]], got[bad[0]], ref[bad[0]], gi[bad[0]], ref_ints[bad[0]])
+        ibad = np.nonzero(valid & (gi != ref_ints).any(axis=1))[0]
+        assert ibad.size == 0, (names, m, a[ibad[0]], b[ibad[0]], gi[ibad[0]], ref_ints[ibad[0]])
+
+
+def test_fused_measures_golden_vectors(native, oracle):
+    """ONE fused launch (short_kernel<MULTI_BASE+groups>) must reproduce every measure's golden bits."""
+    fx = load_fixture()
+    a, b = [r[1] for r in fx], [r[2] for r in fx]
+    before = native.kernel_launches()
+    check_multi(native, oracle, list(range(5)), a, b)
+    assert native.kernel_launches() - before <= 3, "all five measures should come from one fused launch"
+    demo_a = ["phillips", "phillips", "", "", None, None]
+    demo_b = ["phillips", "philips", "phillips", "", "phillips", None]
+    check_multi(native, oracle, list(range(5)), demo_a, demo_b)
+
+
+@pytest.mark.parametrize("ids", FUSED_SETS)
+def test_fused_measures_subsets(native, oracle, ids):
+    """every group combination, on ASCII-only columns (bit-plane path), mixed scripts (register-compare
+    path), with nulls, empties, single characters and rows that overflow to the 64-bit / long kernels"""
+    rng = random.Random(1000 + sum(ids) * 7 + len(ids))
+    # ASCII-only columns, lower-case block (5 planes)
+    a, b = [], []
+    for _ in range(30000):
+        x = "".join(rng.choice("abcdefghijklmnopqrstuvwxyz") for _ in range(rng.randint(0, 30)))
+        y = x
+        if rng.random() < 0.8:
+            y = list(x)
+            for _ in range(rng.randint(0, 3)):
+                p = rng.randint(0, len(y))
+                op = rng.randint(0, 2)
+                if op == 0 and y:
+                    y[min(p, len(y) - 1)] = rng.choice("abcxyz")
+                elif op == 1:
+                    y.insert(p, rng.choice("abcxyz"))
+                elif y:
+                    del y[min(p, len(y) - 1)]
+            y = "".join(y)
+            if rng.random() < 0.2:
+                y = "".join(rng.choice("abcdefghijklmnopqrstuvwxyz") for _ in range(rng.randint(0, 30)))
+        a.append(x)
+        b.append(y)
+    a += ["a", "a", "", "x", "ab", "a" * 32, "a" * 33, "b" * 64, "c" * 65, "d" * 300]
+    b += ["b", "a", "x", "", "ba", "a" * 31 + "b", "a" * 32, "b" * 63 + "c", "c" * 64, "e" * 200]
+    check_multi(native, oracle, ids, a, b)
+    # general ASCII (7 planes) with nulls
+    a2 = [None if rng.random() < 0.05 else "".join(rng.choice("aB-c'D 019.~") for _ in range(rng.randint(0, 28))) for _ in range(8000)]
+    b2 = [None if rng.random() < 0.05 else "".join(rng.choice("aB-c'D 019.~") for _ in range(rng.randint(0, 28))) for _ in range(8000)]
+    check_multi(native, oracle, ids, a2, b2)
+    # mixed scripts, lengths beyond 32 bytes included
+    pairs = [rand_pair(rng, rng.choice([8, 20, 40, 90])) for _ in range(20000)]
+    a3 = [None if rng.random() < 0.03 else p[0] for p in pairs]
+    b3 = [None if rng.random() < 0.03 else p[1] for p in pairs]
+    check_multi(native, oracle, ids, a3, b3)
+    assert sum(native.last_overflow()) > 0
+
+
+def test_fused_measures_chunks_broadcast_device(native, oracle):
+    import pyarrow as pa
+    torch = pytest.importorskip("torch")
+
+    rng = random.Random(77)
+    pairs = [rand_pair(rng, 24) for _ in range(40000)]
+    a = [None if rng.random() < 0.05 else p[0] for p in pairs]
+    b = [None if rng.random() < 0.05 else p[1] for p in pairs]
+    # different chunkings + a sliced chunk
+    A = pa.chunked_array([sv(a[:1000]), sv(a[1000:25000]), sv(["zz"] + a[25000:]).slice(1)])
+    B = pa.chunked_array([sv(b[:17000]), sv(b[17000:])])
+    check_multi(native, oracle, list(range(5)), a, b, A, B)
+    # scalar broadcast, both orientations
+    check_multi(native, oracle, [0, 2, 4], ["smith"] * len(b), b, sv(["smith"]), sv(b))
+    check_multi(native, oracle, [1, 3], a, ["日本語"] * len(a), sv(a), sv(["日本語"]))
+    # device-resident multi API
+    ca, cb = native.DeviceColumn(sv(a)), native.DeviceColumn(sv(b))
+    n = len(a)
+    names = ["jaro_winkler", "sorensen_dice", "levenshtein"]
+    outs = [torch.empty(n, dtype=torch.float64, device="cuda") for _ in names]
+    val = torch.zeros((n + 31) // 32, dtype=torch.int32, device="cuda")
+    before = native.kernel_launches()
+    native.compute_device_multi(names, ca, cb, [o.data_ptr() for o in outs], val.data_ptr(), None,
+                                torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert 1 <= native.kernel_launches() - before <= 2  # fused kernel + validity kernel
+    bits = np.unpackbits(val.cpu().numpy().view(np.uint8), bitorder="little")[:n].astype(bool)
+    for m, o in zip(names, outs):
+        ref, ref_valid, _ = oracle.batch(m, a, b)
+        got = o.cpu().numpy()
+        assert (bits == ref_valid).all()
+        assert (got[ref_valid].view(np.uint64) == ref[ref_valid].view(np.uint64)).all(), m
+    with pytest.raises(native.StrsimError):
+        native.compute_device_multi(["jaro", "jaro"], ca, cb, [outs[0].data_ptr(), outs[1].data_ptr()])
+
+
+def test_fused_measures_fallback_cross_check(oracle):
+    """fused call with STRSIM_B200_FORCE_GENERIC=1: every row leaves through the overflow lists and is
+    finished measure by measure; and STRSIM_B200_NO_FUSE=1 must give the same bits as the fused path."""
+    code = r"""
+import sys, random, numpy as np
+sys.path[:0] = [%r, %r, %r]
+import pyarrow as pa
+from polars_strsim import _native
+from oracle import oracle
+from test_oracle import rand_pair
+rng = random.Random(9)
+pairs = [rand_pair(rng, 50) for _ in range(4000)]
+a = [None if rng.random() < 0.03 else p[0] for p in pairs]; b = [p[1] for p in pairs]
+outs, valid, nulls, ints = _native.compute_host_multi(list(oracle.MEASURES), pa.array(a, type=pa.string_view()), pa.array(b, type=pa.string_view()), debug=True)
+for m, v, gi in zip(oracle.MEASURES, outs, ints):
+    ref, rv, ri = oracle.batch(m, a, b)
+    assert (valid == rv).all() and (v[rv].view(np.uint64) == ref[rv].view(np.uint64)).all() and (gi[rv] == ri[rv]).all(), m
+print("ok")
+""" % (str(ROOT), str(ROOT / "polars-strsim_b200"), str(ROOT / "tests"))
+    for knob in ("STRSIM_B200_FORCE_GENERIC", "STRSIM_B200_NO_FUSE"):
+        env = dict(os.environ, **{knob: "1"})
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0 and "ok" in out.stdout, (knob, out.stderr[-2000:])

@@ -21,8 +21,7 @@ HARNESS = ROOT / "tests" / "host_harness"
 @pytest.fixture(scope="module")
 def algos():
     so = HARNESS / "libpair_algos_host.so"
-    srcs = [HARNESS / "pair_algos_host.cpp", ROOT / "polars-strsim_b200/csrc/row_short.cuh",
-            ROOT / "polars-strsim_b200/csrc/pair_algos.cuh"]
+    srcs = [HARNESS / "pair_algos_host.cpp"] + sorted((ROOT / "polars-strsim_b200/csrc").glob("*.cuh"))
     if not so.exists() or so.stat().st_mtime < max(s.stat().st_mtime for s in srcs):
         subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++",
                         f"-I{ROOT / 'polars-strsim_b200/csrc'}", "-o", str(so), str(srcs[0])], check=True)
@@ -195,3 +194,103 @@ def test_register_compare_unicode_path(algos, oracle):
         assert bad.size == 0, (measure, a[bad[0]], b[bad[0]], vals[bad[0]], ref[bad[0]])
         ib = np.nonzero((ints != ref_ints).any(axis=1))[0]
         assert ib.size == 0, (measure, a[ib[0]], b[ib[0]], ints[ib[0]], ref_ints[ib[0]])
+
+
+GROUP_MEASURES = {1: ["levenshtein"], 2: ["jaro", "jaro_winkler"], 4: ["jaccard", "sorensen_dice"]}
+
+
+def check_multi(oracle, call, a, b):
+    """call(groups, ints[5][n][6], vals[5][n]) runs a fused row function; every measure of the groups
+    must carry the oracle's bits and integer record, the other slots must stay untouched."""
+    from oracle.oracle import MEASURE_ID
+
+    n = len(a)
+    refs = {m: oracle.batch(m, a, b) for m in oracle.MEASURES}
+    for groups in range(1, 8):
+        ints = np.full((5, n, 6), -7, dtype=np.int32)
+        vals = np.full((5, n), -7.0, dtype=np.float64)
+        assert call(groups, ints, vals) == 0
+        wanted = [m for g, ms in GROUP_MEASURES.items() if groups & g for m in ms]
+        for m in oracle.MEASURES:
+            k = MEASURE_ID[m]
+            if m not in wanted:
+                assert (vals[k] == -7.0).all() and (ints[k] == -7).all(), (groups, m)
+                continue
+            ref, _, ref_ints = refs[m]
+            bad = np.nonzero(vals[k].view(np.uint64) != ref.view(np.uint64))[0]
+            assert bad.size == 0, (groups, m, a[bad[0]], b[bad[0]], vals[k][bad[0]], ref[bad[0]])
+            ib = np.nonzero((ints[k] != ref_ints).any(axis=1))[0]
+            assert ib.size == 0, (groups, m, a[ib[0]], b[ib[0]], ints[k][ib[0]], ref_ints[ib[0]])
+
+
+@pytest.mark.parametrize("nbits,alphabet", [(5, "abcdefghijklmnopqrstuvwxyz"), (6, "abcxyzABCXYZ_`{"),
+                                            (7, "ab yz-'09AZ~\x01\x7f!")])
+def test_fused_measures_ascii_reg(algos, oracle, nbits, alphabet):
+    """row_ascii_reg_multi: one pass over a feeds Myers, Jaro and the multiset together."""
+    from oracle.oracle import _pack
+
+    algos.algos_batch_reg_multi.restype = ctypes.c_int
+    algos.algos_batch_reg_multi.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int64] + [ctypes.c_void_p] * 6
+    rng = random.Random(31 + nbits)
+    a, b = [], []
+    for _ in range(6000):
+        x = "".join(rng.choice(alphabet) for _ in range(rng.randint(0, 32)))
+        if rng.random() < 0.6:
+            y = list(x)
+            for _ in range(rng.randint(0, 3)):
+                op, pos = rng.randint(0, 3), rng.randint(0, len(y))
+                if op == 0 and y:
+                    y[min(pos, len(y) - 1)] = rng.choice(alphabet)
+                elif op == 1 and len(y) < 32:
+                    y.insert(pos, rng.choice(alphabet))
+                elif op == 2 and y:
+                    del y[min(pos, len(y) - 1)]
+                elif op == 3 and len(y) > 1:
+                    q = min(pos, len(y) - 2)
+                    y[q], y[q + 1] = y[q + 1], y[q]
+            y = "".join(y)
+        else:
+            y = "".join(rng.choice(alphabet) for _ in range(rng.randint(0, 32)))
+        a.append(x)
+        b.append(y)
+    for la in (0, 1, 2, 3, 31, 32):
+        for lb in (0, 1, 2, 3, 31, 32):
+            a.append(alphabet[0] * la)
+            b.append(alphabet[1] * lb)
+            a.append("".join(rng.choice(alphabet) for _ in range(la)))
+            b.append("".join(rng.choice(alphabet) for _ in range(lb)))
+    if nbits == 5:
+        fx = load_fixture()
+        a += [r[1] for r in fx]
+        b += [r[2] for r in fx]
+    ad, ao, _ = _pack(a)
+    bd, bo, _ = _pack(b)
+    check_multi(oracle, lambda g, ints, vals: algos.algos_batch_reg_multi(
+        g, nbits, len(a), ad.ctypes.data, ao.ctypes.data, bd.ctypes.data, bo.ctypes.data, ints.ctypes.data,
+        vals.ctypes.data), a, b)
+
+
+def test_fused_measures_unicode_reg(algos, oracle):
+    """row_unicode_reg_multi: the same fusion on the register-compare path for any script."""
+    from oracle.oracle import _pack
+
+    algos.algos_batch_ureg_multi.restype = ctypes.c_int
+    algos.algos_batch_ureg_multi.argtypes = [ctypes.c_int, ctypes.c_int64] + [ctypes.c_void_p] * 6
+    rng = random.Random(778)
+    a, b = [], []
+    while len(a) < 12000:
+        x, y = rand_pair(rng, 32)
+        if len(x.encode()) <= 32 and len(y.encode()) <= 32:
+            a.append(x)
+            b.append(y)
+    for ch in ("é", "日", "\U0001f600", "a"):
+        w = len(ch.encode())
+        for la in (0, 1, 2, 32 // w):
+            for lb in (0, 1, 32 // w):
+                a += [ch * la, ch * la]
+                b += [ch * lb, ("z" * lb)]
+    ad, ao, _ = _pack(a)
+    bd, bo, _ = _pack(b)
+    check_multi(oracle, lambda g, ints, vals: algos.algos_batch_ureg_multi(
+        g, len(a), ad.ctypes.data, ao.ctypes.data, bd.ctypes.data, bo.ctypes.data, ints.ctypes.data,
+        vals.ctypes.data), a, b)
