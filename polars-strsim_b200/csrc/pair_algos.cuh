@@ -81,6 +81,13 @@ SS_HD int popc(uint64_t x) {
     return __builtin_popcountll(x);
 #endif
 }
+SS_HD int ctz32(uint32_t x) {  // x != 0
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
 SS_HD int ctz64(uint64_t x) {  // x != 0
 #if defined(__CUDA_ARCH__)
     return __ffsll((long long)x) - 1;
@@ -233,6 +240,37 @@ struct JaroTransStep {
             if (!(tab(c) & low)) t++;
         }
         flag_a = flag_a >> 1;
+    }
+};
+
+// How the transposition count t (strsim.rs:220-237) is obtained once the match pass has left its flags.
+// TransByPass: a second pass over the characters of a (any Tab / any script).
+struct TransByPass {
+    template <class M, class Tab, class Each>
+    SS_HD int operator()(const Tab& tab, const Each& each_a, int la, M flag_a, M flag_b) const {
+        JaroTransStep<M, Tab> trans(tab, flag_a, flag_b);
+        each_a(la, trans);
+        return trans.t;
+    }
+};
+
+// TransByBytes: ASCII strings whose bytes can be fetched at a dynamic position (A(p), B(p): byte p of
+// a / b): walk the two flag sets lowest bit first and compare the k-th flagged characters directly --
+// m iterations of about 16 instructions instead of la iterations that each rebuild a position mask.
+template <class ByteAt>
+struct TransByBytes {
+    ByteAt A, B;
+    template <class M, class Tab, class Each>
+    SS_HD int operator()(const Tab&, const Each&, int, M flag_a, M flag_b) const {
+        int t = 0;
+        while (flag_a) {
+            const int ia = sizeof(M) == 4 ? ctz32((uint32_t)flag_a) : ctz64((uint64_t)flag_a);
+            const int ib = sizeof(M) == 4 ? ctz32((uint32_t)flag_b) : ctz64((uint64_t)flag_b);
+            flag_a &= flag_a - M(1);
+            flag_b &= flag_b - M(1);
+            t += A(ia) != B(ib) ? 1 : 0;
+        }
+        return t;
     }
 };
 

@@ -68,25 +68,41 @@ SS_HD void build_planes(const uint32_t (&P)[REG_WORDS], int m, PlaneTab<NBITS>& 
     tab.valid = m >= 32 ? 0xFFFFFFFFu : ((1u << m) - 1u);
 }
 
-// applies f to the first n bytes of a register-resident string
+// applies f to the first n bytes of a register-resident string.  The loop over words is ROLLED: the
+// working copy is rotated down one register per word, so the body of f exists four times in the code
+// instead of 32 times -- the fully unrolled form made the fused kernel 112 KB of SASS and a fifth of
+// its stall samples were instruction-cache misses (profiles/r1_ncu_fused_C2.md).
 template <class F>
 SS_HD void for_each_byte_reg(const uint32_t (&W)[REG_WORDS], int n, F& f) {
+    uint32_t r[REG_WORDS];
 #pragma unroll
-    for (int w = 0; w < REG_WORDS; w++) {
-        if (4 * w >= n) break;
-        const uint32_t word = W[w];
+    for (int w = 0; w < REG_WORDS; w++) r[w] = W[w];
+#pragma unroll 1
+    for (int left = n; left > 0; left -= 4) {
+        const uint32_t word = r[0];
+#pragma unroll
+        for (int w = 0; w + 1 < REG_WORDS; w++) r[w] = r[w + 1];
         f(word & 0xFFu);
-        if (4 * w + 1 < n) f((word >> 8) & 0xFFu);
-        if (4 * w + 2 < n) f((word >> 16) & 0xFFu);
-        if (4 * w + 3 < n) f(word >> 24);
+        if (left > 1) f((word >> 8) & 0xFFu);
+        if (left > 2) f((word >> 16) & 0xFFu);
+        if (left > 3) f(word >> 24);
     }
 }
 
+struct EachByteReg {
+    const uint32_t (&W)[REG_WORDS];
+    SS_HD explicit EachByteReg(const uint32_t (&w)[REG_WORDS]) : W(w) {}
+    template <class F>
+    SS_HD void operator()(int n, F& f) const {
+        for_each_byte_reg(W, n, f);
+    }
+};
+
 // a, b: zero-padded little-endian words; na, nb <= 32 bytes, every byte < 0x80 and (for NBITS < 7)
 // inside one aligned block of 2^NBITS code points.
-template <int MEASURE, int NBITS>
+template <int MEASURE, int NBITS, class Trans = TransByPass>
 SS_HD double row_ascii_reg(const uint32_t (&a)[REG_WORDS], const uint32_t (&b)[REG_WORDS], int na, int nb,
-                           PairInts& out) {
+                           PairInts& out, const Trans& trans_count = Trans()) {
     out.flag = F_GENERAL;
     out.la = out.lb = out.x0 = out.x1 = out.x2 = 0;
     bool equal = na == nb;
@@ -142,11 +158,10 @@ SS_HD double row_ascii_reg(const uint32_t (&a)[REG_WORDS], const uint32_t (&b)[R
             const int outer = la < lb + bound ? la : lb + bound;
             JaroMatchStep<uint32_t, Tab> match(tab, lb, bound);
             for_each_byte_reg(a, outer, match);
-            JaroTransStep<uint32_t, Tab> trans(tab, match.flag_a, match.flag_b);
-            if (match.m > 0) for_each_byte_reg(a, outer, trans);
+            const int t = match.m > 0 ? trans_count(tab, EachByteReg(a), outer, match.flag_a, match.flag_b) : 0;
             out.x0 = match.m;
-            out.x1 = trans.t;
-            v = match.m == 0 ? 0.0 : jaro_value(match.m, trans.t, la, lb);
+            out.x1 = t;
+            v = match.m == 0 ? 0.0 : jaro_value(match.m, t, la, lb);
             if (MEASURE == JARO_WINKLER && v > 0.7) {  // strsim.rs:260-267
                 const uint32_t x = a[0] ^ b[0];
                 int lim = la < lb ? la : lb;
@@ -173,15 +188,6 @@ SS_HD double row_ascii_reg(const uint32_t (&a)[REG_WORDS], const uint32_t (&b)[R
 }
 
 // ---- fused evaluation of several measures (row_short.cuh: multi_body) ---------------------------------
-struct EachByteReg {
-    const uint32_t (&W)[REG_WORDS];
-    SS_HD explicit EachByteReg(const uint32_t (&w)[REG_WORDS]) : W(w) {}
-    template <class F>
-    SS_HD void operator()(int n, F& f) const {
-        for_each_byte_reg(W, n, f);
-    }
-};
-
 struct PrefixReg {  // common prefix of two ASCII strings, capped at 4 (strsim.rs:261-266)
     uint32_t x;
     int lim;
@@ -192,9 +198,9 @@ struct PrefixReg {  // common prefix of two ASCII strings, capped at 4 (strsim.r
     }
 };
 
-template <int GROUPS, int NBITS, class Emit>
+template <int GROUPS, int NBITS, class Trans, class Emit>
 SS_HD void row_ascii_reg_multi(const uint32_t (&a)[REG_WORDS], const uint32_t (&b)[REG_WORDS], int na, int nb,
-                               Emit& emit) {
+                               const Trans& trans_count, Emit& emit) {
     bool equal = na == nb;
     if (equal) {
         uint32_t diff = 0;
@@ -216,7 +222,7 @@ SS_HD void row_ascii_reg_multi(const uint32_t (&a)[REG_WORDS], const uint32_t (&
     prefix.x = a[0] ^ b[0];
     prefix.lim = na < nb ? na : nb;
     if (prefix.lim > 4) prefix.lim = 4;
-    multi_body<GROUPS, uint32_t>(tab, each_a, na, nb, na == 0 || nb == 0, prefix, emit);
+    multi_body<GROUPS, uint32_t>(tab, each_a, na, nb, na == 0 || nb == 0, prefix, trans_count, emit);
 }
 
 }  // namespace strsim

@@ -224,9 +224,9 @@ SS_HD void emit_groups(Emit& emit, double v, const PairInts& o) {
 // first n characters of a; prefix() = length of the common character prefix, capped at 4
 // (strsim.rs:261-266); one_empty: either string is empty (strsim.rs:184,290,326).  The integer records
 // and values are those of measure_body() / row_short() for each single measure.
-template <int GROUPS, class M, class Tab, class Each, class Prefix, class Emit>
+template <int GROUPS, class M, class Tab, class Each, class Prefix, class Trans, class Emit>
 SS_HD void multi_body(const Tab& tab, const Each& each_a, int la, int lb, bool one_empty, const Prefix& prefix,
-                      Emit& emit) {
+                      const Trans& trans_count, Emit& emit) {
     const int mx = la > lb ? la : lb;
     int bound = mx / 2 - 1;  // strsim.rs:200
     if (bound < 0) bound = 0;  // both strings of at most one character: settled by the row rules below
@@ -258,12 +258,7 @@ SS_HD void multi_body(const Tab& tab, const Each& each_a, int la, int lb, bool o
             emit(JARO_WINKLER, 0.0, o);
             o.flag = F_GENERAL;
         } else {
-            int t = 0;
-            if (f.jm.m > 0) {
-                JaroTransStep<M, Tab> trans(tab, f.jm.flag_a, f.jm.flag_b);
-                each_a(la, trans);
-                t = trans.t;
-            }
+            const int t = f.jm.m > 0 ? trans_count(tab, each_a, la, f.jm.flag_a, f.jm.flag_b) : 0;
             o.x0 = f.jm.m;
             o.x1 = t;
             double v = f.jm.m == 0 ? 0.0 : jaro_value(f.jm.m, t, la, lb);

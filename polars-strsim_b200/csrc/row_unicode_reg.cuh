@@ -158,7 +158,7 @@ SS_HD void row_unicode_reg_multi(Store& s, int na, int nb, bool equal, const War
     decode_to_regs(wb, nb, 7, tab);
     EachChar<Store> each_a(s, false, na);
     PrefixChars<StoreWords<Store>> prefix(wa, wb, na, nb);
-    multi_body<GROUPS, uint32_t>(tab, each_a, la, lb, na == 0 || nb == 0, prefix, emit);
+    multi_body<GROUPS, uint32_t>(tab, each_a, la, lb, na == 0 || nb == 0, prefix, TransByPass(), emit);
 }
 
 struct HostWarpMax {  // host tests: one "lane"

@@ -339,6 +339,16 @@ struct RowEmit {
     }
 };
 
+// byte p of a string that sits in shared memory (inline in its staged view, or in the stage area)
+struct SmemByteAt {
+    uint32_t base;  // shared-space address of the first byte
+    __device__ __forceinline__ uint32_t operator()(int p) const {
+        uint32_t v;
+        asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(base + (uint32_t)p));
+        return v;
+    }
+};
+
 struct WarpMaxDev {  // maximum over the 32 lanes of the warp (all lanes must call it)
     __device__ __forceinline__ int operator()(int v) const { return __reduce_max_sync(0xFFFFFFFFu, v); }
 };
@@ -598,7 +608,9 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
             const uint4 va = sva[i], vb = svb[i];
             // byte-equal pairs score 1.0 (strsim.rs:128,182,288,324): settle them here so that they do
             // not occupy lanes of the compute phase (the 4-byte prefix in the view rejects most rows)
-            if (PREFILTER_EQUAL && va.x == vb.x && (va.x == 0u || ((va.x <= 12u ? va.y : sva_prefix(va, stage_a)) ==
+            // (always in the fused kernel: its per-pair loops are three measures long, so the lanes that a
+            // fifth of equal pairs would idle are worth far more than the prefix compare)
+            if ((PREFILTER_EQUAL || is_multi(MEASURE)) && va.x == vb.x && (va.x == 0u || ((va.x <= 12u ? va.y : sva_prefix(va, stage_a)) ==
                                                 (vb.x <= 12u ? vb.y : sva_prefix(vb, stage_b)))) &&
                 staged_equal(va, vb, stage_a, stage_b)) {
                 const long long idx = tile0 + i;
@@ -730,13 +742,17 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
                 uint32_t ra[REG_WORDS], rb[REG_WORDS];
                 load_string_reg(va, stage_a, ra);
                 load_string_reg(vb, stage_b, rb);
+                // Jaro's transposition count reads the flagged characters straight from the staged tile
+                TransByBytes<SmemByteAt> trans;
+                trans.A.base = va.x <= 12u ? smem_u32(&sva[i]) + 4u : smem_u32(stage_a) + va.y;
+                trans.B.base = vb.x <= 12u ? smem_u32(&svb[i]) + 4u : smem_u32(stage_b) + vb.y;
                 if constexpr (is_multi(MEASURE)) {
                     const long long idx = tile0 + i;
                     RowEmit emit{s, GATHER ? (long long)s.list[idx] : idx, true};
-                    row_ascii_reg_multi<GROUPS, NBITS>(ra, rb, na, nb, emit);
+                    row_ascii_reg_multi<GROUPS, NBITS>(ra, rb, na, nb, trans, emit);
                     continue;
                 }
-                v = row_ascii_reg<is_multi(MEASURE) ? 0 : MEASURE, NBITS>(ra, rb, na, nb, ints);
+                v = row_ascii_reg<is_multi(MEASURE) ? 0 : MEASURE, NBITS>(ra, rb, na, nb, ints, trans);
             } else {
                 const uint32_t or_a = load_string<WORDS, TPB>(va, stage_a, store.wa_);
                 const uint32_t or_b = load_string<WORDS, TPB>(vb, stage_b, store.wb_);

@@ -96,13 +96,26 @@ extern "C" int algos_myers_multiword(const uint32_t* a, int la, const uint32_t* 
 
 // register-resident ASCII path (row_ascii_reg.cuh): planes instead of tables
 #include "row_ascii_reg.cuh"
+struct HostByteAt {  // stands in for short_kernel.cuh's SmemByteAt
+    const uint8_t* p;
+    uint32_t operator()(int i) const { return p[i]; }
+};
+// `by_bytes`: transposition count by direct byte fetches (the kernels' way) or by the second pass
 template <int MEASURE>
 static double reg_dispatch(int nbits, const uint32_t (&a)[REG_WORDS], const uint32_t (&b)[REG_WORDS], int na, int nb,
-                           PairInts& pi) {
+                           PairInts& pi, bool by_bytes = true) {
+    TransByBytes<HostByteAt> tb{{reinterpret_cast<const uint8_t*>(a)}, {reinterpret_cast<const uint8_t*>(b)}};
+    if (!by_bytes) {
+        switch (nbits) {
+            case 5: return row_ascii_reg<MEASURE, 5>(a, b, na, nb, pi);
+            case 6: return row_ascii_reg<MEASURE, 6>(a, b, na, nb, pi);
+            default: return row_ascii_reg<MEASURE, 7>(a, b, na, nb, pi);
+        }
+    }
     switch (nbits) {
-        case 5: return row_ascii_reg<MEASURE, 5>(a, b, na, nb, pi);
-        case 6: return row_ascii_reg<MEASURE, 6>(a, b, na, nb, pi);
-        default: return row_ascii_reg<MEASURE, 7>(a, b, na, nb, pi);
+        case 5: return row_ascii_reg<MEASURE, 5>(a, b, na, nb, pi, tb);
+        case 6: return row_ascii_reg<MEASURE, 6>(a, b, na, nb, pi, tb);
+        default: return row_ascii_reg<MEASURE, 7>(a, b, na, nb, pi, tb);
     }
 }
 extern "C" int algos_batch_reg(int measure, int nbits, int64_t n, const uint8_t* ad, const int64_t* ao,
@@ -117,8 +130,8 @@ extern "C" int algos_batch_reg(int measure, int nbits, int64_t n, const uint8_t*
         double v;
         switch (measure) {
             case 0: v = reg_dispatch<0>(nbits, a, b, na, nb, pi); break;
-            case 1: v = reg_dispatch<1>(nbits, a, b, na, nb, pi); break;
-            case 2: v = reg_dispatch<2>(nbits, a, b, na, nb, pi); break;
+            case 1: v = reg_dispatch<1>(nbits, a, b, na, nb, pi, (r & 1) != 0); break;
+            case 2: v = reg_dispatch<2>(nbits, a, b, na, nb, pi, (r & 1) != 0); break;
             case 3: v = reg_dispatch<3>(nbits, a, b, na, nb, pi); break;
             default: v = reg_dispatch<4>(nbits, a, b, na, nb, pi); break;
         }
@@ -175,10 +188,11 @@ struct HostEmit {
 template <int GROUPS>
 static void reg_multi_dispatch(int nbits, const uint32_t (&a)[REG_WORDS], const uint32_t (&b)[REG_WORDS], int na,
                                int nb, HostEmit& e) {
+    TransByBytes<HostByteAt> tb{{reinterpret_cast<const uint8_t*>(a)}, {reinterpret_cast<const uint8_t*>(b)}};
     switch (nbits) {
-        case 5: row_ascii_reg_multi<GROUPS, 5>(a, b, na, nb, e); break;
-        case 6: row_ascii_reg_multi<GROUPS, 6>(a, b, na, nb, e); break;
-        default: row_ascii_reg_multi<GROUPS, 7>(a, b, na, nb, e); break;
+        case 5: row_ascii_reg_multi<GROUPS, 5>(a, b, na, nb, tb, e); break;
+        case 6: row_ascii_reg_multi<GROUPS, 6>(a, b, na, nb, tb, e); break;
+        default: row_ascii_reg_multi<GROUPS, 7>(a, b, na, nb, tb, e); break;
     }
 }
 

@@ -413,7 +413,9 @@ def test_fused_measures_golden_vectors(native, oracle):
     a, b = [r[1] for r in fx], [r[2] for r in fx]
     before = native.kernel_launches()
     check_multi(native, oracle, list(range(5)), a, b)
-    assert native.kernel_launches() - before <= 3, "all five measures should come from one fused launch"
+    # one fused launch + the four column-statistics launches of the two uploads (five single-measure
+    # launches would make it nine)
+    assert native.kernel_launches() - before <= 6, "all five measures should come from one fused launch"
     demo_a = ["phillips", "phillips", "", "", None, None]
     demo_b = ["phillips", "philips", "phillips", "", "phillips", None]
     check_multi(native, oracle, list(range(5)), demo_a, demo_b)
@@ -485,7 +487,8 @@ def test_fused_measures_chunks_broadcast_device(native, oracle):
     native.compute_device_multi(names, ca, cb, [o.data_ptr() for o in outs], val.data_ptr(), None,
                                 torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
-    assert 1 <= native.kernel_launches() - before <= 2  # fused kernel + validity kernel
+    # fused kernel + validity kernel (+ one 64-bit follow-up per measure for the rows of 33..64 bytes)
+    assert 1 <= native.kernel_launches() - before <= 5
     bits = np.unpackbits(val.cpu().numpy().view(np.uint8), bitorder="little")[:n].astype(bool)
     for m, o in zip(names, outs):
         ref, ref_valid, _ = oracle.batch(m, a, b)

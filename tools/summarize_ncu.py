@@ -60,12 +60,14 @@ def main():
             if k in ix:
                 lines.append(f"| {label} (`{k}`) | {r[ix[k]]} {units[ix[k]]} |")
         lines.append("")
-        m = re.search(r"short_kernel<unsigned int, (\d)", name)
+        m = re.search(r"short_kernel<unsigned int, (\d+)", name)
         if m and "dram__bytes_read.sum" in ix:
             t = to_bytes(r[ix["dram__bytes_read.sum"]], units[ix["dram__bytes_read.sum"]]) + \
                 to_bytes(r[ix["dram__bytes_write.sum"]], units[ix["dram__bytes_write.sum"]])
-            traffic[MEASURES[int(m.group(1))]] = t
-            insts[MEASURES[int(m.group(1))]] = float(r[ix["smsp__inst_executed.sum"]].replace(",", ""))
+            # template value 0..4: one measure; 8 + group mask: the fused kernel (pair_algos.cuh MULTI_BASE)
+            key = MEASURES[int(m.group(1))] if int(m.group(1)) < 5 else "fused"
+            traffic[key] = t
+            insts[key] = float(r[ix["smsp__inst_executed.sum"]].replace(",", ""))
     Path(out_md).write_text("\n".join(lines) + "\n")
     if traffic_path and traffic:
         cur = json.loads(traffic_path.read_text()) if traffic_path.exists() else {}
