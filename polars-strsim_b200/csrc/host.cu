@@ -613,6 +613,14 @@ static int launch_fused(ThreadCtx& ctx, Alphabet al, const SegArgs& args, long l
 template <int GROUPS>
 static int launch_multi(ThreadCtx& ctx, Alphabet al, const SegArgs& args, long long rows, cudaStream_t st) {
     constexpr int ME = MULTI_BASE + GROUPS;
+    static const char* cfg_env = getenv("STRSIM_B200_TILE");  // tuning knob (all-groups kernel only)
+    const int cfg = cfg_env && *cfg_env ? atoi(cfg_env) : 0;
+    if (GROUPS == 7 && al == ALPHA_ASCII32 && cfg != 0) {
+        if (cfg == 1) return launch_short<uint32_t, MULTI_BASE + 7, 256, 3, false, 32, true, true>(ctx, args, rows, st);
+        if (cfg == 2) return launch_short<uint32_t, MULTI_BASE + 7, 128, 4, false, 32, true, true>(ctx, args, rows, st);
+        if (cfg == 3) return launch_short<uint32_t, MULTI_BASE + 7, 256, 2, false, 32, true, true>(ctx, args, rows, st);
+        if (cfg == 4) return launch_short<uint32_t, MULTI_BASE + 7, 512, 2, false, 32, true, true>(ctx, args, rows, st);
+    }
     switch (al) {
         case ALPHA_ASCII32:
             return launch_short<uint32_t, ME, 256, 4, false, 32, true, true>(ctx, args, rows, st);

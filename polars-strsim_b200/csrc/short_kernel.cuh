@@ -613,6 +613,14 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
             if ((PREFILTER_EQUAL || is_multi(MEASURE)) && va.x == vb.x && (va.x == 0u || ((va.x <= 12u ? va.y : sva_prefix(va, stage_a)) ==
                                                 (vb.x <= 12u ? vb.y : sva_prefix(vb, stage_b)))) &&
                 staged_equal(va, vb, stage_a, stage_b)) {
+                if (is_multi(MEASURE)) {
+                    // fused kernel: the equal pairs get the cheapest bucket of their own (key 1 otherwise
+                    // holds only empty/empty pairs, which are equal too) -- whole warps of them leave the
+                    // row function at its first test, and the stores stay dense
+                    key[k] = 1u;
+                    rank[k] = atomicAdd(&hist[1], 1u);
+                    continue;
+                }
                 const long long idx = tile0 + i;
                 const long long row = GATHER ? (long long)s.list[idx] : idx;
                 store_settled<MEASURE>(s, row, 1.0, F_EQUAL);
