@@ -370,11 +370,23 @@ def main():
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
                 "algorithmic_bytes_per_pair": dom_bytes / n, "launch_ms": dom_s * 1e3}
     if warp_inst and clocks and clocks.get("sm_mhz"):
-        # what actually bounds the kernel (ncu: math-pipe throttle): issue rate against 4 warp
-        # instructions / cycle / SM, of which the integer ALU pipe sustains about 2
+        # what actually bounds the kernel (ncu: math-pipe throttle / not-selected stalls): the issue rate.
+        # Ceilings are MEASURED here with bench_support/peaks.cu (MEASURED_PEAKS.json has no integer peak):
+        # LOP3-only = the alu pipe (LOP3/SHF/PRMT/IADD3), LOP3+IMAD mix = both integer-capable pipes
         ipc = warp_inst / (148 * dom_s * clocks["sm_mhz"] * 1e6)
-        roofline["issue"] = {"warp_instructions_per_launch": warp_inst, "ipc_per_sm": ipc, "ipc_peak": 4.0,
-                             "note": "SM integer/ALU pipe bound (LOP3/PRMT/SHF at 2 per cycle per SM), not HBM"}
+        roofline["issue"] = {"warp_instructions_per_launch": warp_inst, "ipc_per_sm": ipc,
+                             "note": "SM integer pipes bound, not HBM; warp instructions per launch from the "
+                                     "ncu capture in profiles/"}
+        try:
+            from bench_support import peaks as int_peaks
+
+            pk = int_peaks.measure(clocks["sm_mhz"])
+            roofline["issue"].update({
+                "ipc_peak_alu_pipe_measured": pk["lop3"]["per_clk_per_sm"],
+                "ipc_peak_alu_plus_fma_measured": pk["lop3_imad_mix"]["per_clk_per_sm"],
+                "frac_of_alu_plus_fma_peak": ipc / pk["lop3_imad_mix"]["per_clk_per_sm"]})
+        except Exception as exc:  # the microbenchmark is evidence, not the product
+            roofline["issue"]["peak_error"] = str(exc)
     per_measure = {m: {"ms": ms, "pairs_per_s": n / (ms * 1e-3), "gbps": alg_bytes / (ms * 1e-3) / 1e9,
                        "hbm_frac": alg_bytes / (ms * 1e-3) / 1e9 / peak} for m, ms in per_measure_ms.items()}
     line = {

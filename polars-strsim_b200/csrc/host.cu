@@ -127,6 +127,16 @@ static int ensure_ctx(ThreadCtx** out) {
         CUDA_TRY(cudaMalloc(&c.d_counters, 4 * sizeof(unsigned int)));
         CUDA_TRY(cudaMallocHost(&c.h_counters, 4 * sizeof(unsigned int)));
         CUDA_TRY(cudaMallocHost(&c.h_stats, sizeof(ColumnStats)));
+        // the quotient table of pair_algos.cuh, once per device (every host thread has its own context)
+        static std::mutex quot_mutex;
+        static bool quot_ready[64] = {false};
+        std::lock_guard<std::mutex> lock(quot_mutex);
+        if (c.device >= 64 || !quot_ready[c.device]) {
+            quotient_table_kernel<<<(QUOT_N * QUOT_N + 255) / 256, 256, 0, c.stream>>>();
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaStreamSynchronize(c.stream));
+            if (c.device < 64) quot_ready[c.device] = true;
+        }
     }
     CUDA_TRY(cudaSetDevice(c.device));
     *out = &c;

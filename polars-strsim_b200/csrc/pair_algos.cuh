@@ -105,17 +105,44 @@ SS_HD M mask_range(int lo, int hi) {
     return upto_hi & ~below_lo;
 }
 
+// ---- quotients of small integers ---------------------------------------------------------------------
+// Every division of the five formulas but Jaro's final "/ 3.0" divides two small non-negative integers
+// (counts and lengths, at most 64 in the short-string kernels).  __ddiv_rn is a ~15-instruction
+// software routine, and a fused launch needs eight of them per pair, so the short-string kernels read
+// the quotient from a 65 x 65 table instead.  The table is FILLED ON THE DEVICE WITH __ddiv_rn ITSELF
+// (quotient_table_kernel, run once per device by host.cu), so a looked-up value is bit for bit the
+// value the division would have produced.
+constexpr int QUOT_N = 65;
+#if defined(__CUDACC__)
+__device__ double g_quotient[QUOT_N * QUOT_N];  // [y][x] = x / y for 0 <= x, 1 <= y <= 64
+__global__ void quotient_table_kernel() {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= QUOT_N * QUOT_N) return;
+    const int y = i / QUOT_N, x = i % QUOT_N;
+    g_quotient[i] = y == 0 ? 0.0 : __ddiv_rn((double)x, (double)y);
+}
+#endif
+// x / y as f64.  SMALL: the caller guarantees 0 <= x <= 64 and 1 <= y <= 64 (device: table lookup)
+template <bool SMALL>
+SS_HD double int_quotient(int x, int y) {
+#if defined(__CUDA_ARCH__)
+    if (SMALL) return g_quotient[y * QUOT_N + x];
+#endif
+    return f_div((double)x, (double)y);
+}
+
 // ---- final f64 formulas (reference order) --------------------------------------------------------
 // strsim.rs:160
+template <bool SMALL = false>
 SS_HD double lev_value(int d, int la, int lb) {
     int mx = la > lb ? la : lb;
-    return f_sub(1.0, f_div((double)d, (double)mx));
+    return f_sub(1.0, int_quotient<SMALL>(d, mx));
 }
 // strsim.rs:238-243 (m > 0); t/2 is the integer floor
+template <bool SMALL = false>
 SS_HD double jaro_value(int m, int t, int la, int lb) {
-    double dm = (double)m;
-    double s = f_add(f_div(dm, (double)la), f_div(dm, (double)lb));
-    s = f_add(s, f_div((double)(m - t / 2), dm));
+    double s = f_add(int_quotient<SMALL>(m, la), int_quotient<SMALL>(m, lb));
+    s = f_add(s, int_quotient<SMALL>(m - t / 2, m));
     return f_div(s, 3.0);
 }
 // strsim.rs:260-270
@@ -123,11 +150,11 @@ SS_HD double winkler_value(double js, int l) {
     return f_add(js, f_mul(f_mul((double)l, 0.1), f_sub(1.0, js)));
 }
 // strsim.rs:306
-SS_HD double jaccard_value(int inter, int uni) { return f_div((double)inter, (double)uni); }
-// strsim.rs:343
-SS_HD double dice_value(int inter, int total) {
-    return f_div(f_mul(2.0, (double)inter), (double)total);
-}
+template <bool SMALL = false>
+SS_HD double jaccard_value(int inter, int uni) { return int_quotient<SMALL>(inter, uni); }
+// strsim.rs:343: 2.0 * inter is exact, so the quotient of the integers 2*inter and la+lb is the same value
+template <bool SMALL = false>
+SS_HD double dice_value(int inter, int total) { return int_quotient<SMALL>(2 * inter, total); }
 
 // =====================================================================================================
 // Step functors.  `Tab` maps a character to the bitmask of the positions where it occurs in the

@@ -149,7 +149,7 @@ SS_HD double row_ascii_reg(const uint32_t (&a)[REG_WORDS], const uint32_t (&b)[R
             d = step.distance(m, n);
         }
         out.x0 = d;
-        v = lev_value(d, la, lb);
+        v = lev_value<true>(d, la, lb);
     } else {
         build_planes<NBITS>(b, lb, tab);
         if (IS_JARO) {
@@ -161,7 +161,7 @@ SS_HD double row_ascii_reg(const uint32_t (&a)[REG_WORDS], const uint32_t (&b)[R
             const int t = match.m > 0 ? trans_count(tab, EachByteReg(a), outer, match.flag_a, match.flag_b) : 0;
             out.x0 = match.m;
             out.x1 = t;
-            v = match.m == 0 ? 0.0 : jaro_value(match.m, t, la, lb);
+            v = match.m == 0 ? 0.0 : jaro_value<true>(match.m, t, la, lb);
             if (MEASURE == JARO_WINKLER && v > 0.7) {  // strsim.rs:260-267
                 const uint32_t x = a[0] ^ b[0];
                 int lim = la < lb ? la : lb;
@@ -177,10 +177,10 @@ SS_HD double row_ascii_reg(const uint32_t (&a)[REG_WORDS], const uint32_t (&b)[R
             out.x0 = ms.inter;
             if (MEASURE == JACCARD) {
                 out.x1 = la + lb - ms.inter;
-                v = jaccard_value(ms.inter, la + lb - ms.inter);
+                v = jaccard_value<true>(ms.inter, la + lb - ms.inter);
             } else {
                 out.x1 = la + lb;
-                v = dice_value(ms.inter, la + lb);
+                v = dice_value<true>(ms.inter, la + lb);
             }
         }
     }

@@ -163,7 +163,7 @@ struct PrefixKeys {  // first (up to) four character keys of a string
 // each_streamed(n, f): applies f to the first n characters of the streamed string (ASCII: bytes;
 // Unicode: decoded keys).  `tab`: position masks of the tabled string (Levenshtein: the shorter
 // one; the other measures: b, with a streamed as in strsim.rs:208).
-template <class M, class Tab, class Each>
+template <class M, bool SMALL = false, class Tab, class Each>
 SS_HD double measure_body(int measure, const Tab& tab, const Each& each_streamed, int la, int lb, int n_tab,
                           int n_str, PairInts& out) {
     switch (measure) {
@@ -175,7 +175,7 @@ SS_HD double measure_body(int measure, const Tab& tab, const Each& each_streamed
                 d = step.distance(n_tab, n_str);
             }
             out.x0 = d;
-            return lev_value(d, la, lb);
+            return lev_value<SMALL>(d, la, lb);
         }
         case JARO:
         case JARO_WINKLER: {
@@ -188,7 +188,7 @@ SS_HD double measure_body(int measure, const Tab& tab, const Each& each_streamed
             if (match.m > 0) each_streamed(outer, trans);
             out.x0 = match.m;
             out.x1 = trans.t;
-            return match.m == 0 ? 0.0 : jaro_value(match.m, trans.t, la, lb);
+            return match.m == 0 ? 0.0 : jaro_value<SMALL>(match.m, trans.t, la, lb);
         }
         default: {
             MultisetStep<M, Tab> ms(tab, lb);
@@ -196,10 +196,10 @@ SS_HD double measure_body(int measure, const Tab& tab, const Each& each_streamed
             out.x0 = ms.inter;
             if (measure == JACCARD) {
                 out.x1 = la + lb - ms.inter;  // sum_c max = la + lb - sum_c min
-                return jaccard_value(ms.inter, la + lb - ms.inter);
+                return jaccard_value<SMALL>(ms.inter, la + lb - ms.inter);
             }
             out.x1 = la + lb;
-            return dice_value(ms.inter, la + lb);
+            return dice_value<SMALL>(ms.inter, la + lb);
         }
     }
 }
@@ -242,7 +242,7 @@ SS_HD void multi_body(const Tab& tab, const Each& each_a, int la, int lb, bool o
         // Pv all ones -> d = lb, an empty pattern (lb = 0) scores no vertical delta -> d = la
         const int d = f.my.distance(lb, la);
         o.x0 = d;
-        emit(LEVENSHTEIN, lev_value(d, la, lb), o);
+        emit(LEVENSHTEIN, lev_value<true>(d, la, lb), o);
     }
     PairInts z;
     z.flag = F_ONE_EMPTY;
@@ -261,7 +261,7 @@ SS_HD void multi_body(const Tab& tab, const Each& each_a, int la, int lb, bool o
             const int t = f.jm.m > 0 ? trans_count(tab, each_a, la, f.jm.flag_a, f.jm.flag_b) : 0;
             o.x0 = f.jm.m;
             o.x1 = t;
-            double v = f.jm.m == 0 ? 0.0 : jaro_value(f.jm.m, t, la, lb);
+            double v = f.jm.m == 0 ? 0.0 : jaro_value<true>(f.jm.m, t, la, lb);
             emit(JARO, v, o);
             if (v > 0.7) {  // strsim.rs:260-267
                 const int l = prefix();
@@ -280,9 +280,9 @@ SS_HD void multi_body(const Tab& tab, const Each& each_a, int la, int lb, bool o
             const int inter = f.ms.inter;
             o.x0 = inter;
             o.x1 = la + lb - inter;
-            emit(JACCARD, jaccard_value(inter, la + lb - inter), o);
+            emit(JACCARD, jaccard_value<true>(inter, la + lb - inter), o);
             o.x1 = la + lb;
-            emit(SORENSEN_DICE, dice_value(inter, la + lb), o);
+            emit(SORENSEN_DICE, dice_value<true>(inter, la + lb), o);
         }
     }
 }

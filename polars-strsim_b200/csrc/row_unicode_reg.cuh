@@ -111,7 +111,7 @@ SS_HD double row_unicode_reg(Store& s, int na, int nb, bool equal, const WarpMax
     }
     decode_to_regs(table_b ? wb : wa, table_b ? nb : na, LAST_WORD, tab);
     EachChar<Store> streamed(s, !table_b, table_b ? na : nb);
-    double v = measure_body<uint32_t>(MEASURE, tab, streamed, la, lb, n_tab, table_b ? la : lb, out);
+    double v = measure_body<uint32_t, true>(MEASURE, tab, streamed, la, lb, n_tab, table_b ? la : lb, out);
     if (MEASURE == JARO_WINKLER && v > 0.7) {  // strsim.rs:260-267
         PrefixKeys pa, pb;
         for_each_char(wa, na, 4, LAST_WORD, pa);
