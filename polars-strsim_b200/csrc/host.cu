@@ -623,23 +623,30 @@ static int launch_fused(ThreadCtx& ctx, Alphabet al, const SegArgs& args, long l
 template <int GROUPS>
 static int launch_multi(ThreadCtx& ctx, Alphabet al, const SegArgs& args, long long rows, cudaStream_t st) {
     constexpr int ME = MULTI_BASE + GROUPS;
+    // tiles of 256 x 3 rows: 48 KB of shared memory per CTA, so four CTAs (32 warps) share an SM; measured
+    // on C2 (all five measures): 256x4 0.775 ms, 256x3 0.748 ms, 128x4 0.81 ms, 256x2 0.80 ms, 512x2 1.05 ms
     static const char* cfg_env = getenv("STRSIM_B200_TILE");  // tuning knob (all-groups kernel only)
     const int cfg = cfg_env && *cfg_env ? atoi(cfg_env) : 0;
-    if (GROUPS == 7 && al == ALPHA_ASCII32 && cfg != 0) {
-        if (cfg == 1) return launch_short<uint32_t, MULTI_BASE + 7, 256, 3, false, 32, true, true>(ctx, args, rows, st);
-        if (cfg == 2) return launch_short<uint32_t, MULTI_BASE + 7, 128, 4, false, 32, true, true>(ctx, args, rows, st);
-        if (cfg == 3) return launch_short<uint32_t, MULTI_BASE + 7, 256, 2, false, 32, true, true>(ctx, args, rows, st);
-        if (cfg == 4) return launch_short<uint32_t, MULTI_BASE + 7, 512, 2, false, 32, true, true>(ctx, args, rows, st);
+    if (GROUPS == 7 && cfg != 0) {
+        if (al == ALPHA_ASCII32) {
+            if (cfg == 1) return launch_short<uint32_t, MULTI_BASE + 7, 256, 4, false, 32, true, true>(ctx, args, rows, st);
+            if (cfg == 2) return launch_short<uint32_t, MULTI_BASE + 7, 128, 4, false, 32, true, true>(ctx, args, rows, st);
+        } else if (al == ALPHA_GENERAL) {
+            if (cfg == 1) return launch_short<uint32_t, MULTI_BASE + 7, 256, 4, false, 128, false, false, true>(ctx, args, rows, st);
+            if (cfg == 2) return launch_short<uint32_t, MULTI_BASE + 7, 128, 4, false, 128, false, false, true>(ctx, args, rows, st);
+            if (cfg == 3) return launch_short<uint32_t, MULTI_BASE + 7, 256, 3, false, 128, false, false, true>(ctx, args, rows, st);
+        }
     }
     switch (al) {
         case ALPHA_ASCII32:
-            return launch_short<uint32_t, ME, 256, 4, false, 32, true, true>(ctx, args, rows, st);
+            return launch_short<uint32_t, ME, 256, 3, false, 32, true, true>(ctx, args, rows, st);
         case ALPHA_ASCII64:
-            return launch_short<uint32_t, ME, 256, 4, false, 64, true, true>(ctx, args, rows, st);
+            return launch_short<uint32_t, ME, 256, 3, false, 64, true, true>(ctx, args, rows, st);
         case ALPHA_ASCII128:
-            return launch_short<uint32_t, ME, 256, 4, false, 128, true, true>(ctx, args, rows, st);
+            return launch_short<uint32_t, ME, 256, 3, false, 128, true, true>(ctx, args, rows, st);
         default:
-            return launch_short<uint32_t, ME, 256, 4, false, 128, false, false, true>(ctx, args, rows, st);
+            // register-compare path: 256 x 2 measured best on C3 (4.82 ms vs 5.11 ms per 10M rows x 5 measures)
+            return launch_short<uint32_t, ME, 256, 2, false, 128, false, false, true>(ctx, args, rows, st);
     }
 }
 
