@@ -165,6 +165,9 @@ STRSIM_API uint64_t strsim_b200_kernel_launches(void);
 /* rows that left the fused short-string kernel for a follow-up kernel in the last call on this
  * thread: [0] 33..64-byte rows, [1] long / generic rows */
 STRSIM_API void strsim_b200_last_overflow(int64_t out[2]);
+/* row slices of the last host call on this thread that were computed a second time because the
+ * progressive upload had not delivered their payload yet (0 for columns laid out sequentially) */
+STRSIM_API int strsim_b200_last_redo_slices(void);
 STRSIM_API const char *strsim_b200_version(void);
 
 /* ---- Polars plugin ABI (polars-ffi 0.43.1 `version_0`) ------------------------------ */

@@ -26,6 +26,8 @@ using namespace strsim;
 // ---- error plumbing --------------------------------------------------------------------------------
 static thread_local std::string g_last_error;
 static thread_local int64_t g_last_overflow[2] = {0, 0};
+static thread_local int g_last_redo_slices = 0;  // slices of the last host call that had to be recomputed
+static thread_local int64_t g_deferred = 0;  // rows left out because their payload was still in flight
 static std::atomic<uint64_t> g_launches{0};
 
 extern "C" void strsim_set_error(const char* fmt, ...) {
@@ -52,6 +54,24 @@ constexpr int MAX_SLICES = 16;
 constexpr long long SLICE_ROWS = 1ll << 21;
 
 // ---- per-thread device context ---------------------------------------------------------------------
+// Small device -> host readbacks (overflow counters, column statistics) go through a tiny kernel that
+// stores into pinned host memory instead of cudaMemcpyAsync: a 20-byte copy queued on the D2H copy
+// engine waits behind the 80 MB result download of the previous row slice, which stalled the upload
+// and compute streams for 0.2-0.35 ms per slice (timeline in profiles/r1_e2e_timeline.md).
+__global__ void publish_words_kernel(const unsigned int* __restrict__ src, unsigned int* __restrict__ dst_host, int n_words) {
+    for (int i = threadIdx.x; i < n_words; i += blockDim.x) dst_host[i] = src[i];
+    __threadfence_system();
+}
+static cudaError_t publish_to_host(void* h_pinned, const void* d_src, size_t bytes, cudaStream_t st) {
+    void* d_alias = nullptr;
+    cudaError_t e = cudaHostGetDevicePointer(&d_alias, h_pinned, 0);
+    if (e != cudaSuccess) return e;
+    publish_words_kernel<<<1, 64, 0, st>>>(static_cast<const unsigned int*>(d_src), static_cast<unsigned int*>(d_alias),
+                                          (int)(bytes / 4));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
 struct Workspace {
     void* ptr = nullptr;
     size_t cap = 0;
@@ -64,6 +84,8 @@ struct ThreadCtx {
     cudaStream_t upload_stream = nullptr;  // H2D of later row slices overlaps compute of earlier ones
     cudaEvent_t done_event[8] = {};
     cudaEvent_t slice_event[MAX_SLICES] = {};
+    cudaEvent_t up_event[MAX_SLICES] = {};  // the H2D copies of a slice have landed
+    cudaStream_t stats_stream = nullptr;    // column statistics of uploaded slices (off the copy queue)
     ColumnStats* d_slice_stats = nullptr;  // [0] data of a, [1] data of b, [2+s] views of slice s
     ColumnStats* h_slice_stats = nullptr;  // pinned
     int sm_count = 0;
@@ -115,6 +137,8 @@ static int ensure_ctx(ThreadCtx** out) {
         CUDA_TRY(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&c.upload_stream, cudaStreamNonBlocking));
         for (auto& ev : c.slice_event) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        for (auto& ev : c.up_event) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CUDA_TRY(cudaStreamCreateWithFlags(&c.stats_stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaMalloc(&c.d_slice_stats, sizeof(ColumnStats) * (2 + MAX_SLICES)));
         CUDA_TRY(cudaMallocHost(&c.h_slice_stats, sizeof(ColumnStats) * (2 + MAX_SLICES)));
         for (auto& ev : c.done_event) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -245,6 +269,10 @@ struct strsim_b200_column {
     int64_t alg_bytes = -1;
     bool has_validity = false;
     unsigned or_byte = 0, and_byte = 0xFF;  // OR / AND over every string byte of the column
+    // distinct data buffers in upload order (chunks made by slicing share buffers) and how much of each
+    // is on the device right now: equal to the size except while a host call uploads progressively
+    std::vector<int64_t> buf_size, buf_resident;
+    std::vector<std::vector<int>> chunk_buf_ids;  // [chunk][buffer index] -> distinct buffer id
 };
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -287,6 +315,9 @@ struct Uploader {
     std::vector<ChunkPlan> plans;
     std::vector<unsigned long long> tables;  // all chunks' buffer tables, alive until the copies ran
     std::vector<size_t> table_pos;
+    std::vector<const void*> buf_src;   // per distinct data buffer: host address ...
+    std::vector<size_t> buf_dev_off;    // ... and offset inside the device block
+    int64_t uploaded = 0;               // progressive upload: linear position over the distinct buffers
 };
 
 static void stats_init_value(ColumnStats* s) {
@@ -310,6 +341,7 @@ static int upload_plan(ThreadCtx& ctx, const strsim_view_chunk* chunks, size_t n
         const void* ptr;
         int64_t size;
         size_t off;
+        int id;
     };
     std::vector<Seen> seen;
     size_t total = 0;
@@ -334,6 +366,7 @@ static int upload_plan(ThreadCtx& ctx, const strsim_view_chunk* chunks, size_t n
         total = align_up(total + 8 * (size_t)(ch.n_data_buffers > 0 ? ch.n_data_buffers : 1), 256);
         p.buf_off.resize((size_t)ch.n_data_buffers);
         p.buf_dup.assign((size_t)ch.n_data_buffers, 0);
+        col->chunk_buf_ids.emplace_back((size_t)ch.n_data_buffers, 0);
         for (int64_t b = 0; b < ch.n_data_buffers; b++) {
             // chunks produced by slicing share their data buffers: upload each distinct buffer once
             bool dup = false;
@@ -341,12 +374,19 @@ static int upload_plan(ThreadCtx& ctx, const strsim_view_chunk* chunks, size_t n
                 if (sn.ptr == ch.data_buffers[b] && sn.size == ch.data_buffer_sizes[b]) {
                     p.buf_off[(size_t)b] = sn.off;
                     p.buf_dup[(size_t)b] = 1;
+                    col->chunk_buf_ids.back()[(size_t)b] = sn.id;
                     dup = true;
                     break;
                 }
             if (dup) continue;
             p.buf_off[(size_t)b] = total;
-            if (seen.size() < 4096) seen.push_back({ch.data_buffers[b], ch.data_buffer_sizes[b], total});
+            const int id = (int)col->buf_size.size();
+            col->chunk_buf_ids.back()[(size_t)b] = id;
+            col->buf_size.push_back(ch.data_buffer_sizes[b] > 0 ? ch.data_buffer_sizes[b] : 0);
+            col->buf_resident.push_back(col->buf_size.back());
+            up->buf_src.push_back(ch.data_buffers[b]);
+            up->buf_dev_off.push_back(total);
+            if (seen.size() < 4096) seen.push_back({ch.data_buffers[b], ch.data_buffer_sizes[b], total, id});
             // 64 spare bytes: TMA spans are rounded to 16 B and word copies read a few bytes past
             total = align_up(total + (size_t)ch.data_buffer_sizes[b] + 64, 256);
             col->data_bytes += ch.data_buffer_sizes[b];
@@ -383,8 +423,7 @@ static int upload_plan(ThreadCtx& ctx, const strsim_view_chunk* chunks, size_t n
     return STRSIM_OK;
 }
 
-static int upload_data(ThreadCtx& ctx, Uploader& up, cudaStream_t st, ColumnStats* d_stats) {
-    (void)ctx;
+static int upload_tables(Uploader& up, cudaStream_t st) {
     char* base = static_cast<char*>(up.col->block);
     for (size_t i = 0; i < up.n_chunks; i++) {
         const strsim_view_chunk& ch = up.chunks[i];
@@ -392,25 +431,157 @@ static int upload_data(ThreadCtx& ctx, Uploader& up, cudaStream_t st, ColumnStat
         const size_t n_tab = ch.n_data_buffers > 0 ? (size_t)ch.n_data_buffers : 1;
         CUDA_TRY(cudaMemcpyAsync(base + p.table_off, up.tables.data() + up.table_pos[i], 8 * n_tab,
                                  cudaMemcpyHostToDevice, st));
-        for (int64_t b = 0; b < ch.n_data_buffers; b++) {
-            const long long bytes = ch.data_buffer_sizes[b];
-            if (p.buf_dup[(size_t)b] || bytes <= 0) continue;
-            CUDA_TRY(cudaMemcpyAsync(base + p.buf_off[(size_t)b], ch.data_buffers[b], (size_t)bytes,
-                                     cudaMemcpyHostToDevice, st));
-            long long blocks = ((bytes >> 4) + 255) / 256;
-            if (blocks > 148 * 16) blocks = 148 * 16;
-            if (blocks < 1) blocks = 1;
-            stats_bytes_kernel<<<(unsigned)blocks, 256, 0, st>>>(
-                reinterpret_cast<const unsigned char*>(base + p.buf_off[(size_t)b]), bytes, d_stats);
-            g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    return STRSIM_OK;
+}
+
+static int64_t total_data_bytes(const strsim_b200_column* col) {
+    int64_t t = 0;
+    for (int64_t b : col->buf_size) t += b;
+    return t;
+}
+
+// Uploads the data bytes of the linear range [up.uploaded, to) -- positions run over the column's
+// distinct data buffers in upload order -- with their byte statistics, and advances up.uploaded.
+// Range ends inside a buffer are multiples of 256 (see frontier_after), so every piece starts aligned.
+static int upload_data_range(Uploader& up, int64_t from, int64_t to, cudaStream_t st, ColumnStats* d_stats,
+                             bool do_copy, bool do_stats) {
+    char* base = static_cast<char*>(up.col->block);
+    int64_t start = 0;
+    for (size_t id = 0; id < up.col->buf_size.size(); id++) {
+        const int64_t size = up.col->buf_size[id];
+        const int64_t lo = from > start ? from - start : 0;
+        const int64_t hi = to - start < size ? to - start : size;
+        if (hi > lo) {
+            if (do_copy)
+                CUDA_TRY(cudaMemcpyAsync(base + up.buf_dev_off[id] + lo, static_cast<const char*>(up.buf_src[id]) + lo,
+                                         (size_t)(hi - lo), cudaMemcpyHostToDevice, st));
+            if (do_stats) {
+                long long blocks = (((hi - lo) >> 4) + 255) / 256;
+                if (blocks > 148 * 16) blocks = 148 * 16;
+                if (blocks < 1) blocks = 1;
+                stats_bytes_kernel<<<(unsigned)blocks, 256, 0, st>>>(
+                    reinterpret_cast<const unsigned char*>(base + up.buf_dev_off[id] + lo), hi - lo, d_stats);
+                g_launches.fetch_add(1, std::memory_order_relaxed);
+            }
         }
+        start += size;
     }
     CUDA_TRY(cudaGetLastError());
     return STRSIM_OK;
 }
+static int upload_data_until(Uploader& up, int64_t to, cudaStream_t st, ColumnStats* d_stats) {
+    if (to <= up.uploaded) return STRSIM_OK;
+    const int rc = upload_data_range(up, up.uploaded, to, st, d_stats, true, true);
+    up.uploaded = to;
+    return rc;
+}
+
+// buffer tables + every distinct data buffer (+ byte statistics of the buffers)
+static int upload_data(ThreadCtx& ctx, Uploader& up, cudaStream_t st, ColumnStats* d_stats) {
+    (void)ctx;
+    int rc = upload_tables(up, st);
+    if (rc) return rc;
+    return upload_data_until(up, total_data_bytes(up.col), st, d_stats);
+}
+
+// ---- progressive upload (host calls) -----------------------------------------------------------------
+// A freshly built column references its data buffers in increasing order, so the rows of slice s need
+// only a PREFIX of the data.  Instead of sending all data before the first kernel can start, the host
+// call sends, slice by slice, the data prefix that slice needs followed by its views; the kernels
+// check every out-of-line view against the residency frontier (DevCol::res_buf / res_off) and count
+// the rows they had to leave out, and a slice with such rows is recomputed once everything has
+// arrived -- so any layout stays correct, and sequential layouts start computing (and downloading
+// results) after the first slice instead of after the whole data upload.
+
+// linear position of the end of view v of chunk c (-1: not an out-of-line view / malformed)
+static int64_t view_end_position(const Uploader& up, size_t c, const int32_t* v) {
+    const int32_t len = v[0];
+    if (len <= 12) return -1;
+    const auto& ids = up.col->chunk_buf_ids[c];
+    const int32_t bi = v[2], off = v[3];
+    if (bi < 0 || (size_t)bi >= ids.size() || off < 0) return -1;
+    int64_t start = 0;
+    for (int id = 0; id < ids[(size_t)bi]; id++) start += up.col->buf_size[(size_t)id];
+    int64_t end = (int64_t)off + len;
+    const int64_t size = up.col->buf_size[(size_t)ids[(size_t)bi]];
+    end = (end + 255) & ~255ll;
+    if (end > size) end = size;
+    return start + end;
+}
+
+// data prefix needed by the rows before `hi`: end of the last out-of-line string, looking back at most
+// 4096 rows from row hi-1; -1 when there is none that close (the caller then sends everything left:
+// a column with so few out-of-line strings has little data to send)
+static int64_t frontier_after(const Uploader& up, int64_t hi) {
+    int64_t left = 4096;
+    for (size_t c = up.n_chunks; c-- > 0 && left > 0;) {
+        const strsim_view_chunk& ch = up.chunks[c];
+        const int64_t row0 = up.plans[c].row0;
+        if (row0 >= hi || ch.length == 0) continue;
+        const int64_t last = hi - row0 < ch.length ? hi - row0 : ch.length;  // exclusive, chunk-relative
+        const int32_t* v = static_cast<const int32_t*>(ch.views) + 4 * ch.offset;
+        for (int64_t r = last; r-- > 0 && left > 0; left--) {
+            const int64_t e = view_end_position(up, c, v + 4 * r);
+            if (e >= 0) return e;
+        }
+    }
+    return -1;
+}
+
+// sampled host-side test: do the views reference the data in increasing order?
+static bool looks_sequential(const Uploader& up) {
+    int64_t prev = -1;
+    const int64_t n = up.col->length;
+    for (int k = 0; k < 64; k++) {
+        const int64_t row = n * k / 64;
+        // the chunk holding `row`
+        size_t c = 0;
+        while (c + 1 < up.n_chunks && up.plans[c + 1].row0 <= row) c++;
+        const strsim_view_chunk& ch = up.chunks[c];
+        const int32_t* v = static_cast<const int32_t*>(ch.views) + 4 * ch.offset;
+        int64_t r = row - up.plans[c].row0;
+        const int64_t stop = r + 64 < ch.length ? r + 64 : ch.length;
+        for (; r < stop; r++) {
+            const int64_t e = view_end_position(up, c, v + 4 * r);
+            if (e < 0) continue;
+            if (e + 256 < prev) return false;
+            prev = e;
+            break;
+        }
+    }
+    return true;
+}
+
+static void set_resident(strsim_b200_column* col, int64_t uploaded) {
+    int64_t start = 0;
+    for (size_t id = 0; id < col->buf_size.size(); id++) {
+        const int64_t size = col->buf_size[id];
+        int64_t r = uploaded - start;
+        col->buf_resident[id] = r < 0 ? 0 : (r > size ? size : r);
+        start += size;
+    }
+}
+
+// residency frontier of one chunk for the kernels (DevCol::res_buf / res_off)
+static void chunk_frontier(const strsim_b200_column* col, size_t chunk, unsigned* res_buf, unsigned* res_off) {
+    *res_buf = 0xFFFFFFFFu;
+    *res_off = 0;
+    if (chunk >= col->chunk_buf_ids.size()) return;
+    const auto& ids = col->chunk_buf_ids[chunk];
+    for (size_t b = 0; b < ids.size(); b++) {
+        const size_t id = (size_t)ids[b];
+        if (col->buf_resident[id] < col->buf_size[id]) {
+            *res_buf = (unsigned)b;
+            *res_off = (unsigned)col->buf_resident[id];
+            return;
+        }
+    }
+}
 
 // rows [lo, hi) of the column (a scalar column of length 1 is copied whenever lo == 0)
-static int upload_rows(ThreadCtx& ctx, Uploader& up, int64_t lo, int64_t hi, cudaStream_t st, ColumnStats* d_stats) {
+static int upload_rows(ThreadCtx& ctx, Uploader& up, int64_t lo, int64_t hi, cudaStream_t st, ColumnStats* d_stats,
+                       bool do_copy = true, bool do_stats = true) {
     (void)ctx;
     char* base = static_cast<char*>(up.col->block);
     for (size_t i = 0; i < up.n_chunks; i++) {
@@ -419,15 +590,17 @@ static int upload_rows(ThreadCtx& ctx, Uploader& up, int64_t lo, int64_t hi, cud
         const int64_t c_lo = lo > p.row0 ? lo - p.row0 : 0;
         const int64_t c_hi = hi - p.row0 < ch.length ? hi - p.row0 : ch.length;
         if (c_lo >= c_hi) continue;
-        CUDA_TRY(cudaMemcpyAsync(base + p.views_off + 16 * c_lo,
-                                 static_cast<const char*>(ch.views) + 16 * (ch.offset + c_lo),
-                                 16 * (size_t)(c_hi - c_lo), cudaMemcpyHostToDevice, st));
-        if (p.validity_bytes) {
+        if (do_copy)
+            CUDA_TRY(cudaMemcpyAsync(base + p.views_off + 16 * c_lo,
+                                     static_cast<const char*>(ch.views) + 16 * (ch.offset + c_lo),
+                                     16 * (size_t)(c_hi - c_lo), cudaMemcpyHostToDevice, st));
+        if (do_copy && p.validity_bytes) {
             const int64_t b_lo = ((ch.offset + c_lo) >> 3) - p.first_byte;
             const int64_t b_hi = ((ch.offset + c_hi + 7) >> 3) - p.first_byte;
             CUDA_TRY(cudaMemcpyAsync(base + p.validity_off + b_lo, ch.validity + p.first_byte + b_lo,
                                      (size_t)(b_hi - b_lo), cudaMemcpyHostToDevice, st));
         }
+        if (!do_stats) continue;
         long long blocks = (c_hi - c_lo + 255) / 256;
         if (blocks > 148 * 16) blocks = 148 * 16;
         stats_views_kernel<<<(unsigned)blocks, 256, 0, st>>>(
@@ -451,7 +624,7 @@ static int upload_column(ThreadCtx& ctx, const strsim_view_chunk* chunks, size_t
         if (rc == STRSIM_OK) rc = upload_rows(ctx, up, 0, up.col->length > 0 ? up.col->length : 1, ctx.stream, ctx.d_stats);
     }
     if (e == cudaSuccess && rc == STRSIM_OK)
-        e = cudaMemcpyAsync(ctx.h_stats, ctx.d_stats, sizeof(ColumnStats), cudaMemcpyDeviceToHost, ctx.stream);
+        e = publish_to_host(ctx.h_stats, ctx.d_stats, sizeof(ColumnStats), ctx.stream);
     if (e == cudaSuccess && rc == STRSIM_OK) e = cudaStreamSynchronize(ctx.stream);
     if (e != cudaSuccess || rc != STRSIM_OK) {
         if (e != cudaSuccess) {
@@ -750,7 +923,7 @@ static int run_long_lev(ThreadCtx& ctx, const SegArgs& args, const Overflow& ov,
         long_lev_kernel<<<(unsigned)((warps + LONG_WPB - 1) / LONG_WPB), 32 * LONG_WPB, 0, st>>>(g);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaMemcpyAsync(ctx.h_counters, ctx.d_counters, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(publish_to_host(ctx.h_counters, ctx.d_counters, 4 * sizeof(unsigned int), st));
         CUDA_TRY(cudaStreamSynchronize(st));
         src.list = g.huge_list;
         src.count = g.huge_count;
@@ -779,10 +952,11 @@ static int prepare_segment(ThreadCtx& ctx, SegArgs& args, int stage32, int64_t s
     return STRSIM_OK;
 }
 
-static int read_overflow(ThreadCtx& ctx, Overflow* ov, cudaStream_t st) {
-    CUDA_TRY(cudaMemcpyAsync(ctx.h_ovf, ctx.d_ovf, sizeof(Overflow), cudaMemcpyDeviceToHost, st));
+static int read_overflow(ThreadCtx& ctx, Overflow* ov, cudaStream_t st, bool first = true) {
+    CUDA_TRY(publish_to_host(ctx.h_ovf, ctx.d_ovf, sizeof(Overflow), st));
     CUDA_TRY(cudaStreamSynchronize(st));
     *ov = *ctx.h_ovf;
+    if (first) g_deferred += ov->ndefer;  // counted once, however often the counters are re-read
     return STRSIM_OK;
 }
 
@@ -832,7 +1006,7 @@ static int run_segment(ThreadCtx& ctx, SegArgs args, Alphabet al, int stage32, i
         rc = finish_64<MEASURE>(ctx, args, ov, st);
         if (rc) return rc;
         // rows the 64-bit kernel could not take are appended to listlong; re-read the counters
-        rc = read_overflow(ctx, &ov, st);
+        rc = read_overflow(ctx, &ov, st, false);
         if (rc) return rc;
     }
     g_last_overflow[1] += ov.nlong;
@@ -900,7 +1074,7 @@ static int run_segment_multi(ThreadCtx& ctx, SegArgs args, int groups, Alphabet 
             rc = finish_64_any(m, ctx, am, ov, st);
             if (rc) return rc;
         }
-        rc = read_overflow(ctx, &ov, st);
+        rc = read_overflow(ctx, &ov, st, false);
         if (rc) return rc;
     }
     g_last_overflow[1] += ov.nlong;
@@ -995,6 +1169,8 @@ static int compute_on_device(ThreadCtx& ctx, const int* measures, size_t n_measu
         s.a.vbit = ca.vbit + (bc_a ? 0 : oa);
         s.a.bufs = ca.bufs;
         s.a.stride = bc_a ? 0 : 1;
+        chunk_frontier(a, bc_a ? 0 : ia, &s.a.res_buf, &s.a.res_off);
+        chunk_frontier(b, bc_b ? 0 : ib, &s.b.res_buf, &s.b.res_off);
         s.b.views = cb.views + (bc_b ? 0 : ob);
         s.b.validity = cb.validity;
         s.b.vbit = cb.vbit + (bc_b ? 0 : ob);
@@ -1075,6 +1251,7 @@ void strsim_b200_last_overflow(int64_t out[2]) {
     out[0] = g_last_overflow[0];
     out[1] = g_last_overflow[1];
 }
+int strsim_b200_last_redo_slices(void) { return g_last_redo_slices; }
 const char* strsim_b200_version(void) { return "polars-strsim_b200 0.1.0 (sm_100a)"; }
 
 int strsim_b200_column_upload(const strsim_view_chunk* chunks, size_t n_chunks, strsim_b200_column** out) {
@@ -1239,35 +1416,89 @@ int strsim_b200_compute_host_multi(const int* measures, size_t n_measures, const
     const bool want_validity = out_validity != nullptr || out_null_count != nullptr;
 
     // ---- queue every upload; statistics slots: [0] data of a, [1] data of b, [2+s] views of slice s
+    // Progressive order (see "progressive upload" above): per slice the data prefix it needs, then its
+    // views.  Otherwise (scalar operand, one slice, views that do not look sequential, test hooks that
+    // bypass the residency check) all data first, as before.
+    static const bool no_progressive = [] {
+        const char* e = getenv("STRSIM_B200_PROGRESSIVE");
+        const char* k = getenv("STRSIM_B200_KERNEL");
+        return (e && !strcmp(e, "0")) || (k && !strcmp(k, "direct"));
+    }();
+    n_slices = (int)((n + slice_rows - 1) / slice_rows);
+    const bool progressive = !no_progressive && !force_generic_rows() && la == lb && n_slices > 1 &&
+                             looks_sequential(ua) && looks_sequential(ub);
+    const int64_t total_a = total_data_bytes(ca), total_b = total_data_bytes(cb);
+    int64_t front_a[MAX_SLICES], front_b[MAX_SLICES];
     cudaError_t ce = cudaSuccess;
+    // STRSIM_B200_TRACE=1: per-slice timeline (upload landed, kernels start/end, download done) on stderr
+    static const bool trace = getenv("STRSIM_B200_TRACE") != nullptr && atoi(getenv("STRSIM_B200_TRACE")) != 0;
+    static thread_local cudaEvent_t tr_t0 = nullptr, tr_u[MAX_SLICES], tr_c0[MAX_SLICES], tr_c1[MAX_SLICES], tr_d1[MAX_SLICES];
+    if (trace) {
+        if (!tr_t0) {
+            cudaEventCreate(&tr_t0);
+            for (int i = 0; i < MAX_SLICES; i++) {
+                cudaEventCreate(&tr_u[i]);
+                cudaEventCreate(&tr_c0[i]);
+                cudaEventCreate(&tr_c1[i]);
+                cudaEventCreate(&tr_d1[i]);
+            }
+        }
+        cudaEventRecord(tr_t0, ctx->upload_stream);
+    }
     for (int i = 0; i < 2 + MAX_SLICES; i++) stats_init_value(&ctx->h_slice_stats[i]);
     ce = cudaMemcpyAsync(ctx->d_slice_stats, ctx->h_slice_stats, sizeof(ColumnStats) * (2 + MAX_SLICES),
                          cudaMemcpyHostToDevice, ctx->upload_stream);
-    if (ce == cudaSuccess) rc = upload_data(*ctx, ua, ctx->upload_stream, ctx->d_slice_stats + 0);
-    if (ce == cudaSuccess && rc == STRSIM_OK) rc = upload_data(*ctx, ub, ctx->upload_stream, ctx->d_slice_stats + 1);
+    if (ce == cudaSuccess) rc = upload_tables(ua, ctx->upload_stream);
+    if (ce == cudaSuccess && rc == STRSIM_OK) rc = upload_tables(ub, ctx->upload_stream);
     for (int sidx = 0; ce == cudaSuccess && rc == STRSIM_OK && sidx < n_slices; sidx++) {
         const int64_t lo = sidx * slice_rows, hi = lo + slice_rows < n ? lo + slice_rows : n;
-        if (lo >= hi) {
-            n_slices = sidx;
-            break;
+        int64_t fa = total_a, fb = total_b;
+        if (progressive && sidx + 1 < n_slices) {
+            fa = frontier_after(ua, hi);
+            fb = frontier_after(ub, hi);
+            if (fa < 0) fa = total_a;
+            if (fb < 0) fb = total_b;
+            if (fa < ua.uploaded) fa = ua.uploaded;
+            if (fb < ub.uploaded) fb = ub.uploaded;
         }
-        // a scalar (length-1) column is uploaded with the first slice
-        rc = upload_rows(*ctx, ua, la == 1 && n != 1 ? 0 : lo, la == 1 && n != 1 ? (sidx == 0 ? 1 : 0) : hi,
-                         ctx->upload_stream, ctx->d_slice_stats + 2 + sidx);
-        if (rc == STRSIM_OK)
-            rc = upload_rows(*ctx, ub, lb == 1 && n != 1 ? 0 : lo, lb == 1 && n != 1 ? (sidx == 0 ? 1 : 0) : hi,
-                             ctx->upload_stream, ctx->d_slice_stats + 2 + sidx);
-        if (rc == STRSIM_OK)
-            ce = cudaMemcpyAsync(ctx->h_slice_stats, ctx->d_slice_stats, sizeof(ColumnStats) * (3 + sidx),
-                                 cudaMemcpyDeviceToHost, ctx->upload_stream);
-        if (rc == STRSIM_OK && ce == cudaSuccess) ce = cudaEventRecord(ctx->slice_event[sidx], ctx->upload_stream);
+        // copies back to back on the upload stream; the statistics kernels follow on their own stream (a
+        // copy -> kernel -> copy chain on one stream costs a copy-engine / compute hand-over per link,
+        // measured at 0.15-0.2 ms per slice)
+        const int64_t from_a = ua.uploaded < fa ? ua.uploaded : fa, from_b = ub.uploaded < fb ? ub.uploaded : fb;
+        const int64_t r_lo_a = la == 1 && n != 1 ? 0 : lo, r_hi_a = la == 1 && n != 1 ? (sidx == 0 ? 1 : 0) : hi;
+        const int64_t r_lo_b = lb == 1 && n != 1 ? 0 : lo, r_hi_b = lb == 1 && n != 1 ? (sidx == 0 ? 1 : 0) : hi;
+        for (int phase = 0; phase < 2 && rc == STRSIM_OK && ce == cudaSuccess; phase++) {
+            const bool cp = phase == 0, stt = phase == 1;
+            cudaStream_t st = cp ? ctx->upload_stream : ctx->stats_stream;
+            if (stt) {
+                ce = cudaEventRecord(ctx->up_event[sidx], ctx->upload_stream);
+                if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->stats_stream, ctx->up_event[sidx], 0);
+                if (ce != cudaSuccess) break;
+            }
+            rc = upload_data_range(ua, from_a, fa, st, ctx->d_slice_stats + 0, cp, stt);
+            if (rc == STRSIM_OK) rc = upload_data_range(ub, from_b, fb, st, ctx->d_slice_stats + 1, cp, stt);
+            // a scalar (length-1) column is uploaded with the first slice
+            if (rc == STRSIM_OK) rc = upload_rows(*ctx, ua, r_lo_a, r_hi_a, st, ctx->d_slice_stats + 2 + sidx, cp, stt);
+            if (rc == STRSIM_OK) rc = upload_rows(*ctx, ub, r_lo_b, r_hi_b, st, ctx->d_slice_stats + 2 + sidx, cp, stt);
+        }
+        if (fa > ua.uploaded) ua.uploaded = fa;
+        if (fb > ub.uploaded) ub.uploaded = fb;
+        front_a[sidx] = ua.uploaded;
+        front_b[sidx] = ub.uploaded;
+        if (rc == STRSIM_OK && ce == cudaSuccess)
+            ce = publish_to_host(ctx->h_slice_stats, ctx->d_slice_stats, sizeof(ColumnStats) * (3 + sidx),
+                                 ctx->stats_stream);
+        if (rc == STRSIM_OK && ce == cudaSuccess) ce = cudaEventRecord(ctx->slice_event[sidx], ctx->stats_stream);
+        if (trace) cudaEventRecord(tr_u[sidx], ctx->upload_stream);
     }
 
     // ---- compute + download slice by slice
-    for (int sidx = 0; ce == cudaSuccess && rc == STRSIM_OK && sidx < n_slices; sidx++) {
+    // redo = false: as soon as the slice's views (and data prefix) have landed; returns in *deferred the
+    // rows whose payload was not there yet -- such a slice is not downloaded but computed again (redo =
+    // true) after the whole upload, without touching the validity bitmap / null count a second time
+    auto run_slice = [&](int sidx, bool redo, int64_t* deferred) {
         const int64_t lo = sidx * slice_rows, hi = lo + slice_rows < n ? lo + slice_rows : n;
-        ce = cudaEventSynchronize(ctx->slice_event[sidx]);  // views + statistics of this slice are here
-        if (ce != cudaSuccess) break;
+        const int last = redo ? n_slices - 1 : sidx;  // statistics slots that are valid by now
         ColumnStats acc = ctx->h_slice_stats[0];
         acc.or_bits |= ctx->h_slice_stats[1].or_bits | ctx->h_slice_stats[2 + sidx].or_bits;
         acc.and_bits &= ctx->h_slice_stats[1].and_bits & ctx->h_slice_stats[2 + sidx].and_bits;
@@ -1278,39 +1509,72 @@ int strsim_b200_compute_host_multi(const int* measures, size_t n_measures, const
         unsigned ob, nb_;
         stats_fold(acc, &ob, &nb_);
         const Alphabet al = classify_alphabet(ob, nb_);
-        ce = cudaStreamWaitEvent(ctx->stream, ctx->slice_event[sidx], 0);
-        if (sidx == 0) g_last_overflow[0] = g_last_overflow[1] = 0;
+        set_resident(ca, redo ? total_a : front_a[sidx]);
+        set_resident(cb, redo ? total_b : front_b[sidx]);
+        ce = cudaStreamWaitEvent(ctx->stream, ctx->slice_event[last], 0);
+        g_deferred = 0;
         // fused: ONE launch per segment evaluates every requested measure (run_segment_multi); otherwise
         // (a single measure, or the same measure requested twice) one pass per measure
         const size_t n_pass = fuse ? 1 : n_measures;
+        double* d_outs[8];
+        int32_t* d_dbgs[8];
+        for (size_t m = 0; m < n_measures; m++) {
+            d_outs[m] = reinterpret_cast<double*>(base + m * out_stride);
+            d_dbgs[m] = (any_dbg && dbg_ints[m]) ? reinterpret_cast<int32_t*>(d_dbg_base + m * dbg_stride) : nullptr;
+        }
         for (size_t p = 0; ce == cudaSuccess && rc == STRSIM_OK && p < n_pass; p++) {
             const size_t m0 = p, m1 = fuse ? n_measures : p + 1;
-            double* d_outs[8];
-            int32_t* d_dbgs[8];
-            for (size_t m = m0; m < m1; m++) {
-                d_outs[m - m0] = reinterpret_cast<double*>(base + m * out_stride);
-                d_dbgs[m - m0] = (any_dbg && dbg_ints[m]) ? reinterpret_cast<int32_t*>(d_dbg_base + m * dbg_stride) : nullptr;
-            }
-            rc = compute_on_device(*ctx, measures + m0, m1 - m0, ca, cb, lo, hi - lo, al, d_outs,
-                                   (want_validity && p == 0) ? d_val : nullptr, d_dbgs, ctx->stream);
-            if (rc) break;
-            // download the finished slice on the copy stream while the next kernel runs
-            cudaEvent_t ev = ctx->done_event[p];
-            ce = cudaEventRecord(ev, ctx->stream);
-            if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->copy_stream, ev, 0);
-            for (size_t m = m0; ce == cudaSuccess && m < m1; m++) {
-                double* d_out = d_outs[m - m0];
-                int32_t* d_dbg = d_dbgs[m - m0];
-                ce = cudaMemcpyAsync(out_values[m] + lo, d_out + lo, 8 * (size_t)(hi - lo), cudaMemcpyDeviceToHost,
-                                     ctx->copy_stream);
-                if (ce == cudaSuccess && d_dbg)
-                    ce = cudaMemcpyAsync(dbg_ints[m] + 6 * lo, d_dbg + 6 * lo, 24 * (size_t)(hi - lo),
-                                         cudaMemcpyDeviceToHost, ctx->copy_stream);
-            }
-            if (ce == cudaSuccess && p == 0 && out_validity)
-                ce = cudaMemcpyAsync(out_validity + lo / 8, reinterpret_cast<const uint8_t*>(d_val) + lo / 8,
-                                     (size_t)((hi - lo + 7) / 8), cudaMemcpyDeviceToHost, ctx->copy_stream);
+            rc = compute_on_device(*ctx, measures + m0, m1 - m0, ca, cb, lo, hi - lo, al, d_outs + m0,
+                                   (want_validity && p == 0 && !redo) ? d_val : nullptr, d_dbgs + m0, ctx->stream);
         }
+        *deferred = g_deferred;
+        if (rc != STRSIM_OK || ce != cudaSuccess || g_deferred > 0) return;
+        // download the finished slice on the copy stream while the next kernel runs
+        cudaEvent_t ev = ctx->done_event[0];
+        ce = cudaEventRecord(ev, ctx->stream);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->copy_stream, ev, 0);
+        for (size_t m = 0; ce == cudaSuccess && m < n_measures; m++) {
+            ce = cudaMemcpyAsync(out_values[m] + lo, d_outs[m] + lo, 8 * (size_t)(hi - lo), cudaMemcpyDeviceToHost,
+                                 ctx->copy_stream);
+            if (ce == cudaSuccess && d_dbgs[m])
+                ce = cudaMemcpyAsync(dbg_ints[m] + 6 * lo, d_dbgs[m] + 6 * lo, 24 * (size_t)(hi - lo),
+                                     cudaMemcpyDeviceToHost, ctx->copy_stream);
+        }
+    };
+    int redo_list[MAX_SLICES], n_redo = 0;
+    for (int sidx = 0; ce == cudaSuccess && rc == STRSIM_OK && sidx < n_slices; sidx++) {
+        ce = cudaEventSynchronize(ctx->slice_event[sidx]);  // views + statistics of this slice are here
+        if (ce != cudaSuccess) break;
+        if (sidx == 0) g_last_overflow[0] = g_last_overflow[1] = 0;
+        int64_t deferred = 0;
+        if (trace) cudaEventRecord(tr_c0[sidx], ctx->stream);
+        run_slice(sidx, false, &deferred);
+        if (trace) {
+            cudaEventRecord(tr_c1[sidx], ctx->stream);
+            cudaEventRecord(tr_d1[sidx], ctx->copy_stream);
+        }
+        if (deferred > 0) redo_list[n_redo++] = sidx;
+    }
+    if (n_redo > 0 && ce == cudaSuccess && rc == STRSIM_OK) {
+        ce = cudaEventSynchronize(ctx->slice_event[n_slices - 1]);  // every byte has arrived
+        for (int k = 0; ce == cudaSuccess && rc == STRSIM_OK && k < n_redo; k++) {
+            int64_t deferred = 0;
+            run_slice(redo_list[k], true, &deferred);
+            if (rc == STRSIM_OK && deferred > 0) {
+                strsim_set_error("internal: rows still deferred after the whole upload");
+                rc = STRSIM_ERR_CUDA;
+            }
+        }
+    }
+    g_last_redo_slices = n_redo;
+    set_resident(ca, total_a);
+    set_resident(cb, total_b);
+    if (ce == cudaSuccess && rc == STRSIM_OK && out_validity) {
+        // the validity bitmap does not depend on the data: one copy once every slice's kernel has run
+        ce = cudaEventRecord(ctx->done_event[1], ctx->stream);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->copy_stream, ctx->done_event[1], 0);
+        if (ce == cudaSuccess)
+            ce = cudaMemcpyAsync(out_validity, d_val, (size_t)((n + 7) / 8), cudaMemcpyDeviceToHost, ctx->copy_stream);
     }
     if (ce == cudaSuccess && rc == STRSIM_OK && want_validity) {
         ce = cudaEventRecord(ctx->done_event[0], ctx->stream);
@@ -1319,6 +1583,7 @@ int strsim_b200_compute_host_multi(const int* measures, size_t n_measures, const
             ce = cudaMemcpyAsync(ctx->h_nulls, ctx->d_nulls, 8, cudaMemcpyDeviceToHost, ctx->copy_stream);
     }
     cudaError_t s0 = cudaStreamSynchronize(ctx->upload_stream);
+    if (s0 == cudaSuccess) s0 = cudaStreamSynchronize(ctx->stats_stream);
     cudaError_t s1 = cudaStreamSynchronize(ctx->stream);
     cudaError_t s2 = cudaStreamSynchronize(ctx->copy_stream);
     if (rc == STRSIM_OK && (ce != cudaSuccess || s0 != cudaSuccess || s1 != cudaSuccess || s2 != cudaSuccess)) {
@@ -1327,6 +1592,19 @@ int strsim_b200_compute_host_multi(const int* measures, size_t n_measures, const
         rc = STRSIM_ERR_CUDA;
     }
     if (rc == STRSIM_OK && out_null_count) *out_null_count = (int64_t)*ctx->h_nulls;
+    if (trace && rc == STRSIM_OK) {
+        fprintf(stderr, "[strsim trace] %d slices of %lld rows, progressive=%d, redo=%d\n", n_slices, (long long)slice_rows,
+                (int)progressive, n_redo);
+        for (int i = 0; i < n_slices; i++) {
+            float u = 0, c0 = 0, c1 = 0, d1 = 0;
+            cudaEventElapsedTime(&u, tr_t0, tr_u[i]);
+            cudaEventElapsedTime(&c0, tr_t0, tr_c0[i]);
+            cudaEventElapsedTime(&c1, tr_t0, tr_c1[i]);
+            cudaEventElapsedTime(&d1, tr_t0, tr_d1[i]);
+            fprintf(stderr, "[strsim trace] slice %2d: uploaded %7.3f  kernels %7.3f .. %7.3f  downloaded %7.3f ms\n", i, u, c0,
+                    c1, d1);
+        }
+    }
     pool_free(ctx->device, d_block, bytes);
     strsim_b200_column_free(ca);
     strsim_b200_column_free(cb);

@@ -34,12 +34,22 @@ struct DevCol {
     long long vbit;           // bit index of row 0 inside validity
     const unsigned long long* bufs;  // device table of data-buffer base addresses
     int stride;               // 1, or 0 for a broadcast scalar (strsim.rs:61-66)
+    // residency frontier of the data buffers while a host call is still uploading them (host.cu:
+    // progressive upload): buffers with index < res_buf are complete, buffer res_buf holds its first
+    // res_off bytes, later buffers nothing yet.  0xFFFFFFFF = everything is resident.
+    unsigned int res_buf, res_off;
 };
+
+// is the out-of-line payload of view v (length > 12) on the device yet?
+__device__ __forceinline__ bool payload_resident(const uint4& v, const DevCol& c) {
+    return v.z < c.res_buf || (v.z == c.res_buf && v.w + v.x <= c.res_off);
+}
 
 struct Overflow {
     unsigned int n64;    // rows for the 64-bit short kernel
     unsigned int nlong;  // rows for the long kernel
     unsigned int max_bytes_a, max_bytes_b;  // over the long rows
+    unsigned int ndefer;  // rows whose payload had not been uploaded yet: the host recomputes the slice
 };
 
 struct SegArgs {
@@ -436,6 +446,8 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
                 const uint32_t mx = va.x > vb.x ? va.x : vb.x;
                 if (!valid) {
                     store_settled<MEASURE>(s, row, 0.0, 0);
+                } else if ((va.x > 12u && !payload_resident(va, s.a)) || (vb.x > 12u && !payload_resident(vb, s.b))) {
+                    atomicAdd(&s.ovf->ndefer, 1u);  // nothing is written for this row in this pass
                 } else if (mx > (uint32_t)CAP) {
                     if (CAP == 32 && mx <= 64u) {
                         s.list64[atomicAdd(&s.ovf->n64, 1u)] = (unsigned int)row;

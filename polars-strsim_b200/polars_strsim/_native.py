@@ -101,6 +101,7 @@ def lib():
     L.strsim_b200_kernel_launches.restype = ctypes.c_uint64
     L.strsim_b200_last_overflow.restype = None
     L.strsim_b200_last_overflow.argtypes = [ctypes.POINTER(I64)]
+    L.strsim_b200_last_redo_slices.restype = ctypes.c_int
     L.strsim_b200_version.restype = ctypes.c_char_p
     _lib = L
     return L
@@ -269,6 +270,10 @@ def set_device(device: int):
 
 def kernel_launches() -> int:
     return int(lib().strsim_b200_kernel_launches())
+
+
+def last_redo_slices() -> int:
+    return int(lib().strsim_b200_last_redo_slices())
 
 
 def last_overflow():
