@@ -622,17 +622,11 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
             // not occupy lanes of the compute phase (the 4-byte prefix in the view rejects most rows)
             // (always in the fused kernel: its per-pair loops are three measures long, so the lanes that a
             // fifth of equal pairs would idle are worth far more than the prefix compare)
-            if ((PREFILTER_EQUAL || is_multi(MEASURE)) && va.x == vb.x && (va.x == 0u || ((va.x <= 12u ? va.y : sva_prefix(va, stage_a)) ==
-                                                (vb.x <= 12u ? vb.y : sva_prefix(vb, stage_b)))) &&
-                staged_equal(va, vb, stage_a, stage_b)) {
-                if (is_multi(MEASURE)) {
-                    // fused kernel: the equal pairs get the cheapest bucket of their own (key 1 otherwise
-                    // holds only empty/empty pairs, which are equal too) -- whole warps of them leave the
-                    // row function at its first test, and the stores stay dense
-                    key[k] = 1u;
-                    rank[k] = atomicAdd(&hist[1], 1u);
-                    continue;
-                }
+            const bool settle_equal = (PREFILTER_EQUAL || is_multi(MEASURE)) && va.x == vb.x &&
+                                      (va.x == 0u || ((va.x <= 12u ? va.y : sva_prefix(va, stage_a)) ==
+                                                      (vb.x <= 12u ? vb.y : sva_prefix(vb, stage_b)))) &&
+                                      staged_equal(va, vb, stage_a, stage_b);
+            if (settle_equal && !is_multi(MEASURE)) {
                 const long long idx = tile0 + i;
                 const long long row = GATHER ? (long long)s.list[idx] : idx;
                 store_settled<MEASURE>(s, row, 1.0, F_EQUAL);
@@ -665,7 +659,10 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
                 const int ca = staged_char_count(va, stage_a), cb = staged_char_count(vb, stage_b);
                 mx = (uint32_t)(ca > cb ? ca : cb);
             }
-            key[k] = 1u + mx + ((hi_bits & 0x80808080u) ? (uint32_t)(CAP + 1) : 0u);
+            // fused kernel: the equal pairs get the cheapest bucket of their own (key 1 otherwise holds only
+            // empty/empty pairs, which are equal too) -- whole warps of them leave the row function at its
+            // first test, and the stores stay dense
+            key[k] = settle_equal ? 1u : 1u + mx + ((hi_bits & 0x80808080u) ? (uint32_t)(CAP + 1) : 0u);
             rank[k] = atomicAdd(&hist[key[k]], 1u);
         }
         __syncthreads();
