@@ -109,6 +109,24 @@ STRSIM_API int strsim_b200_compute_host_multi(const int *measures, size_t n_meas
                                               double *const *out_values, uint8_t *out_validity,
                                               int64_t *out_null_count, int32_t *const *dbg_ints);
 
+/* Host call that can keep what it uploads (the five README expressions are five
+ * separate plugin calls over the same two columns, and end to end the PCIe upload dominates).  Like
+ * strsim_b200_compute_host_multi, but each column is given EITHER as host chunks OR as `resident_x`,
+ * a column already in HBM (then x / n_x are ignored), and with keep_x != NULL the column this call
+ * uploaded -- pipelined with the kernels, as always -- is handed to the caller (*keep_x, to be freed
+ * with strsim_b200_column_free) instead of being dropped.  The Polars plugin entry points use this
+ * with a small cache keyed by the Arrow buffer addresses of the input arrays they own. */
+typedef struct strsim_b200_column strsim_b200_column;
+STRSIM_API int strsim_b200_compute_host_keep(const int *measures, size_t n_measures,
+                                             const strsim_view_chunk *a, size_t n_a_chunks,
+                                             const strsim_b200_column *resident_a,
+                                             strsim_b200_column **keep_a,
+                                             const strsim_view_chunk *b, size_t n_b_chunks,
+                                             const strsim_b200_column *resident_b,
+                                             strsim_b200_column **keep_b,
+                                             double *const *out_values, uint8_t *out_validity,
+                                             int64_t *out_null_count, int32_t *const *dbg_ints);
+
 /* ---- Arrow C Data Interface entry point -----------------------------------------------------------
  * Inputs are BORROWED (not released).  Accepted formats: "vu"/"vz" (Utf8View/BinaryView); "u"/"U"
  * (Utf8/LargeUtf8) are converted to views on the host first.  `out` receives a Float64 array
@@ -128,11 +146,13 @@ STRSIM_API int strsim_b200_compute_arrow(int measure, const struct ArrowSchema *
  * kernels are finished by follow-up kernels after one internal stream synchronisation.
  * d_out_values: device pointer, n_rows doubles.  d_out_validity: device pointer, ceil(n_rows/32)*4
  * bytes or NULL.  d_dbg_ints: device pointer, n_rows*STRSIM_DBG_INTS int32 or NULL. */
-typedef struct strsim_b200_column strsim_b200_column;
 STRSIM_API int strsim_b200_column_upload(const strsim_view_chunk *chunks, size_t n_chunks,
                                          strsim_b200_column **out);
 STRSIM_API void strsim_b200_column_free(strsim_b200_column *col);
 STRSIM_API int64_t strsim_b200_column_length(const strsim_b200_column *col);
+/* bytes of HBM the column occupies, and the device it lives on */
+STRSIM_API int64_t strsim_b200_column_device_bytes(const strsim_b200_column *col);
+STRSIM_API int strsim_b200_column_device(const strsim_b200_column *col);
 /* algorithmic bytes of the column as SURVEY.md 8(d) counts them: 16 B/row of views + out-of-line
  * payload of rows with byte length > 12 (+ validity bits); filled in at upload */
 STRSIM_API int64_t strsim_b200_column_algorithmic_bytes(const strsim_b200_column *col);
@@ -158,6 +178,14 @@ STRSIM_API int strsim_b200_compute_device_multi(const int *measures, size_t n_me
 /* device used by the calling thread's subsequent calls (default: STRSIM_B200_DEVICE env or 0) */
 STRSIM_API int strsim_b200_set_device(int device);
 STRSIM_API int strsim_b200_device_count(void);
+/* device the calling thread's calls use right now (-1: no usable device) */
+STRSIM_API int strsim_b200_get_device(void);
+/* Polars plugin calls keep recently uploaded input columns in HBM (and hold the Arrow arrays they own
+ * alive, so that an address can only ever mean the same bytes): at most STRSIM_B200_CACHE_BYTES of
+ * HBM (default 8 GiB), 8 columns, dropped after 30 s without use; STRSIM_B200_CACHE=0 disables it.
+ * cache_clear drops everything now; cache_stats: [0] hits, [1] misses, [2] columns held, [3] bytes */
+STRSIM_API void strsim_b200_cache_clear(void);
+STRSIM_API void strsim_b200_cache_stats(int64_t out[4]);
 /* thread-local, NUL-terminated description of the last failure on this thread */
 STRSIM_API const char *strsim_b200_last_error(void);
 /* kernels launched by this library since load (all threads); bench.py reports the delta */

@@ -5,9 +5,12 @@
 // `version_0`, Cargo.lock:588-589,874-875): `_polars_plugin_<name>`, `_polars_plugin_field_<name>`,
 // `_polars_plugin_get_last_error_message`, `_polars_plugin_get_version`.  Pure C++ (no CUDA here);
 // all compute goes through strsim_b200_compute_host().
+#include <chrono>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -155,6 +158,138 @@ int column_from_arrow(const char* format, const ArrowArray* const* arrays, size_
     return STRSIM_OK;
 }
 
+// ---- device-side cache of plugin inputs -----------------------------------------------------------------
+// The README evaluates five expressions over the same two columns (README.md:47-51): five plugin
+// calls, each of which would upload the same 50+ bytes per row over PCIe, the slowest link of the
+// whole path.  A plugin call OWNS its input arrays (polars-ffi moves them to the callee), so instead of
+// releasing them at once it may keep them: as long as this library holds the arrays, their buffers
+// stay alive and immutable, and the addresses (views, validity, data buffers, offset, length) identify
+// their bytes.  The next call whose input has the same identity finds the column already in HBM.
+struct ChunkKey {
+    const void* views;
+    const void* validity;
+    int64_t offset, length;
+    std::vector<const void*> bufs;
+    std::vector<int64_t> sizes;
+    bool operator==(const ChunkKey& o) const {
+        return views == o.views && validity == o.validity && offset == o.offset && length == o.length &&
+               bufs == o.bufs && sizes == o.sizes;
+    }
+};
+
+struct CacheEntry {
+    std::vector<ChunkKey> key;
+    strsim_b200_column* col = nullptr;
+    std::vector<ArrowArray> held;  // the moved-in arrays: released when the entry dies
+    int64_t bytes = 0;
+    std::chrono::steady_clock::time_point last_use;
+    ~CacheEntry() {
+        if (col) strsim_b200_column_free(col);
+        for (ArrowArray& a : held)
+            if (a.release) a.release(&a);
+    }
+};
+
+// never destroyed: at process exit the CUDA runtime and the arrays' owner may already be gone
+std::mutex& g_cache_mutex = *new std::mutex();
+std::vector<std::shared_ptr<CacheEntry>>& g_cache = *new std::vector<std::shared_ptr<CacheEntry>>();
+int64_t g_cache_hits = 0, g_cache_misses = 0;
+constexpr size_t CACHE_MAX_COLUMNS = 8;
+constexpr int64_t CACHE_MIN_ROWS = 65536;  // below this the upload is cheaper than the bookkeeping
+constexpr int CACHE_TTL_SECONDS = 30;
+
+bool cache_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("STRSIM_B200_CACHE");
+        return !(e && !strcmp(e, "0"));
+    }();
+    return on;
+}
+int64_t cache_limit() {
+    static const int64_t v = [] {
+        const char* e = getenv("STRSIM_B200_CACHE_BYTES");
+        const long long x = e && *e ? atoll(e) : 0;
+        return x > 0 ? (int64_t)x : (int64_t)8 << 30;
+    }();
+    return v;
+}
+
+std::vector<ChunkKey> key_of(const Column& c) {
+    std::vector<ChunkKey> k(c.chunks.size());
+    for (size_t i = 0; i < c.chunks.size(); i++) {
+        const strsim_view_chunk& ch = c.chunks[i];
+        k[i].views = ch.views;
+        k[i].validity = ch.validity;
+        k[i].offset = ch.offset;
+        k[i].length = ch.length;
+        for (int64_t b = 0; b < ch.n_data_buffers; b++) {
+            k[i].bufs.push_back(ch.data_buffers[b]);
+            k[i].sizes.push_back(ch.data_buffer_sizes[b]);
+        }
+    }
+    return k;
+}
+
+// drops entries that were not used for a while or that exceed the budget (oldest first); mutex held
+void cache_trim(int64_t incoming_bytes) {
+    const auto now = std::chrono::steady_clock::now();
+    for (size_t i = 0; i < g_cache.size();) {
+        if (std::chrono::duration_cast<std::chrono::seconds>(now - g_cache[i]->last_use).count() > CACHE_TTL_SECONDS)
+            g_cache.erase(g_cache.begin() + (long)i);
+        else
+            i++;
+    }
+    for (;;) {
+        int64_t total = incoming_bytes;
+        for (const auto& e : g_cache) total += e->bytes;
+        if (g_cache.empty() || (total <= cache_limit() && g_cache.size() < CACHE_MAX_COLUMNS)) break;
+        size_t oldest = 0;
+        for (size_t i = 1; i < g_cache.size(); i++)
+            if (g_cache[i]->last_use < g_cache[oldest]->last_use) oldest = i;
+        g_cache.erase(g_cache.begin() + (long)oldest);
+    }
+}
+
+std::shared_ptr<CacheEntry> cache_lookup(const std::vector<ChunkKey>& key, int device) {
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    for (auto& e : g_cache)
+        if (e->key == key && strsim_b200_column_device(e->col) == device) {
+            e->last_use = std::chrono::steady_clock::now();
+            g_cache_hits++;
+            return e;
+        }
+    g_cache_misses++;
+    return nullptr;
+}
+
+// takes ownership of `col` and of the contents of the series' arrays (their structs are marked released)
+void cache_insert(std::vector<ChunkKey> key, strsim_b200_column* col, strsim_series_export& series) {
+    auto e = std::make_shared<CacheEntry>();
+    e->key = std::move(key);
+    e->col = col;
+    e->bytes = strsim_b200_column_device_bytes(col);
+    e->last_use = std::chrono::steady_clock::now();
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    for (const auto& o : g_cache)
+        if (o->key == e->key && strsim_b200_column_device(o->col) == strsim_b200_column_device(col))
+            return;  // another thread was faster (or a == b): `e` dies here and frees the column
+    if (e->bytes > cache_limit()) return;
+    cache_trim(e->bytes);
+    e->held.resize(series.len);
+    for (size_t i = 0; i < series.len; i++) {
+        e->held[i] = *series.arrays[i];       // move: Arrow C Data Interface
+        series.arrays[i]->release = nullptr;  // the source struct no longer owns anything
+    }
+    g_cache.push_back(std::move(e));
+}
+
+bool cacheable(const strsim_series_export& s, const Column& c) {
+    if (!cache_enabled() || layout_of(s.field ? s.field->format : nullptr) != L_VIEW) return false;
+    int64_t n = 0;
+    for (const auto& ch : c.chunks) n += ch.length;
+    return n >= CACHE_MIN_ROWS;
+}
+
 // ---- Float64 result array --------------------------------------------------------------------------
 struct ResultPrivate {
     double* values;
@@ -171,7 +306,9 @@ void release_result(ArrowArray* a) {
     a->release = nullptr;
 }
 
-int compute_to_arrow(int measure, const Column& ca, const Column& cb, ArrowArray* out) {
+int compute_to_arrow(int measure, const Column& ca, const Column& cb, ArrowArray* out,
+                     const strsim_b200_column* res_a = nullptr, strsim_b200_column** keep_a = nullptr,
+                     const strsim_b200_column* res_b = nullptr, strsim_b200_column** keep_b = nullptr) {
     int64_t la = 0, lb = 0;
     for (const auto& c : ca.chunks) la += c.length;
     for (const auto& c : cb.chunks) lb += c.length;
@@ -192,8 +329,10 @@ int compute_to_arrow(int measure, const Column& ca, const Column& cb, ArrowArray
         return STRSIM_ERR_NOMEM;
     }
     int64_t nulls = 0;
-    int rc = strsim_b200_compute_host(measure, ca.chunks.data(), ca.chunks.size(), cb.chunks.data(),
-                                      cb.chunks.size(), p->values, p->validity, &nulls, nullptr);
+    double* outs[1] = {p->values};
+    int rc = strsim_b200_compute_host_keep(&measure, 1, ca.chunks.data(), ca.chunks.size(), res_a, keep_a,
+                                           cb.chunks.data(), cb.chunks.size(), res_b, keep_b, outs, p->validity,
+                                           &nulls, nullptr);
     if (rc != STRSIM_OK) {
         free(p->values);
         free(p->validity);
@@ -280,12 +419,25 @@ void plugin_call(int measure, strsim_series_export* inputs, size_t n_inputs,
         rc = column_from_arrow(inputs[1].field ? inputs[1].field->format : nullptr,
                                inputs[1].arrays, inputs[1].len, cb);
     if (rc == STRSIM_OK) {
+        // columns this library already holds in HBM are not uploaded again; the others are uploaded
+        // (pipelined with the kernels) and kept
+        const int device = strsim_b200_get_device();
+        const bool cache_a = device >= 0 && cacheable(inputs[0], ca), cache_b = device >= 0 && cacheable(inputs[1], cb);
+        std::vector<ChunkKey> key_a, key_b;
+        std::shared_ptr<CacheEntry> hit_a, hit_b;
+        if (cache_a) hit_a = cache_lookup(key_a = key_of(ca), device);
+        if (cache_b) hit_b = cache_lookup(key_b = key_of(cb), device);
+        strsim_b200_column *kept_a = nullptr, *kept_b = nullptr;
         result = new ArrowArray();
-        rc = compute_to_arrow(measure, ca, cb, result);
+        rc = compute_to_arrow(measure, ca, cb, result, hit_a ? hit_a->col : nullptr,
+                              cache_a && !hit_a ? &kept_a : nullptr, hit_b ? hit_b->col : nullptr,
+                              cache_b && !hit_b ? &kept_b : nullptr);
         if (rc != STRSIM_OK) {
             delete result;
             result = nullptr;
         }
+        if (kept_a) cache_insert(std::move(key_a), kept_a, inputs[0]);
+        if (kept_b) cache_insert(std::move(key_b), kept_b, inputs[1]);
     }
     // the callee owns the inputs (polars-ffi import_series_buffer semantics): release every chunk's
     // contents, then the SeriesExport boxes
@@ -350,6 +502,23 @@ STRSIM_DEFINE_PLUGIN(jaro, STRSIM_JARO)
 STRSIM_DEFINE_PLUGIN(jaro_winkler, STRSIM_JARO_WINKLER)
 STRSIM_DEFINE_PLUGIN(jaccard, STRSIM_JACCARD)
 STRSIM_DEFINE_PLUGIN(sorensen_dice, STRSIM_SORENSEN_DICE)
+
+void strsim_b200_cache_clear(void) {
+    std::vector<std::shared_ptr<CacheEntry>> drop;
+    {
+        std::lock_guard<std::mutex> lock(g_cache_mutex);
+        drop.swap(g_cache);
+    }
+}
+
+void strsim_b200_cache_stats(int64_t out[4]) {
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    out[0] = g_cache_hits;
+    out[1] = g_cache_misses;
+    out[2] = (int64_t)g_cache.size();
+    out[3] = 0;
+    for (const auto& e : g_cache) out[3] += e->bytes;
+}
 
 const char* _polars_plugin_get_last_error_message(void) { return strsim_b200_last_error(); }
 

@@ -1278,6 +1278,12 @@ void strsim_b200_column_free(strsim_b200_column* col) {
 }
 
 int64_t strsim_b200_column_length(const strsim_b200_column* col) { return col ? col->length : -1; }
+int64_t strsim_b200_column_device_bytes(const strsim_b200_column* col) { return col ? (int64_t)col->block_bytes : -1; }
+int strsim_b200_column_device(const strsim_b200_column* col) { return col ? col->device : -1; }
+int strsim_b200_get_device(void) {
+    ThreadCtx* c;
+    return ensure_ctx(&c) == STRSIM_OK ? c->device : -1;
+}
 int64_t strsim_b200_column_algorithmic_bytes(const strsim_b200_column* col) {
     return col ? col->alg_bytes : -1;
 }
@@ -1334,10 +1340,19 @@ int strsim_b200_compute_device_multi(const int* measures, size_t n_measures, con
                              d_out_validity, d_dbg_ints, st);
 }
 
-int strsim_b200_compute_host_multi(const int* measures, size_t n_measures, const strsim_view_chunk* a, size_t n_a,
-                                   const strsim_view_chunk* b, size_t n_b, double* const* out_values,
-                                   uint8_t* out_validity, int64_t* out_null_count, int32_t* const* dbg_ints) {
-    if ((n_a && !a) || (n_b && !b) || !measures || n_measures == 0 || n_measures > 8 || !out_values) {
+}  // extern "C"
+
+// The host call.  A column is either given as host chunks (uploaded in pipelined row slices) or as
+// `res_x`, a column that is already resident in HBM (then x / n_x are ignored).  keep_x != nullptr: the
+// uploaded column is handed to the caller instead of being freed (strsim_b200_compute_host_keep).
+static int host_call(const int* measures, size_t n_measures, const strsim_view_chunk* a, size_t n_a,
+                     const strsim_b200_column* res_a, strsim_b200_column** keep_a, const strsim_view_chunk* b,
+                     size_t n_b, const strsim_b200_column* res_b, strsim_b200_column** keep_b,
+                     double* const* out_values, uint8_t* out_validity, int64_t* out_null_count,
+                     int32_t* const* dbg_ints) {
+    if (keep_a) *keep_a = nullptr;
+    if (keep_b) *keep_b = nullptr;
+    if ((!res_a && n_a && !a) || (!res_b && n_b && !b) || !measures || n_measures == 0 || n_measures > 8 || !out_values) {
         strsim_set_error("compute_host: NULL / out-of-range argument");
         return STRSIM_ERR_ARGUMENT;
     }
@@ -1347,8 +1362,10 @@ int strsim_b200_compute_host_multi(const int* measures, size_t n_measures, const
             return STRSIM_ERR_ARGUMENT;
         }
     int64_t la = 0, lb = 0;
-    for (size_t i = 0; i < n_a; i++) la += a[i].length;
-    for (size_t i = 0; i < n_b; i++) lb += b[i].length;
+    if (res_a) la = res_a->length;
+    else for (size_t i = 0; i < n_a; i++) la += a[i].length;
+    if (res_b) lb = res_b->length;
+    else for (size_t i = 0; i < n_b; i++) lb += b[i].length;
     if (la != lb && la != 1 && lb != 1) {
         strsim_set_error("Inputs must have the same length, or one of them must be a Utf8 literal.");
         return STRSIM_ERR_SHAPE;
@@ -1363,6 +1380,10 @@ int strsim_b200_compute_host_multi(const int* measures, size_t n_measures, const
     ThreadCtx* ctx;
     int rc = ensure_ctx(&ctx);
     if (rc) return rc;
+    if ((res_a && res_a->device != ctx->device) || (res_b && res_b->device != ctx->device)) {
+        strsim_set_error("resident column lives on another device than the calling thread uses (%d)", ctx->device);
+        return STRSIM_ERR_ARGUMENT;
+    }
     if (n == 0) return STRSIM_OK;
     unsigned seen_measures = 0;
     bool distinct = true;
@@ -1379,14 +1400,24 @@ int strsim_b200_compute_host_multi(const int* measures, size_t n_measures, const
     // on the download stream -- so H2D, kernels and D2H of different slices overlap (PCIe is full
     // duplex) instead of running back to back.
     Uploader ua, ub;
-    rc = upload_plan(*ctx, a, n_a, &ua);
-    if (rc) return rc;
-    rc = upload_plan(*ctx, b, n_b, &ub);
-    if (rc) {
-        strsim_b200_column_free(ua.col);
-        return rc;
+    if (!res_a) {
+        rc = upload_plan(*ctx, a, n_a, &ua);
+        if (rc) return rc;
     }
-    strsim_b200_column *ca = ua.col, *cb = ub.col;
+    if (!res_b) {
+        rc = upload_plan(*ctx, b, n_b, &ub);
+        if (rc) {
+            if (!res_a) strsim_b200_column_free(ua.col);
+            return rc;
+        }
+    }
+    // resident columns are shared (possibly with other host threads): read-only here
+    strsim_b200_column* ca = res_a ? const_cast<strsim_b200_column*>(res_a) : ua.col;
+    strsim_b200_column* cb = res_b ? const_cast<strsim_b200_column*>(res_b) : ub.col;
+    auto free_uploaded = [&]() {
+        if (!res_a) strsim_b200_column_free(ca);
+        if (!res_b) strsim_b200_column_free(cb);
+    };
     static const long long slice_target = [] {
         const char* e = getenv("STRSIM_B200_SLICE_ROWS");
         const long long v = e && *e ? atoll(e) : 0;
@@ -1406,8 +1437,7 @@ int strsim_b200_compute_host_multi(const int* measures, size_t n_measures, const
     void* d_block = nullptr;
     rc = pool_alloc(ctx->device, bytes, &d_block);
     if (rc) {
-        strsim_b200_column_free(ca);
-        strsim_b200_column_free(cb);
+        free_uploaded();
         return rc;
     }
     char* base = static_cast<char*>(d_block);
@@ -1426,8 +1456,10 @@ int strsim_b200_compute_host_multi(const int* measures, size_t n_measures, const
     }();
     n_slices = (int)((n + slice_rows - 1) / slice_rows);
     const bool progressive = !no_progressive && !force_generic_rows() && la == lb && n_slices > 1 &&
-                             looks_sequential(ua) && looks_sequential(ub);
+                             (res_a || looks_sequential(ua)) && (res_b || looks_sequential(ub));
     const int64_t total_a = total_data_bytes(ca), total_b = total_data_bytes(cb);
+    if (res_a) ua.uploaded = total_a;  // nothing to send
+    if (res_b) ub.uploaded = total_b;
     int64_t front_a[MAX_SLICES], front_b[MAX_SLICES];
     cudaError_t ce = cudaSuccess;
     // STRSIM_B200_TRACE=1: per-slice timeline (upload landed, kernels start/end, download done) on stderr
@@ -1448,14 +1480,14 @@ int strsim_b200_compute_host_multi(const int* measures, size_t n_measures, const
     for (int i = 0; i < 2 + MAX_SLICES; i++) stats_init_value(&ctx->h_slice_stats[i]);
     ce = cudaMemcpyAsync(ctx->d_slice_stats, ctx->h_slice_stats, sizeof(ColumnStats) * (2 + MAX_SLICES),
                          cudaMemcpyHostToDevice, ctx->upload_stream);
-    if (ce == cudaSuccess) rc = upload_tables(ua, ctx->upload_stream);
-    if (ce == cudaSuccess && rc == STRSIM_OK) rc = upload_tables(ub, ctx->upload_stream);
+    if (ce == cudaSuccess && !res_a) rc = upload_tables(ua, ctx->upload_stream);
+    if (ce == cudaSuccess && rc == STRSIM_OK && !res_b) rc = upload_tables(ub, ctx->upload_stream);
     for (int sidx = 0; ce == cudaSuccess && rc == STRSIM_OK && sidx < n_slices; sidx++) {
         const int64_t lo = sidx * slice_rows, hi = lo + slice_rows < n ? lo + slice_rows : n;
         int64_t fa = total_a, fb = total_b;
         if (progressive && sidx + 1 < n_slices) {
-            fa = frontier_after(ua, hi);
-            fb = frontier_after(ub, hi);
+            fa = res_a ? total_a : frontier_after(ua, hi);
+            fb = res_b ? total_b : frontier_after(ub, hi);
             if (fa < 0) fa = total_a;
             if (fb < 0) fb = total_b;
             if (fa < ua.uploaded) fa = ua.uploaded;
@@ -1475,11 +1507,13 @@ int strsim_b200_compute_host_multi(const int* measures, size_t n_measures, const
                 if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->stats_stream, ctx->up_event[sidx], 0);
                 if (ce != cudaSuccess) break;
             }
-            rc = upload_data_range(ua, from_a, fa, st, ctx->d_slice_stats + 0, cp, stt);
-            if (rc == STRSIM_OK) rc = upload_data_range(ub, from_b, fb, st, ctx->d_slice_stats + 1, cp, stt);
+            if (!res_a) rc = upload_data_range(ua, from_a, fa, st, ctx->d_slice_stats + 0, cp, stt);
+            if (rc == STRSIM_OK && !res_b) rc = upload_data_range(ub, from_b, fb, st, ctx->d_slice_stats + 1, cp, stt);
             // a scalar (length-1) column is uploaded with the first slice
-            if (rc == STRSIM_OK) rc = upload_rows(*ctx, ua, r_lo_a, r_hi_a, st, ctx->d_slice_stats + 2 + sidx, cp, stt);
-            if (rc == STRSIM_OK) rc = upload_rows(*ctx, ub, r_lo_b, r_hi_b, st, ctx->d_slice_stats + 2 + sidx, cp, stt);
+            if (rc == STRSIM_OK && !res_a)
+                rc = upload_rows(*ctx, ua, r_lo_a, r_hi_a, st, ctx->d_slice_stats + 2 + sidx, cp, stt);
+            if (rc == STRSIM_OK && !res_b)
+                rc = upload_rows(*ctx, ub, r_lo_b, r_hi_b, st, ctx->d_slice_stats + 2 + sidx, cp, stt);
         }
         if (fa > ua.uploaded) ua.uploaded = fa;
         if (fb > ub.uploaded) ub.uploaded = fb;
@@ -1508,9 +1542,17 @@ int strsim_b200_compute_host_multi(const int* measures, size_t n_measures, const
         }
         unsigned ob, nb_;
         stats_fold(acc, &ob, &nb_);
+        if (res_a) {  // a resident column brings the statistics of its own upload
+            ob |= res_a->or_byte;
+            nb_ &= res_a->and_byte;
+        }
+        if (res_b) {
+            ob |= res_b->or_byte;
+            nb_ &= res_b->and_byte;
+        }
         const Alphabet al = classify_alphabet(ob, nb_);
-        set_resident(ca, redo ? total_a : front_a[sidx]);
-        set_resident(cb, redo ? total_b : front_b[sidx]);
+        if (!res_a) set_resident(ca, redo ? total_a : front_a[sidx]);
+        if (!res_b) set_resident(cb, redo ? total_b : front_b[sidx]);
         ce = cudaStreamWaitEvent(ctx->stream, ctx->slice_event[last], 0);
         g_deferred = 0;
         // fused: ONE launch per segment evaluates every requested measure (run_segment_multi); otherwise
@@ -1567,8 +1609,8 @@ int strsim_b200_compute_host_multi(const int* measures, size_t n_measures, const
         }
     }
     g_last_redo_slices = n_redo;
-    set_resident(ca, total_a);
-    set_resident(cb, total_b);
+    if (!res_a) set_resident(ca, total_a);
+    if (!res_b) set_resident(cb, total_b);
     if (ce == cudaSuccess && rc == STRSIM_OK && out_validity) {
         // the validity bitmap does not depend on the data: one copy once every slice's kernel has run
         ce = cudaEventRecord(ctx->done_event[1], ctx->stream);
@@ -1606,9 +1648,51 @@ int strsim_b200_compute_host_multi(const int* measures, size_t n_measures, const
         }
     }
     pool_free(ctx->device, d_block, bytes);
-    strsim_b200_column_free(ca);
-    strsim_b200_column_free(cb);
+    if (rc == STRSIM_OK && (keep_a || keep_b)) {
+        // byte statistics of the kept columns: the union over everything this call uploaded (a superset
+        // of each column's own bytes -- the statistics only ever pick a more general kernel)
+        ColumnStats acc = ctx->h_slice_stats[0];
+        for (int i = 1; i < 2 + n_slices; i++) {
+            acc.or_bits |= ctx->h_slice_stats[i].or_bits;
+            acc.and_bits &= ctx->h_slice_stats[i].and_bits;
+        }
+        unsigned ob, nb_;
+        stats_fold(acc, &ob, &nb_);
+        for (strsim_b200_column* c : {res_a ? nullptr : ca, res_b ? nullptr : cb})
+            if (c) {
+                c->or_byte = ob | (res_a ? res_a->or_byte : 0u) | (res_b ? res_b->or_byte : 0u);
+                c->and_byte = nb_ & (res_a ? res_a->and_byte : 0xFFu) & (res_b ? res_b->and_byte : 0xFFu);
+            }
+    }
+    if (rc == STRSIM_OK && keep_a && !res_a) {
+        *keep_a = ca;
+        ca = nullptr;
+    }
+    if (rc == STRSIM_OK && keep_b && !res_b) {
+        *keep_b = cb;
+        cb = nullptr;
+    }
+    if (!res_a && ca) strsim_b200_column_free(ca);
+    if (!res_b && cb) strsim_b200_column_free(cb);
     return rc;
+}
+
+extern "C" {
+
+int strsim_b200_compute_host_multi(const int* measures, size_t n_measures, const strsim_view_chunk* a, size_t n_a,
+                                   const strsim_view_chunk* b, size_t n_b, double* const* out_values,
+                                   uint8_t* out_validity, int64_t* out_null_count, int32_t* const* dbg_ints) {
+    return host_call(measures, n_measures, a, n_a, nullptr, nullptr, b, n_b, nullptr, nullptr, out_values, out_validity,
+                     out_null_count, dbg_ints);
+}
+
+int strsim_b200_compute_host_keep(const int* measures, size_t n_measures, const strsim_view_chunk* a, size_t n_a,
+                                  const strsim_b200_column* resident_a, strsim_b200_column** keep_a,
+                                  const strsim_view_chunk* b, size_t n_b, const strsim_b200_column* resident_b,
+                                  strsim_b200_column** keep_b, double* const* out_values, uint8_t* out_validity,
+                                  int64_t* out_null_count, int32_t* const* dbg_ints) {
+    return host_call(measures, n_measures, a, n_a, resident_a, keep_a, b, n_b, resident_b, keep_b, out_values,
+                     out_validity, out_null_count, dbg_ints);
 }
 
 int strsim_b200_compute_host(int measure, const strsim_view_chunk* a, size_t n_a, const strsim_view_chunk* b,

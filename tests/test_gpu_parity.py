@@ -569,3 +569,74 @@ print("ok")
     env = dict(os.environ, STRSIM_B200_SLICE_ROWS="4096")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-3000:]
+
+
+def test_plugin_calls_reuse_columns_already_in_hbm(native, oracle):
+    """The five README expressions are five plugin calls over the same two columns: the first call
+    uploads (and keeps) them, the other four must find them in HBM -- and the arrays the library took
+    ownership of stay alive until it lets go of them."""
+    import ctypes
+    import gc
+
+    import pyarrow as pa
+    from polars_strsim._native import ArrowArray
+    from test_abi import SeriesExport, make_series
+
+    L = native.lib()
+    L.strsim_b200_cache_stats.argtypes = [ctypes.POINTER(ctypes.c_int64)]
+    L.strsim_b200_cache_stats.restype = None
+    L.strsim_b200_cache_clear.restype = None
+
+    def stats():
+        out = (ctypes.c_int64 * 4)()
+        L.strsim_b200_cache_stats(out)
+        return list(out)
+
+    def call(measure, A, B):
+        released, keep = [], []
+        inputs = (SeriesExport * 2)()
+        inputs[0], arrs_a = make_series(A, released, keep)
+        inputs[1], arrs_b = make_series(B, released, keep)
+        ret = SeriesExport()
+        getattr(L, f"_polars_plugin_{measure}")(inputs, ctypes.c_size_t(2), None, ctypes.c_size_t(0),
+                                                 ctypes.byref(ret), None)
+        assert ret.private_data and ret.len == 1, L.strsim_b200_last_error()
+        assert len(released) == 2 and all(not x.release for x in arrs_a + arrs_b)
+        moved = ArrowArray.from_address(ret.arrays[0])
+        copy = ArrowArray()
+        ctypes.memmove(ctypes.addressof(copy), ctypes.addressof(moved), ctypes.sizeof(ArrowArray))
+        ret.release(ctypes.byref(ret))
+        return pa.Array._import_from_c(ctypes.addressof(copy), pa.float64())
+
+    def check_out(measure, out, a, b):
+        ref, ref_valid, _ = oracle.batch(measure, a, b)
+        assert (np.array(out.is_valid()) == ref_valid).all()
+        got = out.fill_null(0.0).to_numpy(zero_copy_only=False)
+        assert (got[ref_valid].view(np.uint64) == ref[ref_valid].view(np.uint64)).all(), measure
+
+    L.strsim_b200_cache_clear()
+    rng = random.Random(5)
+    n = 120000
+    a = [None if rng.random() < 0.02 else "".join(rng.choice("abcdefghij") for _ in range(rng.randint(0, 28))) for _ in range(n)]
+    b = [x if x is None or rng.random() < 0.3 else x[: rng.randint(0, len(x))] + rng.choice(["", "xy", "k"]) for x in a]
+    A = pa.chunked_array([sv(a[:50000]), sv(a[50000:])])
+    B = sv(b)
+    h0, m0, _, _ = stats()
+    for k, measure in enumerate(oracle.MEASURES):
+        check_out(measure, call(measure, A, B), a, b)
+        h, m, cols, nbytes = stats()
+        assert (h - h0, m - m0) == (2 * k, 2), (measure, h - h0, m - m0)
+        assert cols == 2 and nbytes > 16 * n
+    # a scalar operand is never cached, the column operand still hits
+    check_out("jaro", call("jaro", A, sv(["abcdef"])), a, ["abcdef"] * n)
+    assert stats()[0] - h0 == 2 * 4 + 1
+    # the library holds the arrays: dropping ours must not invalidate what the cache identifies by address
+    del A, B
+    gc.collect()
+    a2 = [x[::-1] if x else x for x in a]
+    A2, B2 = sv(a2), sv(b)
+    check_out("levenshtein", call("levenshtein", A2, B2), a2, b)  # new buffers: misses, correct results
+    assert stats()[2] == 4
+    L.strsim_b200_cache_clear()
+    assert stats()[2:] == [0, 0]
+    check_out("sorensen_dice", call("sorensen_dice", A2, B2), a2, b)
