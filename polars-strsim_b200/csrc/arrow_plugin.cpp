@@ -7,6 +7,7 @@
 // all compute goes through strsim_b200_compute_host().
 #include <chrono>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -14,6 +15,9 @@
 #include <new>
 #include <string>
 #include <vector>
+#if defined(__linux__)
+#include <sys/mman.h>
+#endif
 
 #include "../../include/strsim_b200.h"
 
@@ -295,12 +299,48 @@ struct ResultPrivate {
     double* values;
     uint8_t* validity;
     const void* buffers[2];
+    void* map_base;    // large results: an anonymous mapping (2 MiB aligned start inside it) ...
+    size_t map_bytes;  // ... so that the kernel may back it with huge pages: 40 first-touch faults for
+                       // 80 MB instead of 20,000
 };
+
+// n doubles; large buffers come from mmap + MADV_HUGEPAGE, small ones from malloc
+double* alloc_values(ResultPrivate* p, size_t n) {
+    const size_t bytes = 8 * (n > 0 ? n : 1);
+    p->map_base = nullptr;
+    p->map_bytes = 0;
+#if defined(__linux__)
+    if (bytes >= ((size_t)4 << 20)) {
+        const size_t huge = (size_t)2 << 20;
+        const size_t len = ((bytes + huge - 1) & ~(huge - 1)) + huge;
+        void* base = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (base != MAP_FAILED) {
+            char* aligned = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(base) + huge - 1) & ~(uintptr_t)(huge - 1));
+            madvise(aligned, len - (size_t)(aligned - static_cast<char*>(base)), MADV_HUGEPAGE);
+            p->map_base = base;
+            p->map_bytes = len;
+            return reinterpret_cast<double*>(aligned);
+        }
+    }
+#endif
+    return static_cast<double*>(malloc(bytes));
+}
+
+void free_values(ResultPrivate* p) {
+#if defined(__linux__)
+    if (p->map_base) {
+        munmap(p->map_base, p->map_bytes);
+        p->map_base = nullptr;
+        return;
+    }
+#endif
+    free(p->values);
+}
 
 void release_result(ArrowArray* a) {
     if (!a || !a->release) return;
     ResultPrivate* p = static_cast<ResultPrivate*>(a->private_data);
-    free(p->values);
+    free_values(p);
     free(p->validity);
     delete p;
     a->release = nullptr;
@@ -319,10 +359,10 @@ int compute_to_arrow(int measure, const Column& ca, const Column& cb, ArrowArray
     const int64_t n = la == 1 ? lb : la;
     ResultPrivate* p = new (std::nothrow) ResultPrivate();
     if (!p) return STRSIM_ERR_NOMEM;
-    p->values = static_cast<double*>(malloc(8 * (size_t)(n > 0 ? n : 1)));
+    p->values = alloc_values(p, (size_t)n);
     p->validity = static_cast<uint8_t*>(calloc((size_t)((n + 7) / 8) + 8, 1));
     if (!p->values || !p->validity) {
-        free(p->values);
+        if (p->values) free_values(p);
         free(p->validity);
         delete p;
         strsim_set_error("out of host memory for %lld results", (long long)n);
@@ -330,11 +370,16 @@ int compute_to_arrow(int measure, const Column& ca, const Column& cb, ArrowArray
     }
     int64_t nulls = 0;
     double* outs[1] = {p->values};
+    static const bool trace = getenv("STRSIM_B200_TRACE") != nullptr && atoi(getenv("STRSIM_B200_TRACE")) != 0;
+    const auto t0 = std::chrono::steady_clock::now();
     int rc = strsim_b200_compute_host_keep(&measure, 1, ca.chunks.data(), ca.chunks.size(), res_a, keep_a,
                                            cb.chunks.data(), cb.chunks.size(), res_b, keep_b, outs, p->validity,
                                            &nulls, nullptr);
+    if (trace)
+        fprintf(stderr, "[strsim trace] plugin compute (upload/kernels/download into the result buffer): %.3f ms\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     if (rc != STRSIM_OK) {
-        free(p->values);
+        free_values(p);
         free(p->validity);
         delete p;
         return rc;

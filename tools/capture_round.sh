@@ -25,3 +25,8 @@ python bench.py --workload C5 --rows 50000000 --steps 5 --no-cpu-baseline > $O/$
 STRSIM_B200_TRACE=1 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>&1 >/dev/null | grep "strsim trace" | tail -6 > $O/${R}_e2e_timeline_C2.txt
 tail -5 $O/bench_err.log
 for f in $O/${R}_bench_*.json; do echo $f; head -c 400 $f; echo; done
+# 5. the README scenario through the plugin symbols: five separate calls, with / without the column cache
+python tools/plugin_e2e.py > $O/${R}_plugin_e2e.jsonl 2>> $O/bench_err.log
+STRSIM_B200_CACHE=0 python tools/plugin_e2e.py >> $O/${R}_plugin_e2e.jsonl 2>> $O/bench_err.log
+STRSIM_B200_STAGED_D2H=0 python tools/plugin_e2e.py >> $O/${R}_plugin_e2e.jsonl 2>> $O/bench_err.log
+cat $O/${R}_plugin_e2e.jsonl
