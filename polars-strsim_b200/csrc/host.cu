@@ -92,12 +92,13 @@ constexpr size_t STAGE_SLOT_BYTES = 4u << 20;
 
 struct StageTask {
     int device;
-    cudaEvent_t ev;
+    cudaEvent_t ev;  // wait for it before copying (downloads); nullptr for uploads (host -> ring)
     const void* src;
     void* dst;
     size_t bytes;
-    std::atomic<int>* slot_busy;
-    std::atomic<long long>* pending;
+    std::atomic<int>* flag;  // set to flag_value once the bytes are copied
+    int flag_value;
+    std::atomic<long long>* pending;  // decremented afterwards (may be nullptr)
 };
 
 class StagePool {
@@ -135,14 +136,16 @@ class StagePool {
                 t = q_.front();
                 q_.pop_front();
             }
-            if (t.device != device) {
-                cudaSetDevice(t.device);
-                device = t.device;
+            if (t.ev) {
+                if (t.device != device) {
+                    cudaSetDevice(t.device);
+                    device = t.device;
+                }
+                cudaEventSynchronize(t.ev);
             }
-            cudaEventSynchronize(t.ev);
             memcpy(t.dst, t.src, t.bytes);
-            t.slot_busy->store(0, std::memory_order_release);
-            t.pending->fetch_sub(1, std::memory_order_acq_rel);
+            t.flag->store(t.flag_value, std::memory_order_release);
+            if (t.pending) t.pending->fetch_sub(1, std::memory_order_acq_rel);
         }
     }
     std::mutex m_;
@@ -179,7 +182,8 @@ struct ThreadCtx {
     unsigned int* h_counters = nullptr;  // pinned
     ColumnStats* h_stats = nullptr;  // pinned
     Workspace lists, scratch;
-    Stager* stager = nullptr;  // created by the first download into pageable memory
+    Stager* stager = nullptr;     // created by the first download into pageable memory
+    Stager* up_stager = nullptr;  // created by the first upload from pageable memory
 };
 
 static thread_local ThreadCtx g_ctx;
@@ -405,7 +409,7 @@ static cudaError_t download(ThreadCtx& ctx, void* dst, const void* d_src, size_t
             sg.pending.fetch_sub(1);
             return e;
         }
-        pool.push(StageTask{ctx.device, sg.ev[slot], pinned, static_cast<char*>(dst) + off, len, &sg.busy[slot], &sg.pending});
+        pool.push(StageTask{ctx.device, sg.ev[slot], pinned, static_cast<char*>(dst) + off, len, &sg.busy[slot], 0, &sg.pending});
     }
     return cudaSuccess;
 }
@@ -414,6 +418,62 @@ static cudaError_t download(ThreadCtx& ctx, void* dst, const void* d_src, size_t
 static void download_wait(ThreadCtx& ctx) {
     if (!ctx.stager) return;
     while (ctx.stager->pending.load(std::memory_order_acquire) > 0) std::this_thread::yield();
+}
+
+// host -> device copy on stream `st`.  Pinned sources are DMA'd directly (asynchronous).  Pageable
+// sources -- what Polars hands a plugin -- would be staged by the driver on this thread at ~12 GB/s; here
+// the pool's threads copy them into a ring of pinned slots in parallel and every filled slot is DMA'd at
+// once.  This call returns when the last DMA of a pageable source has been QUEUED (the source is no
+// longer needed), so a host call interleaves such uploads with the kernels of the previous row slice.
+static cudaError_t upload_copy(ThreadCtx& ctx, void* d_dst, const void* src, size_t bytes, cudaStream_t st) {
+    if (bytes == 0) return cudaSuccess;
+    static const bool no_stage = getenv("STRSIM_B200_STAGED_H2D") != nullptr && !strcmp(getenv("STRSIM_B200_STAGED_H2D"), "0");
+    if (no_stage || bytes < (1u << 20) || is_pinned(src)) return cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, st);
+    if (!ctx.up_stager) {
+        Stager* sg = new Stager();
+        cudaError_t e = cudaMallocHost(&sg->ring, (size_t)STAGE_SLOTS * STAGE_SLOT_BYTES);
+        if (e != cudaSuccess) {
+            delete sg;
+            cudaGetLastError();
+            return cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, st);
+        }
+        for (int i = 0; i < STAGE_SLOTS; i++) {
+            cudaEventCreateWithFlags(&sg->ev[i], cudaEventDisableTiming);
+            cudaEventRecord(sg->ev[i], st);  // so that the first wait on a slot returns at once
+            sg->busy[i].store(0);
+        }
+        ctx.up_stager = sg;
+    }
+    Stager& sg = *ctx.up_stager;
+    StagePool& pool = StagePool::get();
+    const size_t n_chunks = (bytes + STAGE_SLOT_BYTES - 1) / STAGE_SLOT_BYTES;
+    const int base = sg.next;
+    size_t filled = 0, sent = 0;  // chunks handed to the copy threads / chunks whose DMA is queued
+    cudaError_t e = cudaSuccess;
+    while (sent < n_chunks) {
+        while (filled < n_chunks && filled - sent < (size_t)STAGE_SLOTS) {
+            const int slot = (base + (int)(filled % STAGE_SLOTS)) % STAGE_SLOTS;
+            cudaEventSynchronize(sg.ev[slot]);  // the DMA that last read this slot is done
+            const size_t off = filled * STAGE_SLOT_BYTES;
+            const size_t len = bytes - off < STAGE_SLOT_BYTES ? bytes - off : STAGE_SLOT_BYTES;
+            sg.busy[slot].store(1, std::memory_order_relaxed);  // 1 = being filled, 2 = filled
+            pool.push(StageTask{ctx.device, nullptr, static_cast<const char*>(src) + off,
+                                static_cast<char*>(sg.ring) + (size_t)slot * STAGE_SLOT_BYTES, len, &sg.busy[slot], 2, nullptr});
+            filled++;
+        }
+        const int slot = (base + (int)(sent % STAGE_SLOTS)) % STAGE_SLOTS;
+        while (sg.busy[slot].load(std::memory_order_acquire) != 2) std::this_thread::yield();
+        const size_t off = sent * STAGE_SLOT_BYTES;
+        const size_t len = bytes - off < STAGE_SLOT_BYTES ? bytes - off : STAGE_SLOT_BYTES;
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(static_cast<char*>(d_dst) + off, static_cast<char*>(sg.ring) + (size_t)slot * STAGE_SLOT_BYTES, len,
+                                cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaEventRecord(sg.ev[slot], st);
+        sg.busy[slot].store(0, std::memory_order_relaxed);
+        sent++;
+    }
+    sg.next = (base + (int)(n_chunks % STAGE_SLOTS)) % STAGE_SLOTS;
+    return e;
 }
 
 // H2D copy that never blocks on pageable memory longer than needed: pinned sources are DMA'd
@@ -573,8 +633,8 @@ static int64_t total_data_bytes(const strsim_b200_column* col) {
 // Uploads the data bytes of the linear range [up.uploaded, to) -- positions run over the column's
 // distinct data buffers in upload order -- with their byte statistics, and advances up.uploaded.
 // Range ends inside a buffer are multiples of 256 (see frontier_after), so every piece starts aligned.
-static int upload_data_range(Uploader& up, int64_t from, int64_t to, cudaStream_t st, ColumnStats* d_stats,
-                             bool do_copy, bool do_stats) {
+static int upload_data_range(ThreadCtx& ctx, Uploader& up, int64_t from, int64_t to, cudaStream_t st,
+                             ColumnStats* d_stats, bool do_copy, bool do_stats) {
     char* base = static_cast<char*>(up.col->block);
     int64_t start = 0;
     for (size_t id = 0; id < up.col->buf_size.size(); id++) {
@@ -583,8 +643,8 @@ static int upload_data_range(Uploader& up, int64_t from, int64_t to, cudaStream_
         const int64_t hi = to - start < size ? to - start : size;
         if (hi > lo) {
             if (do_copy)
-                CUDA_TRY(cudaMemcpyAsync(base + up.buf_dev_off[id] + lo, static_cast<const char*>(up.buf_src[id]) + lo,
-                                         (size_t)(hi - lo), cudaMemcpyHostToDevice, st));
+                CUDA_TRY(upload_copy(ctx, base + up.buf_dev_off[id] + lo, static_cast<const char*>(up.buf_src[id]) + lo,
+                                     (size_t)(hi - lo), st));
             if (do_stats) {
                 long long blocks = (((hi - lo) >> 4) + 255) / 256;
                 if (blocks > 148 * 16) blocks = 148 * 16;
@@ -599,19 +659,18 @@ static int upload_data_range(Uploader& up, int64_t from, int64_t to, cudaStream_
     CUDA_TRY(cudaGetLastError());
     return STRSIM_OK;
 }
-static int upload_data_until(Uploader& up, int64_t to, cudaStream_t st, ColumnStats* d_stats) {
+static int upload_data_until(ThreadCtx& ctx, Uploader& up, int64_t to, cudaStream_t st, ColumnStats* d_stats) {
     if (to <= up.uploaded) return STRSIM_OK;
-    const int rc = upload_data_range(up, up.uploaded, to, st, d_stats, true, true);
+    const int rc = upload_data_range(ctx, up, up.uploaded, to, st, d_stats, true, true);
     up.uploaded = to;
     return rc;
 }
 
 // buffer tables + every distinct data buffer (+ byte statistics of the buffers)
 static int upload_data(ThreadCtx& ctx, Uploader& up, cudaStream_t st, ColumnStats* d_stats) {
-    (void)ctx;
     int rc = upload_tables(up, st);
     if (rc) return rc;
-    return upload_data_until(up, total_data_bytes(up.col), st, d_stats);
+    return upload_data_until(ctx, up, total_data_bytes(up.col), st, d_stats);
 }
 
 // ---- progressive upload (host calls) -----------------------------------------------------------------
@@ -720,9 +779,8 @@ static int upload_rows(ThreadCtx& ctx, Uploader& up, int64_t lo, int64_t hi, cud
         const int64_t c_hi = hi - p.row0 < ch.length ? hi - p.row0 : ch.length;
         if (c_lo >= c_hi) continue;
         if (do_copy)
-            CUDA_TRY(cudaMemcpyAsync(base + p.views_off + 16 * c_lo,
-                                     static_cast<const char*>(ch.views) + 16 * (ch.offset + c_lo),
-                                     16 * (size_t)(c_hi - c_lo), cudaMemcpyHostToDevice, st));
+            CUDA_TRY(upload_copy(ctx, base + p.views_off + 16 * c_lo,
+                                 static_cast<const char*>(ch.views) + 16 * (ch.offset + c_lo), 16 * (size_t)(c_hi - c_lo), st));
         if (do_copy && p.validity_bytes) {
             const int64_t b_lo = ((ch.offset + c_lo) >> 3) - p.first_byte;
             const int64_t b_hi = ((ch.offset + c_hi + 7) >> 3) - p.first_byte;
@@ -1611,7 +1669,22 @@ static int host_call(const int* measures, size_t n_measures, const strsim_view_c
                          cudaMemcpyHostToDevice, ctx->upload_stream);
     if (ce == cudaSuccess && !res_a) rc = upload_tables(ua, ctx->upload_stream);
     if (ce == cudaSuccess && rc == STRSIM_OK && !res_b) rc = upload_tables(ub, ctx->upload_stream);
-    for (int sidx = 0; ce == cudaSuccess && rc == STRSIM_OK && sidx < n_slices; sidx++) {
+    // Pinned sources: every copy of the call is queued up front (asynchronous DMA).  Pageable sources are
+    // staged through the pinned ring by upload_copy(), which blocks this thread while it feeds the DMA
+    // engine, so their slices are queued one ahead of the slice being computed.
+    auto source_pinned = [](const Uploader& up) {
+        for (size_t i = 0; i < up.n_chunks; i++) {
+            if (up.chunks[i].length > 65536 && !is_pinned(up.chunks[i].views)) return false;
+            for (size_t b = 0; b < up.buf_src.size(); b++)
+                if (up.col->buf_size[b] > (1 << 20) && !is_pinned(up.buf_src[b])) return false;
+        }
+        return true;
+    };
+    const bool queue_all_upfront = (res_a || source_pinned(ua)) && (res_b || source_pinned(ub));
+    int queued_slices = 0;
+    auto queue_slice_upload = [&](int sidx) {
+        if (sidx != queued_slices || sidx >= n_slices || ce != cudaSuccess || rc != STRSIM_OK) return;
+        queued_slices++;
         const int64_t lo = sidx * slice_rows, hi = lo + slice_rows < n ? lo + slice_rows : n;
         int64_t fa = total_a, fb = total_b;
         if (progressive && sidx + 1 < n_slices) {
@@ -1636,8 +1709,8 @@ static int host_call(const int* measures, size_t n_measures, const strsim_view_c
                 if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->stats_stream, ctx->up_event[sidx], 0);
                 if (ce != cudaSuccess) break;
             }
-            if (!res_a) rc = upload_data_range(ua, from_a, fa, st, ctx->d_slice_stats + 0, cp, stt);
-            if (rc == STRSIM_OK && !res_b) rc = upload_data_range(ub, from_b, fb, st, ctx->d_slice_stats + 1, cp, stt);
+            if (!res_a) rc = upload_data_range(*ctx, ua, from_a, fa, st, ctx->d_slice_stats + 0, cp, stt);
+            if (rc == STRSIM_OK && !res_b) rc = upload_data_range(*ctx, ub, from_b, fb, st, ctx->d_slice_stats + 1, cp, stt);
             // a scalar (length-1) column is uploaded with the first slice
             if (rc == STRSIM_OK && !res_a)
                 rc = upload_rows(*ctx, ua, r_lo_a, r_hi_a, st, ctx->d_slice_stats + 2 + sidx, cp, stt);
@@ -1653,7 +1726,8 @@ static int host_call(const int* measures, size_t n_measures, const strsim_view_c
                                  ctx->stats_stream);
         if (rc == STRSIM_OK && ce == cudaSuccess) ce = cudaEventRecord(ctx->slice_event[sidx], ctx->stats_stream);
         if (trace) cudaEventRecord(tr_u[sidx], ctx->upload_stream);
-    }
+    };
+    for (int sidx = 0; sidx < (queue_all_upfront ? n_slices : 1); sidx++) queue_slice_upload(sidx);
 
     // ---- compute + download slice by slice
     // redo = false: as soon as the slice's views (and data prefix) have landed; returns in *deferred the
@@ -1712,6 +1786,8 @@ static int host_call(const int* measures, size_t n_measures, const strsim_view_c
     };
     int redo_list[MAX_SLICES], n_redo = 0;
     for (int sidx = 0; ce == cudaSuccess && rc == STRSIM_OK && sidx < n_slices; sidx++) {
+        queue_slice_upload(sidx + 1);  // no-op when everything was queued up front
+        if (ce != cudaSuccess || rc != STRSIM_OK) break;
         ce = cudaEventSynchronize(ctx->slice_event[sidx]);  // views + statistics of this slice are here
         if (ce != cudaSuccess) break;
         if (sidx == 0) g_last_overflow[0] = g_last_overflow[1] = 0;

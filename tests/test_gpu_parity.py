@@ -640,3 +640,36 @@ def test_plugin_calls_reuse_columns_already_in_hbm(native, oracle):
     L.strsim_b200_cache_clear()
     assert stats()[2:] == [0, 0]
     check_out("sorensen_dice", call("sorensen_dice", A2, B2), a2, b)
+
+
+def test_pageable_inputs_and_outputs_go_through_the_pinned_rings(oracle):
+    """Ordinary (pageable) Arrow buffers in, ordinary numpy arrays out: uploads are staged through the
+    pinned ring by the copy threads, one row slice ahead of the kernels; downloads likewise."""
+    code = r"""
+import sys, random, numpy as np
+sys.path[:0] = [%r, %r, %r]
+import pyarrow as pa
+from polars_strsim import _native
+from oracle import oracle
+rng = random.Random(12)
+n = 450000
+words = ["".join(rng.choice("abcdefghijklmnop") for _ in range(rng.randint(0, 30))) for _ in range(5000)]
+a = [rng.choice(words) for _ in range(n)]
+b = [x[: rng.randint(0, len(x))] + rng.choice(["", "q", "zz"]) if rng.random() < 0.7 else rng.choice(words) for x in a]
+b[11] = None
+A, B = pa.array(a, type=pa.string_view()), pa.array(b, type=pa.string_view())
+assert A.buffers()[1].size > (4 << 20)
+outs, valid, nulls = _native.compute_host_multi(list(oracle.MEASURES), A, B)
+assert _native.last_redo_slices() == 0
+for m, v in zip(oracle.MEASURES, outs):
+    ref, rv, _ = oracle.batch(m, a, b)
+    assert (valid == rv).all() and nulls == 1
+    assert (v[rv].view(np.uint64) == ref[rv].view(np.uint64)).all(), m
+v1, valid1, _ = _native.compute_host("levenshtein", A, B)
+ref, rv, _ = oracle.batch("levenshtein", a, b)
+assert (v1[rv].view(np.uint64) == ref[rv].view(np.uint64)).all()
+print("ok")
+""" % (str(ROOT), str(ROOT / "polars-strsim_b200"), str(ROOT / "tests"))
+    env = dict(os.environ, STRSIM_B200_SLICE_ROWS="100000")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-3000:]

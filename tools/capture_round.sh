@@ -30,3 +30,5 @@ python tools/plugin_e2e.py > $O/${R}_plugin_e2e.jsonl 2>> $O/bench_err.log
 STRSIM_B200_CACHE=0 python tools/plugin_e2e.py >> $O/${R}_plugin_e2e.jsonl 2>> $O/bench_err.log
 STRSIM_B200_STAGED_D2H=0 python tools/plugin_e2e.py >> $O/${R}_plugin_e2e.jsonl 2>> $O/bench_err.log
 cat $O/${R}_plugin_e2e.jsonl
+python tools/plugin_e2e.py --pageable >> $O/${R}_plugin_e2e.jsonl 2>> $O/bench_err.log
+STRSIM_B200_CACHE=0 python tools/plugin_e2e.py --pageable >> $O/${R}_plugin_e2e.jsonl 2>> $O/bench_err.log

@@ -23,9 +23,11 @@ MEASURES = ("levenshtein", "jaro", "jaro_winkler", "jaccard", "sorensen_dice")
 
 
 def main():
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
+    args = [x for x in sys.argv[1:] if not x.startswith("--")]
+    pageable = "--pageable" in sys.argv  # inputs in ordinary (pageable) memory, as Polars hands them over
+    n = int(args[0]) if args else 10_000_000
     L = _native.lib()
-    A, B = workloads.make_pairs(2, n, pinned=True)
+    A, B = workloads.make_pairs(2, n, pinned=not pageable)
     L.strsim_b200_cache_clear.restype = None
 
     def five_calls():
@@ -54,6 +56,7 @@ def main():
         five_calls()
         times.append((time.perf_counter() - t0) * 1e3)
     print(json.dumps({"rows": n, "cache": os.environ.get("STRSIM_B200_CACHE", "1"),
+                      "inputs": "pageable" if pageable else "pinned",
                       "five_plugin_calls_ms": min(times), "all_ms": times,
                       "note": "results land in pageable memory malloc'ed by the plugin (Arrow result buffers)"}))
 
