@@ -42,6 +42,9 @@ WORKLOADS = {
                desc="C3: mixed-Unicode name pairs (Latin-1 diacritics + CJK), 5% nulls, uneven chunks"),
     "C4": dict(config=4, rows=1_000_000, measures=("levenshtein",),
                desc="C4: long-text pairs, 200-4000 codepoints, Levenshtein"),
+    "L1": dict(config=6, rows=10_000_000, measures=MEASURES,
+               desc="L1 (not a BASELINE config): the Latin rows of C3 alone -- names of 4-24 codepoints, 15 % of the "
+                    "characters from U+00C0-U+00FF, no nulls"),
     "C5": dict(config=5, rows=125_000_000, measures=("jaro_winkler", "sorensen_dice"),
                desc="C5: record-linkage pairs (C2 generator, seed 0xC5), Jaro-Winkler + Sorensen-Dice"),
 }

@@ -9,6 +9,8 @@
  *   config 3 (C3): 70 % Latin rows (4..24 codepoints, each w.p. 0.15 from U+00C0..U+00FF except
  *                  U+00D7/U+00F7, else a..z), 30 % CJK rows (2..6 codepoints from U+4E00..U+9FFF);
  *                  name_b mutated as in C2 from the same script
+ *   config 6 (L1): every row a Latin row of config 3, no nulls (not a BASELINE config: shows the
+ *                  Latin-1 bit-plane path of the general kernel on its own)
  *   config 4 (C4): long text, length U{200..4000} codepoints, 90 % a..z/space, 10 % two- and
  *                  three-byte codepoints; b = a with ~10 % random edits w.p. 0.5, else independent
  * Every row is generated from splitmix64(seed, row), so output is independent of the thread count.
@@ -136,7 +138,9 @@ static void gen_row(int config, uint64_t seed, int64_t row, double null_p, rowbu
         }
     } else {
         int script = S_ASCII, lo = 4, hi = 24;
-        if (config == 3) {
+        if (config == 6) {
+            script = S_LATIN; /* the Latin rows of C3 alone: a column of names with diacritics */
+        } else if (config == 3) {
             if (rndf(&r) < 0.7) {
                 script = S_LATIN;
             } else {

@@ -314,19 +314,36 @@ struct ValidityArgs {
     unsigned long long* null_count;
 };
 
+// 32 validity bits of rows [s, s+32) of one column (s >= 0): all ones without a bitmap, the broadcast bit
+// for a scalar operand, else two aligned word loads and a funnel shift (the device copy of a bitmap is
+// 256-byte aligned and padded, host.cu: upload_plan)
+__device__ __forceinline__ uint32_t validity_word(const uint8_t* bm, long long bit0, int stride, long long s) {
+    if (bm == nullptr) return 0xFFFFFFFFu;
+    if (stride == 0) return ((bm[bit0 >> 3] >> (bit0 & 7)) & 1) ? 0xFFFFFFFFu : 0u;
+    const long long b = bit0 + s;
+    const uint32_t* words = reinterpret_cast<const uint32_t*>(bm);
+    const uint32_t lo = __ldg(words + (b >> 5)), hi = __ldg(words + (b >> 5) + 1);
+    return __funnelshift_r(lo, hi, (int)(b & 31));
+}
+
 __global__ void validity_kernel(const ValidityArgs v) {
     const long long w_lo = v.out_row0 >> 5;
     const long long w = w_lo + blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long r_begin = max(w << 5, v.out_row0);
     const long long r_end = min((w + 1) << 5, v.out_row0 + v.n);
     if (r_begin >= r_end) return;
-    uint32_t bits = 0;
-    for (long long r = r_begin; r < r_end; r++) {
-        const long long s = r - v.out_row0;
-        const bool ok = bit_valid(v.va, v.abit + s * v.astride) && bit_valid(v.vb, v.bbit + s * v.bstride);
-        bits |= (ok ? 1u : 0u) << (int)(r & 31);
-    }
     const int rows = (int)(r_end - r_begin);
+    uint32_t bits = 0;
+    if (rows == 32 && (reinterpret_cast<uintptr_t>(v.va) & 3) == 0 && (reinterpret_cast<uintptr_t>(v.vb) & 3) == 0) {
+        const long long s = r_begin - v.out_row0;
+        bits = validity_word(v.va, v.abit, v.astride, s) & validity_word(v.vb, v.bbit, v.bstride, s);
+    } else {
+        for (long long r = r_begin; r < r_end; r++) {
+            const long long s = r - v.out_row0;
+            const bool ok = bit_valid(v.va, v.abit + s * v.astride) && bit_valid(v.vb, v.bbit + s * v.bstride);
+            bits |= (ok ? 1u : 0u) << (int)(r & 31);
+        }
+    }
     if (rows == 32)
         v.out[w] = bits;
     else

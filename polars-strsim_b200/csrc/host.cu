@@ -359,6 +359,9 @@ struct strsim_b200_column {
     // is on the device right now: equal to the size except while a host call uploads progressively
     std::vector<int64_t> buf_size, buf_resident;
     std::vector<std::vector<int>> chunk_buf_ids;  // [chunk][buffer index] -> distinct buffer id
+    // general columns: share of pairs with a character above U+00FF seen by the last Latin-1 launch over
+    // this column (-1: unknown); a hint only, read and written without synchronisation
+    mutable float wide_share = -1.0f;
 };
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -844,10 +847,10 @@ static int upload_column(ThreadCtx& ctx, const strsim_view_chunk* chunks, size_t
 
 // ---- kernel launch helpers -----------------------------------------------------------------------------
 template <class M, int MEASURE, int TPB, int RPT, bool GATHER, int T, bool ASCII_ONLY, bool REG = false,
-          bool UREG = false>
+          bool UREG = false, bool ULAT = false>
 static int launch_short(ThreadCtx& ctx, SegArgs args, long long n_upper, cudaStream_t st) {
     using L = ShortLayout<M, TPB, RPT, T, REG, UREG>;
-    auto kern = short_kernel<M, MEASURE, TPB, RPT, GATHER, T, ASCII_ONLY, REG, UREG>;
+    auto kern = short_kernel<M, MEASURE, TPB, RPT, GATHER, T, ASCII_ONLY, REG, UREG, ULAT>;
     if (args.stage_bytes < 0) {
         // -stage_bytes = mean out-of-line bytes per row (x16) of the heavier column: size the stage
         // area for this tile shape with 25 % headroom (rows that still do not fit take the long path)
@@ -901,6 +904,34 @@ static int launch_direct(ThreadCtx& ctx, const SegArgs& args, long long n_upper,
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CUDA_TRY(cudaGetLastError());
     return STRSIM_OK;
+}
+
+// A general column (some byte >= 0x80) is served by two launches over the same rows: the pairs without
+// a character above U+00FF by the 8-plane path on transcoded bytes (ULAT), the others by the
+// register-compare path; the first launch also settles null rows and fills the overflow lists.
+static thread_local float* g_wide_share = nullptr;  // the current column pair's hint (compute_on_device)
+
+template <int MEASURE, int RPT_LATIN, int RPT_WIDE>
+static int launch_general(ThreadCtx& ctx, const SegArgs& args, long long rows, cudaStream_t st) {
+    static const bool latin = !(getenv("STRSIM_B200_LATIN") && !strcmp(getenv("STRSIM_B200_LATIN"), "0"));
+    SegArgs a = args;
+    a.skip_latin = 0;
+    // Two launches read the views and stage the payload twice: that pays when (nearly) all pairs are
+    // Latin-1 (L1 workload: 1.56 ms vs 2.23 ms per 10 M rows x 5 measures) and costs 6 % on C3, where
+    // 30 % of the rows are CJK -- so once a segment of this column pair has shown a substantial share of
+    // wide pairs, the following segments / slices / calls go to the register-compare kernel alone.
+    const bool mostly_latin = !(g_wide_share && *g_wide_share > 0.15f);
+    if (!latin || !mostly_latin)
+        return launch_short<uint32_t, MEASURE, 256, RPT_WIDE, false, 128, false, false, true>(ctx, a, rows, st);
+    int rc = launch_short<uint32_t, MEASURE, 256, RPT_LATIN, false, 128, false, false, true, true>(ctx, a, rows, st);
+    if (rc) return rc;
+    // a column of Latin-1 text (names with diacritics) has nothing left for the second launch
+    CUDA_TRY(publish_to_host(ctx.h_ovf, ctx.d_ovf, sizeof(Overflow), st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (g_wide_share && rows > 0) *g_wide_share = (float)ctx.h_ovf->nwide / (float)rows;
+    if (ctx.h_ovf->nwide == 0) return STRSIM_OK;
+    a.skip_latin = 1;
+    return launch_short<uint32_t, MEASURE, 256, RPT_WIDE, false, 128, false, false, true>(ctx, a, rows, st);
 }
 
 // Which instantiation of the fused kernel serves a segment (see DevStore): decided from the union of
@@ -961,10 +992,11 @@ static int launch_fused(ThreadCtx& ctx, Alphabet al, const SegArgs& args, long l
             case ALPHA_ASCII128:
                 return launch_short<uint32_t, MEASURE, 256, 4, false, 128, true, true>(ctx, args, rows, st);
             default:
-                // any script: register-compare path (row_unicode_reg.cuh), no table in shared memory
+                // any script: Latin-1 pairs by the plane path, the others by the register-compare path
+                // (row_unicode_reg.cuh); no table in shared memory
                 if (cfg == 1) return launch_short<uint32_t, MEASURE, 128, 4, false, 128, false, false, true>(ctx, args, rows, st);
                 if (cfg == 2) return launch_short<uint32_t, MEASURE, 128, 2, false, 128, false, false, true>(ctx, args, rows, st);
-                return launch_short<uint32_t, MEASURE, 256, 4, false, 128, false, false, true>(ctx, args, rows, st);
+                return launch_general<MEASURE, 4, 4>(ctx, args, rows, st);
         }
     }
     switch (al) {
@@ -1006,7 +1038,7 @@ static int launch_multi(ThreadCtx& ctx, Alphabet al, const SegArgs& args, long l
             return launch_short<uint32_t, ME, 256, 3, false, 128, true, true>(ctx, args, rows, st);
         default:
             // register-compare path: 256 x 2 measured best on C3 (4.82 ms vs 5.11 ms per 10M rows x 5 measures)
-            return launch_short<uint32_t, ME, 256, 2, false, 128, false, false, true>(ctx, args, rows, st);
+            return launch_general<ME, 3, 2>(ctx, args, rows, st);
     }
 }
 
@@ -1154,7 +1186,9 @@ static int finish_64(ThreadCtx& ctx, const SegArgs& args, const Overflow& ov, cu
     a64.list = args.list64;
     a64.list_count = &ctx.d_ovf->n64;
     a64.n = ov.n64;
-    return launch_direct<uint64_t, MEASURE, 64, 4, true, 192, false>(ctx, a64, ov.n64, st);
+    // 64-row tiles: the list is short (C3: 10k of 6.7M rows), so many small CTAs finish it in one wave;
+    // with 256-row tiles a dozen CTAs took 0.1 ms per measure, a quarter of the segment's time
+    return launch_direct<uint64_t, MEASURE, 64, 1, true, 192, false>(ctx, a64, ov.n64, st);
 }
 
 // rows on the long list -> multi-word Myers (Levenshtein; consumes list64 and listlong) or the generic kernel
@@ -1324,6 +1358,7 @@ static int compute_on_device(ThreadCtx& ctx, const int* measures, size_t n_measu
         CUDA_TRY(cudaMemsetAsync(w0, any_validity ? 0 : 0xFF, 4 * words, st));
         if (row_lo == 0) CUDA_TRY(cudaMemsetAsync(ctx.d_nulls, 0, sizeof(unsigned long long), st));
     }
+    g_wide_share = &a->wide_share;
     // walk both chunk lists in lock step (polars-core align_chunks equivalent)
     size_t ia = 0, ib = 0;
     int64_t oa = 0, ob = 0, row = row_lo;

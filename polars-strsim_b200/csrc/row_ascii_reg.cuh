@@ -45,6 +45,7 @@ struct PlaneTab {
         if (NBITS > 4) X |= B[4] ^ sign_fill_byte(u, 2);
         if (NBITS > 5) X |= B[5] ^ sign_fill_byte(u, 1);
         if (NBITS > 6) X |= B[6] ^ sign_fill_byte(u, 0);
+        if (NBITS > 7) X |= B[7] ^ sign_fill_byte(c, 0);  // one byte per character up to U+00FF (Latin-1 rows)
         return ~X & valid;
     }
 };
@@ -223,6 +224,57 @@ SS_HD void row_ascii_reg_multi(const uint32_t (&a)[REG_WORDS], const uint32_t (&
     prefix.lim = na < nb ? na : nb;
     if (prefix.lim > 4) prefix.lim = 4;
     multi_body<GROUPS, uint32_t>(tab, each_a, na, nb, na == 0 || nb == 0, prefix, trans_count, emit);
+}
+
+// ---- Latin-1 rows of a mixed-script column ------------------------------------------------------------
+// A string whose characters are all below U+0100 (no byte >= 0xC4: ASCII, or a C2/C3 lead with one
+// continuation byte) has at most one byte of information per character: the continuation byte with
+// the lead's low bit moved into bit 6 IS the code point (C2 xx -> xx, C3 xx -> xx | 0x40).  Transcoded
+// that way, a pair of such strings runs the bit-plane path with 8 planes instead of the register-compare
+// path, whose position masks cost two ALU operations per tabled character per streamed character.
+//
+// Slab: rd(w) / wr(w, word) over the string's words (zero padded).  In place: the output never
+// overtakes the input.  Returns the number of characters.
+template <class Slab>
+SS_HD int transcode_latin1(Slab& s, int nbytes) {
+    uint64_t acc = 0;
+    int acc_bytes = 0, out_w = 0, total = 0;
+    uint32_t carry = 0;  // low bit of a lead byte that ended the previous word
+    const int nw = (nbytes + 3) >> 2;
+    for (int w = 0; w < nw; w++) {
+        const uint32_t x = s.rd(w);
+        const uint32_t lead = x & (x << 1) & 0x80808080u;  // bit 7 of every 11xxxxxx byte
+        const uint32_t lowbit = x & (lead >> 7);           // bit 0 of the lead bytes ...
+        const uint32_t y = x | (lowbit << 14) | (carry << 6);  // ... into bit 6 of the byte that follows
+        carry = lowbit >> 24;
+        uint32_t z = 0;
+        int cnt = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const bool keep = 4 * w + j < nbytes && !((lead >> (8 * j + 7)) & 1u);
+            if (keep) {
+                z |= ((y >> (8 * j)) & 0xFFu) << (8 * cnt);
+                cnt++;
+            }
+        }
+        acc |= (uint64_t)z << (8 * acc_bytes);
+        acc_bytes += cnt;
+        total += cnt;
+        if (acc_bytes >= 4) {
+            s.wr(out_w++, (uint32_t)acc);
+            acc >>= 32;
+            acc_bytes -= 4;
+        }
+    }
+    if (acc_bytes > 0) s.wr(out_w++, (uint32_t)acc);
+    return total;
+}
+
+// any byte >= 0xC4 (a character above U+00FF) in a zero-padded word?
+SS_HD uint32_t wide_bytes(uint32_t x) {
+    const uint32_t t = x & 0x3C3C3C3Cu;
+    const uint32_t nz = (t + 0x7F7F7F7Fu) & 0x80808080u;  // bit 7 where bits 2..5 are not all zero
+    return x & (x << 1) & nz & 0x80808080u;
 }
 
 }  // namespace strsim

@@ -50,6 +50,7 @@ struct Overflow {
     unsigned int nlong;  // rows for the long kernel
     unsigned int max_bytes_a, max_bytes_b;  // over the long rows
     unsigned int ndefer;  // rows whose payload had not been uploaded yet: the host recomputes the slice
+    unsigned int nwide;   // ULAT launch: pairs with a character above U+00FF, left to the UREG launch
 };
 
 struct SegArgs {
@@ -67,6 +68,9 @@ struct SegArgs {
     unsigned int* list64;
     unsigned int* listlong;
     int stage_bytes;  // capacity of each column's stage area (multiple of 16)
+    // general columns are served by two launches (ULAT, then UREG): the second one skips the Latin-1
+    // pairs and leaves null rows and the overflow lists alone
+    int skip_latin;
 };
 
 // ---- small device helpers ------------------------------------------------------------------------
@@ -244,8 +248,9 @@ __device__ __forceinline__ void load_string_reg(const uint4& v, const unsigned c
     }
 }
 
-// number of characters (bytes that are not UTF-8 continuation bytes) of a staged string
-__device__ __forceinline__ int staged_char_count(const uint4& v, const unsigned char* stage) {
+// number of characters (bytes that are not UTF-8 continuation bytes) of a staged string; `wide` collects
+// the bytes >= 0xC4 (characters above U+00FF, see row_ascii_reg.cuh: wide_bytes)
+__device__ __forceinline__ int staged_char_count(const uint4& v, const unsigned char* stage, uint32_t& wide) {
     const int len = (int)v.x;
     int cont = 0;
     if (len <= 12) {
@@ -253,6 +258,7 @@ __device__ __forceinline__ int staged_char_count(const uint4& v, const unsigned 
                        w2 = v.w & byte_mask(len - 8 < 0 ? 0 : len - 8);
         cont = __popc(((w0 >> 7) & ~(w0 >> 6)) & 0x01010101u) + __popc(((w1 >> 7) & ~(w1 >> 6)) & 0x01010101u) +
                __popc(((w2 >> 7) & ~(w2 >> 6)) & 0x01010101u);
+        wide |= wide_bytes(w0) | wide_bytes(w1) | wide_bytes(w2);
     } else {
         const uint32_t* p = reinterpret_cast<const uint32_t*>(stage) + (v.y >> 2);
         const int head = (int)(v.y & 3u);               // bytes of the first word before the string
@@ -262,6 +268,7 @@ __device__ __forceinline__ int staged_char_count(const uint4& v, const unsigned 
             if (w == 0) x &= ~byte_mask(head);
             if (w == nwords - 1) x &= byte_mask(head + len - 4 * w);
             cont += __popc(((x >> 7) & ~(x >> 6)) & 0x01010101u);
+            wide |= wide_bytes(x);
         }
     }
     return len - cont;
@@ -359,13 +366,40 @@ struct SmemByteAt {
     }
 };
 
+// the thread's slab of shared memory ([word][thread] layout) as transcode_latin1's Slab / as bytes
+template <int TPB>
+struct SlabWords {
+    uint32_t* w;  // &slab[tid]
+    __device__ __forceinline__ uint32_t rd(int i) const { return w[i * TPB]; }
+    __device__ __forceinline__ void wr(int i, uint32_t v) { w[i * TPB] = v; }
+};
+template <int TPB>
+struct SlabByteAt {
+    uint32_t base;  // shared-space address of &slab[tid]
+    __device__ __forceinline__ uint32_t operator()(int p) const {
+        uint32_t v;
+        // "memory": the slab was rewritten by transcode_latin1 just before
+        asm volatile("ld.shared.u8 %0, [%1];"
+                     : "=r"(v)
+                     : "r"(base + (uint32_t)(p >> 2) * (uint32_t)(4 * TPB) + (uint32_t)(p & 3))
+                     : "memory");
+        return v;
+    }
+};
+
 struct WarpMaxDev {  // maximum over the 32 lanes of the warp (all lanes must call it)
     __device__ __forceinline__ int operator()(int v) const { return __reduce_max_sync(0xFFFFFFFFu, v); }
 };
 
+// ULAT (with UREG): the Latin-1 half of a general column -- this instantiation computes only the pairs
+// without a character above U+00FF, by the 8-plane path; the plain UREG launch that follows (with
+// SegArgs::skip_latin) takes the others by the register-compare path.  One kernel holding both paths
+// measured SLOWER than the compare path alone: 121 KB of SASS, a third of the stall samples
+// instruction-cache misses, another third barrier waits of warps with unequal work.
 template <class M, int MEASURE, int TPB, int RPT, bool GATHER, int T, bool ASCII_ONLY, bool REG = false,
-          bool UREG = false>
+          bool UREG = false, bool ULAT = false>
 __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
+    static_assert(!ULAT || UREG, "the Latin-1 instantiation uses the general kernel's slabs");
     static_assert(ASCII_ONLY || UREG || T >= DevStore<M, TPB, T>::HASH_ENTRIES,
                   "the Unicode path keeps its hash slots in the table memory");
     static_assert(!UREG || (!ASCII_ONLY && !REG && sizeof(M) == 4), "register-compare path: general u32 kernel");
@@ -444,11 +478,15 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
                 const bool valid = bit_valid(s.a.validity, s.a.vbit + row * s.a.stride) &&
                                    bit_valid(s.b.validity, s.b.vbit + row * s.b.stride);
                 const uint32_t mx = va.x > vb.x ? va.x : vb.x;
+                const bool second = UREG && !ULAT && s.skip_latin;  // the first launch settled these rows
                 if (!valid) {
-                    store_settled<MEASURE>(s, row, 0.0, 0);
+                    if (!second) store_settled<MEASURE>(s, row, 0.0, 0);
                 } else if ((va.x > 12u && !payload_resident(va, s.a)) || (vb.x > 12u && !payload_resident(vb, s.b))) {
-                    atomicAdd(&s.ovf->ndefer, 1u);  // nothing is written for this row in this pass
+                    if (!second) atomicAdd(&s.ovf->ndefer, 1u);  // nothing is written for this row in this pass
                 } else if (mx > (uint32_t)CAP) {
+                    if (second) {
+                        // already on the lists
+                    } else
                     if (CAP == 32 && mx <= 64u) {
                         s.list64[atomicAdd(&s.ovf->n64, 1u)] = (unsigned int)row;
                     } else {
@@ -565,12 +603,14 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
                 if (v.x <= 12u) continue;
                 const uint32_t padded = (v.x + 3u) & ~3u;
                 if (pos + padded > (uint32_t)s.stage_bytes) {
-                    // stage full: finish this row in the long kernel
+                    // stage full: finish this row in the long kernel (listed once: by the first launch)
                     const long long idx = tile0 + i;
                     const long long row = GATHER ? (long long)s.list[idx] : idx;
-                    s.listlong[atomicAdd(&s.ovf->nlong, 1u)] = (unsigned int)row;
-                    atomicMax(&s.ovf->max_bytes_a, sva[i].x);
-                    atomicMax(&s.ovf->max_bytes_b, svb[i].x);
+                    if (!(UREG && !ULAT && s.skip_latin)) {
+                        s.listlong[atomicAdd(&s.ovf->nlong, 1u)] = (unsigned int)row;
+                        atomicMax(&s.ovf->max_bytes_a, sva[i].x);
+                        atomicMax(&s.ovf->max_bytes_b, svb[i].x);
+                    }
                     active &= ~(1u << k);
                     continue;
                 }
@@ -652,12 +692,22 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
             uint32_t mx = va.x > vb.x ? va.x : vb.x;
             // fused evaluation streams a against the tabled b for every group: the loops run la times
             if (is_multi(MEASURE) && REG) mx = va.x;
+            uint32_t wide = 0;  // UREG: a character above U+00FF somewhere in the pair
             if (UREG) {
                 // the register-compare path costs (streamed characters) x (tabled characters): bucket by
                 // CHARACTER counts so that e.g. 6-character CJK rows do not share a warp with 18-character
-                // Latin rows of the same byte length
-                const int ca = staged_char_count(va, stage_a), cb = staged_char_count(vb, stage_b);
+                // Latin rows of the same byte length.
+                const int ca = staged_char_count(va, stage_a, wide), cb = staged_char_count(vb, stage_b, wide);
                 mx = (uint32_t)(ca > cb ? ca : cb);
+                if (is_multi(MEASURE) && ULAT) mx = (uint32_t)ca;  // the plane path streams a for every group
+                // each of the two launches over a general column takes one class; the first one counts what
+                // it leaves to the second (none in a Latin-1 column: the host then skips that launch)
+                if (ULAT && wide != 0u) {
+                    const unsigned m = __activemask();
+                    if ((int)__ffs(m) - 1 == lane) atomicAdd(&s.ovf->nwide, (unsigned)__popc(m));
+                    continue;
+                }
+                if (!ULAT && s.skip_latin && wide == 0u) continue;
             }
             // fused kernel: the equal pairs get the cheapest bucket of their own (key 1 otherwise holds only
             // empty/empty pairs, which are equal too) -- whole warps of them leave the row function at its
@@ -723,6 +773,37 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
                         for (int w = 0; w < nw; w++) diff |= store.wa(w) ^ store.wb(w);
                         equal = diff == 0;
                     }
+                }
+                if constexpr (ULAT) {
+                    // no character above U+00FF in these pairs: UTF-8 -> one byte per character in the
+                    // slab, then the bit-plane path with 8 planes (row_ascii_reg.cuh: transcode_latin1)
+                    if (!has) continue;
+                    int ca = na, cb = nb;
+                    if (!equal) {
+                        SlabWords<TPB> sa{store.wa_}, sb{store.wb_};
+                        ca = transcode_latin1(sa, na);
+                        cb = transcode_latin1(sb, nb);
+                    }
+                    uint32_t ra[REG_WORDS], rb[REG_WORDS];
+#pragma unroll
+                    for (int w = 0; w < REG_WORDS; w++) {
+                        ra[w] = 4 * w < ca ? store.wa(w) : 0u;
+                        rb[w] = 4 * w < cb ? store.wb(w) : 0u;
+                    }
+                    TransByBytes<SlabByteAt<TPB>> trans;
+                    trans.A.base = smem_u32(store.wa_);
+                    trans.B.base = smem_u32(store.wb_);
+                    const long long idx = tile0 + i;
+                    const long long row = GATHER ? (long long)s.list[idx] : idx;
+                    if constexpr (is_multi(MEASURE)) {
+                        RowEmit emit{s, row, true};
+                        row_ascii_reg_multi<GROUPS, 8>(ra, rb, ca, cb, trans, emit);
+                    } else {
+                        PairInts ints;
+                        s.out[row] = row_ascii_reg<is_multi(MEASURE) ? 0 : MEASURE, 8>(ra, rb, ca, cb, ints, trans);
+                        if (s.dbg) store_dbg(s.dbg + row * 6, ints);
+                    }
+                    continue;
                 }
                 WarpMaxDev wm;
                 if constexpr (is_multi(MEASURE)) {

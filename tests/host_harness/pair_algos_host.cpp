@@ -245,3 +245,49 @@ extern "C" int algos_batch_ureg_multi(int groups, int64_t n, const uint8_t* ad, 
     }
     return 0;
 }
+
+// Latin-1 rows: transcode to one byte per character, then the 8-plane path (row_ascii_reg.cuh)
+struct HostSlab {
+    uint32_t* w;
+    uint32_t rd(int i) const { return w[i]; }
+    void wr(int i, uint32_t v) { w[i] = v; }
+};
+
+// returns -4 when a row is not Latin-1 (a byte >= 0xC4)
+extern "C" int algos_batch_latin1_multi(int groups, int64_t n, const uint8_t* ad, const int64_t* ao, const uint8_t* bd,
+                                        const int64_t* bo, int* ints, double* values) {
+    for (int64_t r = 0; r < n; r++) {
+        const int na = (int)(ao[r + 1] - ao[r]), nb = (int)(bo[r + 1] - bo[r]);
+        if (na > 32 || nb > 32) return -2;
+        uint32_t a[REG_WORDS] = {0}, b[REG_WORDS] = {0};
+        std::memcpy(a, ad + ao[r], na);
+        std::memcpy(b, bd + bo[r], nb);
+        uint32_t wide = 0;
+        for (int w = 0; w < REG_WORDS; w++) wide |= wide_bytes(a[w]) | wide_bytes(b[w]);
+        if (wide) return -4;
+        const bool equal = na == nb && std::memcmp(a, b, sizeof a) == 0;
+        int ca = na, cb = nb;
+        if (!equal) {
+            HostSlab sa{a}, sb{b};
+            ca = transcode_latin1(sa, na);
+            cb = transcode_latin1(sb, nb);
+            for (int w = 0; w < REG_WORDS; w++) {  // what the kernel does when it loads the registers
+                if (4 * w >= ca) a[w] = 0;
+                if (4 * w >= cb) b[w] = 0;
+            }
+        }
+        HostEmit e{r, n, ints, values};
+        TransByBytes<HostByteAt> tb{{reinterpret_cast<const uint8_t*>(a)}, {reinterpret_cast<const uint8_t*>(b)}};
+        switch (groups) {
+            case 1: row_ascii_reg_multi<1, 8>(a, b, ca, cb, tb, e); break;
+            case 2: row_ascii_reg_multi<2, 8>(a, b, ca, cb, tb, e); break;
+            case 3: row_ascii_reg_multi<3, 8>(a, b, ca, cb, tb, e); break;
+            case 4: row_ascii_reg_multi<4, 8>(a, b, ca, cb, tb, e); break;
+            case 5: row_ascii_reg_multi<5, 8>(a, b, ca, cb, tb, e); break;
+            case 6: row_ascii_reg_multi<6, 8>(a, b, ca, cb, tb, e); break;
+            case 7: row_ascii_reg_multi<7, 8>(a, b, ca, cb, tb, e); break;
+            default: return -3;
+        }
+    }
+    return 0;
+}
