@@ -1023,6 +1023,8 @@ static int launch_multi(ThreadCtx& ctx, Alphabet al, const SegArgs& args, long l
         if (al == ALPHA_ASCII32) {
             if (cfg == 1) return launch_short<uint32_t, MULTI_BASE + 7, 256, 4, false, 32, true, true>(ctx, args, rows, st);
             if (cfg == 2) return launch_short<uint32_t, MULTI_BASE + 7, 128, 4, false, 32, true, true>(ctx, args, rows, st);
+            if (cfg == 3) return launch_short<uint32_t, MULTI_BASE + 7, 256, 2, false, 32, true, true>(ctx, args, rows, st);
+            if (cfg == 4) return launch_short<uint32_t, MULTI_BASE + 7, 128, 3, false, 32, true, true>(ctx, args, rows, st);
         } else if (al == ALPHA_GENERAL) {
             if (cfg == 1) return launch_short<uint32_t, MULTI_BASE + 7, 256, 4, false, 128, false, false, true>(ctx, args, rows, st);
             if (cfg == 2) return launch_short<uint32_t, MULTI_BASE + 7, 128, 4, false, 128, false, false, true>(ctx, args, rows, st);

@@ -216,8 +216,8 @@ struct MyersStep {
         const M Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
         M Ph = Mv | ~(Xh | Pv);
         M Mh = Pv & Xh;
-        Ph = (Ph << 1) | M(1);
-        Mh = Mh << 1;
+        Ph = Ph + Ph + M(1);  // (Ph << 1) | 1 as one three-input add
+        Mh = Mh + Mh;
         Pv = Mh | ~(Xv | Ph);
         Mv = Ph & Xv;
     }
@@ -227,29 +227,105 @@ struct MyersStep {
     }
 };
 
-// Jaro match pass (strsim.rs:208-219).  The window [i-bound, i+bound] slides one bit per character:
-// it grows at the top every step and starts dropping bit `lo` once i > bound.
+// bit reversal of a mask
+SS_HD uint32_t brev(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __brev(x);
+#else
+    x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+    x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+    x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4);
+    return __builtin_bswap32(x);
+#endif
+}
+SS_HD uint64_t brev(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return __brevll(x);
+#else
+    return ((uint64_t)brev((uint32_t)x) << 32) | brev((uint32_t)(x >> 32));
+#endif
+}
+SS_HD int flo(uint32_t x) {  // index of the highest set bit, x != 0
+#if defined(__CUDA_ARCH__)
+    return 31 - __clz((int)x);
+#else
+    return 31 - __builtin_clz(x);
+#endif
+}
+SS_HD int flo(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return 63 - __clzll((long long)x);
+#else
+    return 63 - __builtin_clzll(x);
+#endif
+}
+
+// (x << 1) | (top bit of src): one funnel shift
+SS_HD uint32_t shift_in_top(uint32_t x, uint32_t src) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(src, x, 1);
+#else
+    return (x << 1) | (src >> 31);
+#endif
+}
+SS_HD uint64_t shift_in_top(uint64_t x, uint64_t src) { return (x << 1) | (src >> 63); }
+
+// The match window [i-bound, i+bound] of step i (strsim.rs:209-210) as a mask over the positions of b.
+// Generic form: it grows at the top every step and starts dropping its lowest bit once i > bound.
+template <class M>
+struct JaroWindow {
+    M win;
+    int i, bound;
+    SS_HD void init(int bound_) {
+        bound = bound_;
+        i = 0;
+        win = (M(2) << bound_) - M(1);  // bits 0..bound
+    }
+    SS_HD M get() const { return win; }
+    SS_HD void next() {
+        i++;
+        win = (win << 1) | M(i <= bound ? 1 : 0);
+    }
+};
+// 32-bit masks: the window is the high word of a run of 2*bound+1 ones that moves up one bit per step
+// through a 64-bit register (two shifts per step, no counter, no compare).  bound <= 15.
+template <>
+struct JaroWindow<uint32_t> {
+    uint64_t t;
+    SS_HD void init(int bound_) { t = ((2ull << (2 * bound_)) - 1ull) << (32 - bound_); }
+    SS_HD uint32_t get() const { return (uint32_t)(t >> 32); }
+    SS_HD void next() { t += t; }
+};
+
+// Jaro match pass (strsim.rs:208-219), branch-free: `avail` holds the positions of b that exist and are
+// not flagged yet, the flag of a's character i enters `rev_a` at the bottom (so rev_a is flag_a in
+// REVERSED order until finish()); the match count is read off the flags at the end.
 template <class M, class Tab>
 struct JaroMatchStep {
     const Tab& tab;
-    M win, lbmask, flag_a, flag_b, abit;
-    int m, i, bound;
-    SS_HD JaroMatchStep(const Tab& t, int lb, int bound_)
-        : tab(t), flag_a(M(0)), flag_b(M(0)), abit(M(1)), m(0), i(0), bound(bound_) {
-        win = (M(2) << bound_) - M(1);  // bits 0..bound
+    JaroWindow<M> window;
+    M lbmask, avail, rev_a;
+    M flag_a, flag_b;  // valid after finish()
+    int m;             // valid after finish()
+    SS_HD JaroMatchStep(const Tab& t, int lb, int bound_) : tab(t), rev_a(M(0)), flag_a(M(0)), flag_b(M(0)), m(0) {
+        window.init(bound_);
         lbmask = lb >= (int)(sizeof(M) * 8) ? ~M(0) : ((M(1) << lb) - M(1));
+        avail = lbmask;
     }
     SS_HD void operator()(uint32_t c) { step(tab(c)); }
     SS_HD void step(const M Eq) {
-        const M cand = Eq & win & lbmask & ~flag_b;
-        if (cand) {
-            flag_b |= cand & (M(0) - cand);
-            flag_a |= abit;
-            m++;
-        }
-        abit = abit << 1;
-        i++;
-        win = (win << 1) | M(i <= bound ? 1 : 0);
+        const M cand = Eq & window.get() & avail;
+        const M neg = M(0) - cand;
+        avail = avail & ~(cand & neg);  // the lowest candidate is taken (strsim.rs:211-217)
+        const M any = cand | neg;       // top bit set iff there is a candidate
+        rev_a = shift_in_top(rev_a, any);
+        window.next();
+    }
+    // steps = number of characters of a that went through step()
+    SS_HD void finish(int steps) {
+        flag_b = lbmask & ~avail;
+        m = popc(flag_b);
+        flag_a = steps > 0 ? (brev(rev_a) >> ((int)(sizeof(M) * 8) - steps)) : M(0);
     }
 };
 
@@ -289,13 +365,14 @@ struct TransByBytes {
     ByteAt A, B;
     template <class M, class Tab, class Each>
     SS_HD int operator()(const Tab&, const Each&, int, M flag_a, M flag_b) const {
+        // the two flag sets have the same number of bits, so pairing them highest bit first pairs the same
+        // ranks as lowest bit first; the highest set bit is one instruction (FLO), the lowest two
         int t = 0;
         while (flag_a) {
-            const int ia = sizeof(M) == 4 ? ctz32((uint32_t)flag_a) : ctz64((uint64_t)flag_a);
-            const int ib = sizeof(M) == 4 ? ctz32((uint32_t)flag_b) : ctz64((uint64_t)flag_b);
-            flag_a &= flag_a - M(1);
-            flag_b &= flag_b - M(1);
-            t += A(ia) != B(ib) ? 1 : 0;
+            const int ia = flo(flag_a), ib = flo(flag_b);
+            flag_a ^= M(1) << ia;
+            flag_b ^= M(1) << ib;
+            if (A(ia) != B(ib)) t++;
         }
         return t;
     }
@@ -306,17 +383,17 @@ template <class M, class Tab>
 struct MultisetStep {
     const Tab& tab;
     M used;
-    int inter;
+    int pad;    // padding positions >= lb, set in `used` from the start
+    int inter;  // valid after finish()
     SS_HD MultisetStep(const Tab& t, int lb)
-        : tab(t), used(lb >= (int)(sizeof(M) * 8) ? M(0) : ~((M(1) << lb) - M(1))), inter(0) {}
+        : tab(t), used(lb >= (int)(sizeof(M) * 8) ? M(0) : ~((M(1) << lb) - M(1))),
+          pad(lb >= (int)(sizeof(M) * 8) ? 0 : (int)(sizeof(M) * 8) - lb), inter(0) {}
     SS_HD void operator()(uint32_t c) { step(tab(c)); }
-    SS_HD void step(const M Eq) {
+    SS_HD void step(const M Eq) {  // branch-free: the lowest unused equal position of b is consumed
         const M cand = Eq & ~used;
-        if (cand) {
-            used |= cand & (M(0) - cand);
-            inter++;
-        }
+        used |= cand & (M(0) - cand);
     }
+    SS_HD void finish() { inter = popc(used) - pad; }
 };
 
 // ---- fused evaluation of several measures over ONE pass ----------------------------

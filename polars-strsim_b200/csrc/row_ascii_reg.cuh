@@ -50,6 +50,18 @@ struct PlaneTab {
     }
 };
 
+// adds the four characters of word w (characters 4w..4w+3) to the planes
+template <int NBITS>
+SS_HD void planes_add_word(PlaneTab<NBITS>& tab, uint32_t word, int w) {
+#pragma unroll
+    for (int k = 0; k < NBITS; k++) {
+        // bit k of the four bytes -> four adjacent bits (character order) in the top nibble: source bit
+        // 8j+k times 2^(28-7j-k) lands on 28+j; the sixteen partial products fall on distinct bits
+        const uint32_t prod = (word & (0x01010101u << k)) * (0x10204080u >> k);
+        tab.B[k] |= w == 7 ? (prod & 0xF0000000u) : ((prod >> (28 - 4 * w)) & (0xFu << (4 * w)));
+    }
+}
+
 // bit planes of the first m characters of P (zero padded words)
 template <int NBITS>
 SS_HD void build_planes(const uint32_t (&P)[REG_WORDS], int m, PlaneTab<NBITS>& tab) {
@@ -58,13 +70,7 @@ SS_HD void build_planes(const uint32_t (&P)[REG_WORDS], int m, PlaneTab<NBITS>& 
 #pragma unroll
     for (int w = 0; w < REG_WORDS; w++) {
         if (4 * w >= m) break;
-        const uint32_t word = P[w];
-#pragma unroll
-        for (int k = 0; k < NBITS; k++) {
-            // bit k of the four bytes -> four adjacent bits (character order) at nibble w
-            const uint32_t prod = ((word >> k) & 0x01010101u) * 0x10204080u;
-            tab.B[k] |= w == 7 ? (prod & 0xF0000000u) : ((prod >> (28 - 4 * w)) & (0xFu << (4 * w)));
-        }
+        planes_add_word<NBITS>(tab, P[w], w);
     }
     tab.valid = m >= 32 ? 0xFFFFFFFFu : ((1u << m) - 1u);
 }
@@ -78,15 +84,22 @@ SS_HD void for_each_byte_reg(const uint32_t (&W)[REG_WORDS], int n, F& f) {
     uint32_t r[REG_WORDS];
 #pragma unroll
     for (int w = 0; w < REG_WORDS; w++) r[w] = W[w];
+    int left = n;
 #pragma unroll 1
-    for (int left = n; left > 0; left -= 4) {
+    for (; left >= 4; left -= 4) {
         const uint32_t word = r[0];
 #pragma unroll
         for (int w = 0; w + 1 < REG_WORDS; w++) r[w] = r[w + 1];
         f(word & 0xFFu);
-        if (left > 1) f((word >> 8) & 0xFFu);
-        if (left > 2) f((word >> 16) & 0xFFu);
-        if (left > 3) f(word >> 24);
+        f((word >> 8) & 0xFFu);
+        f((word >> 16) & 0xFFu);
+        f(word >> 24);
+    }
+    uint32_t word = r[0];  // the 1..3 bytes of the tail, one at a time
+#pragma unroll 1
+    for (; left > 0; left--) {
+        f(word & 0xFFu);
+        word >>= 8;
     }
 }
 
@@ -159,6 +172,7 @@ SS_HD double row_ascii_reg(const uint32_t (&a)[REG_WORDS], const uint32_t (&b)[R
             const int outer = la < lb + bound ? la : lb + bound;
             JaroMatchStep<uint32_t, Tab> match(tab, lb, bound);
             for_each_byte_reg(a, outer, match);
+            match.finish(outer);
             const int t = match.m > 0 ? trans_count(tab, EachByteReg(a), outer, match.flag_a, match.flag_b) : 0;
             out.x0 = match.m;
             out.x1 = t;
@@ -175,6 +189,7 @@ SS_HD double row_ascii_reg(const uint32_t (&a)[REG_WORDS], const uint32_t (&b)[R
         } else {
             MultisetStep<uint32_t, Tab> ms(tab, lb);
             for_each_byte_reg(a, la, ms);
+            ms.finish();
             out.x0 = ms.inter;
             if (MEASURE == JACCARD) {
                 out.x1 = la + lb - ms.inter;

@@ -184,6 +184,7 @@ SS_HD double measure_body(int measure, const Tab& tab, const Each& each_streamed
             const int outer = la < lb + bound ? la : lb + bound;
             JaroMatchStep<M, Tab> match(tab, lb, bound);
             each_streamed(outer, match);
+            match.finish(outer);
             JaroTransStep<M, Tab> trans(tab, match.flag_a, match.flag_b);
             if (match.m > 0) each_streamed(outer, trans);
             out.x0 = match.m;
@@ -193,6 +194,7 @@ SS_HD double measure_body(int measure, const Tab& tab, const Each& each_streamed
         default: {
             MultisetStep<M, Tab> ms(tab, lb);
             each_streamed(la, ms);
+            ms.finish();
             out.x0 = ms.inter;
             if (measure == JACCARD) {
                 out.x1 = la + lb - ms.inter;  // sum_c max = la + lb - sum_c min
@@ -232,6 +234,8 @@ SS_HD void multi_body(const Tab& tab, const Each& each_a, int la, int lb, bool o
     if (bound < 0) bound = 0;  // both strings of at most one character: settled by the row rules below
     FusedStep<GROUPS, M, Tab> f(tab, lb, bound);
     each_a(la, f);  // Jaro's outer limit min(la, lb+bound) needs no cut: later windows lie beyond b
+    if (GROUPS & G_JARO) f.jm.finish(la);
+    if (GROUPS & G_SET) f.ms.finish();
     PairInts o;
     o.flag = F_GENERAL;
     o.la = la;

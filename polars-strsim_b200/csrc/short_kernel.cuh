@@ -274,6 +274,213 @@ __device__ __forceinline__ int staged_char_count(const uint4& v, const unsigned 
     return len - cont;
 }
 
+// byte p of a string that sits in shared memory (inline in its staged view, or in the stage area)
+struct SmemByteAt {
+    uint32_t base;  // shared-space address of the first byte
+    __device__ __forceinline__ uint32_t operator()(int p) const {
+        uint32_t v;
+        asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(base + (uint32_t)p));
+        return v;
+    }
+};
+
+// A string of the staged tile: both kinds of string sit in shared memory after step 2 -- inline in
+// their staged view (<= 12 bytes, bytes 4..15 of the view) or in the stage area (view.y = offset) -- so
+// one code path reads either: `off` is the byte offset of the first byte from the start of the CTA's
+// shared memory.  Reading whole aligned words overruns the string by at most 7 bytes: the next view,
+// or the 16-byte pad of the stage area.
+struct StagedStr {
+    uint32_t off;
+    int len;
+};
+__device__ __forceinline__ StagedStr staged_str(const uint4& v, int i, uint32_t off_views, uint32_t off_stage) {
+    StagedStr s;
+    s.len = (int)v.x;
+    s.off = v.x <= 12u ? off_views + 16u * (uint32_t)i + 4u : off_stage + v.y;
+    return s;
+}
+
+// Exact byte equality of two staged strings, for the sort key.  EVERY lane of the warp walks the loop
+// (pairs of unequal length with a trip count of zero), so the warp pays max(words) iterations of ten
+// instructions -- the former version (prefix test, then separate inline / out-of-line compares behind
+// branches) ran 160 warp instructions per 32 rows with four or five lanes active.
+__device__ __forceinline__ bool staged_equal_conv(const unsigned char* smem, const StagedStr& A, const StagedStr& B,
+                                                  bool candidate) {
+    const bool eq_len = candidate && A.len == B.len;
+    // rows that are not candidates (null, routed to an overflow list, beyond n) hold no stage offset in
+    // their view: they read word 0 of the shared memory instead
+    const uint32_t oa = candidate ? A.off : 0u, ob = candidate ? B.off : 0u;
+    const uint32_t* pa = reinterpret_cast<const uint32_t*>(smem + (oa & ~3u));
+    const uint32_t* pb = reinterpret_cast<const uint32_t*>(smem + (ob & ~3u));
+    const int sa = (int)(oa & 3u) * 8, sb = (int)(ob & 3u) * 8;
+    const int full = eq_len ? A.len >> 2 : 0;
+    uint32_t la = pa[0], lb = pb[0], diff = 0;
+#pragma unroll 1
+    for (int w = 0; w < full; w++) {
+        const uint32_t ha = pa[w + 1], hb = pb[w + 1];
+        diff |= __funnelshift_r(la, ha, sa) ^ __funnelshift_r(lb, hb, sb);
+        la = ha;
+        lb = hb;
+    }
+    if (eq_len && (A.len & 3))
+        diff |= (__funnelshift_r(la, pa[full + 1], sa) ^ __funnelshift_r(lb, pb[full + 1], sb)) & byte_mask(A.len & 3);
+    return eq_len && diff == 0u;
+}
+
+// streams the bytes of a staged string through f, straight from shared memory (no register copy):
+// whole words first, then the 1..3 bytes of the tail one at a time
+struct EachByteStaged {
+    const unsigned char* smem;
+    uint32_t off;
+    template <class F>
+    __device__ __forceinline__ void operator()(int n, F& f) const {
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(smem + (off & ~3u));
+        const int sh = (int)(off & 3u) * 8;
+        uint32_t lo = p[0];
+#pragma unroll 1
+        for (; n >= 4; n -= 4) {
+            p++;
+            const uint32_t hi = p[0];
+            const uint32_t word = __funnelshift_r(lo, hi, sh);
+            lo = hi;
+            f(word & 0xFFu);
+            f((word >> 8) & 0xFFu);
+            f((word >> 16) & 0xFFu);
+            f(word >> 24);
+        }
+        if (n > 0) {
+            uint32_t word = __funnelshift_r(lo, p[1], sh);
+#pragma unroll 1
+            for (; n > 0; n--) {
+                f(word & 0xFFu);
+                word >>= 8;
+            }
+        }
+    }
+};
+
+// bit planes of a staged string of m <= 32 characters, word by word from shared memory.  The bytes after
+// the string need no masking: PlaneTab::valid keeps them out of every position mask.
+template <int NBITS>
+__device__ __forceinline__ void build_planes_staged(const unsigned char* smem, const StagedStr& S, PlaneTab<NBITS>& tab) {
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(smem + (S.off & ~3u));
+    const int sh = (int)(S.off & 3u) * 8;
+    const int m = S.len;
+#pragma unroll
+    for (int k = 0; k < NBITS; k++) tab.B[k] = 0u;
+    uint32_t lo = p[0];
+#pragma unroll
+    for (int w = 0; w < REG_WORDS; w++) {
+        if (4 * w >= m) break;
+        const uint32_t hi = p[w + 1];
+        const uint32_t word = __funnelshift_r(lo, hi, sh);
+        lo = hi;
+        planes_add_word<NBITS>(tab, word, w);
+    }
+    tab.valid = m >= 32 ? 0xFFFFFFFFu : ((1u << m) - 1u);
+}
+
+// common prefix of two staged ASCII strings, capped at 4 (strsim.rs:261-266); evaluated only when the
+// Jaro score passes the Winkler threshold
+struct PrefixStaged {
+    const unsigned char* smem;
+    StagedStr A, B;
+    __device__ __forceinline__ int operator()() const;
+};
+
+// first word (zero-masked to the string's length) of a staged string
+__device__ __forceinline__ uint32_t staged_first_word(const unsigned char* smem, const StagedStr& S) {
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(smem + (S.off & ~3u));
+    return __funnelshift_r(p[0], p[1], (int)(S.off & 3u) * 8) & byte_mask(S.len);
+}
+
+__device__ __forceinline__ int PrefixStaged::operator()() const {
+    const uint32_t x = staged_first_word(smem, A) ^ staged_first_word(smem, B);
+    int lim = A.len < B.len ? A.len : B.len;
+    if (lim > 4) lim = 4;
+    // bytes beyond the shorter string differ (one side is zero-masked, ASCII bytes are not zero) or lie
+    // beyond lim: the count of equal leading bytes, capped
+    const int l = x == 0u ? 4 : (__ffs((int)x) - 1) >> 3;
+    return l < lim ? l : lim;
+}
+
+// One ASCII pair that is NOT byte-equal, single measure, both strings read straight from the staged tile:
+// the tabled string becomes bit planes word by word, the streamed one goes through the step functor byte
+// by byte -- neither is copied into registers.  Row rules and arithmetic: row_ascii_reg (row_ascii_reg.cuh).
+template <int MEASURE, int NBITS>
+__device__ __forceinline__ double row_ascii_staged(const unsigned char* smem, const StagedStr& A, const StagedStr& B,
+                                                   PairInts& out) {
+    out.flag = F_GENERAL;
+    out.la = out.lb = out.x0 = out.x1 = out.x2 = 0;
+    const int la = A.len, lb = B.len;
+    if (MEASURE != LEVENSHTEIN && (la == 0 || lb == 0)) {  // strsim.rs:184,290,326
+        out.flag = F_ONE_EMPTY;
+        return 0.0;
+    }
+    out.la = la;
+    out.lb = lb;
+    constexpr bool IS_JARO = MEASURE == JARO || MEASURE == JARO_WINKLER;
+    if (IS_JARO && la == 1 && lb == 1) {  // strsim.rs:197
+        out.flag = F_SINGLE_CHAR;
+        return 0.0;
+    }
+    typedef PlaneTab<NBITS> Tab;
+    Tab tab;
+    double v;
+    if (MEASURE == LEVENSHTEIN) {
+        // the shorter string is tabled; the longer one is streamed (the distance is symmetric)
+        const bool table_b = lb <= la;
+        const StagedStr P = table_b ? B : A, X = table_b ? A : B;
+        int d = X.len;
+        if (P.len > 0) {
+            build_planes_staged<NBITS>(smem, P, tab);
+            MyersStep<uint32_t, Tab> step(tab);
+            EachByteStaged each{smem, X.off};
+            each(X.len, step);
+            d = step.distance(P.len, X.len);
+        }
+        out.x0 = d;
+        v = lev_value<true>(d, la, lb);
+    } else {
+        build_planes_staged<NBITS>(smem, B, tab);
+        EachByteStaged each_a{smem, A.off};
+        if (IS_JARO) {
+            const int mx = la > lb ? la : lb;
+            const int bound = mx / 2 - 1;  // strsim.rs:200
+            const int outer = la < lb + bound ? la : lb + bound;
+            JaroMatchStep<uint32_t, Tab> match(tab, lb, bound);
+            each_a(outer, match);
+            match.finish(outer);
+            TransByBytes<SmemByteAt> trans;
+            trans.A.base = smem_u32(smem) + A.off;
+            trans.B.base = smem_u32(smem) + B.off;
+            const int t = match.m > 0 ? trans(tab, each_a, outer, match.flag_a, match.flag_b) : 0;
+            out.x0 = match.m;
+            out.x1 = t;
+            v = match.m == 0 ? 0.0 : jaro_value<true>(match.m, t, la, lb);
+            if (MEASURE == JARO_WINKLER && v > 0.7) {  // strsim.rs:260-267
+                PrefixStaged prefix{smem, A, B};
+                const int l = prefix();
+                out.x2 = l;
+                v = winkler_value(v, l);
+            }
+        } else {
+            MultisetStep<uint32_t, Tab> ms(tab, lb);
+            each_a(la, ms);
+            ms.finish();
+            out.x0 = ms.inter;
+            if (MEASURE == JACCARD) {
+                out.x1 = la + lb - ms.inter;
+                v = jaccard_value<true>(ms.inter, la + lb - ms.inter);
+            } else {
+                out.x1 = la + lb;
+                v = dice_value<true>(ms.inter, la + lb);
+            }
+        }
+    }
+    return v;
+}
+
 // Settling byte-equal pairs before the sort frees their lanes but costs every row a prefix compare;
 // measured on C2 (20 % equal pairs) it LOSES 5-8 % (table path: latency-bound rounds; register path:
 // the extra prefix reads and compares cost more ALU work than the freed lanes give back).  Kept for
@@ -356,16 +563,6 @@ struct RowEmit {
     }
 };
 
-// byte p of a string that sits in shared memory (inline in its staged view, or in the stage area)
-struct SmemByteAt {
-    uint32_t base;  // shared-space address of the first byte
-    __device__ __forceinline__ uint32_t operator()(int p) const {
-        uint32_t v;
-        asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(base + (uint32_t)p));
-        return v;
-    }
-};
-
 // the thread's slab of shared memory ([word][thread] layout) as transcode_latin1's Slab / as bytes
 template <int TPB>
 struct SlabWords {
@@ -427,6 +624,7 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
     uint16_t* perm = reinterpret_cast<uint16_t*>(smem + L::off_perm);
     unsigned char* stage_a = smem + L::off_stage;
     unsigned char* stage_b = stage_a + s.stage_bytes + 16;
+    const uint32_t off_stage_a = (uint32_t)L::off_stage, off_stage_b = off_stage_a + (uint32_t)s.stage_bytes + 16u;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -651,6 +849,18 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
 
         // ---------------- 3. bucket: cost key per row, counting sort (descending) -----------------
         uint32_t key[RPT], rank[RPT];
+        bool row_equal[RPT];
+        if constexpr (REG) {
+            // byte-equal pairs (strsim.rs:128,182,288,324), found by all lanes in lock step
+#pragma unroll
+            for (int k = 0; k < RPT; k++) {
+                const int i = k * TPB + tid;
+                const uint4 va = sva[i], vb = svb[i];
+                row_equal[k] = staged_equal_conv(smem, staged_str(va, i, (uint32_t)L::off_sva, off_stage_a),
+                                                 staged_str(vb, i, (uint32_t)L::off_svb, off_stage_b),
+                                                 ((active >> k) & 1u) != 0u);
+            }
+        }
 #pragma unroll
         for (int k = 0; k < RPT; k++) {
             const int i = k * TPB + tid;
@@ -662,11 +872,16 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
             // not occupy lanes of the compute phase (the 4-byte prefix in the view rejects most rows)
             // (always in the fused kernel: its per-pair loops are three measures long, so the lanes that a
             // fifth of equal pairs would idle are worth far more than the prefix compare)
-            const bool settle_equal = (PREFILTER_EQUAL || is_multi(MEASURE)) && va.x == vb.x &&
-                                      (va.x == 0u || ((va.x <= 12u ? va.y : sva_prefix(va, stage_a)) ==
-                                                      (vb.x <= 12u ? vb.y : sva_prefix(vb, stage_b)))) &&
-                                      staged_equal(va, vb, stage_a, stage_b);
-            if (settle_equal && !is_multi(MEASURE)) {
+            bool settle_equal = false;
+            if constexpr (REG) {
+                settle_equal = row_equal[k];
+            } else {
+                settle_equal = (PREFILTER_EQUAL || is_multi(MEASURE)) && va.x == vb.x &&
+                               (va.x == 0u || ((va.x <= 12u ? va.y : sva_prefix(va, stage_a)) ==
+                                               (vb.x <= 12u ? vb.y : sva_prefix(vb, stage_b)))) &&
+                               staged_equal(va, vb, stage_a, stage_b);
+            }
+            if (settle_equal && !is_multi(MEASURE) && !REG) {
                 const long long idx = tile0 + i;
                 const long long row = GATHER ? (long long)s.list[idx] : idx;
                 store_settled<MEASURE>(s, row, 1.0, F_EQUAL);
@@ -690,8 +905,9 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
                 }
             }
             uint32_t mx = va.x > vb.x ? va.x : vb.x;
-            // fused evaluation streams a against the tabled b for every group: the loops run la times
-            if (is_multi(MEASURE) && REG) mx = va.x;
+            // fused evaluation streams a against the tabled b for every group, and so do the single Jaro and
+            // multiset kernels: the loops run la times (Levenshtein streams the longer string)
+            if (REG && (is_multi(MEASURE) || MEASURE != LEVENSHTEIN)) mx = va.x;
             uint32_t wide = 0;  // UREG: a character above U+00FF somewhere in the pair
             if (UREG) {
                 // the register-compare path costs (streamed characters) x (tabled characters): bucket by
@@ -712,7 +928,11 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
             // fused kernel: the equal pairs get the cheapest bucket of their own (key 1 otherwise holds only
             // empty/empty pairs, which are equal too) -- whole warps of them leave the row function at its
             // first test, and the stores stay dense
-            key[k] = settle_equal ? 1u : 1u + mx + ((hi_bits & 0x80808080u) ? (uint32_t)(CAP + 1) : 0u);
+            // (the register kernels read "key 1" as "byte-equal" in step 4: there a pair with an empty a and a
+            // non-empty b must not share that key, so their other keys start at 2)
+            key[k] = settle_equal ? 1u
+                                  : (REG ? 2u : 1u) + mx +
+                                        ((hi_bits & 0x80808080u) ? (uint32_t)(CAP + 1) : 0u);
             rank[k] = atomicAdd(&hist[key[k]], 1u);
         }
         __syncthreads();
@@ -836,21 +1056,40 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
             const int na = (int)va.x, nb = (int)vb.x;
             PairInts ints;
             double v;
-            if (REG) {
-                uint32_t ra[REG_WORDS], rb[REG_WORDS];
-                load_string_reg(va, stage_a, ra);
-                load_string_reg(vb, stage_b, rb);
-                // Jaro's transposition count reads the flagged characters straight from the staged tile
-                TransByBytes<SmemByteAt> trans;
-                trans.A.base = va.x <= 12u ? smem_u32(&sva[i]) + 4u : smem_u32(stage_a) + va.y;
-                trans.B.base = vb.x <= 12u ? smem_u32(&svb[i]) + 4u : smem_u32(stage_b) + vb.y;
-                if constexpr (is_multi(MEASURE)) {
-                    const long long idx = tile0 + i;
-                    RowEmit emit{s, GATHER ? (long long)s.list[idx] : idx, true};
-                    row_ascii_reg_multi<GROUPS, NBITS>(ra, rb, na, nb, trans, emit);
+            if constexpr (REG && is_multi(MEASURE)) {
+                // the sort put the byte-equal pairs (key 1) last: whole warps of them leave here
+                const long long idx = tile0 + i;
+                RowEmit emit{s, GATHER ? (long long)s.list[idx] : idx, true};
+                if (p >= (int)hist[1]) {
+                    PairInts o;
+                    o.flag = F_EQUAL;
+                    o.la = o.lb = o.x0 = o.x1 = o.x2 = 0;
+                    emit_groups<GROUPS>(emit, 1.0, o);
                     continue;
                 }
-                v = row_ascii_reg<is_multi(MEASURE) ? 0 : MEASURE, NBITS>(ra, rb, na, nb, ints, trans);
+                // b is tabled as bit planes, a is streamed -- both straight from the staged tile
+                const StagedStr A = staged_str(va, i, (uint32_t)L::off_sva, off_stage_a),
+                                B = staged_str(vb, i, (uint32_t)L::off_svb, off_stage_b);
+                PlaneTab<NBITS> ptab;
+                build_planes_staged<NBITS>(smem, B, ptab);
+                TransByBytes<SmemByteAt> trans;
+                trans.A.base = smem_u32(smem) + A.off;
+                trans.B.base = smem_u32(smem) + B.off;
+                EachByteStaged each_a{smem, A.off};
+                PrefixStaged prefix{smem, A, B};
+                multi_body<GROUPS, uint32_t>(ptab, each_a, na, nb, na == 0 || nb == 0, prefix, trans, emit);
+                continue;
+            }
+            if constexpr (REG) {
+                // the sort put the byte-equal pairs (key 1) last: whole warps of them leave here
+                if (p >= (int)hist[1]) {
+                    const long long idx = tile0 + i;
+                    store_settled<MEASURE>(s, GATHER ? (long long)s.list[idx] : idx, 1.0, F_EQUAL);
+                    continue;
+                }
+                v = row_ascii_staged<is_multi(MEASURE) ? 0 : MEASURE, NBITS>(
+                    smem, staged_str(va, i, (uint32_t)L::off_sva, off_stage_a),
+                    staged_str(vb, i, (uint32_t)L::off_svb, off_stage_b), ints);
             } else {
                 const uint32_t or_a = load_string<WORDS, TPB>(va, stage_a, store.wa_);
                 const uint32_t or_b = load_string<WORDS, TPB>(vb, stage_b, store.wb_);
