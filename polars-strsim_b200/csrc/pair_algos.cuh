@@ -247,7 +247,9 @@ SS_HD uint64_t brev(uint64_t x) {
 }
 SS_HD int flo(uint32_t x) {  // index of the highest set bit, x != 0
 #if defined(__CUDA_ARCH__)
-    return 31 - __clz((int)x);
+    int r;  // bfind IS the hardware's find-leading-one; 31 - __clz() costs a subtraction the compiler keeps
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
+    return r;
 #else
     return 31 - __builtin_clz(x);
 #endif
@@ -346,6 +348,15 @@ struct JaroTransStep {
     }
 };
 
+// t += (x != y): one compare and one predicated add
+SS_HD void count_if_differ(int& t, uint32_t x, uint32_t y) {
+#if defined(__CUDA_ARCH__)
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(t) : "r"(x), "r"(y));
+#else
+    if (x != y) t++;
+#endif
+}
+
 // How the transposition count t (strsim.rs:220-237) is obtained once the match pass has left its flags.
 // TransByPass: a second pass over the characters of a (any Tab / any script).
 struct TransByPass {
@@ -372,7 +383,7 @@ struct TransByBytes {
             const int ia = flo(flag_a), ib = flo(flag_b);
             flag_a ^= M(1) << ia;
             flag_b ^= M(1) << ib;
-            if (A(ia) != B(ib)) t++;
+            count_if_differ(t, A(ia), B(ib));
         }
         return t;
     }

@@ -719,15 +719,12 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
         // ---------------- 2. stage the out-of-line payload -----------------------------------------
         // block reduction of the span descriptors (warp shuffle, then warp 0 over the partials)
 #pragma unroll
-        for (int c = 0; c < 2; c++) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                mn_off[c] = min(mn_off[c], __shfl_xor_sync(0xFFFFFFFFu, mn_off[c], o));
-                mx_end[c] = max(mx_end[c], __shfl_xor_sync(0xFFFFFFFFu, mx_end[c], o));
-                mn_buf[c] = min(mn_buf[c], __shfl_xor_sync(0xFFFFFFFFu, mn_buf[c], o));
-                mx_buf[c] = max(mx_buf[c], __shfl_xor_sync(0xFFFFFFFFu, mx_buf[c], o));
-                cnt[c] += __shfl_xor_sync(0xFFFFFFFFu, cnt[c], o);
-            }
+        for (int c = 0; c < 2; c++) {  // one REDUX each
+            mn_off[c] = __reduce_min_sync(0xFFFFFFFFu, mn_off[c]);
+            mx_end[c] = __reduce_max_sync(0xFFFFFFFFu, mx_end[c]);
+            mn_buf[c] = __reduce_min_sync(0xFFFFFFFFu, mn_buf[c]);
+            mx_buf[c] = __reduce_max_sync(0xFFFFFFFFu, mx_buf[c]);
+            cnt[c] = __reduce_add_sync(0xFFFFFFFFu, cnt[c]);
         }
         if (lane == 0) {
 #pragma unroll
@@ -850,7 +847,7 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
         // ---------------- 3. bucket: cost key per row, counting sort (descending) -----------------
         uint32_t key[RPT], rank[RPT];
         bool row_equal[RPT];
-        if constexpr (REG) {
+        if constexpr (REG || is_multi(MEASURE)) {
             // byte-equal pairs (strsim.rs:128,182,288,324), found by all lanes in lock step
 #pragma unroll
             for (int k = 0; k < RPT; k++) {
@@ -873,10 +870,10 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
             // (always in the fused kernel: its per-pair loops are three measures long, so the lanes that a
             // fifth of equal pairs would idle are worth far more than the prefix compare)
             bool settle_equal = false;
-            if constexpr (REG) {
+            if constexpr (REG || is_multi(MEASURE)) {
                 settle_equal = row_equal[k];
-            } else {
-                settle_equal = (PREFILTER_EQUAL || is_multi(MEASURE)) && va.x == vb.x &&
+            } else if (PREFILTER_EQUAL) {
+                settle_equal = va.x == vb.x &&
                                (va.x == 0u || ((va.x <= 12u ? va.y : sva_prefix(va, stage_a)) ==
                                                (vb.x <= 12u ? vb.y : sva_prefix(vb, stage_b)))) &&
                                staged_equal(va, vb, stage_a, stage_b);
