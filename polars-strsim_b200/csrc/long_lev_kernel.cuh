@@ -26,6 +26,11 @@ namespace strsim {
 
 constexpr int LONG_PAT_MAX = 8192;  // codepoints; 128 blocks = 4 per lane
 constexpr int LONG_WPB = 4;         // warps per block
+// The wavefront loop runs without bounds checks: the text's id array carries LONG_TID_PAD entries of the
+// all-zero Peq row before its first and after its last column (lanes that have not started or have
+// finished prefetch those), and the Peq area LONG_PEQ_PAD spare words (the last lane's blocks past W).
+constexpr int LONG_TID_PAD = 48;
+constexpr int LONG_PEQ_PAD = 8;
 
 struct LongLevArgs {
     DevCol a, b;
@@ -60,12 +65,12 @@ __host__ __device__ inline long long long_lev_slab_bytes(int cap_a, int cap_b, i
     long long b = 0;
     b += 4ll * cap_a;
     b += 4ll * cap_b;
-    b += 2ll * ((cap_a > cap_b ? cap_a : cap_b) + 8);
+    b += 2ll * ((cap_a > cap_b ? cap_a : cap_b) + 2 * LONG_TID_PAD);
     b = (b + 15) & ~15ll;
     b += 4ll * hash_size;
     b += 2ll * hash_size;
     b = (b + 15) & ~15ll;
-    b += 8ll * peq_words;
+    b += 8ll * (peq_words + LONG_PEQ_PAD);
     return (b + 255) & ~255ll;
 }
 
@@ -77,7 +82,7 @@ __device__ inline LongLevSlab long_lev_carve(unsigned char* base, const LongLevA
     s.cps_b = reinterpret_cast<uint32_t*>(base + o);
     o += 4ll * g.cap_b;
     s.tid = reinterpret_cast<uint16_t*>(base + o);
-    o += 2ll * ((g.cap_a > g.cap_b ? g.cap_a : g.cap_b) + 8);
+    o += 2ll * ((g.cap_a > g.cap_b ? g.cap_a : g.cap_b) + 2 * LONG_TID_PAD);
     o = (o + 15) & ~15ll;
     s.hkeys = reinterpret_cast<uint32_t*>(base + o);
     o += 4ll * g.hash_size;
@@ -124,56 +129,60 @@ __device__ __forceinline__ uint32_t long_lookup(const LongLevSlab& s, uint32_t h
     }
 }
 
+// tid = the text's ids with LONG_TID_PAD padding entries in front (tid[0] is column 0).
+// Per step a lane does: one shuffle for the carry, one 16-bit load of the id three columns ahead, one
+// IMAD.WIDE + K loads for the Eq words two columns ahead, and -- between its first and last column --
+// K Myers blocks.  The step loop is unrolled three times so that the three Eq buffers and the three
+// ids rotate by renaming, not by moves.
 template <int K>
-__device__ inline int long_wavefront(const LongLevSlab& s, int m, int n, int W, int L, int lane) {
-    uint64_t Pv[K], Mv[K], eq0[K], eq1[K], eq2[K];
+__device__ inline int long_wavefront(const LongLevSlab& s, const uint16_t* tid, int m, int n, int W, int L, int lane) {
+    uint64_t Pv[K], Mv[K], eq[3][K];
+    uint32_t tq[3];
 #pragma unroll
     for (int k = 0; k < K; k++) {
         Pv[k] = ~0ull;
         Mv[k] = 0ull;
-        eq0[k] = eq1[k] = eq2[k] = 0ull;
     }
-    const int blk0 = lane * K;
     const bool lane_on = lane < L;
-    // Software pipeline, two columns deep: while column j is computed, the Eq words of column j+2 are
-    // in flight (their row index tid[j+2] was fetched one step earlier) and those of j+1 have landed.
-    uint32_t t2 = 0, t3 = 0;
-    if (lane_on) {
-        const unsigned long long* r0 = s.peq + (size_t)s.tid[0] * W + blk0;
-        const unsigned long long* r1 = s.peq + (size_t)s.tid[n > 1 ? 1 : 0] * W + blk0;
+    const int blk0 = lane_on ? lane * K : 0;  // idle lanes prefetch block 0 (harmless) and never compute
+    const unsigned n_on = lane_on ? (unsigned)n : 0u;
+    const unsigned long long* rowbase = s.peq + blk0;
+    const unsigned W8 = (unsigned)W;
+    const uint16_t* tp = tid - lane;  // tp[st + c] = id of column (st - lane) + c
+    {
+        const unsigned long long* r0 = rowbase + (size_t)tp[0] * W8;
+        const unsigned long long* r1 = rowbase + (size_t)tp[1] * W8;
 #pragma unroll
-        for (int k = 0; k < K; k++)
-            if (blk0 + k < W) {
-                eq0[k] = r0[k];
-                eq1[k] = r1[k];
-            }
-        t2 = s.tid[n > 2 ? 2 : 0];
+        for (int k = 0; k < K; k++) {
+            eq[0][k] = r0[k];
+            eq[1][k] = r1[k];
+            eq[2][k] = 0ull;
+        }
+        tq[0] = tp[2];
+        tq[1] = tq[2] = 0u;
     }
     uint32_t carry_prev = 0;  // bit 0: hp, bit 1: hm of this lane's last block in the previous step
     const int steps = n + L - 1;
-    for (int st = 0; st < steps; st++) {
-        uint32_t carry = __shfl_up_sync(0xFFFFFFFFu, carry_prev, 1);
-        if (lane == 0) carry = 1u;  // D[0][j] - D[0][j-1] = +1
-        const int j = st - lane;
-        if (lane_on && j >= 0 && j < n) {
-            if (j + 3 < n) t3 = s.tid[j + 3];
-            if (j + 2 < n) {
-                const unsigned long long* row = s.peq + (size_t)t2 * W + blk0;
+#pragma unroll 1
+    const uint16_t* q = tp + 3;  // q[u] = id of the column three ahead of step st0 + u
+    int j0 = -lane;              // this lane's column at step st0
+    for (int st0 = 0; st0 < steps; st0 += 3, q += 3, j0 += 3) {
 #pragma unroll
-                for (int k = 0; k < K; k++)
-                    if (blk0 + k < W) eq2[k] = row[k];
+        for (int u = 0; u < 3; u++) {
+            uint32_t carry = __shfl_up_sync(0xFFFFFFFFu, carry_prev, 1);
+            if (lane == 0) carry = 1u;  // D[0][j] - D[0][j-1] = +1
+            tq[(u + 1) % 3] = q[u];
+            {
+                const unsigned long long* row = rowbase + (size_t)tq[u] * W8;
+#pragma unroll
+                for (int k = 0; k < K; k++) eq[(u + 2) % 3][k] = row[k];
             }
-            uint32_t hp = carry & 1u, hm = carry >> 1;
+            if ((unsigned)(j0 + u) < n_on) {
+                uint32_t hp = carry & 1u, hm = carry >> 1;
 #pragma unroll
-            for (int k = 0; k < K; k++)
-                if (blk0 + k < W) myers_block(Pv[k], Mv[k], eq0[k], hp, hm);
-            carry_prev = hp | (hm << 1);
-#pragma unroll
-            for (int k = 0; k < K; k++) {
-                eq0[k] = eq1[k];
-                eq1[k] = eq2[k];
+                for (int k = 0; k < K; k++) myers_block(Pv[k], Mv[k], eq[u][k], hp, hm);
+                carry_prev = hp | (hm << 1);
             }
-            t2 = t3;
         }
     }
     int score = 0;
@@ -256,7 +265,12 @@ __global__ void __launch_bounds__(32 * LONG_WPB, 8) long_lev_kernel(const LongLe
                 }
                 __syncwarp();
                 // 3. text -> ids (id `distinct` = a codepoint the pattern does not contain: zero row)
-                for (int j = lane; j < n; j += 32) s.tid[j] = (uint16_t)long_lookup(s, hmask, hshift, T[j], distinct);
+                uint16_t* tid = s.tid + LONG_TID_PAD;
+                for (int j = lane; j < n; j += 32) tid[j] = (uint16_t)long_lookup(s, hmask, hshift, T[j], distinct);
+                for (int j = lane; j < LONG_TID_PAD; j += 32) {
+                    s.tid[j] = (uint16_t)distinct;
+                    tid[n + j] = (uint16_t)distinct;
+                }
                 // 4. Peq[id][block]
                 const size_t words = (size_t)(distinct + 1u) * W;
                 if ((long long)words > g.peq_words) {  // needs a bigger slab: second launch
@@ -275,10 +289,10 @@ __global__ void __launch_bounds__(32 * LONG_WPB, 8) long_lev_kernel(const LongLe
                 const int K = (W + 31) >> 5;
                 const int L = (W + K - 1) / K;
                 switch (K) {
-                    case 1: d = long_wavefront<1>(s, m, n, W, L, lane); break;
-                    case 2: d = long_wavefront<2>(s, m, n, W, L, lane); break;
-                    case 3: d = long_wavefront<3>(s, m, n, W, L, lane); break;
-                    default: d = long_wavefront<4>(s, m, n, W, L, lane); break;
+                    case 1: d = long_wavefront<1>(s, tid, m, n, W, L, lane); break;
+                    case 2: d = long_wavefront<2>(s, tid, m, n, W, L, lane); break;
+                    case 3: d = long_wavefront<3>(s, tid, m, n, W, L, lane); break;
+                    default: d = long_wavefront<4>(s, tid, m, n, W, L, lane); break;
                 }
             }
             pi.x0 = d;
