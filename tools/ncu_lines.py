@@ -43,8 +43,7 @@ def main():
     rep, kid, needle = sys.argv[1], sys.argv[2], sys.argv[3]
     obj = Path(sys.argv[4] if len(sys.argv) > 4 else "polars-strsim_b200/csrc/host.o")
     lines = sass_lines(obj, needle)
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-id", f":::{kid}"],
-                         capture_output=True, text=True).stdout
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     name_sub = sys.argv[5] if len(sys.argv) > 5 else ""
     starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
