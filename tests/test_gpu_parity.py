@@ -673,3 +673,71 @@ print("ok")
     env = dict(os.environ, STRSIM_B200_SLICE_ROWS="100000")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-3000:]
+
+
+def _sample_rows(col, idx):
+    import pyarrow as pa
+
+    flat = col.combine_chunks() if isinstance(col, pa.ChunkedArray) else col
+    return flat.cast(pa.large_string()).take(pa.array(idx)).to_pylist()  # take() has no string_view kernel
+
+
+@pytest.mark.parametrize("config,rows", [(2, 10_000_000), (3, 20_000_000)])
+def test_full_size_workloads_by_properties(native, oracle, config, rows):
+    """BASELINE configs at (C2) / near (C3: a fifth of) their full size, where the oracle cannot check every
+    row in seconds: size-independent properties over ALL rows, plus the oracle bit for bit on a seeded
+    sample of 100k rows.  Properties: values in [0, 1]; null mask = AND of the input masks; the symmetric
+    measures (Levenshtein, Jaccard, Sorensen-Dice: edit distance and multiset intersection do not depend
+    on the argument order, strsim.rs:146-160,297-306) give identical bits with the columns swapped --
+    which tables the OTHER string and streams the other one through every kernel; byte-equal rows score
+    exactly 1.0 and only they do for Levenshtein (d = 0 iff equal); Dice = 2J / (1 + J) as integers:
+    inter and the lengths in the debug record satisfy x1_jaccard + inter = x1_dice."""
+    sys.path.insert(0, str(ROOT))
+    from bench_support import workloads
+
+    A, B = workloads.make_pairs(config, rows, uneven_b=(config == 3))
+    names = list(oracle.MEASURES)
+    outs, valid, nulls, ints = native.compute_host_multi(names, A, B, debug=True)
+    swapped, valid_s, nulls_s = native.compute_host_multi(names, B, A)
+    n = rows
+    assert all(len(o) == n for o in outs)
+    # null mask: AND of the inputs
+    def mask(col):
+        import pyarrow as pa
+
+        flat = col.combine_chunks() if isinstance(col, pa.ChunkedArray) else col
+        return np.asarray(flat.is_valid())
+    expect_valid = mask(A) & mask(B)
+    assert (valid == expect_valid).all() and (valid_s == expect_valid).all()
+    assert nulls == int((~expect_valid).sum()) == nulls_s
+    by = dict(zip(names, outs))
+    by_s = dict(zip(names, swapped))
+    for m in names:
+        v = by[m][valid]
+        assert np.isfinite(v).all() and (v >= 0.0).all() and (v <= 1.0).all(), m
+    for m in ("levenshtein", "jaccard", "sorensen_dice"):
+        assert (by[m][valid].view(np.uint64) == by_s[m][valid].view(np.uint64)).all(), (m, "not symmetric")
+    iby = dict(zip(names, ints))
+    equal_rows = valid & (iby["levenshtein"][:, 0] == 1)  # F_EQUAL in the kernel's record
+    for m in names:
+        assert (by[m][equal_rows] == 1.0).all(), m
+        assert (iby[m][:, 0][valid] == 1).sum() == equal_rows.sum(), (m, "equal rows differ between measures")
+    assert ((by["levenshtein"] == 1.0) & valid).sum() == equal_rows.sum()
+    gen = valid & (iby["jaccard"][:, 0] == 0)
+    assert (iby["jaccard"][gen, 3] == iby["sorensen_dice"][gen, 3]).all()                      # same intersection
+    assert (iby["jaccard"][gen, 4] + iby["jaccard"][gen, 3] == iby["sorensen_dice"][gen, 4]).all()  # uni + inter = la + lb
+    assert (iby["jaro"][valid, 3] == iby["jaro_winkler"][valid, 3]).all()                      # same match count
+    assert (iby["jaro"][valid, 4] == iby["jaro_winkler"][valid, 4]).all()                      # same transpositions
+    assert (by["jaro_winkler"][valid] >= by["jaro"][valid]).all()
+    # the oracle on a seeded sample
+    rng = np.random.default_rng(config)
+    idx = np.sort(rng.choice(n, size=100_000, replace=False))
+    a, b = _sample_rows(A, idx), _sample_rows(B, idx)
+    for m in names:
+        ref, ref_valid, ref_ints = oracle.batch(m, a, b)
+        got, gi, gv = by[m][idx], iby[m][idx], valid[idx]
+        assert (gv == ref_valid).all(), m
+        bad = np.nonzero(gv & (got.view(np.uint64) != ref.view(np.uint64)))[0]
+        assert bad.size == 0, (m, a[bad[0]], b[bad[0]], got[bad[0]], ref[bad[0]])
+        ibad = np.nonzero(gv & (gi != ref_ints).any(axis=1))[0]
+        assert ibad.size == 0, (m, a[ibad[0]], b[ibad[0]], gi[ibad[0]], ref_ints[ibad[0]])
