@@ -741,3 +741,30 @@ def test_full_size_workloads_by_properties(native, oracle, config, rows):
         assert bad.size == 0, (m, a[bad[0]], b[bad[0]], got[bad[0]], ref[bad[0]])
         ibad = np.nonzero(gv & (gi != ref_ints).any(axis=1))[0]
         assert ibad.size == 0, (m, a[ibad[0]], b[ibad[0]], gi[ibad[0]], ref_ints[ibad[0]])
+
+
+def test_long_levenshtein_c4_by_properties(native, oracle):
+    """C4 (long-text pairs, 200-4000 codepoints, Levenshtein) at a tenth of its full size: symmetry under
+    swapped columns over ALL rows (the warp-cooperative kernel then tables the same shorter string but
+    reads it from the other column), the bounds |la - lb| <= d <= max(la, lb) from the kernel's own
+    record, and the oracle (two-row DP, strsim.rs:146-159) bit for bit on a seeded sample of 300 rows."""
+    sys.path.insert(0, str(ROOT))
+    from bench_support import workloads
+
+    n = 100_000
+    A, B = workloads.make_pairs(4, n)
+    vals, valid, nulls, ints = native.compute_host("levenshtein", A, B, debug=True)
+    swapped, valid_s, _, ints_s = native.compute_host("levenshtein", B, A, debug=True)
+    assert valid.all() and valid_s.all() and nulls == 0
+    assert (vals.view(np.uint64) == swapped.view(np.uint64)).all()
+    assert (ints[:, 3] == ints_s[:, 3]).all() and (ints[:, 1] == ints_s[:, 2]).all()
+    gen = ints[:, 0] == 0
+    la, lb, d = ints[gen, 1].astype(np.int64), ints[gen, 2].astype(np.int64), ints[gen, 3].astype(np.int64)
+    assert (d >= np.abs(la - lb)).all() and (d <= np.maximum(la, lb)).all() and (d > 0).all()
+    assert ((vals >= 0.0) & (vals <= 1.0)).all()
+    rng = np.random.default_rng(4)
+    idx = np.sort(rng.choice(n, size=300, replace=False))
+    a, b = _sample_rows(A, idx), _sample_rows(B, idx)
+    ref, ref_valid, ref_ints = oracle.batch("levenshtein", a, b)
+    assert (vals[idx].view(np.uint64) == ref.view(np.uint64)).all()
+    assert (ints[idx] == ref_ints).all()
