@@ -1119,7 +1119,7 @@ static int run_long_lev(ThreadCtx& ctx, const SegArgs& args, const Overflow& ov,
     src.n = ov.nlong;
     CUDA_TRY(cudaMemsetAsync(ctx.d_counters, 0, 4 * sizeof(unsigned int), st));
     for (int tier = 0; tier < 2 && src.n > 0; tier++) {
-        long long peq_words = tier == 0 ? (128ll << 10) : worst_words;  // tier 0: 1 MiB of Peq per warp
+        long long peq_words = tier == 0 ? (64ll << 10) : worst_words;  // tier 0: 512 KiB of Peq per slab
         if (peq_words > worst_words) peq_words = worst_words;
         g.peq_words = peq_words;
         g.slab_bytes = long_lev_slab_bytes(g.cap_a, g.cap_b, g.hash_size, peq_words);
@@ -1128,15 +1128,32 @@ static int run_long_lev(ThreadCtx& ctx, const SegArgs& args, const Overflow& ov,
             const int v = e && *e ? atoi(e) : 0;
             return v > 0 ? v : 32;
         }();
+        // a warp works on two pairs at a time (long_lev_kernel.cuh): two slabs per warp
         long long warps = (long long)ctx.sm_count * (tier == 0 ? tier0_warps : 8);
-        if ((long long)src.n < warps) warps = src.n;
-        if (warps * g.slab_bytes > budget) warps = budget / g.slab_bytes;
-        if (warps < 1) break;  // not even one slab fits the budget: the generic kernel takes `src`
-        int rc = ws_reserve(ctx.scratch, (size_t)(warps * g.slab_bytes));
+        if (((long long)src.n + 1) / 2 < warps) warps = ((long long)src.n + 1) / 2;
+        if (2 * warps * g.slab_bytes > budget) warps = budget / (2 * g.slab_bytes);
+        if (warps < 1) break;  // not even two slabs fit the budget: the generic kernel takes `src`
+        // the list sorted by cost (longest first, neighbours alike) lives in front of the slabs
+        const size_t hist_bytes = ((size_t)LONG_KEYS * sizeof(unsigned int) + 255) & ~(size_t)255;
+        const size_t sort_bytes = hist_bytes + (((size_t)src.n * sizeof(unsigned int) + 255) & ~(size_t)255);
+        int rc = ws_reserve(ctx.scratch, sort_bytes + (size_t)(2 * warps * g.slab_bytes));
         if (rc) return rc;
-        g.scratch = static_cast<unsigned char*>(ctx.scratch.ptr);
+        unsigned char* base = static_cast<unsigned char*>(ctx.scratch.ptr);
+        unsigned int* hist = reinterpret_cast<unsigned int*>(base);
+        unsigned int* sorted = reinterpret_cast<unsigned int*>(base + hist_bytes);
+        {
+            CUDA_TRY(cudaMemsetAsync(hist, 0, (size_t)LONG_KEYS * sizeof(unsigned int), st));
+            unsigned int blocks = (unsigned int)((src.n + 255) / 256);
+            if (blocks > 4u * (unsigned int)ctx.sm_count) blocks = 4u * (unsigned int)ctx.sm_count;
+            long_sort_hist_kernel<<<blocks, 256, 0, st>>>(g.a, g.b, src.list, src.count, hist);
+            long_sort_scan_kernel<<<1, 1024, 0, st>>>(hist);
+            long_sort_scatter_kernel<<<blocks, 256, 0, st>>>(g.a, g.b, src.list, src.count, hist, sorted);
+            g_launches.fetch_add(3, std::memory_order_relaxed);
+            CUDA_TRY(cudaGetLastError());
+        }
+        g.scratch = base + sort_bytes;
         g.n_warps = (int)warps;
-        g.list = src.list;
+        g.list = sorted;
         g.list_count = src.count;
         g.huge_list = tier == 0 ? spare_list : args.listlong;
         g.huge_count = ctx.d_counters + 1 + tier;

@@ -28,8 +28,9 @@ constexpr int LONG_PAT_MAX = 8192;  // codepoints; 128 blocks = 4 per lane
 constexpr int LONG_WPB = 4;         // warps per block
 // The wavefront loop runs without bounds checks: the text's id array carries LONG_TID_PAD entries of the
 // all-zero Peq row before its first and after its last column (lanes that have not started or have
-// finished prefetch those), and the Peq area LONG_PEQ_PAD spare words (the last lane's blocks past W).
-constexpr int LONG_TID_PAD = 48;
+// finished -- or wait for the longer pair of the warp -- prefetch those), and the Peq area LONG_PEQ_PAD spare words (the last lane's blocks past W).
+constexpr int LONG_TID_PAD = 304;   // 48 for one pair's own lanes + LONG_PAIR_SLACK
+constexpr int LONG_PAIR_SLACK = 256;  // two pairs share a warp only if their step counts differ by less
 constexpr int LONG_PEQ_PAD = 8;
 
 struct LongLevArgs {
@@ -134,8 +135,11 @@ __device__ __forceinline__ uint32_t long_lookup(const LongLevSlab& s, uint32_t h
 // IMAD.WIDE + K loads for the Eq words two columns ahead, and -- between its first and last column --
 // K Myers blocks.  The step loop is unrolled three times so that the three Eq buffers and the three
 // ids rotate by renaming, not by moves.
-template <int K>
-__device__ inline int long_wavefront(const LongLevSlab& s, const uint16_t* tid, int m, int n, int W, int L, int lane) {
+// WIDTH = lanes per pair: 32 (one pair per warp) or 16 (two pairs per warp, each half with its own slab,
+// lengths and lane count; `lane` is the lane inside the group, `steps` the step count of the whole warp).
+template <int K, int WIDTH>
+__device__ inline int long_wavefront(const LongLevSlab& s, const uint16_t* tid, int m, int n, int W, int L, int lane,
+                                     int steps) {
     uint64_t Pv[K], Mv[K], eq[3][K];
     uint32_t tq[3];
 #pragma unroll
@@ -162,14 +166,13 @@ __device__ inline int long_wavefront(const LongLevSlab& s, const uint16_t* tid, 
         tq[1] = tq[2] = 0u;
     }
     uint32_t carry_prev = 0;  // bit 0: hp, bit 1: hm of this lane's last block in the previous step
-    const int steps = n + L - 1;
 #pragma unroll 1
     const uint16_t* q = tp + 3;  // q[u] = id of the column three ahead of step st0 + u
     int j0 = -lane;              // this lane's column at step st0
     for (int st0 = 0; st0 < steps; st0 += 3, q += 3, j0 += 3) {
 #pragma unroll
         for (int u = 0; u < 3; u++) {
-            uint32_t carry = __shfl_up_sync(0xFFFFFFFFu, carry_prev, 1);
+            uint32_t carry = __shfl_up_sync(0xFFFFFFFFu, carry_prev, 1, WIDTH);
             if (lane == 0) carry = 1u;  // D[0][j] - D[0][j-1] = +1
             tq[(u + 1) % 3] = q[u];
             {
@@ -190,127 +193,261 @@ __device__ inline int long_wavefront(const LongLevSlab& s, const uint16_t* tid, 
     for (int k = 0; k < K; k++)
         if (lane_on && blk0 + k < W) score += myers_block_score(Pv[k], Mv[k], m - 64 * (blk0 + k));
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) score += __shfl_xor_sync(0xFFFFFFFFu, score, o);
+    for (int o = WIDTH / 2; o > 0; o >>= 1) score += __shfl_xor_sync(0xFFFFFFFFu, score, o);
     return n + score;
 }
 
+// What the prelude of one pair leaves behind.
+struct LongPair {
+    int status;  // 0: run the wavefront, 1: settled (v, pi), 2: deferred to the huge list (nothing is written)
+    long long row;
+    int la, lb, m, n, W;
+    const uint16_t* tid;
+    double v;
+    PairInts pi;
+};
+
+// Equality test, decoding, pattern hash, text ids and Peq of one pair, by the whole warp, into slab s.
+__device__ inline void long_prepare(const LongLevArgs& g, const LongLevSlab& s, long long row, int lane, LongPair& o) {
+    o.row = row;
+    o.status = 1;
+    o.pi = {F_GENERAL, 0, 0, 0, 0, 0};
+    o.v = 0.0;
+    o.m = o.n = o.W = o.la = o.lb = 0;
+    o.tid = s.tid + LONG_TID_PAD;
+    int na, nb;
+    const unsigned char* pa = view_ptr(g.a, row, na);
+    const unsigned char* pb = view_ptr(g.b, row, nb);
+    bool differ = na != nb;
+    if (!differ) {
+        bool d = false;
+        for (int i = lane; i < na; i += 32) d = d || pa[i] != pb[i];
+        differ = __any_sync(0xFFFFFFFFu, d);
+    }
+    if (!differ) {
+        o.pi.flag = F_EQUAL;
+        o.v = 1.0;
+        return;
+    }
+    const int la = warp_decode(pa, na, s.cps_a, lane);
+    const int lb = warp_decode(pb, nb, s.cps_b, lane);
+    o.la = o.pi.la = la;
+    o.lb = o.pi.lb = lb;
+    const bool pat_is_b = lb <= la;
+    const uint32_t* P = pat_is_b ? s.cps_b : s.cps_a;
+    const uint32_t* T = pat_is_b ? s.cps_a : s.cps_b;
+    const int m = pat_is_b ? lb : la, n = pat_is_b ? la : lb;
+    o.m = m;
+    o.n = n;
+    if (m > g.cap_pat) {  // Peq would not fit the slab: the generic kernel finishes this row
+        if (lane == 0) g.huge_list[atomicAdd(g.huge_count, 1u)] = (unsigned int)row;
+        o.status = 2;
+        return;
+    }
+    if (m == 0) {
+        o.pi.x0 = n;
+        o.v = lev_value(n, la, lb);
+        return;
+    }
+    const int W = (m + 63) >> 6;
+    o.W = W;
+    // 1. hash set of the pattern's codepoints (table sized for this pattern, load <= 1/2)
+    int hbits = 6;
+    while ((1 << hbits) < 2 * m) hbits++;
+    const int hsize = 1 << hbits, hshift = 32 - hbits;
+    const uint32_t hmask = (uint32_t)hsize - 1u;
+    for (int i = lane; i < hsize; i += 32) s.hkeys[i] = 0u;
+    __syncwarp();
+    for (int i = lane; i < m; i += 32) {
+        const uint32_t key = P[i] + 1u;
+        uint32_t slot = long_hash(P[i], hshift);
+        for (;;) {
+            const uint32_t old = atomicCAS(&s.hkeys[slot], 0u, key);
+            if (old == 0u || old == key) break;
+            slot = (slot + 1u) & hmask;
+        }
+    }
+    __syncwarp();
+    // 2. dense ids in slot order
+    uint32_t distinct = 0;
+    for (int base = 0; base < hsize; base += 32) {
+        const bool occ = __ldcg(&s.hkeys[base + lane]) != 0u;
+        const unsigned mask = __ballot_sync(0xFFFFFFFFu, occ);
+        if (occ) s.hvals[base + lane] = (uint16_t)(distinct + __popc(mask & ((1u << lane) - 1u)));
+        distinct += __popc(mask);
+    }
+    __syncwarp();
+    // 3. text -> ids (id `distinct` = a codepoint the pattern does not contain: zero row), padded on both sides
+    uint16_t* tid = s.tid + LONG_TID_PAD;
+    for (int j = lane; j < n; j += 32) tid[j] = (uint16_t)long_lookup(s, hmask, hshift, T[j], distinct);
+    for (int j = lane; j < LONG_TID_PAD; j += 32) {
+        s.tid[j] = (uint16_t)distinct;
+        tid[n + j] = (uint16_t)distinct;
+    }
+    // 4. Peq[id][block]
+    const size_t words = (size_t)(distinct + 1u) * W;
+    if ((long long)words > g.peq_words) {  // needs a bigger slab: second launch
+        if (lane == 0) g.huge_list[atomicAdd(g.huge_count, 1u)] = (unsigned int)row;
+        o.status = 2;
+        return;
+    }
+    for (size_t i = lane; i < words; i += 32) s.peq[i] = 0ull;
+    __syncwarp();
+    for (int i = lane; i < m; i += 32) {
+        const uint32_t id = long_lookup(s, hmask, hshift, P[i], distinct);
+        atomicOr(&s.peq[(size_t)id * W + (i >> 6)], 1ull << (i & 63));
+    }
+    __syncwarp();
+    __threadfence();  // the atomics landed in L2; drop possibly stale L1 lines before reading Peq
+    o.status = 0;
+}
+
+__device__ inline void long_store(const LongLevArgs& g, const LongPair& o) {
+    g.out[o.row] = o.v;
+    if (g.dbg) {
+        int* d = g.dbg + o.row * 6;
+        d[0] = o.pi.flag;
+        d[1] = o.pi.la;
+        d[2] = o.pi.lb;
+        d[3] = o.pi.x0;
+        d[4] = o.pi.x1;
+        d[5] = o.pi.x2;
+    }
+}
+
+// one pair on all 32 lanes
+__device__ inline int long_run_single(const LongLevSlab& s, const LongPair& o, int lane) {
+    const int K = (o.W + 31) >> 5;
+    const int L = (o.W + K - 1) / K;
+    const int steps = o.n + L - 1;
+    switch (K) {
+        case 1: return long_wavefront<1, 32>(s, o.tid, o.m, o.n, o.W, L, lane, steps);
+        case 2: return long_wavefront<2, 32>(s, o.tid, o.m, o.n, o.W, L, lane, steps);
+        case 3: return long_wavefront<3, 32>(s, o.tid, o.m, o.n, o.W, L, lane, steps);
+        default: return long_wavefront<4, 32>(s, o.tid, o.m, o.n, o.W, L, lane, steps);
+    }
+}
+
+// Each warp owns TWO slabs and takes two list entries at a time.  The host sorts the list by (text
+// blocks, pattern blocks), so neighbours cost nearly the same number of steps and blocks: when both fit
+// 16 lanes (W <= 64 blocks at up to four per lane) the two wavefronts run side by side, lanes 0-15 on
+// the first pair and lanes 16-31 on the second -- a pattern of W blocks keeps ceil(W/K) lanes busy, so
+// one pair per warp left a third of the lanes idle on C4, and every step's fixed cost (carry shuffle,
+// id and Eq loads, bounds test) is now shared by up to four blocks per lane instead of two.
 __global__ void __launch_bounds__(32 * LONG_WPB, 8) long_lev_kernel(const LongLevArgs g) {
     const int lane = threadIdx.x & 31;
     const int warp = blockIdx.x * LONG_WPB + (threadIdx.x >> 5);
     if (warp >= g.n_warps) return;
-    const LongLevSlab s = long_lev_carve(g.scratch + (long long)warp * g.slab_bytes, g);
+    const LongLevSlab s0 = long_lev_carve(g.scratch + (long long)(2 * warp) * g.slab_bytes, g);
+    const LongLevSlab s1 = long_lev_carve(g.scratch + (long long)(2 * warp + 1) * g.slab_bytes, g);
     const unsigned int count = *g.list_count;
     for (;;) {
         unsigned int e = 0;
-        if (lane == 0) e = atomicAdd(g.cursor, 1u);
+        if (lane == 0) e = atomicAdd(g.cursor, 2u);
         e = __shfl_sync(0xFFFFFFFFu, e, 0);
         if (e >= count) break;
-        const long long row = g.list[e];
-        int na, nb;
-        const unsigned char* pa = view_ptr(g.a, row, na);
-        const unsigned char* pb = view_ptr(g.b, row, nb);
-        PairInts pi = {F_GENERAL, 0, 0, 0, 0, 0};
-        double v;
-        bool differ = na != nb;
-        if (!differ) {
-            bool d = false;
-            for (int i = lane; i < na; i += 32) d = d || pa[i] != pb[i];
-            differ = __any_sync(0xFFFFFFFFu, d);
-        }
-        if (!differ) {
-            pi.flag = F_EQUAL;
-            v = 1.0;
-        } else {
-            const int la = warp_decode(pa, na, s.cps_a, lane);
-            const int lb = warp_decode(pb, nb, s.cps_b, lane);
-            pi.la = la;
-            pi.lb = lb;
-            const bool pat_is_b = lb <= la;
-            const uint32_t* P = pat_is_b ? s.cps_b : s.cps_a;
-            const uint32_t* T = pat_is_b ? s.cps_a : s.cps_b;
-            const int m = pat_is_b ? lb : la, n = pat_is_b ? la : lb;
-            if (m > g.cap_pat) {  // Peq would not fit the slab: the generic kernel finishes this row
-                if (lane == 0) g.huge_list[atomicAdd(g.huge_count, 1u)] = (unsigned int)row;
-                continue;
-            }
+        LongPair p0, p1;
+        long_prepare(g, s0, g.list[e], lane, p0);
+        p1.status = 2;
+        if (e + 1 < count) long_prepare(g, s1, g.list[e + 1], lane, p1);
+        const int K0 = (p0.W + 15) >> 4, K1 = (p1.W + 15) >> 4;
+        const int K = K0 > K1 ? K0 : K1;
+        const int L0 = K ? (p0.W + K - 1) / K : 0, L1 = K ? (p1.W + K - 1) / K : 0;
+        const int st0 = p0.n + L0 - 1, st1 = p1.n + L1 - 1;
+        const int steps = st0 > st1 ? st0 : st1;
+        if (p0.status == 0 && p1.status == 0 && K <= 4 && steps - (st0 < st1 ? st0 : st1) < LONG_PAIR_SLACK) {
+            const bool hi = lane >= 16;
+            const LongLevSlab& s = hi ? s1 : s0;
+            const LongPair& p = hi ? p1 : p0;
+            const int L = hi ? L1 : L0;
             int d;
-            if (m == 0) {
-                d = n;
-            } else {
-                const int W = (m + 63) >> 6;
-                // 1. hash set of the pattern's codepoints (table sized for this pattern, load <= 1/2)
-                int hbits = 6;
-                while ((1 << hbits) < 2 * m) hbits++;
-                const int hsize = 1 << hbits, hshift = 32 - hbits;
-                const uint32_t hmask = (uint32_t)hsize - 1u;
-                for (int i = lane; i < hsize; i += 32) s.hkeys[i] = 0u;
-                __syncwarp();
-                for (int i = lane; i < m; i += 32) {
-                    const uint32_t key = P[i] + 1u;
-                    uint32_t slot = long_hash(P[i], hshift);
-                    for (;;) {
-                        const uint32_t old = atomicCAS(&s.hkeys[slot], 0u, key);
-                        if (old == 0u || old == key) break;
-                        slot = (slot + 1u) & hmask;
-                    }
-                }
-                __syncwarp();
-                // 2. dense ids in slot order
-                uint32_t distinct = 0;
-                for (int base = 0; base < hsize; base += 32) {
-                    const bool occ = __ldcg(&s.hkeys[base + lane]) != 0u;
-                    const unsigned mask = __ballot_sync(0xFFFFFFFFu, occ);
-                    if (occ) s.hvals[base + lane] = (uint16_t)(distinct + __popc(mask & ((1u << lane) - 1u)));
-                    distinct += __popc(mask);
-                }
-                __syncwarp();
-                // 3. text -> ids (id `distinct` = a codepoint the pattern does not contain: zero row)
-                uint16_t* tid = s.tid + LONG_TID_PAD;
-                for (int j = lane; j < n; j += 32) tid[j] = (uint16_t)long_lookup(s, hmask, hshift, T[j], distinct);
-                for (int j = lane; j < LONG_TID_PAD; j += 32) {
-                    s.tid[j] = (uint16_t)distinct;
-                    tid[n + j] = (uint16_t)distinct;
-                }
-                // 4. Peq[id][block]
-                const size_t words = (size_t)(distinct + 1u) * W;
-                if ((long long)words > g.peq_words) {  // needs a bigger slab: second launch
-                    if (lane == 0) g.huge_list[atomicAdd(g.huge_count, 1u)] = (unsigned int)row;
-                    continue;
-                }
-                for (size_t i = lane; i < words; i += 32) s.peq[i] = 0ull;
-                __syncwarp();
-                for (int i = lane; i < m; i += 32) {
-                    const uint32_t id = long_lookup(s, hmask, hshift, P[i], distinct);
-                    atomicOr(&s.peq[(size_t)id * W + (i >> 6)], 1ull << (i & 63));
-                }
-                __syncwarp();
-                __threadfence();  // the atomics landed in L2; drop possibly stale L1 lines before reading Peq
-                // 5. wavefront over the blocks
-                const int K = (W + 31) >> 5;
-                const int L = (W + K - 1) / K;
-                switch (K) {
-                    case 1: d = long_wavefront<1>(s, tid, m, n, W, L, lane); break;
-                    case 2: d = long_wavefront<2>(s, tid, m, n, W, L, lane); break;
-                    case 3: d = long_wavefront<3>(s, tid, m, n, W, L, lane); break;
-                    default: d = long_wavefront<4>(s, tid, m, n, W, L, lane); break;
-                }
+            switch (K) {
+                case 1: d = long_wavefront<1, 16>(s, p.tid, p.m, p.n, p.W, L, lane & 15, steps); break;
+                case 2: d = long_wavefront<2, 16>(s, p.tid, p.m, p.n, p.W, L, lane & 15, steps); break;
+                case 3: d = long_wavefront<3, 16>(s, p.tid, p.m, p.n, p.W, L, lane & 15, steps); break;
+                default: d = long_wavefront<4, 16>(s, p.tid, p.m, p.n, p.W, L, lane & 15, steps); break;
             }
-            pi.x0 = d;
-            v = lev_value(d, la, lb);
+            const int d0 = __shfl_sync(0xFFFFFFFFu, d, 0), d1 = __shfl_sync(0xFFFFFFFFu, d, 16);
+            p0.pi.x0 = d0;
+            p0.v = lev_value(d0, p0.la, p0.lb);
+            p1.pi.x0 = d1;
+            p1.v = lev_value(d1, p1.la, p1.lb);
+            p0.status = p1.status = 1;
+        } else {
+            if (p0.status == 0) {
+                const int d = long_run_single(s0, p0, lane);
+                p0.pi.x0 = d;
+                p0.v = lev_value(d, p0.la, p0.lb);
+                p0.status = 1;
+            }
+            if (p1.status == 0) {
+                const int d = long_run_single(s1, p1, lane);
+                p1.pi.x0 = d;
+                p1.v = lev_value(d, p1.la, p1.lb);
+                p1.status = 1;
+            }
         }
         if (lane == 0) {
-            g.out[row] = v;
-            if (g.dbg) {
-                int* o = g.dbg + row * 6;
-                o[0] = pi.flag;
-                o[1] = pi.la;
-                o[2] = pi.lb;
-                o[3] = pi.x0;
-                o[4] = pi.x1;
-                o[5] = pi.x2;
-            }
+            if (p0.status == 1) long_store(g, p0);
+            if (p1.status == 1) long_store(g, p1);
         }
         __syncwarp();
+    }
+}
+
+// ---- sorting the long list by cost ----------------------------------------------------------------------
+// key = (64-byte blocks of the longer string, 64-byte blocks of the shorter one), both clamped to 127:
+// bytes bound codepoints from above and are what the views hold.  Longest first, so that the tail of the
+// launch is made of short pairs.  Counting sort in three small launches over the list.
+constexpr int LONG_KEY_BITS = 7;
+constexpr int LONG_KEYS = 1 << (2 * LONG_KEY_BITS);
+
+__device__ __forceinline__ unsigned int long_sort_key(const DevCol& a, const DevCol& b, long long row) {
+    const unsigned int na = a.views[row * a.stride].x, nb = b.views[row * b.stride].x;
+    unsigned int hi = (na > nb ? na : nb) >> 6, lo = (na > nb ? nb : na) >> 6;
+    const unsigned int top = (1u << LONG_KEY_BITS) - 1u;
+    if (hi > top) hi = top;
+    if (lo > top) lo = top;
+    return (unsigned int)LONG_KEYS - 1u - ((hi << LONG_KEY_BITS) | lo);  // descending cost
+}
+
+__global__ void long_sort_hist_kernel(DevCol a, DevCol b, const unsigned int* list, const unsigned int* list_count,
+                                      unsigned int* hist) {
+    const unsigned int n = *list_count;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        atomicAdd(&hist[long_sort_key(a, b, list[i])], 1u);
+}
+
+// exclusive scan of LONG_KEYS bins by one CTA of 1024 threads (16 bins per thread)
+__global__ void long_sort_scan_kernel(unsigned int* hist) {
+    __shared__ unsigned int part[1024];
+    constexpr int PER = LONG_KEYS / 1024;
+    unsigned int local[PER], sum = 0;
+    for (int q = 0; q < PER; q++) {
+        local[q] = hist[threadIdx.x * PER + q];
+        sum += local[q];
+    }
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const unsigned int t = threadIdx.x >= o ? part[threadIdx.x - o] : 0u;
+        __syncthreads();
+        part[threadIdx.x] += t;
+        __syncthreads();
+    }
+    unsigned int run = part[threadIdx.x] - sum;
+    for (int q = 0; q < PER; q++) {
+        hist[threadIdx.x * PER + q] = run;
+        run += local[q];
+    }
+}
+
+__global__ void long_sort_scatter_kernel(DevCol a, DevCol b, const unsigned int* list, const unsigned int* list_count,
+                                         unsigned int* start, unsigned int* sorted) {
+    const unsigned int n = *list_count;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned int row = list[i];
+        sorted[atomicAdd(&start[long_sort_key(a, b, row)], 1u)] = row;
     }
 }
 
