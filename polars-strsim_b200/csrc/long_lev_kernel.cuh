@@ -58,7 +58,7 @@ struct LongLevSlab {
     uint32_t* cps_b;
     uint16_t* tid;
     uint32_t* hkeys;
-    uint16_t* hvals;
+    uint32_t* hvals;  // per hash slot: occurrence count while the pattern is inserted, then the character's code
     unsigned long long* peq;
 };
 
@@ -69,7 +69,7 @@ __host__ __device__ inline long long long_lev_slab_bytes(int cap_a, int cap_b, i
     b += 2ll * ((cap_a > cap_b ? cap_a : cap_b) + 2 * LONG_TID_PAD);
     b = (b + 15) & ~15ll;
     b += 4ll * hash_size;
-    b += 2ll * hash_size;
+    b += 4ll * hash_size;
     b = (b + 15) & ~15ll;
     b += 8ll * (peq_words + LONG_PEQ_PAD);
     return (b + 255) & ~255ll;
@@ -87,8 +87,8 @@ __device__ inline LongLevSlab long_lev_carve(unsigned char* base, const LongLevA
     o = (o + 15) & ~15ll;
     s.hkeys = reinterpret_cast<uint32_t*>(base + o);
     o += 4ll * g.hash_size;
-    s.hvals = reinterpret_cast<uint16_t*>(base + o);
-    o += 2ll * g.hash_size;
+    s.hvals = reinterpret_cast<uint32_t*>(base + o);
+    o += 4ll * g.hash_size;
     o = (o + 15) & ~15ll;
     s.peq = reinterpret_cast<unsigned long long*>(base + o);
     return s;
@@ -117,15 +117,22 @@ __device__ inline int warp_decode(const unsigned char* p, int nbytes, uint32_t* 
 
 __device__ __forceinline__ uint32_t long_hash(uint32_t cp, int shift) { return (cp * 2654435761u) >> shift; }
 
-// id of codepoint cp, or `absent` when the pattern does not contain it
-__device__ __forceinline__ uint32_t long_lookup(const LongLevSlab& s, uint32_t hmask, int hshift, uint32_t cp,
-                                                uint32_t absent) {
-    const uint32_t key = cp + 1u;
+// Character codes (16 bit, what the text is translated to): a character that occurs at least twice in the
+// pattern owns a Peq row, code = row id (< 0x8000); a character that occurs ONCE has no row -- its position
+// mask is a single bit, code = LONG_SINGLE | position, and the lane that owns that block sets the bit in
+// registers; a character the pattern does not contain gets the id of the all-zero row.  On C4 (a quarter
+// of the characters are spaces and letters, the rest rare 2- and 3-byte code points) this shrinks the Peq
+// of a pair from ~230 rows to ~40: the matrix used to stream from HBM and now stays in L2.
+constexpr uint32_t LONG_SINGLE = 0x8000u;
+constexpr uint32_t LONG_PENDING = 0xFFFFFFFFu;  // a single character whose position is not recorded yet
+
+__device__ __forceinline__ uint32_t long_find_slot(const LongLevSlab& s, uint32_t hmask, int hshift, uint32_t cp) {
+    const uint32_t key = cp + 1u;  // returns the slot holding cp, or ~0u when the pattern does not contain it
     uint32_t slot = long_hash(cp, hshift);
     for (;;) {
         const uint32_t k = __ldcg(&s.hkeys[slot]);  // written with atomicCAS (L2): do not trust L1
-        if (k == key) return s.hvals[slot];
-        if (k == 0u) return absent;
+        if (k == key) return slot;
+        if (k == 0u) return ~0u;
         slot = (slot + 1u) & hmask;
     }
 }
@@ -138,8 +145,8 @@ __device__ __forceinline__ uint32_t long_lookup(const LongLevSlab& s, uint32_t h
 // WIDTH = lanes per pair: 32 (one pair per warp) or 16 (two pairs per warp, each half with its own slab,
 // lengths and lane count; `lane` is the lane inside the group, `steps` the step count of the whole warp).
 template <int K, int WIDTH>
-__device__ inline int long_wavefront(const LongLevSlab& s, const uint16_t* tid, int m, int n, int W, int L, int lane,
-                                     int steps) {
+__device__ inline int long_wavefront(const LongLevSlab& s, const uint16_t* tid, uint32_t zero_row, int m, int n, int W,
+                                     int L, int lane, int steps) {
     uint64_t Pv[K], Mv[K], eq[3][K];
     uint32_t tq[3];
 #pragma unroll
@@ -153,17 +160,19 @@ __device__ inline int long_wavefront(const LongLevSlab& s, const uint16_t* tid, 
     const unsigned long long* rowbase = s.peq + blk0;
     const unsigned W8 = (unsigned)W;
     const uint16_t* tp = tid - lane;  // tp[st + c] = id of column (st - lane) + c
+    // codes of this lane's columns j, j+1, j+2 sit in tq[1], tq[2], tq[0] at step 0 and rotate from there
+    tq[1] = tp[0];
+    tq[2] = tp[1];
+    tq[0] = tp[2];
     {
-        const unsigned long long* r0 = rowbase + (size_t)tp[0] * W8;
-        const unsigned long long* r1 = rowbase + (size_t)tp[1] * W8;
+        const unsigned long long* r0 = rowbase + (size_t)((tq[1] & LONG_SINGLE) ? zero_row : tq[1]) * W8;
+        const unsigned long long* r1 = rowbase + (size_t)((tq[2] & LONG_SINGLE) ? zero_row : tq[2]) * W8;
 #pragma unroll
         for (int k = 0; k < K; k++) {
             eq[0][k] = r0[k];
             eq[1][k] = r1[k];
             eq[2][k] = 0ull;
         }
-        tq[0] = tp[2];
-        tq[1] = tq[2] = 0u;
     }
     uint32_t carry_prev = 0;  // bit 0: hp, bit 1: hm of this lane's last block in the previous step
 #pragma unroll 1
@@ -174,13 +183,23 @@ __device__ inline int long_wavefront(const LongLevSlab& s, const uint16_t* tid, 
         for (int u = 0; u < 3; u++) {
             uint32_t carry = __shfl_up_sync(0xFFFFFFFFu, carry_prev, 1, WIDTH);
             if (lane == 0) carry = 1u;  // D[0][j] - D[0][j-1] = +1
+            const uint32_t tcur = tq[(u + 1) % 3];  // code of the column computed in this step
             tq[(u + 1) % 3] = q[u];
             {
-                const unsigned long long* row = rowbase + (size_t)tq[u] * W8;
+                const uint32_t t = tq[u];
+                const unsigned long long* row = rowbase + (size_t)((t & LONG_SINGLE) ? zero_row : t) * W8;
 #pragma unroll
                 for (int k = 0; k < K; k++) eq[(u + 2) % 3][k] = row[k];
             }
             if ((unsigned)(j0 + u) < n_on) {
+                // a character that occurs once in the pattern: its bit, if it falls into this lane's blocks
+                const unsigned rel = ((tcur & (LONG_SINGLE - 1u)) >> 6) - (unsigned)blk0;
+                if ((tcur & LONG_SINGLE) && rel < (unsigned)K) {
+                    const uint64_t bit = 1ull << (tcur & 63u);
+#pragma unroll
+                    for (int k = 0; k < K; k++)
+                        if (rel == (unsigned)k) eq[u][k] |= bit;
+                }
                 uint32_t hp = carry & 1u, hm = carry >> 1;
 #pragma unroll
                 for (int k = 0; k < K; k++) myers_block(Pv[k], Mv[k], eq[u][k], hp, hm);
@@ -203,12 +222,13 @@ struct LongPair {
     long long row;
     int la, lb, m, n, W;
     const uint16_t* tid;
+    uint32_t zero_row;
     double v;
     PairInts pi;
 };
 
 // Equality test, decoding, pattern hash, text ids and Peq of one pair, by the whole warp, into slab s.
-__device__ inline void long_prepare(const LongLevArgs& g, const LongLevSlab& s, long long row, int lane, LongPair& o) {
+__device__ __noinline__ void long_prepare(const LongLevArgs& g, const LongLevSlab& s, long long row, int lane, LongPair& o) {
     o.row = row;
     o.status = 1;
     o.pi = {F_GENERAL, 0, 0, 0, 0, 0};
@@ -256,7 +276,10 @@ __device__ inline void long_prepare(const LongLevArgs& g, const LongLevSlab& s, 
     while ((1 << hbits) < 2 * m) hbits++;
     const int hsize = 1 << hbits, hshift = 32 - hbits;
     const uint32_t hmask = (uint32_t)hsize - 1u;
-    for (int i = lane; i < hsize; i += 32) s.hkeys[i] = 0u;
+    for (int i = lane; i < hsize; i += 32) {
+        s.hkeys[i] = 0u;
+        s.hvals[i] = 0u;
+    }
     __syncwarp();
     for (int i = lane; i < m; i += 32) {
         const uint32_t key = P[i] + 1u;
@@ -266,26 +289,24 @@ __device__ inline void long_prepare(const LongLevArgs& g, const LongLevSlab& s, 
             if (old == 0u || old == key) break;
             slot = (slot + 1u) & hmask;
         }
+        atomicAdd(&s.hvals[slot], 1u);  // occurrences of this character in the pattern
     }
     __syncwarp();
-    // 2. dense ids in slot order
-    uint32_t distinct = 0;
+    // 2. dense row ids, in slot order, for the characters that occur at least twice
+    uint32_t rows = 0;
     for (int base = 0; base < hsize; base += 32) {
-        const bool occ = __ldcg(&s.hkeys[base + lane]) != 0u;
-        const unsigned mask = __ballot_sync(0xFFFFFFFFu, occ);
-        if (occ) s.hvals[base + lane] = (uint16_t)(distinct + __popc(mask & ((1u << lane) - 1u)));
-        distinct += __popc(mask);
+        const uint32_t cnt = __ldcg(&s.hvals[base + lane]);
+        const unsigned mask = __ballot_sync(0xFFFFFFFFu, cnt >= 2u);
+        if (cnt >= 2u)
+            s.hvals[base + lane] = rows + __popc(mask & ((1u << lane) - 1u));
+        else if (cnt == 1u)
+            s.hvals[base + lane] = LONG_PENDING;
+        rows += __popc(mask);
     }
     __syncwarp();
-    // 3. text -> ids (id `distinct` = a codepoint the pattern does not contain: zero row), padded on both sides
-    uint16_t* tid = s.tid + LONG_TID_PAD;
-    for (int j = lane; j < n; j += 32) tid[j] = (uint16_t)long_lookup(s, hmask, hshift, T[j], distinct);
-    for (int j = lane; j < LONG_TID_PAD; j += 32) {
-        s.tid[j] = (uint16_t)distinct;
-        tid[n + j] = (uint16_t)distinct;
-    }
-    // 4. Peq[id][block]
-    const size_t words = (size_t)(distinct + 1u) * W;
+    o.zero_row = rows;  // row `rows` stays all zero: characters the pattern does not contain
+    // 3. Peq[row][block]; single characters record their position instead
+    const size_t words = (size_t)(rows + 1u) * W;
     if ((long long)words > g.peq_words) {  // needs a bigger slab: second launch
         if (lane == 0) g.huge_list[atomicAdd(g.huge_count, 1u)] = (unsigned int)row;
         o.status = 2;
@@ -294,11 +315,26 @@ __device__ inline void long_prepare(const LongLevArgs& g, const LongLevSlab& s, 
     for (size_t i = lane; i < words; i += 32) s.peq[i] = 0ull;
     __syncwarp();
     for (int i = lane; i < m; i += 32) {
-        const uint32_t id = long_lookup(s, hmask, hshift, P[i], distinct);
-        atomicOr(&s.peq[(size_t)id * W + (i >> 6)], 1ull << (i & 63));
+        const uint32_t slot = long_find_slot(s, hmask, hshift, P[i]);
+        const uint32_t code = __ldcg(&s.hvals[slot]);
+        if (code == LONG_PENDING)
+            s.hvals[slot] = LONG_SINGLE | (uint32_t)i;  // the only occurrence: nobody else writes this slot
+        else
+            atomicOr(&s.peq[(size_t)code * W + (i >> 6)], 1ull << (i & 63));
     }
     __syncwarp();
     __threadfence();  // the atomics landed in L2; drop possibly stale L1 lines before reading Peq
+    // 4. text -> codes, padded on both sides with the all-zero row
+    uint16_t* tid = s.tid + LONG_TID_PAD;
+    for (int j = lane; j < n; j += 32) {
+        const uint32_t slot = long_find_slot(s, hmask, hshift, T[j]);
+        tid[j] = (uint16_t)(slot == ~0u ? rows : __ldcg(&s.hvals[slot]));
+    }
+    for (int j = lane; j < LONG_TID_PAD; j += 32) {
+        s.tid[j] = (uint16_t)rows;
+        tid[n + j] = (uint16_t)rows;
+    }
+    __syncwarp();
     o.status = 0;
 }
 
@@ -321,10 +357,10 @@ __device__ inline int long_run_single(const LongLevSlab& s, const LongPair& o, i
     const int L = (o.W + K - 1) / K;
     const int steps = o.n + L - 1;
     switch (K) {
-        case 1: return long_wavefront<1, 32>(s, o.tid, o.m, o.n, o.W, L, lane, steps);
-        case 2: return long_wavefront<2, 32>(s, o.tid, o.m, o.n, o.W, L, lane, steps);
-        case 3: return long_wavefront<3, 32>(s, o.tid, o.m, o.n, o.W, L, lane, steps);
-        default: return long_wavefront<4, 32>(s, o.tid, o.m, o.n, o.W, L, lane, steps);
+        case 1: return long_wavefront<1, 32>(s, o.tid, o.zero_row, o.m, o.n, o.W, L, lane, steps);
+        case 2: return long_wavefront<2, 32>(s, o.tid, o.zero_row, o.m, o.n, o.W, L, lane, steps);
+        case 3: return long_wavefront<3, 32>(s, o.tid, o.zero_row, o.m, o.n, o.W, L, lane, steps);
+        default: return long_wavefront<4, 32>(s, o.tid, o.zero_row, o.m, o.n, o.W, L, lane, steps);
     }
 }
 
@@ -362,10 +398,10 @@ __global__ void __launch_bounds__(32 * LONG_WPB, 8) long_lev_kernel(const LongLe
             const int L = hi ? L1 : L0;
             int d;
             switch (K) {
-                case 1: d = long_wavefront<1, 16>(s, p.tid, p.m, p.n, p.W, L, lane & 15, steps); break;
-                case 2: d = long_wavefront<2, 16>(s, p.tid, p.m, p.n, p.W, L, lane & 15, steps); break;
-                case 3: d = long_wavefront<3, 16>(s, p.tid, p.m, p.n, p.W, L, lane & 15, steps); break;
-                default: d = long_wavefront<4, 16>(s, p.tid, p.m, p.n, p.W, L, lane & 15, steps); break;
+                case 1: d = long_wavefront<1, 16>(s, p.tid, p.zero_row, p.m, p.n, p.W, L, lane & 15, steps); break;
+                case 2: d = long_wavefront<2, 16>(s, p.tid, p.zero_row, p.m, p.n, p.W, L, lane & 15, steps); break;
+                case 3: d = long_wavefront<3, 16>(s, p.tid, p.zero_row, p.m, p.n, p.W, L, lane & 15, steps); break;
+                default: d = long_wavefront<4, 16>(s, p.tid, p.zero_row, p.m, p.n, p.W, L, lane & 15, steps); break;
             }
             const int d0 = __shfl_sync(0xFFFFFFFFu, d, 0), d1 = __shfl_sync(0xFFFFFFFFu, d, 16);
             p0.pi.x0 = d0;
