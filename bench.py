@@ -413,6 +413,23 @@ def main():
         ms = per_measure_ms["levenshtein"]
         line["long_levenshtein"] = {"cells_per_launch": cells, "gcups": cells / (ms * 1e-3) / 1e9,
                                     "note": "cells = sum la*lb (codepoints) over pairs with a != b"}
+        # the roofline of this kernel is the SM integer issue rate, not HBM: warp
+        # instructions per cell from the ncu capture in profiles/, ceilings measured here (peaks.cu)
+        per_cell = json.loads(tp.read_text()).get("C4_warp_instructions_per_cell", {}).get("long_lev_kernel") \
+            if tp.exists() else None
+        if per_cell and clocks and clocks.get("sm_mhz"):
+            ipc = cells * per_cell / (148 * ms * 1e-3 * clocks["sm_mhz"] * 1e6)
+            issue = {"warp_instructions_per_cell": per_cell, "ipc_per_sm": ipc}
+            try:
+                from bench_support import peaks as int_peaks
+
+                pk = int_peaks.measure(clocks["sm_mhz"])
+                issue.update({"ipc_peak_alu_pipe_measured": pk["lop3"]["per_clk_per_sm"],
+                              "ipc_peak_alu_plus_fma_measured": pk["lop3_imad_mix"]["per_clk_per_sm"],
+                              "frac_of_alu_plus_fma_peak": ipc / pk["lop3_imad_mix"]["per_clk_per_sm"]})
+            except Exception as exc:
+                issue["peak_error"] = str(exc)
+            line["long_levenshtein"]["issue"] = issue
     if e2e:
         line["e2e"] = e2e
     if not args.no_cpu_baseline and world == 1:
