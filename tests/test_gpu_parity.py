@@ -768,3 +768,55 @@ def test_long_levenshtein_c4_by_properties(native, oracle):
     ref, ref_valid, ref_ints = oracle.batch("levenshtein", a, b)
     assert (vals[idx].view(np.uint64) == ref.view(np.uint64)).all()
     assert (ints[idx] == ref_ints).all()
+
+
+def test_concurrent_calls_from_engine_threads(native, oracle):
+    """`is_elementwise=True` (polars_strsim/__init__.py:15) lets the engine call the plugin per chunk from
+    any of its threads at the same time: the exports must be re-entrant.  Eight threads call the C ABI
+    concurrently (ctypes drops the GIL), each with its own rows -- short ASCII, mixed scripts, nulls, rows
+    for the 64-bit and the long kernels -- single measures and fused sets, three rounds each; every result
+    is compared with the oracle bit for bit."""
+    import threading
+
+    rng = random.Random(77)
+    jobs = []
+    for t in range(8):
+        a, b = [], []
+        for _ in range(3000):
+            x, y = rand_pair(rng)
+            a.append(x)
+            b.append(y)
+        for k in range(40):  # some rows for the 64-bit and the long kernels, some nulls
+            s = "".join(rng.choice("abcdefgh ") for _ in range(rng.randrange(30, 400)))
+            a.append(s)
+            b.append(s[: len(s) // 2] + "x" + s[len(s) // 2 + (k % 3):])
+        a[5] = None
+        b[t + 10] = None
+        names = [oracle.MEASURES[(t + i) % 5] for i in range(1 + t % 3)]
+        jobs.append((a, b, names))
+    refs = [[oracle.batch(m, a, b) for m in names] for a, b, names in jobs]
+    errors = []
+
+    def work(idx):
+        a, b, names = jobs[idx]
+        try:
+            A, B = sv(a), sv(b)
+            for _ in range(3):
+                if len(names) == 1:
+                    vals, valid, nulls, ints = native.compute_host(names[0], A, B, debug=True)
+                    outs, all_ints = [vals], [ints]
+                else:
+                    outs, valid, nulls, all_ints = native.compute_host_multi(names, A, B, debug=True)
+                for (ref, ref_valid, ref_ints), got, gi in zip(refs[idx], outs, all_ints):
+                    assert (valid == ref_valid).all()
+                    assert (got.view(np.uint64)[valid] == ref.view(np.uint64)[valid]).all()
+                    assert (gi[valid] == ref_ints[valid]).all()
+        except BaseException as exc:  # noqa: BLE001 -- reported by the main thread
+            errors.append((idx, repr(exc)))
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(jobs))]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
