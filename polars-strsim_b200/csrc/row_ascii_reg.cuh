@@ -292,4 +292,176 @@ SS_HD uint32_t wide_bytes(uint32_t x) {
     return x & (x << 1) & nz & 0x80808080u;
 }
 
+
+// =========================================================================================================
+// The plane path over string SOURCES.  A source is wherever a string of at most 32 one-byte characters
+// lives -- the staged tile in shared memory (StagedSrc, short_kernel.cuh), a thread's slab after the
+// Latin-1 transcoding (SlabSrc below), plain host memory in the tests -- and offers exactly what the
+// measures need:
+//     int len;                          characters
+//     planes(tab)                       bit planes of the string (it is the tabled one)
+//     each(n, f)                        f(c) for the first n characters (it is the streamed one)
+//     first_word()                      characters 0..3, zero-masked to len (Winkler prefix)
+//     byte_at() -> ByteAt               functor: character p (Jaro's transposition walk)
+// Nothing is copied into registers: the tabled string becomes planes word by word, the streamed one
+// is read once, byte by byte.  The pair is known NOT to be byte-equal (the sort key of the kernels
+// settles equal pairs; strsim.rs:128,182,288,324).
+// =========================================================================================================
+SS_HD uint32_t low_bytes_mask(int nbytes) {  // low nbytes bytes set, nbytes >= 0
+    return nbytes >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nbytes)) - 1u);
+}
+
+// words at w[i * STRIDE] (STRIDE = threads per CTA for a slab in shared memory, 1 for plain memory),
+// word-aligned, one byte per character; bytes past len are arbitrary
+template <int STRIDE, class BA>
+struct SlabSrc {
+    const uint32_t* w;
+    int len;
+    BA ba;
+    typedef BA ByteAt;
+    SS_HD const BA& byte_at() const { return ba; }
+    SS_HD uint32_t first_word() const { return w[0] & low_bytes_mask(len); }
+    template <int NBITS>
+    SS_HD void planes(PlaneTab<NBITS>& tab) const {
+#pragma unroll
+        for (int k = 0; k < NBITS; k++) tab.B[k] = 0u;
+#pragma unroll
+        for (int i = 0; i < REG_WORDS; i++) {
+            if (4 * i >= len) break;
+            planes_add_word<NBITS>(tab, w[i * STRIDE], i);
+        }
+        tab.valid = len >= 32 ? 0xFFFFFFFFu : ((1u << len) - 1u);
+    }
+    template <class F>
+    SS_HD void each(int n, F& f) const {
+        const uint32_t* p = w;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (; n >= 4; n -= 4, p += STRIDE) {
+            const uint32_t word = p[0];
+            f(word & 0xFFu);
+            f((word >> 8) & 0xFFu);
+            f((word >> 16) & 0xFFu);
+            f(word >> 24);
+        }
+        if (n > 0) {
+            uint32_t word = p[0];
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (; n > 0; n--) {
+                f(word & 0xFFu);
+                word >>= 8;
+            }
+        }
+    }
+};
+
+template <class Src>
+struct EachOf {
+    const Src& s;
+    template <class F>
+    SS_HD void operator()(int n, F& f) const {
+        s.each(n, f);
+    }
+};
+
+template <class Src>
+struct PrefixOf {  // common prefix in characters, capped at 4 (strsim.rs:261-266)
+    const Src &A, &B;
+    SS_HD int operator()() const {
+        const uint32_t x = A.first_word() ^ B.first_word();
+        int lim = A.len < B.len ? A.len : B.len;
+        if (lim > 4) lim = 4;
+        // bytes past the shorter string may or may not differ (a NUL character equals the zero mask):
+        // the count of equal leading bytes, capped by lim
+        const int l = x == 0u ? 4 : ctz32(x) >> 3;
+        return l < lim ? l : lim;
+    }
+};
+
+// one measure; row rules and arithmetic of row_ascii_reg()
+template <int MEASURE, int NBITS, class Src>
+SS_HD double row_planes(const Src& A, const Src& B, PairInts& out) {
+    out.flag = F_GENERAL;
+    out.la = out.lb = out.x0 = out.x1 = out.x2 = 0;
+    const int la = A.len, lb = B.len;
+    if (MEASURE != LEVENSHTEIN && (la == 0 || lb == 0)) {  // strsim.rs:184,290,326
+        out.flag = F_ONE_EMPTY;
+        return 0.0;
+    }
+    out.la = la;
+    out.lb = lb;
+    constexpr bool IS_JARO = MEASURE == JARO || MEASURE == JARO_WINKLER;
+    if (IS_JARO && la == 1 && lb == 1) {  // strsim.rs:197
+        out.flag = F_SINGLE_CHAR;
+        return 0.0;
+    }
+    typedef PlaneTab<NBITS> Tab;
+    Tab tab;
+    double v;
+    if (MEASURE == LEVENSHTEIN) {
+        // the shorter string is tabled; the longer one is streamed (the distance is symmetric)
+        const bool table_b = lb <= la;
+        const Src& P = table_b ? B : A;
+        const Src& X = table_b ? A : B;
+        int d = X.len;
+        if (P.len > 0) {
+            P.planes(tab);
+            MyersStep<uint32_t, Tab> step(tab);
+            X.each(X.len, step);
+            d = step.distance(P.len, X.len);
+        }
+        out.x0 = d;
+        v = lev_value<true>(d, la, lb);
+    } else {
+        B.planes(tab);
+        if (IS_JARO) {
+            const int mx = la > lb ? la : lb;
+            const int bound = mx / 2 - 1;  // strsim.rs:200
+            const int outer = la < lb + bound ? la : lb + bound;
+            JaroMatchStep<uint32_t, Tab> match(tab, lb, bound);
+            A.each(outer, match);
+            match.finish(outer);
+            TransByBytes<typename Src::ByteAt> trans{A.byte_at(), B.byte_at()};
+            EachOf<Src> each_a{A};
+            const int t = match.m > 0 ? trans(tab, each_a, outer, match.flag_a, match.flag_b) : 0;
+            out.x0 = match.m;
+            out.x1 = t;
+            v = match.m == 0 ? 0.0 : jaro_value<true>(match.m, t, la, lb);
+            if (MEASURE == JARO_WINKLER && v > 0.7) {  // strsim.rs:260-267
+                PrefixOf<Src> prefix{A, B};
+                const int l = prefix();
+                out.x2 = l;
+                v = winkler_value(v, l);
+            }
+        } else {
+            MultisetStep<uint32_t, Tab> ms(tab, lb);
+            A.each(la, ms);
+            ms.finish();
+            out.x0 = ms.inter;
+            if (MEASURE == JACCARD) {
+                out.x1 = la + lb - ms.inter;
+                v = jaccard_value<true>(ms.inter, la + lb - ms.inter);
+            } else {
+                out.x1 = la + lb;
+                v = dice_value<true>(ms.inter, la + lb);
+            }
+        }
+    }
+    return v;
+}
+
+// several measures in one pass: b tabled, a streamed for every group (row_short.cuh: multi_body)
+template <int GROUPS, int NBITS, class Src, class Emit>
+SS_HD void row_planes_multi(const Src& A, const Src& B, Emit& emit) {
+    PlaneTab<NBITS> tab;
+    B.planes(tab);
+    TransByBytes<typename Src::ByteAt> trans{A.byte_at(), B.byte_at()};
+    EachOf<Src> each_a{A};
+    PrefixOf<Src> prefix{A, B};
+    multi_body<GROUPS, uint32_t>(tab, each_a, A.len, B.len, A.len == 0 || B.len == 0, prefix, trans, emit);
+}
+
 }  // namespace strsim

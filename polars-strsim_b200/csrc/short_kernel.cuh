@@ -380,106 +380,30 @@ __device__ __forceinline__ void build_planes_staged(const unsigned char* smem, c
     tab.valid = m >= 32 ? 0xFFFFFFFFu : ((1u << m) - 1u);
 }
 
-// common prefix of two staged ASCII strings, capped at 4 (strsim.rs:261-266); evaluated only when the
-// Jaro score passes the Winkler threshold
-struct PrefixStaged {
-    const unsigned char* smem;
-    StagedStr A, B;
-    __device__ __forceinline__ int operator()() const;
-};
-
 // first word (zero-masked to the string's length) of a staged string
 __device__ __forceinline__ uint32_t staged_first_word(const unsigned char* smem, const StagedStr& S) {
     const uint32_t* p = reinterpret_cast<const uint32_t*>(smem + (S.off & ~3u));
     return __funnelshift_r(p[0], p[1], (int)(S.off & 3u) * 8) & byte_mask(S.len);
 }
 
-__device__ __forceinline__ int PrefixStaged::operator()() const {
-    const uint32_t x = staged_first_word(smem, A) ^ staged_first_word(smem, B);
-    int lim = A.len < B.len ? A.len : B.len;
-    if (lim > 4) lim = 4;
-    // bytes beyond the shorter string differ (one side is zero-masked, ASCII bytes are not zero) or lie
-    // beyond lim: the count of equal leading bytes, capped
-    const int l = x == 0u ? 4 : (__ffs((int)x) - 1) >> 3;
-    return l < lim ? l : lim;
-}
-
-// One ASCII pair that is NOT byte-equal, single measure, both strings read straight from the staged tile:
-// the tabled string becomes bit planes word by word, the streamed one goes through the step functor byte
-// by byte -- neither is copied into registers.  Row rules and arithmetic: row_ascii_reg (row_ascii_reg.cuh).
-template <int MEASURE, int NBITS>
-__device__ __forceinline__ double row_ascii_staged(const unsigned char* smem, const StagedStr& A, const StagedStr& B,
-                                                   PairInts& out) {
-    out.flag = F_GENERAL;
-    out.la = out.lb = out.x0 = out.x1 = out.x2 = 0;
-    const int la = A.len, lb = B.len;
-    if (MEASURE != LEVENSHTEIN && (la == 0 || lb == 0)) {  // strsim.rs:184,290,326
-        out.flag = F_ONE_EMPTY;
-        return 0.0;
+// a string of the staged tile as a source of the plane path (row_ascii_reg.cuh: row_planes)
+struct StagedSrc {
+    const unsigned char* smem;
+    uint32_t off;
+    int len;
+    typedef SmemByteAt ByteAt;
+    __device__ __forceinline__ SmemByteAt byte_at() const { return SmemByteAt{smem_u32(smem) + off}; }
+    __device__ __forceinline__ uint32_t first_word() const { return staged_first_word(smem, StagedStr{off, len}); }
+    template <int NBITS>
+    __device__ __forceinline__ void planes(PlaneTab<NBITS>& tab) const {
+        build_planes_staged<NBITS>(smem, StagedStr{off, len}, tab);
     }
-    out.la = la;
-    out.lb = lb;
-    constexpr bool IS_JARO = MEASURE == JARO || MEASURE == JARO_WINKLER;
-    if (IS_JARO && la == 1 && lb == 1) {  // strsim.rs:197
-        out.flag = F_SINGLE_CHAR;
-        return 0.0;
+    template <class F>
+    __device__ __forceinline__ void each(int n, F& f) const {
+        EachByteStaged e{smem, off};
+        e(n, f);
     }
-    typedef PlaneTab<NBITS> Tab;
-    Tab tab;
-    double v;
-    if (MEASURE == LEVENSHTEIN) {
-        // the shorter string is tabled; the longer one is streamed (the distance is symmetric)
-        const bool table_b = lb <= la;
-        const StagedStr P = table_b ? B : A, X = table_b ? A : B;
-        int d = X.len;
-        if (P.len > 0) {
-            build_planes_staged<NBITS>(smem, P, tab);
-            MyersStep<uint32_t, Tab> step(tab);
-            EachByteStaged each{smem, X.off};
-            each(X.len, step);
-            d = step.distance(P.len, X.len);
-        }
-        out.x0 = d;
-        v = lev_value<true>(d, la, lb);
-    } else {
-        build_planes_staged<NBITS>(smem, B, tab);
-        EachByteStaged each_a{smem, A.off};
-        if (IS_JARO) {
-            const int mx = la > lb ? la : lb;
-            const int bound = mx / 2 - 1;  // strsim.rs:200
-            const int outer = la < lb + bound ? la : lb + bound;
-            JaroMatchStep<uint32_t, Tab> match(tab, lb, bound);
-            each_a(outer, match);
-            match.finish(outer);
-            TransByBytes<SmemByteAt> trans;
-            trans.A.base = smem_u32(smem) + A.off;
-            trans.B.base = smem_u32(smem) + B.off;
-            const int t = match.m > 0 ? trans(tab, each_a, outer, match.flag_a, match.flag_b) : 0;
-            out.x0 = match.m;
-            out.x1 = t;
-            v = match.m == 0 ? 0.0 : jaro_value<true>(match.m, t, la, lb);
-            if (MEASURE == JARO_WINKLER && v > 0.7) {  // strsim.rs:260-267
-                PrefixStaged prefix{smem, A, B};
-                const int l = prefix();
-                out.x2 = l;
-                v = winkler_value(v, l);
-            }
-        } else {
-            MultisetStep<uint32_t, Tab> ms(tab, lb);
-            each_a(la, ms);
-            ms.finish();
-            out.x0 = ms.inter;
-            if (MEASURE == JACCARD) {
-                out.x1 = la + lb - ms.inter;
-                v = jaccard_value<true>(ms.inter, la + lb - ms.inter);
-            } else {
-                out.x1 = la + lb;
-                v = dice_value<true>(ms.inter, la + lb);
-            }
-        }
-    }
-    return v;
-}
+};
 
 // Settling byte-equal pairs before the sort frees their lanes but costs every row a prefix compare;
 // measured on C2 (20 % equal pairs) it LOSES 5-8 % (table path: latency-bound rounds; register path:
@@ -847,7 +771,7 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
         // ---------------- 3. bucket: cost key per row, counting sort (descending) -----------------
         uint32_t key[RPT], rank[RPT];
         bool row_equal[RPT];
-        if constexpr (REG || is_multi(MEASURE)) {
+        if constexpr (REG || ULAT || is_multi(MEASURE)) {
             // byte-equal pairs (strsim.rs:128,182,288,324), found by all lanes in lock step
 #pragma unroll
             for (int k = 0; k < RPT; k++) {
@@ -870,7 +794,7 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
             // (always in the fused kernel: its per-pair loops are three measures long, so the lanes that a
             // fifth of equal pairs would idle are worth far more than the prefix compare)
             bool settle_equal = false;
-            if constexpr (REG || is_multi(MEASURE)) {
+            if constexpr (REG || ULAT || is_multi(MEASURE)) {
                 settle_equal = row_equal[k];
             } else if (PREFILTER_EQUAL) {
                 settle_equal = va.x == vb.x &&
@@ -878,7 +802,7 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
                                                (vb.x <= 12u ? vb.y : sva_prefix(vb, stage_b)))) &&
                                staged_equal(va, vb, stage_a, stage_b);
             }
-            if (settle_equal && !is_multi(MEASURE) && !REG) {
+            if (settle_equal && !is_multi(MEASURE) && !REG && !ULAT) {
                 const long long idx = tile0 + i;
                 const long long row = GATHER ? (long long)s.list[idx] : idx;
                 store_settled<MEASURE>(s, row, 1.0, F_EQUAL);
@@ -928,7 +852,7 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
             // (the register kernels read "key 1" as "byte-equal" in step 4: there a pair with an empty a and a
             // non-empty b must not share that key, so their other keys start at 2)
             key[k] = settle_equal ? 1u
-                                  : (REG ? 2u : 1u) + mx +
+                                  : (REG || ULAT ? 2u : 1u) + mx +
                                         ((hi_bits & 0x80808080u) ? (uint32_t)(CAP + 1) : 0u);
             rank[k] = atomicAdd(&hist[key[k]], 1u);
         }
@@ -970,6 +894,37 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
 #pragma unroll 1
         for (int k = 0; k < RPT; k++) {
             const int p = k * TPB + ((k & 1) ? (TPB - 1 - tid) : tid);  // snake order balances warps
+            if constexpr (ULAT) {
+                // the Latin-1 half of a general column: no character above U+00FF in these pairs.  The sort put
+                // the byte-equal pairs (key 1) last; the others are copied into the thread's slab, rewritten
+                // there to one byte per character (row_ascii_reg.cuh: transcode_latin1) and run the plane
+                // path with 8 planes straight from the slab
+                if (p >= n_active) continue;
+                const int i = perm[p];
+                const long long idx = tile0 + i;
+                const long long row = GATHER ? (long long)s.list[idx] : idx;
+                if (p >= (int)hist[1]) {
+                    store_settled<MEASURE>(s, row, 1.0, F_EQUAL);
+                    continue;
+                }
+                const uint4 va = sva[i], vb = svb[i];
+                load_string<WORDS, TPB>(va, stage_a, store.wa_);
+                load_string<WORDS, TPB>(vb, stage_b, store.wb_);
+                SlabWords<TPB> sa{store.wa_}, sb{store.wb_};
+                const int ca = transcode_latin1(sa, (int)va.x), cb = transcode_latin1(sb, (int)vb.x);
+                typedef SlabSrc<TPB, SlabByteAt<TPB>> Src;
+                const Src A{store.wa_, ca, SlabByteAt<TPB>{smem_u32(store.wa_)}},
+                          B{store.wb_, cb, SlabByteAt<TPB>{smem_u32(store.wb_)}};
+                if constexpr (is_multi(MEASURE)) {
+                    RowEmit emit{s, row, true};
+                    row_planes_multi<GROUPS, 8>(A, B, emit);
+                } else {
+                    PairInts ints;
+                    s.out[row] = row_planes<is_multi(MEASURE) ? 0 : MEASURE, 8>(A, B, ints);
+                    if (s.dbg) store_dbg(s.dbg + row * 6, ints);
+                }
+                continue;
+            }
             if (UREG) {
                 // every lane of the warp runs the row function (idle lanes on an empty, "equal" pair):
                 // the compare loops are bounded by a warp-wide maximum
@@ -990,37 +945,6 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
                         for (int w = 0; w < nw; w++) diff |= store.wa(w) ^ store.wb(w);
                         equal = diff == 0;
                     }
-                }
-                if constexpr (ULAT) {
-                    // no character above U+00FF in these pairs: UTF-8 -> one byte per character in the
-                    // slab, then the bit-plane path with 8 planes (row_ascii_reg.cuh: transcode_latin1)
-                    if (!has) continue;
-                    int ca = na, cb = nb;
-                    if (!equal) {
-                        SlabWords<TPB> sa{store.wa_}, sb{store.wb_};
-                        ca = transcode_latin1(sa, na);
-                        cb = transcode_latin1(sb, nb);
-                    }
-                    uint32_t ra[REG_WORDS], rb[REG_WORDS];
-#pragma unroll
-                    for (int w = 0; w < REG_WORDS; w++) {
-                        ra[w] = 4 * w < ca ? store.wa(w) : 0u;
-                        rb[w] = 4 * w < cb ? store.wb(w) : 0u;
-                    }
-                    TransByBytes<SlabByteAt<TPB>> trans;
-                    trans.A.base = smem_u32(store.wa_);
-                    trans.B.base = smem_u32(store.wb_);
-                    const long long idx = tile0 + i;
-                    const long long row = GATHER ? (long long)s.list[idx] : idx;
-                    if constexpr (is_multi(MEASURE)) {
-                        RowEmit emit{s, row, true};
-                        row_ascii_reg_multi<GROUPS, 8>(ra, rb, ca, cb, trans, emit);
-                    } else {
-                        PairInts ints;
-                        s.out[row] = row_ascii_reg<is_multi(MEASURE) ? 0 : MEASURE, 8>(ra, rb, ca, cb, ints, trans);
-                        if (s.dbg) store_dbg(s.dbg + row * 6, ints);
-                    }
-                    continue;
                 }
                 WarpMaxDev wm;
                 if constexpr (is_multi(MEASURE)) {
@@ -1067,14 +991,7 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
                 // b is tabled as bit planes, a is streamed -- both straight from the staged tile
                 const StagedStr A = staged_str(va, i, (uint32_t)L::off_sva, off_stage_a),
                                 B = staged_str(vb, i, (uint32_t)L::off_svb, off_stage_b);
-                PlaneTab<NBITS> ptab;
-                build_planes_staged<NBITS>(smem, B, ptab);
-                TransByBytes<SmemByteAt> trans;
-                trans.A.base = smem_u32(smem) + A.off;
-                trans.B.base = smem_u32(smem) + B.off;
-                EachByteStaged each_a{smem, A.off};
-                PrefixStaged prefix{smem, A, B};
-                multi_body<GROUPS, uint32_t>(ptab, each_a, na, nb, na == 0 || nb == 0, prefix, trans, emit);
+                row_planes_multi<GROUPS, NBITS>(StagedSrc{smem, A.off, A.len}, StagedSrc{smem, B.off, B.len}, emit);
                 continue;
             }
             if constexpr (REG) {
@@ -1084,9 +1001,10 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
                     store_settled<MEASURE>(s, GATHER ? (long long)s.list[idx] : idx, 1.0, F_EQUAL);
                     continue;
                 }
-                v = row_ascii_staged<is_multi(MEASURE) ? 0 : MEASURE, NBITS>(
-                    smem, staged_str(va, i, (uint32_t)L::off_sva, off_stage_a),
-                    staged_str(vb, i, (uint32_t)L::off_svb, off_stage_b), ints);
+                const StagedStr A = staged_str(va, i, (uint32_t)L::off_sva, off_stage_a),
+                                B = staged_str(vb, i, (uint32_t)L::off_svb, off_stage_b);
+                v = row_planes<is_multi(MEASURE) ? 0 : MEASURE, NBITS>(StagedSrc{smem, A.off, A.len},
+                                                                      StagedSrc{smem, B.off, B.len}, ints);
             } else {
                 const uint32_t or_a = load_string<WORDS, TPB>(va, stage_a, store.wa_);
                 const uint32_t or_b = load_string<WORDS, TPB>(vb, stage_b, store.wb_);
