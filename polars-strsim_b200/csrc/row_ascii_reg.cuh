@@ -1,16 +1,18 @@
-// row_ascii_reg.cuh -- one ASCII pair, strings and position masks entirely in REGISTERS.
+// row_ascii_reg.cuh -- the PLANE PATH: one pair of strings of one-byte characters (ASCII, or Latin-1 after
+// transcoding), position masks computed from bit planes, no table.
 //
 // The table-driven path of row_short.cuh keeps a 32..128-entry position-mask table and a copy of the
-// pair per thread in shared memory; profiles show that this shared memory is what limits the resident
-// warps and that its load/store traffic keeps the LSU half busy.  For ASCII pairs of at most 32 bytes
-// this variant needs neither:
-//   * the two strings live in 2 x 8 registers (all loops are fully unrolled, indices are static);
+// pair per thread in shared memory; profiles showed that this shared memory limited the resident warps
+// and that its load/store traffic kept the LSU half busy.  For strings of at most 32 characters:
 //   * instead of table[c], the position mask of a character is computed from BIT PLANES of the
 //     tabled string: plane k holds bit k of every character (bit i of B[k] = bit k of char i), and
 //         Eq(c) = valid & ~( OR_k ( B[k] ^ S_k(c) ) ),   S_k(c) = all-ones if bit k of c is set.
-//     The seven S_k come from two multiplies that park bit k in the sign bit of some byte, and one
+//     The S_k come from two multiplies that park bit k in the sign bit of some byte, and one
 //     byte-permute with sign replication each (PRMT); with the column statistics proving a 32- or
-//     64-code-point alphabet block only 5 or 6 planes are needed.
+//     64-code-point alphabet block only 5 or 6 planes are needed, 7 for any ASCII, 8 for Latin-1;
+//   * the strings are read where they lie, through a "source" (second half of this file): the tabled
+//     one becomes planes word by word, the streamed one is consumed byte by byte -- nothing is copied
+//     into registers.
 // Arithmetic and row rules are those of row_short.cuh (same step functors, same f64 formulas).
 #pragma once
 #include "row_short.cuh"
@@ -60,185 +62,6 @@ SS_HD void planes_add_word(PlaneTab<NBITS>& tab, uint32_t word, int w) {
         const uint32_t prod = (word & (0x01010101u << k)) * (0x10204080u >> k);
         tab.B[k] |= w == 7 ? (prod & 0xF0000000u) : ((prod >> (28 - 4 * w)) & (0xFu << (4 * w)));
     }
-}
-
-// bit planes of the first m characters of P (zero padded words)
-template <int NBITS>
-SS_HD void build_planes(const uint32_t (&P)[REG_WORDS], int m, PlaneTab<NBITS>& tab) {
-#pragma unroll
-    for (int k = 0; k < NBITS; k++) tab.B[k] = 0u;
-#pragma unroll
-    for (int w = 0; w < REG_WORDS; w++) {
-        if (4 * w >= m) break;
-        planes_add_word<NBITS>(tab, P[w], w);
-    }
-    tab.valid = m >= 32 ? 0xFFFFFFFFu : ((1u << m) - 1u);
-}
-
-// applies f to the first n bytes of a register-resident string.  The loop over words is ROLLED: the
-// working copy is rotated down one register per word, so the body of f exists four times in the code
-// instead of 32 times -- the fully unrolled form made the fused kernel 112 KB of SASS and a fifth of
-// its stall samples were instruction-cache misses (profiles/r1_ncu_fused_C2.md).
-template <class F>
-SS_HD void for_each_byte_reg(const uint32_t (&W)[REG_WORDS], int n, F& f) {
-    uint32_t r[REG_WORDS];
-#pragma unroll
-    for (int w = 0; w < REG_WORDS; w++) r[w] = W[w];
-    int left = n;
-#pragma unroll 1
-    for (; left >= 4; left -= 4) {
-        const uint32_t word = r[0];
-#pragma unroll
-        for (int w = 0; w + 1 < REG_WORDS; w++) r[w] = r[w + 1];
-        f(word & 0xFFu);
-        f((word >> 8) & 0xFFu);
-        f((word >> 16) & 0xFFu);
-        f(word >> 24);
-    }
-    uint32_t word = r[0];  // the 1..3 bytes of the tail, one at a time
-#pragma unroll 1
-    for (; left > 0; left--) {
-        f(word & 0xFFu);
-        word >>= 8;
-    }
-}
-
-struct EachByteReg {
-    const uint32_t (&W)[REG_WORDS];
-    SS_HD explicit EachByteReg(const uint32_t (&w)[REG_WORDS]) : W(w) {}
-    template <class F>
-    SS_HD void operator()(int n, F& f) const {
-        for_each_byte_reg(W, n, f);
-    }
-};
-
-// a, b: zero-padded little-endian words; na, nb <= 32 bytes, every byte < 0x80 and (for NBITS < 7)
-// inside one aligned block of 2^NBITS code points.
-template <int MEASURE, int NBITS, class Trans = TransByPass>
-SS_HD double row_ascii_reg(const uint32_t (&a)[REG_WORDS], const uint32_t (&b)[REG_WORDS], int na, int nb,
-                           PairInts& out, const Trans& trans_count = Trans()) {
-    out.flag = F_GENERAL;
-    out.la = out.lb = out.x0 = out.x1 = out.x2 = 0;
-    bool equal = na == nb;
-    if (equal) {
-        uint32_t diff = 0;
-#pragma unroll
-        for (int w = 0; w < REG_WORDS; w++) diff |= a[w] ^ b[w];
-        equal = diff == 0u;
-    }
-    if (equal) {  // strsim.rs:128,182,288,324
-        out.flag = F_EQUAL;
-        return 1.0;
-    }
-    if (MEASURE != LEVENSHTEIN && (na == 0 || nb == 0)) {  // strsim.rs:184,290,326
-        out.flag = F_ONE_EMPTY;
-        return 0.0;
-    }
-    const int la = na, lb = nb;
-    out.la = la;
-    out.lb = lb;
-    constexpr bool IS_JARO = MEASURE == JARO || MEASURE == JARO_WINKLER;
-    if (IS_JARO && la == 1 && lb == 1) {  // strsim.rs:197
-        out.flag = F_SINGLE_CHAR;
-        return 0.0;
-    }
-    typedef PlaneTab<NBITS> Tab;
-    Tab tab;
-    double v;
-    if (MEASURE == LEVENSHTEIN) {
-        // the shorter string is tabled; the longer one is streamed (the distance is symmetric)
-        const bool table_b = lb <= la;
-        uint32_t P[REG_WORDS], X[REG_WORDS];
-#pragma unroll
-        for (int w = 0; w < REG_WORDS; w++) {
-            P[w] = table_b ? b[w] : a[w];
-            X[w] = table_b ? a[w] : b[w];
-        }
-        const int m = table_b ? lb : la, n = table_b ? la : lb;
-        int d = n;
-        if (m > 0) {
-            build_planes<NBITS>(P, m, tab);
-            MyersStep<uint32_t, Tab> step(tab);
-            for_each_byte_reg(X, n, step);
-            d = step.distance(m, n);
-        }
-        out.x0 = d;
-        v = lev_value<true>(d, la, lb);
-    } else {
-        build_planes<NBITS>(b, lb, tab);
-        if (IS_JARO) {
-            const int mx = la > lb ? la : lb;
-            const int bound = mx / 2 - 1;  // strsim.rs:200
-            const int outer = la < lb + bound ? la : lb + bound;
-            JaroMatchStep<uint32_t, Tab> match(tab, lb, bound);
-            for_each_byte_reg(a, outer, match);
-            match.finish(outer);
-            const int t = match.m > 0 ? trans_count(tab, EachByteReg(a), outer, match.flag_a, match.flag_b) : 0;
-            out.x0 = match.m;
-            out.x1 = t;
-            v = match.m == 0 ? 0.0 : jaro_value<true>(match.m, t, la, lb);
-            if (MEASURE == JARO_WINKLER && v > 0.7) {  // strsim.rs:260-267
-                const uint32_t x = a[0] ^ b[0];
-                int lim = la < lb ? la : lb;
-                if (lim > 4) lim = 4;
-                int l = 0;
-                while (l < lim && ((x >> (8 * l)) & 0xFFu) == 0) l++;
-                out.x2 = l;
-                v = winkler_value(v, l);
-            }
-        } else {
-            MultisetStep<uint32_t, Tab> ms(tab, lb);
-            for_each_byte_reg(a, la, ms);
-            ms.finish();
-            out.x0 = ms.inter;
-            if (MEASURE == JACCARD) {
-                out.x1 = la + lb - ms.inter;
-                v = jaccard_value<true>(ms.inter, la + lb - ms.inter);
-            } else {
-                out.x1 = la + lb;
-                v = dice_value<true>(ms.inter, la + lb);
-            }
-        }
-    }
-    return v;
-}
-
-// ---- fused evaluation of several measures (row_short.cuh: multi_body) ---------------------------------
-struct PrefixReg {  // common prefix of two ASCII strings, capped at 4 (strsim.rs:261-266)
-    uint32_t x;
-    int lim;
-    SS_HD int operator()() const {
-        int l = 0;
-        while (l < lim && ((x >> (8 * l)) & 0xFFu) == 0) l++;
-        return l;
-    }
-};
-
-template <int GROUPS, int NBITS, class Trans, class Emit>
-SS_HD void row_ascii_reg_multi(const uint32_t (&a)[REG_WORDS], const uint32_t (&b)[REG_WORDS], int na, int nb,
-                               const Trans& trans_count, Emit& emit) {
-    bool equal = na == nb;
-    if (equal) {
-        uint32_t diff = 0;
-#pragma unroll
-        for (int w = 0; w < REG_WORDS; w++) diff |= a[w] ^ b[w];
-        equal = diff == 0u;
-    }
-    if (equal) {  // strsim.rs:128,182,288,324
-        PairInts o;
-        o.flag = F_EQUAL;
-        o.la = o.lb = o.x0 = o.x1 = o.x2 = 0;
-        emit_groups<GROUPS>(emit, 1.0, o);
-        return;
-    }
-    PlaneTab<NBITS> tab;
-    build_planes<NBITS>(b, nb, tab);
-    EachByteReg each_a(a);
-    PrefixReg prefix;
-    prefix.x = a[0] ^ b[0];
-    prefix.lim = na < nb ? na : nb;
-    if (prefix.lim > 4) prefix.lim = 4;
-    multi_body<GROUPS, uint32_t>(tab, each_a, na, nb, na == 0 || nb == 0, prefix, trans_count, emit);
 }
 
 // ---- Latin-1 rows of a mixed-script column ------------------------------------------------------------

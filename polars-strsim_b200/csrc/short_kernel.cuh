@@ -156,7 +156,8 @@ struct DevStore {
     __device__ __forceinline__ uint32_t wb(int k) const { return wb_[k * TPB]; }
 };
 
-// REG: register-resident ASCII path (row_ascii_reg.cuh) -- no table, no slabs in shared memory
+// REG: plane path for ASCII-only columns (row_ascii_reg.cuh), strings read from the staged tile -- no table,
+// no slabs in shared memory
 // UREG: register-compare path for any script (row_unicode_reg.cuh) -- no table, slabs only
 template <class M, int TPB, int RPT, int T, bool REG = false, bool UREG = false>
 struct ShortLayout {
@@ -218,34 +219,6 @@ __device__ __forceinline__ uint32_t load_string(const uint4& v, const unsigned c
         }
     }
     return acc;
-}
-
-// Same as load_string, but into registers (static indices: the loop is fully unrolled).
-__device__ __forceinline__ void load_string_reg(const uint4& v, const unsigned char* stage,
-                                                uint32_t (&r)[REG_WORDS]) {
-    const int len = (int)v.x;
-#pragma unroll
-    for (int w = 0; w < REG_WORDS; w++) r[w] = 0u;
-    if (len <= 12) {
-        r[0] = v.y & byte_mask(len);
-        r[1] = v.z & byte_mask(len - 4 < 0 ? 0 : len - 4);
-        r[2] = v.w & byte_mask(len - 8 < 0 ? 0 : len - 8);
-    } else {
-        const uint32_t soff = v.y;
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(stage) + (soff >> 2);
-        const int sh = (int)(soff & 3) * 8;
-        uint32_t lo = src[0];
-#pragma unroll
-        for (int w = 0; w < REG_WORDS; w++) {
-            if (4 * w < len) {
-                const uint32_t hi = src[w + 1];
-                uint32_t word = __funnelshift_r(lo, hi, sh);
-                lo = hi;
-                if (4 * w + 4 > len) word &= byte_mask(len - 4 * w);
-                r[w] = word;
-            }
-        }
-    }
 }
 
 // number of characters (bytes that are not UTF-8 continuation bytes) of a staged string; `wide` collects

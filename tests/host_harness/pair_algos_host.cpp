@@ -100,24 +100,6 @@ struct HostByteAt {  // stands in for short_kernel.cuh's SmemByteAt
     const uint8_t* p;
     uint32_t operator()(int i) const { return p[i]; }
 };
-// `by_bytes`: transposition count by direct byte fetches (the kernels' way) or by the second pass
-template <int MEASURE>
-static double reg_dispatch(int nbits, const uint32_t (&a)[REG_WORDS], const uint32_t (&b)[REG_WORDS], int na, int nb,
-                           PairInts& pi, bool by_bytes = true) {
-    TransByBytes<HostByteAt> tb{{reinterpret_cast<const uint8_t*>(a)}, {reinterpret_cast<const uint8_t*>(b)}};
-    if (!by_bytes) {
-        switch (nbits) {
-            case 5: return row_ascii_reg<MEASURE, 5>(a, b, na, nb, pi);
-            case 6: return row_ascii_reg<MEASURE, 6>(a, b, na, nb, pi);
-            default: return row_ascii_reg<MEASURE, 7>(a, b, na, nb, pi);
-        }
-    }
-    switch (nbits) {
-        case 5: return row_ascii_reg<MEASURE, 5>(a, b, na, nb, pi, tb);
-        case 6: return row_ascii_reg<MEASURE, 6>(a, b, na, nb, pi, tb);
-        default: return row_ascii_reg<MEASURE, 7>(a, b, na, nb, pi, tb);
-    }
-}
 typedef SlabSrc<1, HostByteAt> HostSrc;
 static HostSrc host_src(const uint32_t* w, int len) { return HostSrc{w, len, HostByteAt{reinterpret_cast<const uint8_t*>(w)}}; }
 template <int MEASURE>
@@ -140,7 +122,7 @@ extern "C" int algos_batch_reg(int measure, int nbits, int64_t n, const uint8_t*
         std::memcpy(b, bd + bo[r], nb);
         PairInts pi;
         double v;
-        if (r % 3 != 0) {
+        {
             // the kernels' form: strings behind sources, pair known not to be byte-equal (row_planes)
             const bool equal = na == nb && std::memcmp(a, b, sizeof a) == 0;
             if (equal) {
@@ -158,13 +140,6 @@ extern "C" int algos_batch_reg(int measure, int nbits, int64_t n, const uint8_t*
                     default: v = planes_dispatch<4>(nbits, a, b, na, nb, pi); break;
                 }
             }
-        } else
-        switch (measure) {
-            case 0: v = reg_dispatch<0>(nbits, a, b, na, nb, pi); break;
-            case 1: v = reg_dispatch<1>(nbits, a, b, na, nb, pi, (r & 1) != 0); break;
-            case 2: v = reg_dispatch<2>(nbits, a, b, na, nb, pi, (r & 1) != 0); break;
-            case 3: v = reg_dispatch<3>(nbits, a, b, na, nb, pi); break;
-            default: v = reg_dispatch<4>(nbits, a, b, na, nb, pi); break;
         }
         values[r] = v;
         int* o = ints + 6 * r;
@@ -219,29 +194,20 @@ struct HostEmit {
 template <int GROUPS>
 static void reg_multi_dispatch(int nbits, uint32_t (&a)[REG_WORDS], uint32_t (&b)[REG_WORDS], int na,
                                int nb, HostEmit& e) {
-    if (e.r % 3 != 0) {  // the kernels' form (row_planes_multi over sources), equal pairs settled before
-        if (na == nb && std::memcmp(a, b, sizeof a) == 0) {
-            const PairInts o = {F_EQUAL, 0, 0, 0, 0, 0};
-            emit_groups<GROUPS>(e, 1.0, o);
-            return;
-        }
-        std::memset(reinterpret_cast<uint8_t*>(a) + na, 0xA5, sizeof a - na);
-        std::memset(reinterpret_cast<uint8_t*>(b) + nb, 0x5A, sizeof b - nb);
-        const HostSrc A = host_src(a, na), B = host_src(b, nb);
-        switch (nbits) {
-            case 5: row_planes_multi<GROUPS, 5>(A, B, e); break;
-            case 6: row_planes_multi<GROUPS, 6>(A, B, e); break;
-            case 7: row_planes_multi<GROUPS, 7>(A, B, e); break;
-            default: row_planes_multi<GROUPS, 8>(A, B, e); break;
-        }
+    // the kernels' form (row_planes_multi over sources), equal pairs settled before
+    if (na == nb && std::memcmp(a, b, sizeof a) == 0) {
+        const PairInts o = {F_EQUAL, 0, 0, 0, 0, 0};
+        emit_groups<GROUPS>(e, 1.0, o);
         return;
     }
-    TransByBytes<HostByteAt> tb{{reinterpret_cast<const uint8_t*>(a)}, {reinterpret_cast<const uint8_t*>(b)}};
+    std::memset(reinterpret_cast<uint8_t*>(a) + na, 0xA5, sizeof a - na);
+    std::memset(reinterpret_cast<uint8_t*>(b) + nb, 0x5A, sizeof b - nb);
+    const HostSrc A = host_src(a, na), B = host_src(b, nb);
     switch (nbits) {
-        case 5: row_ascii_reg_multi<GROUPS, 5>(a, b, na, nb, tb, e); break;
-        case 6: row_ascii_reg_multi<GROUPS, 6>(a, b, na, nb, tb, e); break;
-        case 7: row_ascii_reg_multi<GROUPS, 7>(a, b, na, nb, tb, e); break;
-        default: row_ascii_reg_multi<GROUPS, 8>(a, b, na, nb, tb, e); break;
+        case 5: row_planes_multi<GROUPS, 5>(A, B, e); break;
+        case 6: row_planes_multi<GROUPS, 6>(A, B, e); break;
+        case 7: row_planes_multi<GROUPS, 7>(A, B, e); break;
+        default: row_planes_multi<GROUPS, 8>(A, B, e); break;
     }
 }
 
