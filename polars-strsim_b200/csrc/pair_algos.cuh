@@ -203,6 +203,16 @@ struct ClearTable {
     SS_HD void operator()(uint32_t c) { tab(c) = M(0); }
 };
 
+// (x << 1) | (top bit of src): one funnel shift
+SS_HD uint32_t shift_in_top(uint32_t x, uint32_t src) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(src, x, 1);
+#else
+    return (x << 1) | (src >> 31);
+#endif
+}
+SS_HD uint64_t shift_in_top(uint64_t x, uint64_t src) { return (x << 1) | (src >> 63); }
+
 // One Myers / Hyyro column per text character.  The distance is read off the final vertical delta
 // vectors: D[m][n] = D[0][n] + sum_{i<m} (Pv_i - Mv_i) with D[0][n] = n, so no per-step score update.
 template <class M, class Tab>
@@ -216,7 +226,7 @@ struct MyersStep {
         const M Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
         M Ph = Mv | ~(Xh | Pv);
         M Mh = Pv & Xh;
-        Ph = Ph + Ph + M(1);  // (Ph << 1) | 1 as one three-input add
+        Ph = shift_in_top(Ph, ~M(0));  // (Ph << 1) | 1: one funnel shift
         Mh = Mh + Mh;
         Pv = Mh | ~(Xv | Ph);
         Mv = Ph & Xv;
@@ -262,15 +272,20 @@ SS_HD int flo(uint64_t x) {
 #endif
 }
 
-// (x << 1) | (top bit of src): one funnel shift
-SS_HD uint32_t shift_in_top(uint32_t x, uint32_t src) {
+// below = x - 1 and reg = (reg << 1) | (x != 0), the latter through the carry of the former:
+// x + 0xFFFFFFFF carries out exactly when x >= 1 (add.cc / addc, two instructions)
+SS_HD void dec_and_shift_in(uint32_t x, uint32_t& below, uint32_t& reg) {
 #if defined(__CUDA_ARCH__)
-    return __funnelshift_l(src, x, 1);
+    asm("add.cc.u32 %0, %2, 0xFFFFFFFF;\n\taddc.u32 %1, %1, %1;" : "=r"(below), "+r"(reg) : "r"(x));
 #else
-    return (x << 1) | (src >> 31);
+    below = x - 1u;
+    reg = (reg << 1) | (x != 0u ? 1u : 0u);
 #endif
 }
-SS_HD uint64_t shift_in_top(uint64_t x, uint64_t src) { return (x << 1) | (src >> 63); }
+SS_HD void dec_and_shift_in(uint64_t x, uint64_t& below, uint64_t& reg) {
+    below = x - 1ull;
+    reg = (reg << 1) | (x != 0ull ? 1ull : 0ull);
+}
 
 // The match window [i-bound, i+bound] of step i (strsim.rs:209-210) as a mask over the positions of b.
 // Generic form: it grows at the top every step and starts dropping its lowest bit once i > bound.
@@ -317,10 +332,9 @@ struct JaroMatchStep {
     SS_HD void operator()(uint32_t c) { step(tab(c)); }
     SS_HD void step(const M Eq) {
         const M cand = Eq & window.get() & avail;
-        const M neg = M(0) - cand;
-        avail = avail & ~(cand & neg);  // the lowest candidate is taken (strsim.rs:211-217)
-        const M any = cand | neg;       // top bit set iff there is a candidate
-        rev_a = shift_in_top(rev_a, any);
+        M below;  // cand - 1; the borrow-free carry of that subtraction says "there is a candidate"
+        dec_and_shift_in(cand, below, rev_a);
+        avail = avail & ~(cand & ~below);  // the lowest candidate is taken (strsim.rs:211-217)
         window.next();
     }
     // steps = number of characters of a that went through step()
