@@ -916,11 +916,18 @@ static int launch_general(ThreadCtx& ctx, const SegArgs& args, long long rows, c
     static const bool latin = !(getenv("STRSIM_B200_LATIN") && !strcmp(getenv("STRSIM_B200_LATIN"), "0"));
     SegArgs a = args;
     a.skip_latin = 0;
-    // Two launches read the views and stage the payload twice: that pays when (nearly) all pairs are
-    // Latin-1 (L1 workload: 1.56 ms vs 2.23 ms per 10 M rows x 5 measures) and costs 6 % on C3, where
-    // 30 % of the rows are CJK -- so once a segment of this column pair has shown a substantial share of
-    // wide pairs, the following segments / slices / calls go to the register-compare kernel alone.
-    const bool mostly_latin = !(g_wide_share && *g_wide_share > 0.15f);
+    // The first launch (ULAT) reads every row, computes the Latin-1 pairs and LISTS the others; the second
+    // one (UREG) gathers the listed rows only.  Measured per 50 M rows x 5 measures on C3 (30 % of the rows
+    // CJK): 8.9 ms against 10.2 ms for the register-compare kernel alone (single measures: within 3 % either
+    // way, Jaro 13 % faster); L1 (no wide pairs, one launch): 1.49 ms vs 2.23 ms per 10 M rows.  When most
+    // pairs are wide the first launch is a wasted pass: once a segment of this column pair has shown more
+    // than half of its pairs wide, the following segments / slices / calls go to the register-compare
+    // kernel alone.
+    static const float wide_limit = [] {
+        const char* e = getenv("STRSIM_B200_WIDE_SHARE");  // tuning knob: share of wide pairs above which one launch serves all
+        return e && *e ? (float)atof(e) : 0.5f;
+    }();
+    const bool mostly_latin = !(g_wide_share && *g_wide_share > wide_limit);
     if (!latin || !mostly_latin)
         return launch_short<uint32_t, MEASURE, 256, RPT_WIDE, false, 128, false, false, true>(ctx, a, rows, st);
     int rc = launch_short<uint32_t, MEASURE, 256, RPT_LATIN, false, 128, false, false, true, true>(ctx, a, rows, st);
@@ -930,8 +937,13 @@ static int launch_general(ThreadCtx& ctx, const SegArgs& args, long long rows, c
     CUDA_TRY(cudaStreamSynchronize(st));
     if (g_wide_share && rows > 0) *g_wide_share = (float)ctx.h_ovf->nwide / (float)rows;
     if (ctx.h_ovf->nwide == 0) return STRSIM_OK;
+    // the pairs the first launch listed: gather mode over that list only (null rows and the overflow
+    // lists were settled by the first launch: skip_latin)
     a.skip_latin = 1;
-    return launch_short<uint32_t, MEASURE, 256, RPT_WIDE, false, 128, false, false, true>(ctx, a, rows, st);
+    a.list = args.listwide;
+    a.list_count = &ctx.d_ovf->nwide;
+    a.n = ctx.h_ovf->nwide;
+    return launch_short<uint32_t, MEASURE, 256, RPT_WIDE, true, 128, false, false, true>(ctx, a, (long long)ctx.h_ovf->nwide, st);
 }
 
 // Which instantiation of the fused kernel serves a segment (see DevStore): decided from the union of
@@ -1178,10 +1190,11 @@ static bool force_generic_rows() {
 
 // overflow lists (worst case every row) and counters for one segment
 static int prepare_segment(ThreadCtx& ctx, SegArgs& args, int stage32, int64_t seg_rows, cudaStream_t st) {
-    int rc = ws_reserve(ctx.lists, 2 * sizeof(unsigned int) * (size_t)seg_rows + 64);
+    int rc = ws_reserve(ctx.lists, 3 * sizeof(unsigned int) * (size_t)seg_rows + 64);
     if (rc) return rc;
     args.list64 = static_cast<unsigned int*>(ctx.lists.ptr);
     args.listlong = args.list64 + seg_rows;
+    args.listwide = args.listlong + seg_rows;
     args.ovf = ctx.d_ovf;
     CUDA_TRY(cudaMemsetAsync(ctx.d_ovf, 0, sizeof(Overflow), st));
     args.stage_bytes = stage32;

@@ -67,6 +67,7 @@ struct SegArgs {
     Overflow* ovf;
     unsigned int* list64;
     unsigned int* listlong;
+    unsigned int* listwide;  // ULAT launch: the pairs it leaves to the register-compare launch (count: ovf->nwide)
     int stage_bytes;  // capacity of each column's stage area (multiple of 16)
     // general columns are served by two launches (ULAT, then UREG): the second one skips the Latin-1
     // pairs and leaves null rows and the overflow lists alone
@@ -813,8 +814,15 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
                 // each of the two launches over a general column takes one class; the first one counts what
                 // it leaves to the second (none in a Latin-1 column: the host then skips that launch)
                 if (ULAT && wide != 0u) {
+                    // listed (one atomic per warp), so that the second launch gathers these rows only
                     const unsigned m = __activemask();
-                    if ((int)__ffs(m) - 1 == lane) atomicAdd(&s.ovf->nwide, (unsigned)__popc(m));
+                    const int leader = (int)__ffs(m) - 1;
+                    unsigned base = 0;
+                    if (lane == leader) base = atomicAdd(&s.ovf->nwide, (unsigned)__popc(m));
+                    base = __shfl_sync(m, base, leader);
+                    const long long idx = tile0 + i;
+                    s.listwide[base + __popc(m & ((1u << lane) - 1u))] =
+                        (unsigned int)(GATHER ? (long long)s.list[idx] : idx);
                     continue;
                 }
                 if (!ULAT && s.skip_latin && wide == 0u) continue;
