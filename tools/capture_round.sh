@@ -12,7 +12,7 @@ python bench.py > $O/${R}_bench_C2.json 2> $O/bench_err.log
 python bench.py --impl reference --steps 3 --warmup 1 > $O/${R}_bench_C2_reference.json 2>> $O/bench_err.log
 python bench.py --workload C3 --steps 5 > $O/${R}_bench_C3_100M.json 2>> $O/bench_err.log
 python bench.py --workload C4 --steps 3 --no-e2e > $O/${R}_bench_C4_1M.json 2>> $O/bench_err.log
-python bench.py --workload C5 --rows 50000000 --steps 5 --no-cpu-baseline > $O/${R}_bench_C5_50M.json 2>> $O/bench_err.log
+python bench.py --workload C5 --steps 5 --no-cpu-baseline > $O/${R}_bench_C5_125M.json 2>> $O/bench_err.log
 python bench.py --workload L1 --steps 10 --no-cpu-baseline --no-e2e > $O/${R}_bench_L1.json 2>> $O/bench_err.log
 # end-to-end timeline of one host call (upload landed / kernels / download done per row slice)
 STRSIM_B200_TRACE=1 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>&1 >/dev/null | grep "strsim trace" | tail -6 > $O/${R}_e2e_timeline_C2.txt
