@@ -217,6 +217,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: polars-strsim_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     _native.set_device(local)
+    # several ranks on one host: keep this rank's generator threads and pinned buffers on the NUMA node of
+    # its GPU, so that its copies do not cross the socket interconnect
+    numa_node = _native.bind_thread_near_device(local) if world > 1 else -1
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -400,6 +403,7 @@ def main():
         "dtype": "u8/u32 codepoints, u32/u64 bit-vectors, f64 results", "data": "synthetic",
         "config": {"workload": wl["desc"], "rows_per_gpu": n, "measures": list(measures),
                    "parallelism": f"row-range x{world}, no collective",
+                   "host_numa_node_rank0": numa_node,
                    "l2": "inputs per launch (views+payload %.0f MB) exceed the 126 MB L2; no flush needed" % (alg_bytes / 1e6)},
         "per_measure": per_measure, "roofline": roofline, "clocks": clocks, "gpu_launches": launches,
         "overflow_rows_last_call": {"to_64bit_kernel": overflow[0], "to_long_kernel": overflow[1]},

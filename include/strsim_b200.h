@@ -180,6 +180,12 @@ STRSIM_API int strsim_b200_set_device(int device);
 STRSIM_API int strsim_b200_device_count(void);
 /* device the calling thread's calls use right now (-1: no usable device) */
 STRSIM_API int strsim_b200_get_device(void);
+/* Multi-GPU hosts: binds the calling thread (and the threads and pinned buffers it creates from now on,
+ * first-touch) to the CPUs of the NUMA node the device's PCIe link hangs off, so that host<->device
+ * copies do not cross the socket interconnect.  Returns the node, or -1 when there is nothing to do
+ * (one node, no topology information, or the node's CPUs are outside the thread's affinity mask).
+ * The reference has no counterpart: rayon's pool is node-agnostic (strsim.rs:72-73). */
+STRSIM_API int strsim_b200_bind_thread_near_device(int device);
 /* Polars plugin calls keep recently uploaded input columns in HBM (and hold the Arrow arrays they own
  * alive, so that an address can only ever mean the same bytes): at most STRSIM_B200_CACHE_BYTES of
  * HBM (default 8 GiB), 8 columns, dropped after 30 s without use; STRSIM_B200_CACHE=0 disables it.

@@ -5,6 +5,8 @@
 // No CPU fallback: every path ends in the CUDA kernels of short_kernel.cuh / generic_kernel.cuh /
 // long_lev_kernel.cuh, and fails with STRSIM_ERR_CUDA when no device is usable.
 #include <cuda_runtime.h>
+#include <ctype.h>
+#include <sched.h>
 
 #include <atomic>
 #include <condition_variable>
@@ -1488,6 +1490,50 @@ int strsim_b200_set_device(int device) {
     g_requested_device = device;
     ThreadCtx* c;
     return ensure_ctx(&c);
+}
+
+int strsim_b200_bind_thread_near_device(int device) {
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, (int)sizeof bus, device) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    for (char* p = bus; *p; p++) *p = (char)tolower((unsigned char)*p);
+    char path[160];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    int node = -1;
+    if (FILE* f = fopen(path, "r")) {
+        if (fscanf(f, "%d", &node) != 1) node = -1;
+        fclose(f);
+    }
+    if (node < 0) return -1;
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    FILE* f = fopen(path, "r");
+    if (!f) return -1;
+    cpu_set_t have, want;
+    CPU_ZERO(&want);
+    if (sched_getaffinity(0, sizeof have, &have) != 0) {
+        fclose(f);
+        return -1;
+    }
+    int lo, hi, any = 0;  // "0-15,32-47"
+    while (fscanf(f, "%d", &lo) == 1) {
+        hi = lo;
+        int c = fgetc(f);
+        if (c == '-') {
+            if (fscanf(f, "%d", &hi) != 1) break;
+            c = fgetc(f);
+        }
+        for (int cpu = lo; cpu <= hi && cpu < CPU_SETSIZE; cpu++)
+            if (CPU_ISSET(cpu, &have)) {
+                CPU_SET(cpu, &want);
+                any++;
+            }
+        if (c != ',') break;
+    }
+    fclose(f);
+    if (!any || sched_setaffinity(0, sizeof want, &want) != 0) return -1;
+    return node;
 }
 
 int strsim_b200_device_count(void) {

@@ -268,6 +268,12 @@ def set_device(device: int):
     _check(lib().strsim_b200_set_device(device))
 
 
+def bind_thread_near_device(device: int) -> int:
+    """Binds the calling thread (threads and pinned buffers created from now on follow) to the NUMA node
+    of the device's PCIe link; -1 = nothing to do."""
+    return int(lib().strsim_b200_bind_thread_near_device(device))
+
+
 def kernel_launches() -> int:
     return int(lib().strsim_b200_kernel_launches())
 
