@@ -820,3 +820,23 @@ def test_concurrent_calls_from_engine_threads(native, oracle):
     for th in threads:
         th.join()
     assert not errors, errors
+
+
+def test_edge_rows_of_the_plane_kernels(native, oracle):
+    """Rows that sit on the special cases of the plane kernels' sort key and sources: NUL and control
+    characters (a zero byte equals the zero padding, so only the lengths may tell them apart), columns in
+    which every row is byte-equal (all rows in the 'equal' bucket), an empty string against a non-empty
+    one in ASCII and in Latin-1 columns (key of the empty streamed string next to the equal bucket),
+    strings of exactly 32 one-byte characters, and prefixes that differ only past the shorter string."""
+    cases = [
+        (["a\x00b", "\x00", "\x00\x00", "ab\x00", "\x00abc", "abc", ""], ["a\x00c", "", "\x00", "ab", "\x00abd", "abc\x00", "\x00"]),
+        (["same", "same", "", "x" * 32, "yy"] * 300, ["same", "same", "", "x" * 32, "yy"] * 300),
+        (["", "abc", "", "é", "", "ab"] * 50, ["abc", "", "é", "", "", "ab"] * 50),
+        (["é" * 16, "a" * 32, "ab" * 16, "é" * 16 + "a", "z" * 31 + "é"], ["é" * 15 + "e", "a" * 31 + "b", "ba" * 16, "é" * 16, "z" * 32]),
+        (["abcd", "abc", "abcde", "ab"], ["abc", "abcd", "abcdx", "abxx"]),
+    ]
+    for a, b in cases:
+        for m in oracle.MEASURES:
+            check(native, oracle, m, a, b)
+        check_multi(native, oracle, list(range(5)), a, b)
+        check_multi(native, oracle, [2, 4], a, b)
