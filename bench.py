@@ -45,6 +45,9 @@ WORKLOADS = {
     "L1": dict(config=6, rows=10_000_000, measures=MEASURES,
                desc="L1 (not a BASELINE config): the Latin rows of C3 alone -- names of 4-24 codepoints, 15 % of the "
                     "characters from U+00C0-U+00FF, no nulls"),
+    "M1": dict(config=7, rows=10_000_000, measures=MEASURES,
+               desc="M1 (not a BASELINE config): medium ASCII strings of 20-60 characters (addresses) -- a third of the "
+                    "rows fit the 32-byte kernels, the rest run the 64-bit instantiation"),
     "C5": dict(config=5, rows=125_000_000, measures=("jaro_winkler", "sorensen_dice"),
                desc="C5: record-linkage pairs (C2 generator, seed 0xC5), Jaro-Winkler + Sorensen-Dice"),
 }

@@ -140,6 +140,9 @@ static void gen_row(int config, uint64_t seed, int64_t row, double null_p, rowbu
         int script = S_ASCII, lo = 4, hi = 24;
         if (config == 6) {
             script = S_LATIN; /* the Latin rows of C3 alone: a column of names with diacritics */
+        } else if (config == 7) {
+            lo = 20; /* medium ASCII strings (street addresses): most rows leave the 32-byte kernels */
+            hi = 60;
         } else if (config == 3) {
             if (rndf(&r) < 0.7) {
                 script = S_LATIN;

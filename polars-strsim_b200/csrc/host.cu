@@ -1213,9 +1213,25 @@ static int read_overflow(ThreadCtx& ctx, Overflow* ov, cudaStream_t st, bool fir
     return STRSIM_OK;
 }
 
+// rows of 33..64 bytes of ASCII-only columns: the plane path with 64-bit masks (two registers per plane),
+// gather mode over list64; tiles of 128 x 3 rows with a worst-case stage area (every listed string is
+// out of line).  MEASURE may be a fused set (MULTI_BASE + groups).  Medium ASCII strings (M1 workload,
+// 20-60 characters, 73 % of the rows on this list): 22.8 -> see profiles/r1_bench_M1.json ms per 10 M rows.
+template <int MEASURE>
+static int finish_64_planes(ThreadCtx& ctx, const SegArgs& args, const Overflow& ov, cudaStream_t st) {
+    SegArgs a64 = args;
+    a64.list = args.list64;
+    a64.list_count = &ctx.d_ovf->n64;
+    a64.n = ov.n64;
+    a64.stage_bytes = 64 * 128 * 3;
+    return launch_short<uint64_t, MEASURE, 128, 3, true, 128, true, true>(ctx, a64, ov.n64, st);
+}
+
 // rows of 33..64 bytes -> 64-bit instantiation in gather mode
 template <int MEASURE>
-static int finish_64(ThreadCtx& ctx, const SegArgs& args, const Overflow& ov, cudaStream_t st) {
+static int finish_64(ThreadCtx& ctx, const SegArgs& args, const Overflow& ov, cudaStream_t st, bool ascii = false) {
+    static const bool planes64 = !(getenv("STRSIM_B200_PLANES64") && !strcmp(getenv("STRSIM_B200_PLANES64"), "0"));
+    if (ascii && planes64) return finish_64_planes<MEASURE>(ctx, args, ov, st);
     SegArgs a64 = args;
     a64.list = args.list64;
     a64.list_count = &ctx.d_ovf->n64;
@@ -1258,7 +1274,7 @@ static int run_segment(ThreadCtx& ctx, SegArgs args, Alphabet al, int stage32, i
     if (rc) return rc;
     g_last_overflow[0] += ov.n64;
     if (ov.n64 > 0) {
-        rc = finish_64<MEASURE>(ctx, args, ov, st);
+        rc = finish_64<MEASURE>(ctx, args, ov, st, al != ALPHA_GENERAL);
         if (rc) return rc;
         // rows the 64-bit kernel could not take are appended to listlong; re-read the counters
         rc = read_overflow(ctx, &ov, st, false);
@@ -1320,7 +1336,19 @@ static int run_segment_multi(ThreadCtx& ctx, SegArgs args, int groups, Alphabet 
     rc = read_overflow(ctx, &ov, st);
     if (rc) return rc;
     g_last_overflow[0] += ov.n64;
-    if (ov.n64 > 0) {
+    static const bool planes64 = !(getenv("STRSIM_B200_PLANES64") && !strcmp(getenv("STRSIM_B200_PLANES64"), "0"));
+    if (ov.n64 > 0 && al != ALPHA_GENERAL && groups >= 2 && planes64) {
+        // ASCII-only columns: ONE fused launch of the 64-bit plane path over list64
+        switch (groups) {
+            case 2: rc = finish_64_planes<MULTI_BASE + 2>(ctx, args, ov, st); break;
+            case 3: rc = finish_64_planes<MULTI_BASE + 3>(ctx, args, ov, st); break;
+            case 4: rc = finish_64_planes<MULTI_BASE + 4>(ctx, args, ov, st); break;
+            case 5: rc = finish_64_planes<MULTI_BASE + 5>(ctx, args, ov, st); break;
+            case 6: rc = finish_64_planes<MULTI_BASE + 6>(ctx, args, ov, st); break;
+            default: rc = finish_64_planes<MULTI_BASE + 7>(ctx, args, ov, st); break;
+        }
+        if (rc) return rc;
+    } else if (ov.n64 > 0) {
         for (int m = 0; m < 5; m++) {
             if (!args.outs[m]) continue;
             SegArgs am = args;
@@ -1329,6 +1357,8 @@ static int run_segment_multi(ThreadCtx& ctx, SegArgs args, int groups, Alphabet 
             rc = finish_64_any(m, ctx, am, ov, st);
             if (rc) return rc;
         }
+    }
+    if (ov.n64 > 0) {  // rows the 64-bit kernels could not take are appended to listlong: re-read the counters
         rc = read_overflow(ctx, &ov, st, false);
         if (rc) return rc;
     }

@@ -33,34 +33,48 @@ SS_HD uint32_t sign_fill_byte(uint32_t x, int byte) {  // all-ones if bit 7 of b
 #endif
 }
 
-template <int NBITS>
+// a 32-bit pattern over every 32-bit half of M
+template <class M>
+SS_HD M rep32(uint32_t s) {
+    return sizeof(M) == 4 ? (M)s : (M)(((uint64_t)s << 32) | s);
+}
+
+// M = uint32_t: strings of at most 32 characters; uint64_t: at most 64 (every plane is two registers)
+template <int NBITS, class M = uint32_t>
 struct PlaneTab {
-    uint32_t B[NBITS];
-    uint32_t valid;  // bits < m
-    SS_HD uint32_t operator()(uint32_t c) const {
+    typedef M mask_type;
+    M B[NBITS];
+    M valid;  // bits < m
+    SS_HD M operator()(uint32_t c) const {
         // u: bits 6,5,4,3 of c in the sign bits of bytes 0..3; v: bits 2,1,0 in bytes 0..2
         const uint32_t u = c * 0x10080402u, v = c * 0x00804020u;
-        uint32_t X = B[0] ^ sign_fill_byte(v, 2);
-        if (NBITS > 1) X |= B[1] ^ sign_fill_byte(v, 1);
-        if (NBITS > 2) X |= B[2] ^ sign_fill_byte(v, 0);
-        if (NBITS > 3) X |= B[3] ^ sign_fill_byte(u, 3);
-        if (NBITS > 4) X |= B[4] ^ sign_fill_byte(u, 2);
-        if (NBITS > 5) X |= B[5] ^ sign_fill_byte(u, 1);
-        if (NBITS > 6) X |= B[6] ^ sign_fill_byte(u, 0);
-        if (NBITS > 7) X |= B[7] ^ sign_fill_byte(c, 0);  // one byte per character up to U+00FF (Latin-1 rows)
+        M X = B[0] ^ rep32<M>(sign_fill_byte(v, 2));
+        if (NBITS > 1) X |= B[1] ^ rep32<M>(sign_fill_byte(v, 1));
+        if (NBITS > 2) X |= B[2] ^ rep32<M>(sign_fill_byte(v, 0));
+        if (NBITS > 3) X |= B[3] ^ rep32<M>(sign_fill_byte(u, 3));
+        if (NBITS > 4) X |= B[4] ^ rep32<M>(sign_fill_byte(u, 2));
+        if (NBITS > 5) X |= B[5] ^ rep32<M>(sign_fill_byte(u, 1));
+        if (NBITS > 6) X |= B[6] ^ rep32<M>(sign_fill_byte(u, 0));
+        if (NBITS > 7) X |= B[7] ^ rep32<M>(sign_fill_byte(c, 0));  // one byte per character up to U+00FF (Latin-1 rows)
         return ~X & valid;
+    }
+    SS_HD void set_valid(int m) {
+        valid = m >= (int)(sizeof(M) * 8) ? ~M(0) : ((M(1) << m) - M(1));
     }
 };
 
 // adds the four characters of word w (characters 4w..4w+3) to the planes
-template <int NBITS>
-SS_HD void planes_add_word(PlaneTab<NBITS>& tab, uint32_t word, int w) {
+template <int NBITS, class M>
+SS_HD void planes_add_word(PlaneTab<NBITS, M>& tab, uint32_t word, int w) {
 #pragma unroll
     for (int k = 0; k < NBITS; k++) {
         // bit k of the four bytes -> four adjacent bits (character order) in the top nibble: source bit
         // 8j+k times 2^(28-7j-k) lands on 28+j; the sixteen partial products fall on distinct bits
         const uint32_t prod = (word & (0x01010101u << k)) * (0x10204080u >> k);
-        tab.B[k] |= w == 7 ? (prod & 0xF0000000u) : ((prod >> (28 - 4 * w)) & (0xFu << (4 * w)));
+        if (sizeof(M) == 4)
+            tab.B[k] |= (M)(w == 7 ? (prod & 0xF0000000u) : ((prod >> (28 - 4 * w)) & (0xFu << (4 * w))));
+        else
+            tab.B[k] |= (M)(prod >> 28) << (4 * w);
     }
 }
 
@@ -144,16 +158,16 @@ struct SlabSrc {
     typedef BA ByteAt;
     SS_HD const BA& byte_at() const { return ba; }
     SS_HD uint32_t first_word() const { return w[0] & low_bytes_mask(len); }
-    template <int NBITS>
-    SS_HD void planes(PlaneTab<NBITS>& tab) const {
+    template <int NBITS, class M>
+    SS_HD void planes(PlaneTab<NBITS, M>& tab) const {
 #pragma unroll
-        for (int k = 0; k < NBITS; k++) tab.B[k] = 0u;
+        for (int k = 0; k < NBITS; k++) tab.B[k] = M(0);
 #pragma unroll
-        for (int i = 0; i < REG_WORDS; i++) {
+        for (int i = 0; i < (int)sizeof(M) * 2; i++) {
             if (4 * i >= len) break;
-            planes_add_word<NBITS>(tab, w[i * STRIDE], i);
+            planes_add_word<NBITS, M>(tab, w[i * STRIDE], i);
         }
-        tab.valid = len >= 32 ? 0xFFFFFFFFu : ((1u << len) - 1u);
+        tab.set_valid(len);
     }
     template <class F>
     SS_HD void each(int n, F& f) const {
@@ -205,7 +219,7 @@ struct PrefixOf {  // common prefix in characters, capped at 4 (strsim.rs:261-26
 };
 
 // one measure; row rules and arithmetic of row_ascii_reg()
-template <int MEASURE, int NBITS, class Src>
+template <int MEASURE, int NBITS, class M = uint32_t, class Src>
 SS_HD double row_planes(const Src& A, const Src& B, PairInts& out) {
     out.flag = F_GENERAL;
     out.la = out.lb = out.x0 = out.x1 = out.x2 = 0;
@@ -221,7 +235,7 @@ SS_HD double row_planes(const Src& A, const Src& B, PairInts& out) {
         out.flag = F_SINGLE_CHAR;
         return 0.0;
     }
-    typedef PlaneTab<NBITS> Tab;
+    typedef PlaneTab<NBITS, M> Tab;
     Tab tab;
     double v;
     if (MEASURE == LEVENSHTEIN) {
@@ -232,7 +246,7 @@ SS_HD double row_planes(const Src& A, const Src& B, PairInts& out) {
         int d = X.len;
         if (P.len > 0) {
             P.planes(tab);
-            MyersStep<uint32_t, Tab> step(tab);
+            MyersStep<M, Tab> step(tab);
             X.each(X.len, step);
             d = step.distance(P.len, X.len);
         }
@@ -244,7 +258,7 @@ SS_HD double row_planes(const Src& A, const Src& B, PairInts& out) {
             const int mx = la > lb ? la : lb;
             const int bound = mx / 2 - 1;  // strsim.rs:200
             const int outer = la < lb + bound ? la : lb + bound;
-            JaroMatchStep<uint32_t, Tab> match(tab, lb, bound);
+            JaroMatchStep<M, Tab> match(tab, lb, bound);
             A.each(outer, match);
             match.finish(outer);
             TransByBytes<typename Src::ByteAt> trans{A.byte_at(), B.byte_at()};
@@ -260,16 +274,16 @@ SS_HD double row_planes(const Src& A, const Src& B, PairInts& out) {
                 v = winkler_value(v, l);
             }
         } else {
-            MultisetStep<uint32_t, Tab> ms(tab, lb);
+            MultisetStep<M, Tab> ms(tab, lb);
             A.each(la, ms);
             ms.finish();
             out.x0 = ms.inter;
             if (MEASURE == JACCARD) {
                 out.x1 = la + lb - ms.inter;
-                v = jaccard_value<true>(ms.inter, la + lb - ms.inter);
+                v = jaccard_value<sizeof(M) == 4>(ms.inter, la + lb - ms.inter);
             } else {
                 out.x1 = la + lb;
-                v = dice_value<true>(ms.inter, la + lb);
+                v = dice_value<sizeof(M) == 4>(ms.inter, la + lb);
             }
         }
     }
@@ -277,14 +291,14 @@ SS_HD double row_planes(const Src& A, const Src& B, PairInts& out) {
 }
 
 // several measures in one pass: b tabled, a streamed for every group (row_short.cuh: multi_body)
-template <int GROUPS, int NBITS, class Src, class Emit>
+template <int GROUPS, int NBITS, class M = uint32_t, class Src, class Emit>
 SS_HD void row_planes_multi(const Src& A, const Src& B, Emit& emit) {
-    PlaneTab<NBITS> tab;
+    PlaneTab<NBITS, M> tab;
     B.planes(tab);
     TransByBytes<typename Src::ByteAt> trans{A.byte_at(), B.byte_at()};
     EachOf<Src> each_a{A};
     PrefixOf<Src> prefix{A, B};
-    multi_body<GROUPS, uint32_t>(tab, each_a, A.len, B.len, A.len == 0 || B.len == 0, prefix, trans, emit);
+    multi_body<GROUPS, M>(tab, each_a, A.len, B.len, A.len == 0 || B.len == 0, prefix, trans, emit);
 }
 
 }  // namespace strsim

@@ -284,9 +284,9 @@ SS_HD void multi_body(const Tab& tab, const Each& each_a, int la, int lb, bool o
             const int inter = f.ms.inter;
             o.x0 = inter;
             o.x1 = la + lb - inter;
-            emit(JACCARD, jaccard_value<true>(inter, la + lb - inter), o);
+            emit(JACCARD, jaccard_value<sizeof(M) == 4>(inter, la + lb - inter), o);
             o.x1 = la + lb;
-            emit(SORENSEN_DICE, dice_value<true>(inter, la + lb), o);
+            emit(SORENSEN_DICE, dice_value<sizeof(M) == 4>(inter, la + lb), o);
         }
     }
 }

@@ -335,23 +335,24 @@ struct EachByteStaged {
 
 // bit planes of a staged string of m <= 32 characters, word by word from shared memory.  The bytes after
 // the string need no masking: PlaneTab::valid keeps them out of every position mask.
-template <int NBITS>
-__device__ __forceinline__ void build_planes_staged(const unsigned char* smem, const StagedStr& S, PlaneTab<NBITS>& tab) {
+template <int NBITS, class M>
+__device__ __forceinline__ void build_planes_staged(const unsigned char* smem, const StagedStr& S,
+                                                    PlaneTab<NBITS, M>& tab) {
     const uint32_t* p = reinterpret_cast<const uint32_t*>(smem + (S.off & ~3u));
     const int sh = (int)(S.off & 3u) * 8;
     const int m = S.len;
 #pragma unroll
-    for (int k = 0; k < NBITS; k++) tab.B[k] = 0u;
+    for (int k = 0; k < NBITS; k++) tab.B[k] = M(0);
     uint32_t lo = p[0];
 #pragma unroll
-    for (int w = 0; w < REG_WORDS; w++) {
+    for (int w = 0; w < (int)sizeof(M) * 2; w++) {
         if (4 * w >= m) break;
         const uint32_t hi = p[w + 1];
         const uint32_t word = __funnelshift_r(lo, hi, sh);
         lo = hi;
-        planes_add_word<NBITS>(tab, word, w);
+        planes_add_word<NBITS, M>(tab, word, w);
     }
-    tab.valid = m >= 32 ? 0xFFFFFFFFu : ((1u << m) - 1u);
+    tab.set_valid(m);
 }
 
 // first word (zero-masked to the string's length) of a staged string
@@ -368,9 +369,9 @@ struct StagedSrc {
     typedef SmemByteAt ByteAt;
     __device__ __forceinline__ SmemByteAt byte_at() const { return SmemByteAt{smem_u32(smem) + off}; }
     __device__ __forceinline__ uint32_t first_word() const { return staged_first_word(smem, StagedStr{off, len}); }
-    template <int NBITS>
-    __device__ __forceinline__ void planes(PlaneTab<NBITS>& tab) const {
-        build_planes_staged<NBITS>(smem, StagedStr{off, len}, tab);
+    template <int NBITS, class M>
+    __device__ __forceinline__ void planes(PlaneTab<NBITS, M>& tab) const {
+        build_planes_staged<NBITS, M>(smem, StagedStr{off, len}, tab);
     }
     template <class F>
     __device__ __forceinline__ void each(int n, F& f) const {
@@ -498,8 +499,8 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
     static_assert(ASCII_ONLY || UREG || T >= DevStore<M, TPB, T>::HASH_ENTRIES,
                   "the Unicode path keeps its hash slots in the table memory");
     static_assert(!UREG || (!ASCII_ONLY && !REG && sizeof(M) == 4), "register-compare path: general u32 kernel");
-    static_assert(!REG || (ASCII_ONLY && sizeof(M) == 4 && (T == 32 || T == 64 || T == 128)),
-                  "the register path serves ASCII-only columns with strings of at most 32 bytes");
+    static_assert(!REG || (ASCII_ONLY && (T == 32 || T == 64 || T == 128)),
+                  "the plane path serves ASCII-only columns (strings of at most 32 bytes for M = u32, 64 for u64)");
     static_assert(!is_multi(MEASURE) || REG || UREG, "fused evaluation: register paths only");
     constexpr int GROUPS = is_multi(MEASURE) ? MEASURE - MULTI_BASE : 0;
     constexpr int NBITS = T == 32 ? 5 : T == 64 ? 6 : 7;
@@ -972,7 +973,7 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
                 // b is tabled as bit planes, a is streamed -- both straight from the staged tile
                 const StagedStr A = staged_str(va, i, (uint32_t)L::off_sva, off_stage_a),
                                 B = staged_str(vb, i, (uint32_t)L::off_svb, off_stage_b);
-                row_planes_multi<GROUPS, NBITS>(StagedSrc{smem, A.off, A.len}, StagedSrc{smem, B.off, B.len}, emit);
+                row_planes_multi<GROUPS, NBITS, M>(StagedSrc{smem, A.off, A.len}, StagedSrc{smem, B.off, B.len}, emit);
                 continue;
             }
             if constexpr (REG) {
@@ -984,8 +985,8 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
                 }
                 const StagedStr A = staged_str(va, i, (uint32_t)L::off_sva, off_stage_a),
                                 B = staged_str(vb, i, (uint32_t)L::off_svb, off_stage_b);
-                v = row_planes<is_multi(MEASURE) ? 0 : MEASURE, NBITS>(StagedSrc{smem, A.off, A.len},
-                                                                      StagedSrc{smem, B.off, B.len}, ints);
+                v = row_planes<is_multi(MEASURE) ? 0 : MEASURE, NBITS, M>(StagedSrc{smem, A.off, A.len},
+                                                                         StagedSrc{smem, B.off, B.len}, ints);
             } else {
                 const uint32_t or_a = load_string<WORDS, TPB>(va, stage_a, store.wa_);
                 const uint32_t or_b = load_string<WORDS, TPB>(vb, stage_b, store.wb_);

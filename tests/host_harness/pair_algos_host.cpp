@@ -112,12 +112,17 @@ static double planes_dispatch(int nbits, const uint32_t* a, const uint32_t* b, i
         default: return row_planes<MEASURE, 8>(A, B, pi);
     }
 }
+template <int MEASURE>
+static double planes_dispatch64(const uint32_t* a, const uint32_t* b, int na, int nb, PairInts& pi) {
+    return row_planes<MEASURE, 7, uint64_t>(host_src(a, na), host_src(b, nb), pi);  // strings of up to 64 characters
+}
 extern "C" int algos_batch_reg(int measure, int nbits, int64_t n, const uint8_t* ad, const int64_t* ao,
                                const uint8_t* bd, const int64_t* bo, int* ints, double* values) {
     for (int64_t r = 0; r < n; r++) {
         const int na = (int)(ao[r + 1] - ao[r]), nb = (int)(bo[r + 1] - bo[r]);
-        if (na > 32 || nb > 32) return -2;
-        uint32_t a[REG_WORDS] = {0}, b[REG_WORDS] = {0};
+        const bool wide64 = nbits >= 100;  // 107: 64-bit masks, 7 planes, strings of up to 64 characters
+        if (na > (wide64 ? 64 : 32) || nb > (wide64 ? 64 : 32)) return -2;
+        uint32_t a[2 * REG_WORDS] = {0}, b[2 * REG_WORDS] = {0};
         std::memcpy(a, ad + ao[r], na);
         std::memcpy(b, bd + bo[r], nb);
         PairInts pi;
@@ -132,6 +137,13 @@ extern "C" int algos_batch_reg(int measure, int nbits, int64_t n, const uint8_t*
                 // bytes past the string are arbitrary for a source: poison them
                 std::memset(reinterpret_cast<uint8_t*>(a) + na, 0xA5, sizeof a - na);
                 std::memset(reinterpret_cast<uint8_t*>(b) + nb, 0x5A, sizeof b - nb);
+                if (wide64) switch (measure) {
+                    case 0: v = planes_dispatch64<0>(a, b, na, nb, pi); break;
+                    case 1: v = planes_dispatch64<1>(a, b, na, nb, pi); break;
+                    case 2: v = planes_dispatch64<2>(a, b, na, nb, pi); break;
+                    case 3: v = planes_dispatch64<3>(a, b, na, nb, pi); break;
+                    default: v = planes_dispatch64<4>(a, b, na, nb, pi); break;
+                } else
                 switch (measure) {
                     case 0: v = planes_dispatch<0>(nbits, a, b, na, nb, pi); break;
                     case 1: v = planes_dispatch<1>(nbits, a, b, na, nb, pi); break;
@@ -192,7 +204,7 @@ struct HostEmit {
 };
 
 template <int GROUPS>
-static void reg_multi_dispatch(int nbits, uint32_t (&a)[REG_WORDS], uint32_t (&b)[REG_WORDS], int na,
+static void reg_multi_dispatch(int nbits, uint32_t (&a)[2 * REG_WORDS], uint32_t (&b)[2 * REG_WORDS], int na,
                                int nb, HostEmit& e) {
     // the kernels' form (row_planes_multi over sources), equal pairs settled before
     if (na == nb && std::memcmp(a, b, sizeof a) == 0) {
@@ -203,6 +215,10 @@ static void reg_multi_dispatch(int nbits, uint32_t (&a)[REG_WORDS], uint32_t (&b
     std::memset(reinterpret_cast<uint8_t*>(a) + na, 0xA5, sizeof a - na);
     std::memset(reinterpret_cast<uint8_t*>(b) + nb, 0x5A, sizeof b - nb);
     const HostSrc A = host_src(a, na), B = host_src(b, nb);
+    if (nbits >= 100) {
+        row_planes_multi<GROUPS, 7, uint64_t>(A, B, e);
+        return;
+    }
     switch (nbits) {
         case 5: row_planes_multi<GROUPS, 5>(A, B, e); break;
         case 6: row_planes_multi<GROUPS, 6>(A, B, e); break;
@@ -215,8 +231,8 @@ extern "C" int algos_batch_reg_multi(int groups, int nbits, int64_t n, const uin
                                      const uint8_t* bd, const int64_t* bo, int* ints, double* values) {
     for (int64_t r = 0; r < n; r++) {
         const int na = (int)(ao[r + 1] - ao[r]), nb = (int)(bo[r + 1] - bo[r]);
-        if (na > 32 || nb > 32) return -2;
-        uint32_t a[REG_WORDS] = {0}, b[REG_WORDS] = {0};
+        if (na > (nbits >= 100 ? 64 : 32) || nb > (nbits >= 100 ? 64 : 32)) return -2;
+        uint32_t a[2 * REG_WORDS] = {0}, b[2 * REG_WORDS] = {0};
         std::memcpy(a, ad + ao[r], na);
         std::memcpy(b, bd + bo[r], nb);
         HostEmit e{r, n, ints, values};
@@ -274,7 +290,7 @@ extern "C" int algos_batch_latin1_multi(int groups, int64_t n, const uint8_t* ad
     for (int64_t r = 0; r < n; r++) {
         const int na = (int)(ao[r + 1] - ao[r]), nb = (int)(bo[r + 1] - bo[r]);
         if (na > 32 || nb > 32) return -2;
-        uint32_t a[REG_WORDS] = {0}, b[REG_WORDS] = {0};
+        uint32_t a[2 * REG_WORDS] = {0}, b[2 * REG_WORDS] = {0};
         std::memcpy(a, ad + ao[r], na);
         std::memcpy(b, bd + bo[r], nb);
         uint32_t wide = 0;

@@ -682,9 +682,11 @@ def _sample_rows(col, idx):
     return flat.cast(pa.large_string()).take(pa.array(idx)).to_pylist()  # take() has no string_view kernel
 
 
-@pytest.mark.parametrize("config,rows", [(2, 10_000_000), (3, 20_000_000)])
+@pytest.mark.parametrize("config,rows", [(2, 10_000_000), (3, 20_000_000), (7, 2_000_000)])
 def test_full_size_workloads_by_properties(native, oracle, config, rows):
-    """BASELINE configs at (C2) / near (C3: a fifth of) their full size, where the oracle cannot check every
+    """BASELINE configs at (C2) / near (C3: a fifth of) their full size -- and 2 M medium ASCII strings of
+    20-60 characters (config 7: three quarters of the rows run the 64-bit plane kernel) -- where the oracle
+    cannot check every
     row in seconds: size-independent properties over ALL rows, plus the oracle bit for bit on a seeded
     sample of 100k rows.  Properties: values in [0, 1]; null mask = AND of the input masks; the symmetric
     measures (Levenshtein, Jaccard, Sorensen-Dice: edit distance and multiset intersection do not depend

@@ -113,7 +113,8 @@ def test_multiword_myers_block(algos, oracle):
 
 
 @pytest.mark.parametrize("nbits,alphabet", [(5, "abcdefghijklmnopqrstuvwxyz"), (5, "ABCXYZ@["),
-                                            (6, "abcxyzABCXYZ_`{"), (7, "ab yz-'09AZ~\x01\x7f!")])
+                                            (6, "abcxyzABCXYZ_`{"), (7, "ab yz-'09AZ~\x01\x7f!"),
+                                            (107, "ab yz-'09AZ~\x01\x7f!"), (107, "abcdefghij ")])
 def test_register_resident_ascii_path(algos, oracle, nbits, alphabet):
     """row_ascii_reg.cuh: strings in registers, position masks from bit planes (no table)."""
     from oracle.oracle import _pack, MEASURE_ID
@@ -121,16 +122,17 @@ def test_register_resident_ascii_path(algos, oracle, nbits, alphabet):
     algos.algos_batch_reg.restype = ctypes.c_int
     algos.algos_batch_reg.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int64] + [ctypes.c_void_p] * 6
     rng = random.Random(1000 + nbits)
+    cap = 64 if nbits >= 100 else 32  # nbits 107 = 64-bit masks (strings of up to 64 characters), 7 planes
     a, b = [], []
     for _ in range(20000):
-        x = "".join(rng.choice(alphabet) for _ in range(rng.randint(0, 32)))
+        x = "".join(rng.choice(alphabet) for _ in range(rng.randint(0, cap)))
         if rng.random() < 0.6:
             y = list(x)
             for _ in range(rng.randint(0, 3)):
                 op, pos = rng.randint(0, 3), rng.randint(0, len(y))
                 if op == 0 and y:
                     y[min(pos, len(y) - 1)] = rng.choice(alphabet)
-                elif op == 1 and len(y) < 32:
+                elif op == 1 and len(y) < cap:
                     y.insert(pos, rng.choice(alphabet))
                 elif op == 2 and y:
                     del y[min(pos, len(y) - 1)]
@@ -139,11 +141,11 @@ def test_register_resident_ascii_path(algos, oracle, nbits, alphabet):
                     y[p], y[p + 1] = y[p + 1], y[p]
             y = "".join(y)
         else:
-            y = "".join(rng.choice(alphabet) for _ in range(rng.randint(0, 32)))
+            y = "".join(rng.choice(alphabet) for _ in range(rng.randint(0, cap)))
         a.append(x)
         b.append(y)
-    for la in (0, 1, 2, 31, 32):
-        for lb in (0, 1, 2, 31, 32):
+    for la in (0, 1, 2, 31, 32, cap - 1, cap):
+        for lb in (0, 1, 2, 31, 32, cap - 1, cap):
             a.append(alphabet[0] * la)
             b.append((alphabet[1] * lb))
             a.append("".join(rng.choice(alphabet) for _ in range(la)))
@@ -224,7 +226,7 @@ def check_multi(oracle, call, a, b):
 
 
 @pytest.mark.parametrize("nbits,alphabet", [(5, "abcdefghijklmnopqrstuvwxyz"), (6, "abcxyzABCXYZ_`{"),
-                                            (7, "ab yz-'09AZ~\x01\x7f!")])
+                                            (7, "ab yz-'09AZ~\x01\x7f!"), (107, "abcdefghij -'")])
 def test_fused_measures_ascii_reg(algos, oracle, nbits, alphabet):
     """row_ascii_reg_multi: one pass over a feeds Myers, Jaro and the multiset together."""
     from oracle.oracle import _pack
@@ -232,16 +234,17 @@ def test_fused_measures_ascii_reg(algos, oracle, nbits, alphabet):
     algos.algos_batch_reg_multi.restype = ctypes.c_int
     algos.algos_batch_reg_multi.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int64] + [ctypes.c_void_p] * 6
     rng = random.Random(31 + nbits)
+    cap = 64 if nbits >= 100 else 32
     a, b = [], []
     for _ in range(6000):
-        x = "".join(rng.choice(alphabet) for _ in range(rng.randint(0, 32)))
+        x = "".join(rng.choice(alphabet) for _ in range(rng.randint(0, cap)))
         if rng.random() < 0.6:
             y = list(x)
             for _ in range(rng.randint(0, 3)):
                 op, pos = rng.randint(0, 3), rng.randint(0, len(y))
                 if op == 0 and y:
                     y[min(pos, len(y) - 1)] = rng.choice(alphabet)
-                elif op == 1 and len(y) < 32:
+                elif op == 1 and len(y) < cap:
                     y.insert(pos, rng.choice(alphabet))
                 elif op == 2 and y:
                     del y[min(pos, len(y) - 1)]
@@ -250,11 +253,11 @@ def test_fused_measures_ascii_reg(algos, oracle, nbits, alphabet):
                     y[q], y[q + 1] = y[q + 1], y[q]
             y = "".join(y)
         else:
-            y = "".join(rng.choice(alphabet) for _ in range(rng.randint(0, 32)))
+            y = "".join(rng.choice(alphabet) for _ in range(rng.randint(0, cap)))
         a.append(x)
         b.append(y)
-    for la in (0, 1, 2, 3, 31, 32):
-        for lb in (0, 1, 2, 3, 31, 32):
+    for la in (0, 1, 2, 3, 31, 32, cap - 1, cap):
+        for lb in (0, 1, 2, 3, 31, 32, cap - 1, cap):
             a.append(alphabet[0] * la)
             b.append(alphabet[1] * lb)
             a.append("".join(rng.choice(alphabet) for _ in range(la)))
