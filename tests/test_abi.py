@@ -119,3 +119,18 @@ def test_plugin_call_fails_loudly_without_gpu(native):
     assert b"no CPU fallback" in L._polars_plugin_get_last_error_message()
     with pytest.raises(native.StrsimError, match="no CPU fallback"):
         native.compute_host("jaro", pa.array(["a"], type=pa.string_view()), pa.array(["b"], type=pa.string_view()))
+
+
+def test_bind_thread_near_device_is_a_no_op_without_topology(native):
+    """strsim_b200_bind_thread_near_device: -1 (nothing done, affinity untouched) when there is no device
+    or the host exposes no NUMA locality for it -- never an error."""
+    import os
+
+    before = os.sched_getaffinity(0)
+    node = native.bind_thread_near_device(0)
+    assert node >= -1
+    if node == -1:
+        assert os.sched_getaffinity(0) == before
+    else:
+        assert os.sched_getaffinity(0) <= before
+        os.sched_setaffinity(0, before)
