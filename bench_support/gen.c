@@ -11,6 +11,8 @@
  *                  name_b mutated as in C2 from the same script
  *   config 6 (L1): every row a Latin row of config 3, no nulls (not a BASELINE config: shows the
  *                  Latin-1 bit-plane path of the general kernel on its own)
+ *   config 8 (N1): C2 with real-name spelling: words start with a capital, positions inside a name are a
+ *                  space / hyphen / apostrophe w.p. 0.08 (any ASCII: the 7-plane kernel instantiation)
  *   config 4 (C4): long text, length U{200..4000} codepoints, 90 % a..z/space, 10 % two- and
  *                  three-byte codepoints; b = a with ~10 % random edits w.p. 0.5, else independent
  * Every row is generated from splitmix64(seed, row), so output is independent of the thread count.
@@ -39,7 +41,7 @@ static inline uint32_t rnd(rng_t *r, uint32_t n) { /* uniform in [0, n) */
 }
 static inline double rndf(rng_t *r) { return (double)(splitmix(&r->s) >> 11) * (1.0 / 9007199254740992.0); }
 
-enum { S_ASCII, S_LATIN, S_CJK, S_TEXT };
+enum { S_ASCII, S_LATIN, S_CJK, S_TEXT, S_NAME };
 
 static uint32_t draw_char(rng_t *r, int script) {
     switch (script) {
@@ -53,6 +55,12 @@ static uint32_t draw_char(rng_t *r, int script) {
             }
             return 'a' + rnd(r, 26);
         case S_CJK: return 0x4E00 + rnd(r, 0x9FFF - 0x4E00 + 1);
+        case S_NAME: {
+            double u = rndf(r);
+            if (u < 0.80) return 'a' + rnd(r, 26);
+            if (u < 0.92) return 'A' + rnd(r, 26);
+            return " -'"[rnd(r, 3)];
+        }
         default: {
             double u = rndf(r);
             if (u < 0.75) return 'a' + rnd(r, 26);
@@ -65,6 +73,19 @@ static uint32_t draw_char(rng_t *r, int script) {
 
 static int draw_string(rng_t *r, int script, int lo, int hi, uint32_t *out) {
     int n = lo + (int)rnd(r, (uint32_t)(hi - lo + 1));
+    if (script == S_NAME) { /* "Mary-Ann O'Neil": capital after every separator */
+        int start = 1;
+        for (int i = 0; i < n; i++) {
+            if (!start && i + 1 < n && rndf(r) < 0.08) {
+                out[i] = " -'"[rnd(r, 3)];
+                start = 1;
+            } else {
+                out[i] = (start ? 'A' : 'a') + rnd(r, 26);
+                start = 0;
+            }
+        }
+        return n;
+    }
     for (int i = 0; i < n; i++) out[i] = draw_char(r, script);
     return n;
 }
@@ -140,6 +161,8 @@ static void gen_row(int config, uint64_t seed, int64_t row, double null_p, rowbu
         int script = S_ASCII, lo = 4, hi = 24;
         if (config == 6) {
             script = S_LATIN; /* the Latin rows of C3 alone: a column of names with diacritics */
+        } else if (config == 8) {
+            script = S_NAME;
         } else if (config == 7) {
             lo = 20; /* medium ASCII strings (street addresses): most rows leave the 32-byte kernels */
             hi = 60;

@@ -156,6 +156,14 @@ STRSIM_API int strsim_b200_column_device(const strsim_b200_column *col);
 /* algorithmic bytes of the column as SURVEY.md 8(d) counts them: 16 B/row of views + out-of-line
  * payload of rows with byte length > 12 (+ validity bits); filled in at upload */
 STRSIM_API int64_t strsim_b200_column_algorithmic_bytes(const strsim_b200_column *col);
+/* Re-runs the column-statistics pre-pass over a resident column on `stream` (NULL = the library's
+ * per-thread stream) and waits for it: OR / AND of every string byte (stats_views_kernel over the views'
+ * inline bytes, stats_bytes_kernel over the data buffers), which choose the kernel instantiation (5 / 6 /
+ * 7 bit planes for ASCII columns, the general launches otherwise).  An upload runs the same kernels once;
+ * bench.py calls this to time the pre-pass next to the measure kernel ("all kernels of the
+ * measure incl. pre-pass").  No counterpart in the reference (its per-row decode looks at every byte
+ * anyway, strsim.rs:131-140). */
+STRSIM_API int strsim_b200_column_restat(strsim_b200_column *col, void *stream);
 STRSIM_API int strsim_b200_compute_device(int measure, const strsim_b200_column *a,
                                           const strsim_b200_column *b, double *d_out_values,
                                           uint32_t *d_out_validity, int32_t *d_dbg_ints, void *stream);

@@ -14,6 +14,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 #if defined(__linux__)
 #include <sys/mman.h>
@@ -57,9 +58,12 @@ enum Layout { L_VIEW, L_OFFSET32, L_OFFSET64, L_BAD };
 
 Layout layout_of(const char* fmt) {
     if (!fmt) return L_BAD;
-    if (!strcmp(fmt, "vu") || !strcmp(fmt, "vz")) return L_VIEW;
-    if (!strcmp(fmt, "u") || !strcmp(fmt, "z")) return L_OFFSET32;
-    if (!strcmp(fmt, "U") || !strcmp(fmt, "Z")) return L_OFFSET64;
+    // String layouts only, like the reference's `inputs[i].str()?` (strsim.rs:46-47).  Binary / BinaryView
+    // columns ("z", "Z", "vz") are rejected: the kernels key characters by their UTF-8 bytes and rely on
+    // well-formed sequences, which only a String column guarantees.
+    if (!strcmp(fmt, "vu")) return L_VIEW;
+    if (!strcmp(fmt, "u")) return L_OFFSET32;
+    if (!strcmp(fmt, "U")) return L_OFFSET64;
     return L_BAD;
 }
 
@@ -200,7 +204,17 @@ std::vector<std::shared_ptr<CacheEntry>>& g_cache = *new std::vector<std::shared
 int64_t g_cache_hits = 0, g_cache_misses = 0;
 constexpr size_t CACHE_MAX_COLUMNS = 8;
 constexpr int64_t CACHE_MIN_ROWS = 65536;  // below this the upload is cheaper than the bookkeeping
-constexpr int CACHE_TTL_SECONDS = 30;
+// An entry pins the caller's host buffers (the moved-in Arrow arrays) and a copy in HBM, so it must not
+// outlive the query by much: entries unused for CACHE_TTL seconds are dropped by a reaper thread even
+// when no further plugin call arrives (STRSIM_B200_CACHE_TTL, seconds; default 10).
+int cache_ttl_seconds() {
+    static const int v = [] {
+        const char* e = getenv("STRSIM_B200_CACHE_TTL");
+        const int x = e && *e ? atoi(e) : 0;
+        return x > 0 ? x : 10;
+    }();
+    return v;
+}
 
 bool cache_enabled() {
     static const bool on = [] {
@@ -213,7 +227,7 @@ int64_t cache_limit() {
     static const int64_t v = [] {
         const char* e = getenv("STRSIM_B200_CACHE_BYTES");
         const long long x = e && *e ? atoll(e) : 0;
-        return x > 0 ? (int64_t)x : (int64_t)8 << 30;
+        return x > 0 ? (int64_t)x : (int64_t)4 << 30;
     }();
     return v;
 }
@@ -238,7 +252,8 @@ std::vector<ChunkKey> key_of(const Column& c) {
 void cache_trim(int64_t incoming_bytes) {
     const auto now = std::chrono::steady_clock::now();
     for (size_t i = 0; i < g_cache.size();) {
-        if (std::chrono::duration_cast<std::chrono::seconds>(now - g_cache[i]->last_use).count() > CACHE_TTL_SECONDS)
+        if (std::chrono::duration_cast<std::chrono::milliseconds>(now - g_cache[i]->last_use).count() >
+            1000ll * cache_ttl_seconds())
             g_cache.erase(g_cache.begin() + (long)i);
         else
             i++;
@@ -251,6 +266,53 @@ void cache_trim(int64_t incoming_bytes) {
         for (size_t i = 1; i < g_cache.size(); i++)
             if (g_cache[i]->last_use < g_cache[oldest]->last_use) oldest = i;
         g_cache.erase(g_cache.begin() + (long)oldest);
+    }
+}
+
+// Idle processes: nothing would ever call cache_trim() again after the last query, and the entries (host
+// buffers of a DataFrame that may be long gone, gigabytes of HBM) would stay for good.  The first insert
+// starts a reaper thread that wakes once a second while the cache holds anything, drops what has
+// expired, hands idle blocks of the device pool back to the driver, and exits when nothing is left.
+bool g_reaper_running = false;  // guarded by g_cache_mutex
+extern "C" void strsim_pool_trim(int idle_seconds);
+
+void reaper_main() {
+    for (;;) {
+        std::this_thread::sleep_for(std::chrono::seconds(1));
+        std::vector<std::shared_ptr<CacheEntry>> expired;  // destroyed outside the lock (frees HBM, releases arrays)
+        bool done = false;
+        {
+            std::lock_guard<std::mutex> lock(g_cache_mutex);
+            const auto now = std::chrono::steady_clock::now();
+            for (size_t i = 0; i < g_cache.size();) {
+                if (std::chrono::duration_cast<std::chrono::milliseconds>(now - g_cache[i]->last_use).count() >
+                    1000ll * cache_ttl_seconds()) {
+                    expired.push_back(std::move(g_cache[i]));
+                    g_cache.erase(g_cache.begin() + (long)i);
+                } else {
+                    i++;
+                }
+            }
+            if (g_cache.empty()) {
+                g_reaper_running = false;
+                done = true;
+            }
+        }
+        expired.clear();
+        if (done) {
+            strsim_pool_trim(0);
+            return;
+        }
+    }
+}
+
+// mutex held
+void reaper_ensure() {
+    if (g_reaper_running) return;
+    try {
+        std::thread(reaper_main).detach();
+        g_reaper_running = true;
+    } catch (...) {  // no thread: the entries are still trimmed by the next plugin call
     }
 }
 
@@ -285,6 +347,7 @@ void cache_insert(std::vector<ChunkKey> key, strsim_b200_column* col, strsim_ser
         series.arrays[i]->release = nullptr;  // the source struct no longer owns anything
     }
     g_cache.push_back(std::move(e));
+    reaper_ensure();
 }
 
 bool cacheable(const strsim_series_export& s, const Column& c) {
@@ -448,8 +511,22 @@ void release_series(strsim_series_export* e) {
     e->private_data = nullptr;
 }
 
+void release_inputs(strsim_series_export* inputs, size_t n_inputs) {
+    for (size_t s = 0; inputs && s < n_inputs; s++) {
+        for (size_t i = 0; inputs[s].arrays && i < inputs[s].len; i++) {
+            ArrowArray* a = inputs[s].arrays[i];
+            if (a && a->release) a->release(a);
+        }
+        if (inputs[s].release) inputs[s].release(&inputs[s]);
+    }
+}
+
 void plugin_call(int measure, strsim_series_export* inputs, size_t n_inputs,
                  strsim_series_export* return_value) {
+    {   // expired cache entries go before anything new is uploaded
+        std::lock_guard<std::mutex> lock(g_cache_mutex);
+        cache_trim(0);
+    }
     int rc = STRSIM_OK;
     Column ca, cb;
     ArrowArray* result = nullptr;
@@ -486,13 +563,7 @@ void plugin_call(int measure, strsim_series_export* inputs, size_t n_inputs,
     }
     // the callee owns the inputs (polars-ffi import_series_buffer semantics): release every chunk's
     // contents, then the SeriesExport boxes
-    for (size_t s = 0; inputs && s < n_inputs; s++) {
-        for (size_t i = 0; i < inputs[s].len; i++) {
-            ArrowArray* a = inputs[s].arrays[i];
-            if (a && a->release) a->release(a);
-        }
-        if (inputs[s].release) inputs[s].release(&inputs[s]);
-    }
+    release_inputs(inputs, n_inputs);
     if (rc != STRSIM_OK) return;  // return_value untouched => Polars raises with the stored message
     SeriesPrivate* p = new SeriesPrivate();
     p->field = new ArrowSchema();
@@ -512,6 +583,26 @@ void plugin_field(ArrowSchema* input_fields, size_t n_fields, ArrowSchema* retur
     make_f64_schema(return_field, n_fields > 0 && input_fields ? input_fields[0].name : "");
 }
 
+// Nothing may unwind across the C ABI into the engine's Rust frames (undefined behaviour); the reference's
+// derive wrapper catches panics and reports them through the last-error message.  Same here: an exception
+// (std::bad_alloc from the chunk vectors, ...) becomes the last-error message, the inputs are released as
+// the ABI demands, and `return_value` stays untouched.
+void plugin_call_guarded(int measure, strsim_series_export* inputs, size_t n_inputs,
+                         strsim_series_export* return_value) noexcept {
+    try {
+        plugin_call(measure, inputs, n_inputs, return_value);
+        return;
+    } catch (const std::exception& e) {
+        strsim_set_error("plugin call failed: %s", e.what());
+    } catch (...) {
+        strsim_set_error("plugin call failed: unknown exception");
+    }
+    try {
+        release_inputs(inputs, n_inputs);  // idempotent: released structs carry a null callback
+    } catch (...) {
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -523,23 +614,35 @@ int strsim_b200_compute_arrow(int measure, const ArrowSchema* a_schema, const Ar
         strsim_set_error("compute_arrow: NULL argument");
         return STRSIM_ERR_ARGUMENT;
     }
-    Column ca, cb;
-    int rc = column_from_arrow(a_schema->format, a_chunks, n_a, ca);
-    if (rc) return rc;
-    rc = column_from_arrow(b_schema->format, b_chunks, n_b, cb);
-    if (rc) return rc;
-    return compute_to_arrow(measure, ca, cb, out);
+    try {
+        Column ca, cb;
+        int rc = column_from_arrow(a_schema->format, a_chunks, n_a, ca);
+        if (rc) return rc;
+        rc = column_from_arrow(b_schema->format, b_chunks, n_b, cb);
+        if (rc) return rc;
+        return compute_to_arrow(measure, ca, cb, out);
+    } catch (const std::exception& e) {
+        strsim_set_error("compute_arrow failed: %s", e.what());
+        return STRSIM_ERR_NOMEM;
+    } catch (...) {
+        strsim_set_error("compute_arrow failed: unknown exception");
+        return STRSIM_ERR_NOMEM;
+    }
 }
 
 #define STRSIM_DEFINE_PLUGIN(name, id)                                                             \
     void _polars_plugin_##name(strsim_series_export* inputs, size_t n_inputs, const uint8_t*,      \
                                size_t, strsim_series_export* return_value, strsim_caller_context*) \
     {                                                                                              \
-        plugin_call(id, inputs, n_inputs, return_value);                                           \
+        plugin_call_guarded(id, inputs, n_inputs, return_value);                                   \
     }                                                                                              \
     void _polars_plugin_field_##name(ArrowSchema* input_fields, size_t n_fields,                   \
                                      ArrowSchema* return_field) {                                  \
-        plugin_field(input_fields, n_fields, return_field);                                        \
+        try {                                                                                      \
+            plugin_field(input_fields, n_fields, return_field);                                    \
+        } catch (...) {                                                                            \
+            strsim_set_error("field resolution failed: out of memory");                            \
+        }                                                                                          \
     }
 
 STRSIM_DEFINE_PLUGIN(levenshtein, STRSIM_LEVENSHTEIN)

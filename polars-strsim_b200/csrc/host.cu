@@ -9,12 +9,15 @@
 #include <sched.h>
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <mutex>
+#include <new>
 #include <deque>
 #include <string>
 #include <thread>
@@ -53,6 +56,24 @@ extern "C" void strsim_set_error(const char* fmt, ...) {
             return STRSIM_ERR_CUDA;                                                           \
         }                                                                                     \
     } while (0)
+
+// Nothing unwinds across the C ABI: an exception on the host side (std::bad_alloc from the bookkeeping
+// vectors) becomes a status code and a last-error message, like every other failure.
+template <class F>
+static int guarded(const char* what, F&& body) noexcept {
+    try {
+        return body();
+    } catch (const std::bad_alloc&) {
+        strsim_set_error("%s: out of host memory", what);
+        return STRSIM_ERR_NOMEM;
+    } catch (const std::exception& e) {
+        strsim_set_error("%s: %s", what, e.what());
+        return STRSIM_ERR_ARGUMENT;
+    } catch (...) {
+        strsim_set_error("%s: unknown exception", what);
+        return STRSIM_ERR_ARGUMENT;
+    }
+}
 
 // row slices of one host call (compute_host_multi): H2D of slice s+1 overlaps compute / D2H of slice s
 constexpr int MAX_SLICES = 16;
@@ -202,6 +223,69 @@ static int default_device() {
     return 0;
 }
 
+static void destroy_ctx(ThreadCtx& c) {
+    // best effort: the context may be half built (failed initialisation) or belong to a device that is
+    // still busy with other threads' work; every handle is checked before it is released
+    if (c.device < 0) return;
+    cudaSetDevice(c.device);
+    for (cudaStream_t st : {c.stream, c.copy_stream, c.upload_stream, c.stats_stream})
+        if (st) {
+            cudaStreamSynchronize(st);
+            cudaStreamDestroy(st);
+        }
+    for (auto& ev : c.done_event) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : c.slice_event) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : c.up_event) if (ev) cudaEventDestroy(ev);
+    for (void* p : {(void*)c.d_slice_stats, (void*)c.d_ovf, (void*)c.d_nulls, (void*)c.d_stats, (void*)c.d_counters,
+                    c.lists.ptr, c.scratch.ptr})
+        if (p) cudaFree(p);
+    for (void* p : {(void*)c.h_slice_stats, (void*)c.h_ovf, (void*)c.h_nulls, (void*)c.h_counters, (void*)c.h_stats})
+        if (p) cudaFreeHost(p);
+    for (Stager* sg : {c.stager, c.up_stager})
+        if (sg) {
+            while (sg->pending.load(std::memory_order_acquire) > 0) std::this_thread::yield();
+            for (auto& ev : sg->ev) if (ev) cudaEventDestroy(ev);
+            if (sg->ring) cudaFreeHost(sg->ring);
+            delete sg;
+        }
+    cudaGetLastError();
+    c = ThreadCtx();
+}
+
+static int init_ctx(ThreadCtx& c, int device) {
+    c.device = device;
+    CUDA_TRY(cudaSetDevice(c.device));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c.upload_stream, cudaStreamNonBlocking));
+    for (auto& ev : c.slice_event) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto& ev : c.up_event) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c.stats_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaMalloc(&c.d_slice_stats, sizeof(ColumnStats) * (2 + MAX_SLICES)));
+    CUDA_TRY(cudaMallocHost(&c.h_slice_stats, sizeof(ColumnStats) * (2 + MAX_SLICES)));
+    for (auto& ev : c.done_event) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CUDA_TRY(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, c.device));
+    CUDA_TRY(cudaMalloc(&c.d_ovf, sizeof(Overflow)));
+    CUDA_TRY(cudaMallocHost(&c.h_ovf, sizeof(Overflow)));
+    CUDA_TRY(cudaMalloc(&c.d_nulls, sizeof(unsigned long long)));
+    CUDA_TRY(cudaMallocHost(&c.h_nulls, sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc(&c.d_stats, sizeof(ColumnStats)));
+    CUDA_TRY(cudaMalloc(&c.d_counters, 4 * sizeof(unsigned int)));
+    CUDA_TRY(cudaMallocHost(&c.h_counters, 4 * sizeof(unsigned int)));
+    CUDA_TRY(cudaMallocHost(&c.h_stats, sizeof(ColumnStats)));
+    // the quotient table of pair_algos.cuh, once per device (every host thread has its own context)
+    static std::mutex quot_mutex;
+    static bool quot_ready[64] = {false};
+    std::lock_guard<std::mutex> lock(quot_mutex);
+    if (c.device >= 64 || !quot_ready[c.device]) {
+        quotient_table_kernel<<<(QUOT_N * QUOT_N + 255) / 256, 256, 0, c.stream>>>();
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(c.stream));
+        if (c.device < 64) quot_ready[c.device] = true;
+    }
+    return STRSIM_OK;
+}
+
 static int ensure_ctx(ThreadCtx** out) {
     if (g_requested_device == -2) g_requested_device = default_device();
     ThreadCtx& c = g_ctx;
@@ -218,37 +302,19 @@ static int ensure_ctx(ThreadCtx** out) {
             strsim_set_error("device %d out of range (0..%d)", g_requested_device, n - 1);
             return STRSIM_ERR_ARGUMENT;
         }
-        c = ThreadCtx();
-        c.device = g_requested_device;
-        CUDA_TRY(cudaSetDevice(c.device));
-        CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&c.upload_stream, cudaStreamNonBlocking));
-        for (auto& ev : c.slice_event) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        for (auto& ev : c.up_event) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        CUDA_TRY(cudaStreamCreateWithFlags(&c.stats_stream, cudaStreamNonBlocking));
-        CUDA_TRY(cudaMalloc(&c.d_slice_stats, sizeof(ColumnStats) * (2 + MAX_SLICES)));
-        CUDA_TRY(cudaMallocHost(&c.h_slice_stats, sizeof(ColumnStats) * (2 + MAX_SLICES)));
-        for (auto& ev : c.done_event) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        CUDA_TRY(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, c.device));
-        CUDA_TRY(cudaMalloc(&c.d_ovf, sizeof(Overflow)));
-        CUDA_TRY(cudaMallocHost(&c.h_ovf, sizeof(Overflow)));
-        CUDA_TRY(cudaMalloc(&c.d_nulls, sizeof(unsigned long long)));
-        CUDA_TRY(cudaMallocHost(&c.h_nulls, sizeof(unsigned long long)));
-        CUDA_TRY(cudaMalloc(&c.d_stats, sizeof(ColumnStats)));
-        CUDA_TRY(cudaMalloc(&c.d_counters, 4 * sizeof(unsigned int)));
-        CUDA_TRY(cudaMallocHost(&c.h_counters, 4 * sizeof(unsigned int)));
-        CUDA_TRY(cudaMallocHost(&c.h_stats, sizeof(ColumnStats)));
-        // the quotient table of pair_algos.cuh, once per device (every host thread has its own context)
-        static std::mutex quot_mutex;
-        static bool quot_ready[64] = {false};
-        std::lock_guard<std::mutex> lock(quot_mutex);
-        if (c.device >= 64 || !quot_ready[c.device]) {
-            quotient_table_kernel<<<(QUOT_N * QUOT_N + 255) / 256, 256, 0, c.stream>>>();
-            CUDA_TRY(cudaGetLastError());
-            CUDA_TRY(cudaStreamSynchronize(c.stream));
-            if (c.device < 64) quot_ready[c.device] = true;
+        // the context is built aside and committed only when every stream, event and buffer exists: a
+        // failed initialisation (out of memory) must not leave a half-built context that the next call
+        // would take for a usable one, and a thread that switches device gives the old resources back
+        destroy_ctx(c);
+        ThreadCtx fresh;
+        const int rc = init_ctx(fresh, g_requested_device);
+        if (rc != STRSIM_OK) {
+            const std::string msg = g_last_error;
+            destroy_ctx(fresh);
+            g_last_error = msg;
+            return rc;
         }
+        c = fresh;
     }
     CUDA_TRY(cudaSetDevice(c.device));
     *out = &c;
@@ -276,6 +342,7 @@ struct PoolBlock {
     int device;
     void* ptr;
     size_t bytes;
+    std::chrono::steady_clock::time_point freed_at;
 };
 static std::mutex g_pool_mutex;
 static std::vector<PoolBlock> g_pool;
@@ -334,7 +401,30 @@ static void pool_free(int device, void* ptr, size_t bytes) {
         cudaFree(ptr);
         return;
     }
-    g_pool.push_back({device, ptr, bytes});
+    g_pool.push_back({device, ptr, bytes, std::chrono::steady_clock::now()});
+}
+
+// hands the blocks that sat unused for at least `idle_seconds` back to the driver (the plugin's cache reaper
+// calls this once the cache has emptied, so an idle process does not sit on gigabytes of HBM)
+extern "C" void strsim_pool_trim(int idle_seconds) {
+    std::vector<PoolBlock> drop;
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        const auto now = std::chrono::steady_clock::now();
+        for (size_t i = g_pool.size(); i-- > 0;)
+            if (std::chrono::duration_cast<std::chrono::seconds>(now - g_pool[i].freed_at).count() >= idle_seconds) {
+                drop.push_back(g_pool[i]);
+                g_pool.erase(g_pool.begin() + (long)i);
+            }
+    }
+    int prev = -1;
+    cudaGetDevice(&prev);
+    for (const PoolBlock& b : drop) {
+        cudaSetDevice(b.device);
+        cudaFree(b.ptr);
+    }
+    if (prev >= 0) cudaSetDevice(prev);
+    cudaGetLastError();
 }
 
 // ---- device-resident column --------------------------------------------------------------------------
@@ -356,10 +446,12 @@ struct strsim_b200_column {
     int64_t data_bytes = 0;
     int64_t alg_bytes = -1;
     bool has_validity = false;
+    bool scalar_null = false;  // the column has exactly one row and that row is null
     unsigned or_byte = 0, and_byte = 0xFF;  // OR / AND over every string byte of the column
     // distinct data buffers in upload order (chunks made by slicing share buffers) and how much of each
     // is on the device right now: equal to the size except while a host call uploads progressively
     std::vector<int64_t> buf_size, buf_resident;
+    std::vector<size_t> buf_dev_off;  // per distinct data buffer: offset inside `block`
     std::vector<std::vector<int>> chunk_buf_ids;  // [chunk][buffer index] -> distinct buffer id
     // general columns: share of pairs with a character above U+00FF seen by the last Latin-1 launch over
     // this column (-1: unknown); a hint only, read and written without synchronisation
@@ -524,6 +616,26 @@ static void stats_fold(const ColumnStats& s, unsigned* or_byte, unsigned* and_by
     *and_byte = (a & (a >> 8) & (a >> 16) & (a >> 24)) & 0xFFu;
 }
 
+// is the single row of a length-1 column null?
+static bool host_scalar_is_null(const strsim_view_chunk* chunks, size_t n_chunks) {
+    for (size_t i = 0; i < n_chunks; i++)
+        if (chunks[i].length == 1)
+            return chunks[i].validity && !((chunks[i].validity[chunks[i].offset >> 3] >> (chunks[i].offset & 7)) & 1);
+    return false;
+}
+
+// The null-literal rule.  A length-1 operand against a longer column is a literal (strsim.rs:61-66,85-92).
+// The reference unwraps it (`b.get(0).unwrap()`, strsim.rs:62,65,87,90) and PANICS on a null literal; the
+// derive wrapper turns that into a failed query.  Here the query fails too, as an ordinary error with a
+// message that says why.  A one-row frame (both operands of length 1) is not a literal: nulls propagate
+// as for any other row (the reference panics there as well when b is null -- a side effect of the same
+// unwrap that is not reproduced).
+static int null_literal_error() {
+    strsim_set_error("the literal operand is null: a String literal compared with a column must not be null "
+                     "(polars-strsim unwraps it and panics, strsim.rs:62,65)");
+    return STRSIM_ERR_ARGUMENT;
+}
+
 static int upload_plan(ThreadCtx& ctx, const strsim_view_chunk* chunks, size_t n_chunks, Uploader* up) {
     auto* col = new strsim_b200_column();
     col->device = ctx.device;
@@ -580,6 +692,7 @@ static int upload_plan(ThreadCtx& ctx, const strsim_view_chunk* chunks, size_t n
             col->buf_resident.push_back(col->buf_size.back());
             up->buf_src.push_back(ch.data_buffers[b]);
             up->buf_dev_off.push_back(total);
+            col->buf_dev_off.push_back(total);
             if (seen.size() < 4096) seen.push_back({ch.data_buffers[b], ch.data_buffer_sizes[b], total, id});
             // 64 spare bytes: TMA spans are rounded to 16 B and word copies read a few bytes past
             total = align_up(total + (size_t)ch.data_buffer_sizes[b] + 64, 256);
@@ -588,6 +701,7 @@ static int upload_plan(ThreadCtx& ctx, const strsim_view_chunk* chunks, size_t n
         col->length += ch.length;
         if (p.validity_bytes) col->has_validity = true;
     }
+    col->scalar_null = col->length == 1 && host_scalar_is_null(chunks, n_chunks);
     total += 256;
     int rc = pool_alloc(ctx.device, total, &col->block);
     if (rc) {
@@ -848,6 +962,23 @@ static int upload_column(ThreadCtx& ctx, const strsim_view_chunk* chunks, size_t
 }
 
 // ---- kernel launch helpers -----------------------------------------------------------------------------
+// raises the dynamic shared memory limit of `kern` on `device` to `bytes` (capped at what a CTA may opt
+// into) the first time the pair (device, kernel) is seen; process-wide, safe from any host thread
+static cudaError_t configure_smem(const void* kern, int device, size_t bytes) {
+    static std::mutex m;
+    static std::vector<std::pair<const void*, int>> done;
+    std::lock_guard<std::mutex> lock(m);
+    for (const auto& d : done)
+        if (d.first == kern && d.second == device) return cudaSuccess;
+    int optin = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (e != cudaSuccess) return e;
+    if (bytes > (size_t)optin) bytes = (size_t)optin;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) done.emplace_back(kern, device);
+    return e;
+}
+
 template <class M, int MEASURE, int TPB, int RPT, bool GATHER, int T, bool ASCII_ONLY, bool REG = false,
           bool UREG = false, bool ULAT = false>
 static int launch_short(ThreadCtx& ctx, SegArgs args, long long n_upper, cudaStream_t st) {
@@ -862,12 +993,12 @@ static int launch_short(ThreadCtx& ctx, SegArgs args, long long n_upper, cudaStr
         args.stage_bytes = (int)((stage + 15) & ~15ll);
     }
     const size_t smem = L::bytes(args.stage_bytes);
-    static thread_local size_t configured = 0;
-    static thread_local int per_sm = 0;
-    if (smem > configured || per_sm == 0) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    // cudaFuncAttributeMaxDynamicSharedMemorySize belongs to (device, kernel) and is shared by every host
+    // thread (Polars calls the plugin from several): it is raised ONCE per device to the most this
+    // instantiation can ever ask for -- a per-thread cache of the last size set would let one thread lower
+    // the limit under another thread's larger launch
+    CUDA_TRY(configure_smem(reinterpret_cast<const void*>(kern), ctx.device, L::bytes(L::CAP * L::TILE)));
+    int per_sm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TPB, smem));
     if (per_sm < 1) {
         strsim_set_error("short kernel does not fit an SM (smem %zu)", smem);
@@ -888,15 +1019,12 @@ static int launch_direct(ThreadCtx& ctx, const SegArgs& args, long long n_upper,
     using L = DirectLayout<M, TPB, RPT, T>;
     auto kern = direct_kernel<M, MEASURE, TPB, RPT, GATHER, T, ASCII_ONLY>;
     const size_t smem = L::bytes;
-    static thread_local int per_sm = 0;
-    if (per_sm == 0) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TPB, smem));
-        if (per_sm < 1) {
-            per_sm = 0;
-            strsim_set_error("direct kernel does not fit an SM (smem %zu)", smem);
-            return STRSIM_ERR_CUDA;
-        }
+    CUDA_TRY(configure_smem(reinterpret_cast<const void*>(kern), ctx.device, smem));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TPB, smem));
+    if (per_sm < 1) {
+        strsim_set_error("direct kernel does not fit an SM (smem %zu)", smem);
+        return STRSIM_ERR_CUDA;
     }
     const long long tiles = (n_upper + L::TILE - 1) / L::TILE;
     long long grid = (long long)per_sm * ctx.sm_count;
@@ -1411,6 +1539,7 @@ static int compute_on_device(ThreadCtx& ctx, const int* measures, size_t n_measu
         return STRSIM_ERR_SHAPE;
     }
     const int64_t n_total = (la == 1) ? lb : la;
+    if ((la == 1 && lb != 1 && a->scalar_null) || (lb == 1 && la != 1 && b->scalar_null)) return null_literal_error();
     if (n_total == 0 || n_rows <= 0) return STRSIM_OK;
     const int64_t n = row_lo + n_rows;  // exclusive end row
     const bool bc_a = la == 1 && n_total != 1, bc_b = lb == 1 && n_total != 1;
@@ -1592,7 +1721,7 @@ int strsim_b200_column_upload(const strsim_view_chunk* chunks, size_t n_chunks, 
     ThreadCtx* ctx;
     int rc = ensure_ctx(&ctx);
     if (rc) return rc;
-    rc = upload_column(*ctx, chunks, n_chunks, true, out);
+    rc = guarded("column_upload", [&] { return upload_column(*ctx, chunks, n_chunks, true, out); });
     if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return STRSIM_OK;
@@ -1616,6 +1745,46 @@ int strsim_b200_get_device(void) {
 }
 int64_t strsim_b200_column_algorithmic_bytes(const strsim_b200_column* col) {
     return col ? col->alg_bytes : -1;
+}
+
+int strsim_b200_column_restat(strsim_b200_column* col, void* stream) {
+    if (!col) {
+        strsim_set_error("column_restat: NULL column");
+        return STRSIM_ERR_ARGUMENT;
+    }
+    ThreadCtx* ctx;
+    int rc = ensure_ctx(&ctx);
+    if (rc) return rc;
+    if (col->device != ctx->device) {
+        strsim_set_error("column lives on device %d, calling thread uses device %d", col->device, ctx->device);
+        return STRSIM_ERR_ARGUMENT;
+    }
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    stats_init_value(ctx->h_stats);
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_stats, ctx->h_stats, sizeof(ColumnStats), cudaMemcpyHostToDevice, st));
+    char* base = static_cast<char*>(col->block);
+    for (size_t id = 0; id < col->buf_size.size(); id++) {
+        const int64_t size = col->buf_size[id];
+        if (size <= 0) continue;
+        long long blocks = ((size >> 4) + 255) / 256;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        if (blocks < 1) blocks = 1;
+        stats_bytes_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const unsigned char*>(base + col->buf_dev_off[id]),
+                                                            size, ctx->d_stats);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    for (const DevChunk& dc : col->chunks) {
+        if (dc.length <= 0) continue;
+        long long blocks = (dc.length + 255) / 256;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        stats_views_kernel<<<(unsigned)blocks, 256, 0, st>>>(dc.views, dc.length, ctx->d_stats);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(publish_to_host(ctx->h_stats, ctx->d_stats, sizeof(ColumnStats), st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    stats_fold(*ctx->h_stats, &col->or_byte, &col->and_byte);
+    return STRSIM_OK;
 }
 
 int strsim_b200_compute_device(int measure, const strsim_b200_column* a, const strsim_b200_column* b,
@@ -1675,11 +1844,28 @@ int strsim_b200_compute_device_multi(const int* measures, size_t n_measures, con
 // The host call.  A column is either given as host chunks (uploaded in pipelined row slices) or as
 // `res_x`, a column that is already resident in HBM (then x / n_x are ignored).  keep_x != nullptr: the
 // uploaded column is handed to the caller instead of being freed (strsim_b200_compute_host_keep).
+static int host_call_impl(const int* measures, size_t n_measures, const strsim_view_chunk* a, size_t n_a,
+                          const strsim_b200_column* res_a, strsim_b200_column** keep_a, const strsim_view_chunk* b,
+                          size_t n_b, const strsim_b200_column* res_b, strsim_b200_column** keep_b,
+                          double* const* out_values, uint8_t* out_validity, int64_t* out_null_count,
+                          int32_t* const* dbg_ints);
+
 static int host_call(const int* measures, size_t n_measures, const strsim_view_chunk* a, size_t n_a,
                      const strsim_b200_column* res_a, strsim_b200_column** keep_a, const strsim_view_chunk* b,
                      size_t n_b, const strsim_b200_column* res_b, strsim_b200_column** keep_b,
                      double* const* out_values, uint8_t* out_validity, int64_t* out_null_count,
                      int32_t* const* dbg_ints) {
+    return guarded("compute_host", [&] {
+        return host_call_impl(measures, n_measures, a, n_a, res_a, keep_a, b, n_b, res_b, keep_b, out_values, out_validity,
+                              out_null_count, dbg_ints);
+    });
+}
+
+static int host_call_impl(const int* measures, size_t n_measures, const strsim_view_chunk* a, size_t n_a,
+                          const strsim_b200_column* res_a, strsim_b200_column** keep_a, const strsim_view_chunk* b,
+                          size_t n_b, const strsim_b200_column* res_b, strsim_b200_column** keep_b,
+                          double* const* out_values, uint8_t* out_validity, int64_t* out_null_count,
+                          int32_t* const* dbg_ints) {
     if (keep_a) *keep_a = nullptr;
     if (keep_b) *keep_b = nullptr;
     if ((!res_a && n_a && !a) || (!res_b && n_b && !b) || !measures || n_measures == 0 || n_measures > 8 || !out_values) {
@@ -1701,6 +1887,11 @@ static int host_call(const int* measures, size_t n_measures, const strsim_view_c
         return STRSIM_ERR_SHAPE;
     }
     const int64_t n = la == 1 ? lb : la;
+    if (la != lb) {
+        const bool null_a = la == 1 && (res_a ? res_a->scalar_null : host_scalar_is_null(a, n_a));
+        const bool null_b = lb == 1 && (res_b ? res_b->scalar_null : host_scalar_is_null(b, n_b));
+        if (null_a || null_b) return null_literal_error();
+    }
     if (out_null_count) *out_null_count = 0;
     for (size_t m = 0; n > 0 && m < n_measures; m++)
         if (!out_values[m]) {

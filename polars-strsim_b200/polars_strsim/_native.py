@@ -89,6 +89,8 @@ def lib():
     L.strsim_b200_column_length.argtypes = [P]
     L.strsim_b200_column_algorithmic_bytes.restype = I64
     L.strsim_b200_column_algorithmic_bytes.argtypes = [P]
+    L.strsim_b200_column_restat.restype = ctypes.c_int
+    L.strsim_b200_column_restat.argtypes = [P, P]
     L.strsim_b200_compute_device.restype = ctypes.c_int
     L.strsim_b200_compute_device.argtypes = [ctypes.c_int, P, P, P, P, P, P]
     L.strsim_b200_compute_device_multi.restype = ctypes.c_int
@@ -118,7 +120,7 @@ def measure_id(measure) -> int:
 
 def as_chunks(col):
     """pyarrow Array / ChunkedArray of string_view (or string / large_string, which pyarrow casts to
-    views zero-copy) -> (ctypes array of ViewChunk, keepalive list)."""
+    views zero-copy) -> (ctypes array of ViewChunk, keepalive list).  Other types are a SchemaMismatch."""
     import pyarrow as pa
 
     if isinstance(col, (str, bytes)) or col is None:
@@ -127,10 +129,11 @@ def as_chunks(col):
     keep = []
     out = (ViewChunk * max(1, len(arrays)))()
     for i, arr in enumerate(arrays):
-        if arr.type in (pa.string(), pa.large_string(), pa.binary(), pa.large_binary()):
-            arr = arr.cast(pa.string_view() if pa.types.is_string(arr.type) or pa.types.is_large_string(arr.type)
-                           else pa.binary_view())
-        if arr.type not in (pa.string_view(), pa.binary_view()):
+        if arr.type in (pa.string(), pa.large_string()):
+            arr = arr.cast(pa.string_view())
+        if arr.type != pa.string_view():
+            # String columns only, like the reference's `inputs[i].str()?` (strsim.rs:46-47): binary data
+            # carries no UTF-8 guarantee
             raise StrsimError(2, f"invalid series dtype: expected `String`, got `{arr.type}`")
         bufs = arr.buffers()
         data = [b for b in bufs[2:]]
@@ -232,6 +235,10 @@ class DeviceColumn:
     @property
     def algorithmic_bytes(self) -> int:
         return int(lib().strsim_b200_column_algorithmic_bytes(self._h))
+
+    def restat(self, stream: int = 0):
+        """re-runs the column-statistics pre-pass (what an upload does once) on `stream` and waits for it"""
+        _check(lib().strsim_b200_column_restat(self._h, stream or None))
 
     def free(self):
         if self._h:

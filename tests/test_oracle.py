@@ -217,31 +217,3 @@ def test_batch_views_threads_and_nulls(oracle):
     assert len(out) == n  # NOT the reference's 1-row quirk (strsim.rs:73)
     with pytest.raises(ValueError):
         oracle.batch_views("jaro", A.slice(0, 10), B.slice(0, 11))
-
-
-def test_markstein_small_quotients():
-    """The kernels compute m/la etc. for short strings as q0=i*y, r=fma(-j,q0,i), q=fma(r,y,q0) with
-    y=RN(1/j).  This proves that equals IEEE i/j for every reachable operand (exhaustive)."""
-    N = 1024
-    i = np.arange(0, N + 1, dtype=np.float64)[:, None]
-    j = np.arange(1, N + 1, dtype=np.float64)[None, :]
-    y = 1.0 / j
-    q0 = i * y
-    # exact residual i - j*q0 evaluated with one rounding (fma) via long double-free trick:
-    # use math.fma when available (3.13+), else Fraction on a sample
-    if hasattr(math, "fma"):
-        fma = np.frompyfunc(math.fma, 3, 1)
-        r = fma(-j + 0 * i, q0, i + 0 * j).astype(np.float64)
-        q = fma(r, y + 0 * i, q0).astype(np.float64)
-        assert (q == i / j).all()
-    else:
-        from fractions import Fraction
-
-        rng = random.Random(5)
-        for _ in range(20000):
-            a_, b_ = rng.randint(0, N), rng.randint(1, N)
-            yy = 1.0 / b_
-            q0_ = a_ * yy
-            r_ = float(Fraction(a_) - Fraction(b_) * Fraction(q0_))  # exact: representable
-            q_ = float(Fraction(q0_) + Fraction(r_) * Fraction(yy))  # one rounding
-            assert q_ == a_ / b_
