@@ -6,6 +6,7 @@
 // `_polars_plugin_get_last_error_message`, `_polars_plugin_get_version`.  Pure C++ (no CUDA here);
 // all compute goes through strsim_b200_compute_host().
 #include <chrono>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -23,6 +24,10 @@
 #include "../../include/strsim_b200.h"
 
 extern "C" void strsim_set_error(const char* fmt, ...);
+extern "C" void* strsim_result_alloc(size_t bytes);  // host.cu: pool of pinned result buffers
+extern "C" int strsim_result_free(void* p);
+extern "C" int strsim_result_pool_trim(int idle_seconds);
+extern "C" void strsim_pool_trim(int idle_seconds);  // host.cu: idle device blocks back to the driver
 
 // ---- Arrow C Data Interface (stable ABI, https://arrow.apache.org/docs/format/CDataInterface.html)
 extern "C" {
@@ -274,8 +279,6 @@ void cache_trim(int64_t incoming_bytes) {
 // starts a reaper thread that wakes once a second while the cache holds anything, drops what has
 // expired, hands idle blocks of the device pool back to the driver, and exits when nothing is left.
 bool g_reaper_running = false;  // guarded by g_cache_mutex
-extern "C" void strsim_pool_trim(int idle_seconds);
-
 void reaper_main() {
     for (;;) {
         std::this_thread::sleep_for(std::chrono::seconds(1));
@@ -293,15 +296,17 @@ void reaper_main() {
                     i++;
                 }
             }
-            if (g_cache.empty()) {
-                g_reaper_running = false;
-                done = true;
-            }
+            done = g_cache.empty();
         }
         expired.clear();
-        if (done) {
-            strsim_pool_trim(0);
-            return;
+        const int pinned_left = strsim_result_pool_trim(cache_ttl_seconds());
+        if (done && pinned_left == 0) {
+            std::lock_guard<std::mutex> lock(g_cache_mutex);
+            if (g_cache.empty()) {  // nothing was inserted meanwhile
+                g_reaper_running = false;
+                strsim_pool_trim(0);
+                return;
+            }
         }
     }
 }
@@ -316,16 +321,55 @@ void reaper_ensure() {
     }
 }
 
-std::shared_ptr<CacheEntry> cache_lookup(const std::vector<ChunkKey>& key, int device) {
-    std::lock_guard<std::mutex> lock(g_cache_mutex);
-    for (auto& e : g_cache)
-        if (e->key == key && strsim_b200_column_device(e->col) == device) {
-            e->last_use = std::chrono::steady_clock::now();
-            g_cache_hits++;
-            return e;
+// Uploads in flight.  Polars evaluates the expressions of one `with_columns` on several threads, so the five
+// README calls (README.md:47-51) may arrive TOGETHER: every one of them would miss the cache and upload the
+// same two columns.  The first call to miss claims the key; the others wait until its upload is in the
+// cache (or has failed -- then one of them claims the key in turn).
+struct InFlight {
+    std::vector<ChunkKey> key;
+    int device;
+};
+std::vector<InFlight>& g_inflight = *new std::vector<InFlight>();
+std::condition_variable& g_inflight_cv = *new std::condition_variable();
+
+// hit: the entry.  miss: nullptr, and *claimed says whether this call now owns the upload of `key` (it must
+// call cache_unclaim afterwards, whatever happened).  may_wait = false: never blocks.
+std::shared_ptr<CacheEntry> cache_lookup(const std::vector<ChunkKey>& key, int device, bool* claimed, bool may_wait) {
+    std::unique_lock<std::mutex> lock(g_cache_mutex);
+    *claimed = false;
+    for (int round = 0; round < 64; round++) {
+        for (auto& e : g_cache)
+            if (e->key == key && strsim_b200_column_device(e->col) == device) {
+                e->last_use = std::chrono::steady_clock::now();
+                g_cache_hits++;
+                return e;
+            }
+        bool flying = false;
+        for (const InFlight& f : g_inflight) flying = flying || (f.device == device && f.key == key);
+        if (!flying) {
+            g_inflight.push_back({key, device});
+            *claimed = true;
+            break;
         }
+        // a call that already owns one upload never waits for another one (two calls with their operands
+        // crossed would wait for each other): it uploads this column itself
+        if (!may_wait) break;
+        g_inflight_cv.wait_for(lock, std::chrono::seconds(2));
+    }
     g_cache_misses++;
     return nullptr;
+}
+
+void cache_unclaim(const std::vector<ChunkKey>& key, int device) {
+    {
+        std::lock_guard<std::mutex> lock(g_cache_mutex);
+        for (size_t i = 0; i < g_inflight.size(); i++)
+            if (g_inflight[i].device == device && g_inflight[i].key == key) {
+                g_inflight.erase(g_inflight.begin() + (long)i);
+                break;
+            }
+    }
+    g_inflight_cv.notify_all();
 }
 
 // takes ownership of `col` and of the contents of the series' arrays (their structs are marked released)
@@ -357,11 +401,17 @@ bool cacheable(const strsim_series_export& s, const Column& c) {
     return n >= CACHE_MIN_ROWS;
 }
 
+void reaper_wanted() {
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    reaper_ensure();
+}
+
 // ---- Float64 result array --------------------------------------------------------------------------
 struct ResultPrivate {
     double* values;
     uint8_t* validity;
     const void* buffers[2];
+    bool pinned;       // `values` is a block of the pinned result pool (DMA'd into directly)
     void* map_base;    // large results: an anonymous mapping (2 MiB aligned start inside it) ...
     size_t map_bytes;  // ... so that the kernel may back it with huge pages: 40 first-touch faults for
                        // 80 MB instead of 20,000
@@ -372,6 +422,12 @@ double* alloc_values(ResultPrivate* p, size_t n) {
     const size_t bytes = 8 * (n > 0 ? n : 1);
     p->map_base = nullptr;
     p->map_bytes = 0;
+    p->pinned = false;
+    if (void* pin = strsim_result_alloc(bytes)) {
+        p->pinned = true;
+        reaper_wanted();  // someone has to unpin the block once it has come back and sat idle
+        return static_cast<double*>(pin);
+    }
 #if defined(__linux__)
     if (bytes >= ((size_t)4 << 20)) {
         const size_t huge = (size_t)2 << 20;
@@ -390,6 +446,11 @@ double* alloc_values(ResultPrivate* p, size_t n) {
 }
 
 void free_values(ResultPrivate* p) {
+    if (p->pinned) {
+        strsim_result_free(p->values);
+        p->pinned = false;
+        return;
+    }
 #if defined(__linux__)
     if (p->map_base) {
         munmap(p->map_base, p->map_bytes);
@@ -547,8 +608,22 @@ void plugin_call(int measure, strsim_series_export* inputs, size_t n_inputs,
         const bool cache_a = device >= 0 && cacheable(inputs[0], ca), cache_b = device >= 0 && cacheable(inputs[1], cb);
         std::vector<ChunkKey> key_a, key_b;
         std::shared_ptr<CacheEntry> hit_a, hit_b;
-        if (cache_a) hit_a = cache_lookup(key_a = key_of(ca), device);
-        if (cache_b) hit_b = cache_lookup(key_b = key_of(cb), device);
+        bool claimed_a = false, claimed_b = false;
+        if (cache_a) hit_a = cache_lookup(key_a = key_of(ca), device, &claimed_a, true);
+        if (cache_b) {
+            key_b = key_of(cb);
+            // the same column on both sides: this call already owns that upload and must not wait for itself
+            if (!(claimed_a && key_b == key_a)) hit_b = cache_lookup(key_b, device, &claimed_b, !claimed_a);
+        }
+        struct Unclaim {  // whatever happens below (errors, exceptions), waiting calls are woken
+            const std::vector<ChunkKey>*key_a, *key_b;
+            bool a, b;
+            int device;
+            ~Unclaim() {
+                if (a) cache_unclaim(*key_a, device);
+                if (b) cache_unclaim(*key_b, device);
+            }
+        } unclaim{&key_a, &key_b, claimed_a, claimed_b, device};
         strsim_b200_column *kept_a = nullptr, *kept_b = nullptr;
         result = new ArrowArray();
         rc = compute_to_arrow(measure, ca, cb, result, hit_a ? hit_a->col : nullptr,
@@ -558,8 +633,8 @@ void plugin_call(int measure, strsim_series_export* inputs, size_t n_inputs,
             delete result;
             result = nullptr;
         }
-        if (kept_a) cache_insert(std::move(key_a), kept_a, inputs[0]);
-        if (kept_b) cache_insert(std::move(key_b), kept_b, inputs[1]);
+        if (kept_a) cache_insert(key_a, kept_a, inputs[0]);
+        if (kept_b) cache_insert(key_b, kept_b, inputs[1]);
     }
     // the callee owns the inputs (polars-ffi import_series_buffer semantics): release every chunk's
     // contents, then the SeriesExport boxes

@@ -262,32 +262,54 @@ __device__ __forceinline__ void stats_commit(ColumnStats* out, uint32_t o, uint3
     }
 }
 
-__global__ void stats_views_kernel(const uint4* views, long long n, ColumnStats* out) {
+__device__ __forceinline__ void stats_of_view(const uint4& v, uint32_t& o, uint32_t& a) {
+    const int len = (int)v.x;
+    if (len > 12) {  // prefix; the rest is in the data buffer
+        o |= v.y;
+        a &= v.y;
+    } else {
+        const uint32_t m0 = byte_mask(len), m1 = byte_mask(len - 4 < 0 ? 0 : len - 4),
+                       m2 = byte_mask(len - 8 < 0 ? 0 : len - 8);
+        o |= (v.y & m0) | (v.z & m1) | (v.w & m2);
+        a &= (v.y | ~m0) & (v.z | ~m1) & (v.w | ~m2);
+    }
+}
+
+// Both statistics kernels are pure streaming reads: four independent 16-byte loads per thread and
+// iteration keep enough bytes in flight to run at the HBM rate (one load per iteration: half of it).
+__global__ void __launch_bounds__(256) stats_views_kernel(const uint4* views, long long n, ColumnStats* out) {
     uint32_t o = 0, a = 0xFFFFFFFFu;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-         i += (long long)gridDim.x * blockDim.x) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {
+        const uint4 v0 = ld_view(views + i), v1 = ld_view(views + i + stride), v2 = ld_view(views + i + 2 * stride),
+                    v3 = ld_view(views + i + 3 * stride);
+        stats_of_view(v0, o, a);
+        stats_of_view(v1, o, a);
+        stats_of_view(v2, o, a);
+        stats_of_view(v3, o, a);
+    }
+    for (; i < n; i += stride) {
         const uint4 v = ld_view(views + i);
-        const int len = (int)v.x;
-        if (len > 12) {  // prefix; the rest is in the data buffer
-            o |= v.y;
-            a &= v.y;
-        } else {
-            const uint32_t m0 = byte_mask(len), m1 = byte_mask(len - 4 < 0 ? 0 : len - 4),
-                           m2 = byte_mask(len - 8 < 0 ? 0 : len - 8);
-            o |= (v.y & m0) | (v.z & m1) | (v.w & m2);
-            a &= (v.y | ~m0) & (v.z | ~m1) & (v.w | ~m2);
-        }
+        stats_of_view(v, o, a);
     }
     stats_commit(out, o, a);
 }
 
 // data: 16-byte aligned device buffer, `bytes` valid bytes
-__global__ void stats_bytes_kernel(const unsigned char* data, long long bytes, ColumnStats* out) {
+__global__ void __launch_bounds__(256) stats_bytes_kernel(const unsigned char* data, long long bytes, ColumnStats* out) {
     uint32_t o = 0, a = 0xFFFFFFFFu;
     const long long n16 = bytes >> 4;
     const uint4* d4 = reinterpret_cast<const uint4*>(data);
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16;
-         i += (long long)gridDim.x * blockDim.x) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n16; i += 4 * stride) {
+        const uint4 v0 = ld_view(d4 + i), v1 = ld_view(d4 + i + stride), v2 = ld_view(d4 + i + 2 * stride),
+                    v3 = ld_view(d4 + i + 3 * stride);
+        o |= (v0.x | v0.y | v0.z | v0.w) | (v1.x | v1.y | v1.z | v1.w) | (v2.x | v2.y | v2.z | v2.w) | (v3.x | v3.y | v3.z | v3.w);
+        a &= (v0.x & v0.y & v0.z & v0.w) & (v1.x & v1.y & v1.z & v1.w) & (v2.x & v2.y & v2.z & v2.w) & (v3.x & v3.y & v3.z & v3.w);
+    }
+    for (; i < n16; i += stride) {
         const uint4 v = ld_view(d4 + i);
         o |= v.x | v.y | v.z | v.w;
         a &= v.x & v.y & v.z & v.w;

@@ -6,6 +6,9 @@
 // long_lev_kernel.cuh, and fails with STRSIM_ERR_CUDA when no device is usable.
 #include <cuda_runtime.h>
 #include <ctype.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <sched.h>
 
 #include <atomic>
@@ -122,7 +125,36 @@ struct StageTask {
     std::atomic<int>* flag;  // set to flag_value once the bytes are copied
     int flag_value;
     std::atomic<long long>* pending;  // decremented afterwards (may be nullptr)
+    bool streaming;  // destination is the write-combined upload ring: non-temporal stores
 };
+
+// memcpy with non-temporal stores: the destination (a slot of the pinned upload ring) is next read by the
+// DMA engine, not by a CPU, so the lines need neither be fetched for ownership nor stay in a cache.
+// Measured on the pool's 16-core host (exp/stage_bw.cu, 8 threads feeding a ring that is DMA'd
+// concurrently): memcpy 39.6 GB/s, this into a write-combined ring 49.2 GB/s.
+static void stream_copy(void* dst, const void* src, size_t bytes) {
+#if defined(__SSE2__)
+    char* d = static_cast<char*>(dst);
+    const char* s = static_cast<const char*>(src);
+    size_t i = 0;
+    if ((reinterpret_cast<uintptr_t>(d) & 15) == 0) {
+        for (; i + 64 <= bytes; i += 64) {
+            const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i));
+            const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i + 16));
+            const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i + 32));
+            const __m128i e = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i + 48));
+            _mm_stream_si128(reinterpret_cast<__m128i*>(d + i), a);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(d + i + 16), b);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(d + i + 32), c);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(d + i + 48), e);
+        }
+    }
+    if (i < bytes) memcpy(d + i, s + i, bytes - i);
+    _mm_sfence();
+#else
+    memcpy(dst, src, bytes);
+#endif
+}
 
 class StagePool {
    public:
@@ -166,7 +198,10 @@ class StagePool {
                 }
                 cudaEventSynchronize(t.ev);
             }
-            memcpy(t.dst, t.src, t.bytes);
+            if (t.streaming)
+                stream_copy(t.dst, t.src, t.bytes);
+            else
+                memcpy(t.dst, t.src, t.bytes);
             t.flag->store(t.flag_value, std::memory_order_release);
             if (t.pending) t.pending->fetch_sub(1, std::memory_order_acq_rel);
         }
@@ -206,7 +241,7 @@ struct ThreadCtx {
     ColumnStats* h_stats = nullptr;  // pinned
     Workspace lists, scratch;
     Stager* stager = nullptr;     // created by the first download into pageable memory
-    Stager* up_stager = nullptr;  // created by the first upload from pageable memory
+    struct UpStager* up_stager = nullptr;  // created by the first upload from pageable memory
 };
 
 static thread_local ThreadCtx g_ctx;
@@ -222,6 +257,8 @@ static int default_device() {
     }
     return 0;
 }
+
+static void destroy_up_stager(struct UpStager* sg);
 
 static void destroy_ctx(ThreadCtx& c) {
     // best effort: the context may be half built (failed initialisation) or belong to a device that is
@@ -241,7 +278,8 @@ static void destroy_ctx(ThreadCtx& c) {
         if (p) cudaFree(p);
     for (void* p : {(void*)c.h_slice_stats, (void*)c.h_ovf, (void*)c.h_nulls, (void*)c.h_counters, (void*)c.h_stats})
         if (p) cudaFreeHost(p);
-    for (Stager* sg : {c.stager, c.up_stager})
+    destroy_up_stager(c.up_stager);
+    for (Stager* sg : {c.stager})
         if (sg) {
             while (sg->pending.load(std::memory_order_acquire) > 0) std::this_thread::yield();
             for (auto& ev : sg->ev) if (ev) cudaEventDestroy(ev);
@@ -427,6 +465,125 @@ extern "C" void strsim_pool_trim(int idle_seconds) {
     cudaGetLastError();
 }
 
+// ---- pinned result buffers ------------------------------------------------------------------------------
+// A plugin call returns its Float64 column in a buffer the plugin allocates.  When that buffer is PINNED the
+// results are DMA'd straight into it (1.5 ms per 80 MB); a pageable buffer costs a second pass through the
+// pinned ring plus every first-touch page fault of fresh memory (3+ ms).  Pinning is expensive (tens of
+// milliseconds per 80 MB), so buffers are pooled: a call takes a free block when there is one -- otherwise
+// it falls back to pageable memory AND asks a background thread to pin a block of that size for the calls
+// to come; the release callback of the Arrow array hands the block back.  At most
+// STRSIM_B200_PINNED_RESULT_BYTES (default 1 GiB) are pinned at any time; blocks idle for the cache's
+// time-to-live are unpinned by the plugin's reaper (strsim_result_pool_trim).
+struct PinnedBlock {
+    void* ptr;
+    size_t bytes;
+    bool in_use;
+    std::chrono::steady_clock::time_point freed_at;
+};
+static std::mutex g_pinned_mutex;
+static std::condition_variable g_pinned_cv;
+static std::vector<PinnedBlock> g_pinned;
+static std::deque<size_t> g_pinned_requests;
+static bool g_pinned_grower_running = false;
+
+static size_t pinned_limit() {
+    static const size_t lim = [] {
+        const char* e = getenv("STRSIM_B200_PINNED_RESULT_BYTES");
+        return e && *e ? (size_t)strtoull(e, nullptr, 10) : ((size_t)1 << 30);
+    }();
+    return lim;
+}
+
+static void pinned_grower_main() {
+    for (;;) {
+        size_t want = 0;
+        {
+            std::unique_lock<std::mutex> lock(g_pinned_mutex);
+            if (!g_pinned_cv.wait_for(lock, std::chrono::seconds(5), [] { return !g_pinned_requests.empty(); })) {
+                g_pinned_grower_running = false;  // idle: the next request starts a new thread
+                return;
+            }
+            want = g_pinned_requests.front();
+            g_pinned_requests.pop_front();
+            size_t total = want, free_fit = 0;
+            for (const PinnedBlock& b : g_pinned) {
+                total += b.bytes;
+                if (!b.in_use && b.bytes >= want && b.bytes <= want + want / 2 + (1u << 20)) free_fit++;
+            }
+            if (total > pinned_limit() || free_fit > 0) continue;  // over budget, or a fitting block came back meanwhile
+        }
+        void* p = nullptr;
+        if (cudaHostAlloc(&p, want, cudaHostAllocPortable) != cudaSuccess) {
+            cudaGetLastError();
+            continue;
+        }
+        std::lock_guard<std::mutex> lock(g_pinned_mutex);
+        g_pinned.push_back({p, want, false, std::chrono::steady_clock::now()});
+    }
+}
+
+extern "C" void* strsim_result_alloc(size_t bytes) {
+    if (bytes < (1u << 20) || pinned_limit() == 0) return nullptr;
+    const size_t want = (bytes + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
+    std::lock_guard<std::mutex> lock(g_pinned_mutex);
+    size_t best = g_pinned.size();
+    for (size_t i = 0; i < g_pinned.size(); i++) {
+        const PinnedBlock& b = g_pinned[i];
+        if (!b.in_use && b.bytes >= bytes && b.bytes <= want + want / 2 + (1u << 20) &&
+            (best == g_pinned.size() || b.bytes < g_pinned[best].bytes))
+            best = i;
+    }
+    if (best != g_pinned.size()) {
+        g_pinned[best].in_use = true;
+        return g_pinned[best].ptr;
+    }
+    if (g_pinned_requests.size() < 16) {
+        g_pinned_requests.push_back(want);
+        if (!g_pinned_grower_running) {
+            try {
+                std::thread(pinned_grower_main).detach();
+                g_pinned_grower_running = true;
+            } catch (...) {
+                g_pinned_requests.clear();
+            }
+        }
+        g_pinned_cv.notify_one();
+    }
+    return nullptr;
+}
+
+// true when `p` was a block of the pool (now free again); callable from any thread, makes no CUDA call
+extern "C" int strsim_result_free(void* p) {
+    std::lock_guard<std::mutex> lock(g_pinned_mutex);
+    for (PinnedBlock& b : g_pinned)
+        if (b.ptr == p) {
+            b.in_use = false;
+            b.freed_at = std::chrono::steady_clock::now();
+            return 1;
+        }
+    return 0;
+}
+
+// returns the number of blocks the pool still owns
+extern "C" int strsim_result_pool_trim(int idle_seconds) {
+    std::vector<void*> drop;
+    int left = 0;
+    {
+        std::lock_guard<std::mutex> lock(g_pinned_mutex);
+        const auto now = std::chrono::steady_clock::now();
+        for (size_t i = g_pinned.size(); i-- > 0;)
+            if (!g_pinned[i].in_use &&
+                std::chrono::duration_cast<std::chrono::seconds>(now - g_pinned[i].freed_at).count() >= idle_seconds) {
+                drop.push_back(g_pinned[i].ptr);
+                g_pinned.erase(g_pinned.begin() + (long)i);
+            }
+        left = (int)g_pinned.size();
+    }
+    for (void* p : drop) cudaFreeHost(p);
+    cudaGetLastError();
+    return left;
+}
+
 // ---- device-resident column --------------------------------------------------------------------------
 struct DevChunk {
     const uint4* views;  // row 0 of the chunk's logical range
@@ -506,7 +663,7 @@ static cudaError_t download(ThreadCtx& ctx, void* dst, const void* d_src, size_t
             sg.pending.fetch_sub(1);
             return e;
         }
-        pool.push(StageTask{ctx.device, sg.ev[slot], pinned, static_cast<char*>(dst) + off, len, &sg.busy[slot], 0, &sg.pending});
+        pool.push(StageTask{ctx.device, sg.ev[slot], pinned, static_cast<char*>(dst) + off, len, &sg.busy[slot], 0, &sg.pending, false});
     }
     return cudaSuccess;
 }
@@ -517,59 +674,108 @@ static void download_wait(ThreadCtx& ctx) {
     while (ctx.stager->pending.load(std::memory_order_acquire) > 0) std::this_thread::yield();
 }
 
-// host -> device copy on stream `st`.  Pinned sources are DMA'd directly (asynchronous).  Pageable
-// sources -- what Polars hands a plugin -- would be staged by the driver on this thread at ~12 GB/s; here
-// the pool's threads copy them into a ring of pinned slots in parallel and every filled slot is DMA'd at
-// once.  This call returns when the last DMA of a pageable source has been QUEUED (the source is no
-// longer needed), so a host call interleaves such uploads with the kernels of the previous row slice.
+// ---- uploads from pageable host memory --------------------------------------------------------------------
+// Pinned sources are DMA'd directly (asynchronous).  Pageable sources -- what Polars hands a plugin -- would
+// be staged by the driver on the calling thread at ~12 GB/s; here the pool's threads copy them (non-temporal
+// stores) into a ring of write-combined pinned slots and every filled slot is DMA'd at once.  The ring is a
+// pipeline ACROSS upload_copy() calls: a call only hands its chunks to the copy threads and sends whatever
+// slots are full by then; upload_flush() sends the rest.  (The first version drained the ring at the end of
+// every call -- four calls per row slice, each with a start-up and a tail of one slot's copy time during
+// which the other threads idled: 29 GB/s where the same threads reach 49 GB/s in exp/stage_bw.cu.)
+constexpr int UP_SLOTS = 32;
+constexpr size_t UP_SLOT_BYTES = 2u << 20;
+
+struct UpStager {  // one per host thread (ThreadCtx)
+    void* ring = nullptr;  // UP_SLOTS x UP_SLOT_BYTES, pinned, write-combined
+    cudaEvent_t ev[UP_SLOTS] = {};  // the DMA that last read the slot
+    std::atomic<int> state[UP_SLOTS];  // 0 free, 1 being filled, 2 filled
+    struct Pending {
+        void* d_dst;
+        size_t len;
+        cudaStream_t st;
+    } pend[UP_SLOTS];
+    unsigned long long head = 0, tail = 0;  // chunks handed to the copy threads / chunks whose DMA is queued
+};
+
+static void destroy_up_stager(UpStager* sg) {
+    if (!sg) return;
+    while (sg->tail < sg->head) {  // copy threads may still be writing into the ring
+        if (sg->state[sg->tail % UP_SLOTS].load(std::memory_order_acquire) == 2) sg->tail++;
+        else std::this_thread::yield();
+    }
+    for (auto& ev : sg->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (sg->ring) cudaFreeHost(sg->ring);
+    delete sg;
+}
+
+// sends the filled slots at the tail of the ring, in order; `all`: waits for the copy threads and sends
+// everything that was handed out
+static cudaError_t upload_pump(UpStager& sg, bool all) {
+    cudaError_t e = cudaSuccess;
+    while (sg.tail < sg.head) {
+        const int slot = (int)(sg.tail % UP_SLOTS);
+        if (sg.state[slot].load(std::memory_order_acquire) != 2) {
+            if (!all) break;
+            std::this_thread::yield();
+            continue;
+        }
+        const UpStager::Pending& p = sg.pend[slot];
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(p.d_dst, static_cast<char*>(sg.ring) + (size_t)slot * UP_SLOT_BYTES, p.len, cudaMemcpyHostToDevice, p.st);
+        if (e == cudaSuccess) e = cudaEventRecord(sg.ev[slot], p.st);
+        sg.state[slot].store(0, std::memory_order_relaxed);
+        sg.tail++;
+    }
+    return e;
+}
+
+// every chunk handed to upload_copy() so far has been copied out of its (pageable) source and its DMA is
+// queued: call before recording an event that stands for "the upload has landed", and before the sources
+// may go away
+static cudaError_t upload_flush(ThreadCtx& ctx) {
+    return ctx.up_stager ? upload_pump(*ctx.up_stager, true) : cudaSuccess;
+}
+
 static cudaError_t upload_copy(ThreadCtx& ctx, void* d_dst, const void* src, size_t bytes, cudaStream_t st) {
     if (bytes == 0) return cudaSuccess;
     static const bool no_stage = getenv("STRSIM_B200_STAGED_H2D") != nullptr && !strcmp(getenv("STRSIM_B200_STAGED_H2D"), "0");
     if (no_stage || bytes < (1u << 20) || is_pinned(src)) return cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, st);
     if (!ctx.up_stager) {
-        Stager* sg = new Stager();
-        cudaError_t e = cudaMallocHost(&sg->ring, (size_t)STAGE_SLOTS * STAGE_SLOT_BYTES);
+        UpStager* sg = new UpStager();
+        cudaError_t e = cudaHostAlloc(&sg->ring, (size_t)UP_SLOTS * UP_SLOT_BYTES, cudaHostAllocWriteCombined);
         if (e != cudaSuccess) {
             delete sg;
             cudaGetLastError();
             return cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, st);
         }
-        for (int i = 0; i < STAGE_SLOTS; i++) {
+        for (int i = 0; i < UP_SLOTS; i++) {
             cudaEventCreateWithFlags(&sg->ev[i], cudaEventDisableTiming);
-            cudaEventRecord(sg->ev[i], st);  // so that the first wait on a slot returns at once
-            sg->busy[i].store(0);
+            sg->state[i].store(0);
         }
         ctx.up_stager = sg;
     }
-    Stager& sg = *ctx.up_stager;
+    UpStager& sg = *ctx.up_stager;
     StagePool& pool = StagePool::get();
-    const size_t n_chunks = (bytes + STAGE_SLOT_BYTES - 1) / STAGE_SLOT_BYTES;
-    const int base = sg.next;
-    size_t filled = 0, sent = 0;  // chunks handed to the copy threads / chunks whose DMA is queued
     cudaError_t e = cudaSuccess;
-    while (sent < n_chunks) {
-        while (filled < n_chunks && filled - sent < (size_t)STAGE_SLOTS) {
-            const int slot = (base + (int)(filled % STAGE_SLOTS)) % STAGE_SLOTS;
-            cudaEventSynchronize(sg.ev[slot]);  // the DMA that last read this slot is done
-            const size_t off = filled * STAGE_SLOT_BYTES;
-            const size_t len = bytes - off < STAGE_SLOT_BYTES ? bytes - off : STAGE_SLOT_BYTES;
-            sg.busy[slot].store(1, std::memory_order_relaxed);  // 1 = being filled, 2 = filled
-            pool.push(StageTask{ctx.device, nullptr, static_cast<const char*>(src) + off,
-                                static_cast<char*>(sg.ring) + (size_t)slot * STAGE_SLOT_BYTES, len, &sg.busy[slot], 2, nullptr});
-            filled++;
+    for (size_t off = 0; off < bytes && e == cudaSuccess; off += UP_SLOT_BYTES) {
+        const size_t len = bytes - off < UP_SLOT_BYTES ? bytes - off : UP_SLOT_BYTES;
+        while (sg.head - sg.tail >= (unsigned long long)UP_SLOTS && e == cudaSuccess) {  // ring full: send the oldest slot
+            if (sg.state[sg.tail % UP_SLOTS].load(std::memory_order_acquire) != 2) std::this_thread::yield();
+            e = upload_pump(sg, false);
         }
-        const int slot = (base + (int)(sent % STAGE_SLOTS)) % STAGE_SLOTS;
-        while (sg.busy[slot].load(std::memory_order_acquire) != 2) std::this_thread::yield();
-        const size_t off = sent * STAGE_SLOT_BYTES;
-        const size_t len = bytes - off < STAGE_SLOT_BYTES ? bytes - off : STAGE_SLOT_BYTES;
-        if (e == cudaSuccess)
-            e = cudaMemcpyAsync(static_cast<char*>(d_dst) + off, static_cast<char*>(sg.ring) + (size_t)slot * STAGE_SLOT_BYTES, len,
-                                cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess) e = cudaEventRecord(sg.ev[slot], st);
-        sg.busy[slot].store(0, std::memory_order_relaxed);
-        sent++;
+        if (e != cudaSuccess) break;
+        const int slot = (int)(sg.head % UP_SLOTS);
+        if (sg.head >= (unsigned long long)UP_SLOTS) e = cudaEventSynchronize(sg.ev[slot]);  // the DMA that last read this slot is done
+        if (e != cudaSuccess) break;
+        sg.pend[slot] = UpStager::Pending{static_cast<char*>(d_dst) + off, len, st};
+        sg.state[slot].store(1, std::memory_order_relaxed);
+        pool.push(StageTask{ctx.device, nullptr, static_cast<const char*>(src) + off,
+                            static_cast<char*>(sg.ring) + (size_t)slot * UP_SLOT_BYTES, len, &sg.state[slot], 2, nullptr, true});
+        sg.head++;
+        e = upload_pump(sg, false);
     }
-    sg.next = (base + (int)(n_chunks % STAGE_SLOTS)) % STAGE_SLOTS;
+    if (e != cudaSuccess) upload_pump(sg, true);  // never leave copy threads writing into a ring nobody drains
     return e;
 }
 
@@ -765,6 +971,7 @@ static int upload_data_range(ThreadCtx& ctx, Uploader& up, int64_t from, int64_t
                 CUDA_TRY(upload_copy(ctx, base + up.buf_dev_off[id] + lo, static_cast<const char*>(up.buf_src[id]) + lo,
                                      (size_t)(hi - lo), st));
             if (do_stats) {
+                if (do_copy) CUDA_TRY(upload_flush(ctx));  // the kernel below must be queued behind every DMA of the copy
                 long long blocks = (((hi - lo) >> 4) + 255) / 256;
                 if (blocks > 148 * 16) blocks = 148 * 16;
                 if (blocks < 1) blocks = 1;
@@ -907,6 +1114,7 @@ static int upload_rows(ThreadCtx& ctx, Uploader& up, int64_t lo, int64_t hi, cud
                                      (size_t)(b_hi - b_lo), cudaMemcpyHostToDevice, st));
         }
         if (!do_stats) continue;
+        if (do_copy) CUDA_TRY(upload_flush(ctx));  // the kernel below must be queued behind every DMA of the copy
         long long blocks = (c_hi - c_lo + 255) / 256;
         if (blocks > 148 * 16) blocks = 148 * 16;
         stats_views_kernel<<<(unsigned)blocks, 256, 0, st>>>(
@@ -937,6 +1145,7 @@ static int upload_column(ThreadCtx& ctx, const strsim_view_chunk* chunks, size_t
             strsim_set_error("CUDA error during column upload: %s", cudaGetErrorString(e));
             rc = STRSIM_ERR_CUDA;
         }
+        upload_flush(ctx);
         cudaStreamSynchronize(ctx.stream);
         strsim_b200_column_free(up.col);
         return rc;
@@ -2050,6 +2259,9 @@ static int host_call_impl(const int* measures, size_t n_measures, const strsim_v
                 rc = upload_rows(*ctx, ua, r_lo_a, r_hi_a, st, ctx->d_slice_stats + 2 + sidx, cp, stt);
             if (rc == STRSIM_OK && !res_b)
                 rc = upload_rows(*ctx, ub, r_lo_b, r_hi_b, st, ctx->d_slice_stats + 2 + sidx, cp, stt);
+            // pageable sources: the four copies above shared one pipeline through the pinned ring; what is
+            // still in it is sent now, before the event that stands for "this slice has landed"
+            if (cp && ce == cudaSuccess) ce = upload_flush(*ctx);
         }
         if (fa > ua.uploaded) ua.uploaded = fa;
         if (fb > ub.uploaded) ub.uploaded = fb;
@@ -2161,6 +2373,7 @@ static int host_call_impl(const int* measures, size_t n_measures, const strsim_v
         if (ce == cudaSuccess)
             ce = cudaMemcpyAsync(ctx->h_nulls, ctx->d_nulls, 8, cudaMemcpyDeviceToHost, ctx->copy_stream);
     }
+    upload_flush(*ctx);  // error paths: nothing may stay in the ring (it would be sent into freed memory later)
     cudaError_t s0 = cudaStreamSynchronize(ctx->upload_stream);
     if (s0 == cudaSuccess) s0 = cudaStreamSynchronize(ctx->stats_stream);
     cudaError_t s1 = cudaStreamSynchronize(ctx->stream);

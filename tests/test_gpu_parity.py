@@ -648,6 +648,59 @@ def test_plugin_calls_reuse_columns_already_in_hbm(native, oracle):
     check_out("sorensen_dice", call("sorensen_dice", A2, B2), a2, b)
 
 
+def test_concurrent_plugin_calls_share_one_upload(native, oracle):
+    """Polars evaluates the expressions of one `with_columns` on several threads: the five README calls may
+    arrive together.  Exactly ONE of them uploads each column (two misses in all); the others wait for that
+    upload instead of repeating it, and every result is bit-exact.  Results of this size land in pinned
+    buffers of the plugin's pool once the pool has grown (second round)."""
+    import ctypes
+    import threading
+    import time
+
+    sys.path.insert(0, str(ROOT))
+    from bench_support import plugin_driver, workloads
+
+    L = native.lib()
+    L.strsim_b200_cache_stats.argtypes = [ctypes.POINTER(ctypes.c_int64)]
+    L.strsim_b200_cache_stats.restype = None
+
+    def stats():
+        out = (ctypes.c_int64 * 4)()
+        L.strsim_b200_cache_stats(out)
+        return list(out)
+
+    n = 1_500_000
+    A, B = workloads.make_pairs(2, n)
+    a, b = A.to_pylist(), B.to_pylist()
+    refs = {m: oracle.batch(m, a, b)[0] for m in oracle.MEASURES}
+    for round_ in range(2):
+        plugin_driver.cache_clear()
+        h0, m0, _, _ = stats()
+        got, errors = {}, []
+
+        def work(measure):
+            try:
+                r = plugin_driver.call(measure, A, B)
+                got[measure] = np.concatenate(r.values()).copy()
+                r.release()
+            except Exception as exc:  # noqa: BLE001
+                errors.append((measure, exc))
+
+        threads = [threading.Thread(target=work, args=(m,)) for m in oracle.MEASURES]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        assert not errors, errors
+        h, m, cols, _ = stats()
+        assert m - m0 == 2 and cols == 2, ("every column must be uploaded exactly once", h - h0, m - m0, cols)
+        assert h - h0 == 8
+        for measure in oracle.MEASURES:
+            assert (got[measure].view(np.uint64) == refs[measure].view(np.uint64)).all(), measure
+        time.sleep(0.5)  # lets the background thread pin result buffers for the second round
+    plugin_driver.cache_clear()
+
+
 def test_pageable_inputs_and_outputs_go_through_the_pinned_rings(oracle):
     """Ordinary (pageable) Arrow buffers in, ordinary numpy arrays out: uploads are staged through the
     pinned ring by the copy threads, one row slice ahead of the kernels; downloads likewise."""
