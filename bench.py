@@ -260,6 +260,141 @@ def input_bytes(A, B) -> int:
     return total
 
 
+def run_strong(args, wl):
+    """--strong: ONE process drives all --gpus devices.  `value`: the workload's rows cut into one contiguous
+    range per GPU (the library's own rule: split_offsets on 64-row units), every range resident on its GPU,
+    one fused launch per GPU and step from one host thread per GPU, time = max over the GPUs (CUDA events).
+    `e2e`: every `_polars_plugin_<measure>` call is sharded over the GPUs INSIDE the library
+    (STRSIM_B200_DEVICES): each device uploads its rows' views and its stretch of the data buffers, computes,
+    and downloads into its range of the one result buffer."""
+    import numpy as np
+    import torch
+
+    from bench_support import plugin_driver, workloads
+    from polars_strsim import _native
+
+    G = args.gpus
+    if torch.cuda.device_count() < G:
+        raise SystemExit(f"--strong --gpus {G}: only {torch.cuda.device_count()} devices visible")
+    measures = wl["measures"]
+    n = args.rows
+    A, B = workloads.make_pairs(wl["config"], n, pinned=False, uneven_b=(wl["config"] == 3))
+    alg_bytes = workloads.algorithmic_bytes(A, B)
+    units, per = (n + 63) // 64, ((n + 63) // 64) // G
+    cuts = [g * per * 64 for g in range(G)] + [n]
+    barrier = threading.Barrier(G)
+    ms, sums, errors = [0.0] * G, [None] * G, []
+
+    def worker(g):
+        try:
+            torch.cuda.set_device(g)
+            _native.set_device(g)
+            lo, hi = cuts[g], cuts[g + 1]
+            colA, colB = _native.DeviceColumn(A.slice(lo, hi - lo)), _native.DeviceColumn(B.slice(lo, hi - lo))
+            outs = [torch.empty(hi - lo, dtype=torch.float64, device=f"cuda:{g}") for _ in measures]
+            ptrs = [o.data_ptr() for o in outs]
+            nulls = A.null_count + B.null_count > 0
+            val = torch.zeros((hi - lo + 31) // 32, dtype=torch.int32, device=f"cuda:{g}") if nulls else None
+            stream = torch.cuda.current_stream(g)
+
+            def step():
+                if len(measures) > 1:
+                    _native.compute_device_multi(measures, colA, colB, ptrs, val.data_ptr() if nulls else 0, None,
+                                                 stream.cuda_stream)
+                else:
+                    _native.compute_device(measures[0], colA, colB, ptrs[0], val.data_ptr() if nulls else 0, 0,
+                                           stream.cuda_stream)
+
+            for _ in range(args.warmup):
+                step()
+            torch.cuda.synchronize(g)
+            barrier.wait()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(args.steps):
+                step()
+            e1.record(stream)
+            torch.cuda.synchronize(g)
+            ms[g] = e0.elapsed_time(e1)
+            sums[g] = [float(o.sum().item()) for o in outs]
+        except Exception as exc:  # noqa: BLE001
+            errors.append((g, exc))
+            try:
+                barrier.abort()
+            except Exception:  # noqa: BLE001
+                pass
+
+    sampler = ClockSampler(0)
+    sampler.start()
+    launches0 = _native.kernel_launches()
+    threads = [threading.Thread(target=worker, args=(g,)) for g in range(G)]
+    t_wall = time.perf_counter()
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    t_wall = time.perf_counter() - t_wall
+    if errors:
+        raise SystemExit(f"--strong: device worker failed: {errors}")
+    launches = _native.kernel_launches() - launches0
+    elapsed_ms = max(ms)
+    checksums = {m: float(sum(sums[g][i] for g in range(G))) for i, m in enumerate(measures)}
+
+    # ---- end to end: the sharded plugin calls
+    def plugin_step(keep=False):
+        plugin_driver.cache_clear()
+        results = []
+        for m in measures:
+            r = plugin_driver.call(m, A, B)
+            if keep:
+                results.append(r)
+            else:
+                r.release()
+        return results
+
+    plugin_step()
+    plugin_step()
+    e2e_steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        plugin_step()
+    dt = time.perf_counter() - t0
+    res = plugin_step(keep=True)
+    e2e_sums = [float(sum(float(v.sum()) for v in r.values())) for r in res]
+    for r in res:
+        r.release()
+    plugin_driver.cache_clear()
+    clocks = sampler.stop()
+    has_nulls = A.null_count + B.null_count > 0
+    peak, peak_src = peaks()
+    dom_bytes = alg_bytes + 8 * n * (len(measures) - 1)
+    dom_s = elapsed_ms / args.steps * 1e-3
+    line = {
+        "metric": METRIC, "value": n * len(measures) * args.steps / (elapsed_ms * 1e-3), "unit": UNIT, "n_gpus": G,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+        "config": run_config(args, wl, 1),
+        "notes": {"value_is": "device-resident: one row range per GPU, one fused launch per GPU and step, max over GPUs",
+                  "ms_per_gpu": [m / args.steps for m in ms], "rows_per_gpu": [cuts[g + 1] - cuts[g] for g in range(G)]},
+        "roofline": {"bound": "hbm", "kernel": "short_kernel<fused>", "achieved": dom_bytes / dom_s / 1e9,
+                     "peak": peak * G, "unit": "GB/s", "frac": dom_bytes / dom_s / 1e9 / (peak * G), "traffic": None,
+                     "peak_source": peak_src + f" x {G} GPUs", "algorithmic_bytes_per_launch": dom_bytes / G,
+                     "launch_ms": dom_s * 1e3},
+        "clocks": clocks, "gpu_launches": launches, "checksums": checksums,
+        "e2e": {"value": n * len(measures) * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": input_bytes(A, B),
+                "d2h_bytes_per_step": (8 * n + ((n + 7) // 8 if has_nulls else 0)) * len(measures),
+                "ms_per_step": dt / e2e_steps * 1e3, "steps": e2e_steps, "devices": os.environ["STRSIM_B200_DEVICES"],
+                "api": "one _polars_plugin_<measure> call per measure, each sharded by the library over the devices "
+                       "(row ranges, no collective); pageable Arrow buffers in, one result buffer out; cache cleared "
+                       "before every step",
+                "checksum_matches_device": bool(all(
+                    abs(s - checksums[m]) <= 1e-9 * max(1.0, abs(checksums[m])) for s, m in zip(e2e_sums, measures)))},
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(A, B, measures)
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -289,6 +424,8 @@ def main():
         if world > 1:
             raise SystemExit("--strong is one process that drives all GPUs: run it without torchrun")
         os.environ["STRSIM_B200_DEVICES"] = ",".join(str(d) for d in range(args.gpus))
+        run_strong(args, wl)
+        return
 
     import numpy as np
     import torch

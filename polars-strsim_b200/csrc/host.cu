@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <exception>
+#include <functional>
 #include <mutex>
 #include <new>
 #include <deque>
@@ -77,6 +78,9 @@ static int guarded(const char* what, F&& body) noexcept {
         return STRSIM_ERR_ARGUMENT;
     }
 }
+
+constexpr int STRSIM_RETRY_UNTRIMMED = 100;  // internal status of host_call_impl(trim = true), never returned to callers
+constexpr int SHARD_DEVICE_BASE = 1000;      // strsim_b200_column_device() of a column kept by a sharded call
 
 // row slices of one host call (compute_host_multi): H2D of slice s+1 overlaps compute / D2H of slice s
 constexpr int MAX_SLICES = 16;
@@ -259,6 +263,7 @@ static int default_device() {
 }
 
 static void destroy_up_stager(struct UpStager* sg);
+static const std::vector<int>& shard_devices();
 
 static void destroy_ctx(ThreadCtx& c) {
     // best effort: the context may be half built (failed initialisation) or belong to a device that is
@@ -596,6 +601,11 @@ struct DevChunk {
 
 struct strsim_b200_column {
     int device = 0;
+    // A column a SHARDED host call kept (STRSIM_B200_DEVICES): one resident column per device, shard g
+    // holding rows [shard_lo[g], shard_lo[g+1]); `device` is then the marker SHARD_DEVICE_BASE + number of
+    // shards and no other field but `length` is used.
+    std::vector<strsim_b200_column*> shards;
+    std::vector<int64_t> shard_lo;
     void* block = nullptr;  // one allocation holds everything
     size_t block_bytes = 0;
     std::vector<DevChunk> chunks;
@@ -608,7 +618,13 @@ struct strsim_b200_column {
     // distinct data buffers in upload order (chunks made by slicing share buffers) and how much of each
     // is on the device right now: equal to the size except while a host call uploads progressively
     std::vector<int64_t> buf_size, buf_resident;
-    std::vector<size_t> buf_dev_off;  // per distinct data buffer: offset inside `block`
+    // the part of each distinct buffer this column's rows reference, [buf_lo, buf_hi) (multiples of 256 unless
+    // they are 0 / the size): everything for a whole column; a row shard of a sequentially built column
+    // (one GPU's slice of a sharded call) needs -- and uploads -- only its own stretch of the data
+    std::vector<int64_t> buf_lo, buf_hi;
+    // per distinct data buffer: offset of the buffer's (virtual) byte 0 inside `block`; bytes below buf_lo
+    // have no storage, so the offset may be negative
+    std::vector<int64_t> buf_dev_off;
     std::vector<std::vector<int>> chunk_buf_ids;  // [chunk][buffer index] -> distinct buffer id
     // general columns: share of pairs with a character above U+00FF seen by the last Latin-1 launch over
     // this column (-1: unknown); a hint only, read and written without synchronisation
@@ -793,8 +809,6 @@ static int h2d(void* dst, const void* src, size_t bytes, cudaStream_t st) {
 //   upload_rows  : views + validity of a row range (+ byte statistics of the inline strings)
 struct ChunkPlan {
     size_t views_off, validity_off, table_off;
-    std::vector<size_t> buf_off;
-    std::vector<char> buf_dup;  // buffer already planned for an earlier chunk (slices share buffers)
     size_t validity_bytes;
     int64_t first_byte;
     int64_t row0;  // first row of the chunk in the column
@@ -807,8 +821,7 @@ struct Uploader {
     std::vector<ChunkPlan> plans;
     std::vector<unsigned long long> tables;  // all chunks' buffer tables, alive until the copies ran
     std::vector<size_t> table_pos;
-    std::vector<const void*> buf_src;   // per distinct data buffer: host address ...
-    std::vector<size_t> buf_dev_off;    // ... and offset inside the device block
+    std::vector<const void*> buf_src;   // per distinct data buffer: host address
     int64_t uploaded = 0;               // progressive upload: linear position over the distinct buffers
 };
 
@@ -842,7 +855,14 @@ static int null_literal_error() {
     return STRSIM_ERR_ARGUMENT;
 }
 
-static int upload_plan(ThreadCtx& ctx, const strsim_view_chunk* chunks, size_t n_chunks, Uploader* up) {
+static int64_t view_end_position(const Uploader& up, size_t c, const int32_t* v);
+static bool looks_sequential(const Uploader& up);
+
+// `trim`: the chunks are a row shard cut out of a longer column (sharded host call).  When the views look
+// sequential, only the stretch of the data buffers between the shard's first and last out-of-line string
+// gets device storage and is uploaded; the kernels check every view against that stretch (DevCol::lo_* /
+// res_*) and the host falls back to whole buffers should a view point outside it.
+static int upload_plan(ThreadCtx& ctx, const strsim_view_chunk* chunks, size_t n_chunks, Uploader* up, bool trim = false) {
     auto* col = new strsim_b200_column();
     col->device = ctx.device;
     up->col = col;
@@ -852,14 +872,13 @@ static int upload_plan(ThreadCtx& ctx, const strsim_view_chunk* chunks, size_t n
     struct Seen {
         const void* ptr;
         int64_t size;
-        size_t off;
         int id;
     };
     std::vector<Seen> seen;
-    size_t total = 0;
+    // pass 1: rows, distinct data buffers (chunks produced by slicing share theirs: each is uploaded once)
     for (size_t i = 0; i < n_chunks; i++) {
         const strsim_view_chunk& ch = chunks[i];
-        if (ch.length < 0 || ch.offset < 0 || (ch.length > 0 && !ch.views)) {
+        if (ch.length < 0 || ch.offset < 0 || (ch.length > 0 && !ch.views) || ch.n_data_buffers < 0) {
             strsim_set_error("chunk %zu: bad length/offset/views", i);
             delete col;
             up->col = nullptr;
@@ -867,47 +886,95 @@ static int upload_plan(ThreadCtx& ctx, const strsim_view_chunk* chunks, size_t n
         }
         ChunkPlan& p = up->plans[i];
         p.row0 = col->length;
-        p.views_off = total;
-        total = align_up(total + 16 * (size_t)ch.length, 256);
         p.first_byte = ch.offset >> 3;
         p.validity_bytes =
             ch.validity && ch.length > 0 ? (size_t)(((ch.offset + ch.length + 7) >> 3) - p.first_byte) : 0;
-        p.validity_off = total;
-        total = align_up(total + p.validity_bytes, 256);
-        p.table_off = total;
-        total = align_up(total + 8 * (size_t)(ch.n_data_buffers > 0 ? ch.n_data_buffers : 1), 256);
-        p.buf_off.resize((size_t)ch.n_data_buffers);
-        p.buf_dup.assign((size_t)ch.n_data_buffers, 0);
         col->chunk_buf_ids.emplace_back((size_t)ch.n_data_buffers, 0);
         for (int64_t b = 0; b < ch.n_data_buffers; b++) {
-            // chunks produced by slicing share their data buffers: upload each distinct buffer once
             bool dup = false;
             for (const Seen& sn : seen)
                 if (sn.ptr == ch.data_buffers[b] && sn.size == ch.data_buffer_sizes[b]) {
-                    p.buf_off[(size_t)b] = sn.off;
-                    p.buf_dup[(size_t)b] = 1;
                     col->chunk_buf_ids.back()[(size_t)b] = sn.id;
                     dup = true;
                     break;
                 }
             if (dup) continue;
-            p.buf_off[(size_t)b] = total;
             const int id = (int)col->buf_size.size();
             col->chunk_buf_ids.back()[(size_t)b] = id;
             col->buf_size.push_back(ch.data_buffer_sizes[b] > 0 ? ch.data_buffer_sizes[b] : 0);
-            col->buf_resident.push_back(col->buf_size.back());
             up->buf_src.push_back(ch.data_buffers[b]);
-            up->buf_dev_off.push_back(total);
-            col->buf_dev_off.push_back(total);
-            if (seen.size() < 4096) seen.push_back({ch.data_buffers[b], ch.data_buffer_sizes[b], total, id});
-            // 64 spare bytes: TMA spans are rounded to 16 B and word copies read a few bytes past
-            total = align_up(total + (size_t)ch.data_buffer_sizes[b] + 64, 256);
-            col->data_bytes += ch.data_buffer_sizes[b];
+            if (seen.size() < 4096) seen.push_back({ch.data_buffers[b], ch.data_buffer_sizes[b], id});
         }
         col->length += ch.length;
         if (p.validity_bytes) col->has_validity = true;
     }
     col->scalar_null = col->length == 1 && host_scalar_is_null(chunks, n_chunks);
+    col->buf_lo.assign(col->buf_size.size(), 0);
+    col->buf_hi = col->buf_size;
+    col->buf_resident = col->buf_size;
+    // pass 2 (row shards only): the stretch of the data the shard references
+    if (trim && col->length > 0 && !col->buf_size.empty() && looks_sequential(*up)) {
+        // linear positions (over the distinct buffers in upload order) of the first out-of-line string's
+        // start and of the last one's end, each found within 4096 rows of the shard's ends
+        int64_t first = -1, last = -1, left = 4096;
+        for (size_t c = 0; c < n_chunks && left > 0 && first < 0; c++) {
+            const int32_t* v = static_cast<const int32_t*>(chunks[c].views) + 4 * chunks[c].offset;
+            for (int64_t r = 0; r < chunks[c].length && left > 0; r++, left--) {
+                const int64_t e = view_end_position(*up, c, v + 4 * r);
+                if (e < 0) continue;
+                // start of that string: the end position is rounded up to 256, so recompute from the view
+                const auto& ids = col->chunk_buf_ids[c];
+                int64_t start = 0;
+                for (int id = 0; id < ids[(size_t)v[4 * r + 2]]; id++) start += col->buf_size[(size_t)id];
+                first = start + ((int64_t)v[4 * r + 3] & ~255ll);
+                break;
+            }
+        }
+        left = 4096;
+        for (size_t c = n_chunks; c-- > 0 && left > 0 && last < 0;) {
+            const int32_t* v = static_cast<const int32_t*>(chunks[c].views) + 4 * chunks[c].offset;
+            for (int64_t r = chunks[c].length; r-- > 0 && left > 0; left--) {
+                const int64_t e = view_end_position(*up, c, v + 4 * r);
+                if (e >= 0) {
+                    last = e;
+                    break;
+                }
+            }
+        }
+        if (first >= 0 && last >= first) {
+            int64_t start = 0;
+            for (size_t id = 0; id < col->buf_size.size(); id++) {
+                const int64_t size = col->buf_size[id];
+                int64_t lo = first - start, hi = last - start;
+                lo = lo < 0 ? 0 : (lo > size ? size : lo);
+                hi = hi < 0 ? 0 : (hi > size ? size : hi);
+                if (hi < lo) hi = lo;
+                col->buf_lo[id] = lo;
+                col->buf_hi[id] = hi;
+                start += size;
+            }
+        }
+    }
+    // pass 3: one device block for everything
+    size_t total = 0;
+    for (size_t i = 0; i < n_chunks; i++) {
+        const strsim_view_chunk& ch = chunks[i];
+        ChunkPlan& p = up->plans[i];
+        p.views_off = total;
+        total = align_up(total + 16 * (size_t)ch.length, 256);
+        p.validity_off = total;
+        total = align_up(total + p.validity_bytes, 256);
+        p.table_off = total;
+        total = align_up(total + 8 * (size_t)(ch.n_data_buffers > 0 ? ch.n_data_buffers : 1), 256);
+    }
+    col->buf_dev_off.assign(col->buf_size.size(), 0);
+    for (size_t id = 0; id < col->buf_size.size(); id++) {
+        const int64_t lo = col->buf_lo[id], hi = col->buf_hi[id];  // lo is a multiple of 256
+        col->buf_dev_off[id] = (int64_t)total - lo;
+        // 64 spare bytes: TMA spans are rounded to 16 B and word copies read a few bytes past
+        total = align_up(total + (size_t)(hi - lo) + 64, 256);
+        col->data_bytes += hi - lo;
+    }
     total += 256;
     int rc = pool_alloc(ctx.device, total, &col->block);
     if (rc) {
@@ -931,7 +998,8 @@ static int upload_plan(ThreadCtx& ctx, const strsim_view_chunk* chunks, size_t n
         up->table_pos[i] = up->tables.size();
         if (ch.n_data_buffers == 0) up->tables.push_back(0ull);
         for (int64_t b = 0; b < ch.n_data_buffers; b++)
-            up->tables.push_back(reinterpret_cast<unsigned long long>(base + p.buf_off[(size_t)b]));
+            up->tables.push_back(reinterpret_cast<unsigned long long>(base) +
+                                 (unsigned long long)col->buf_dev_off[(size_t)col->chunk_buf_ids[i][(size_t)b]]);
         col->chunks.push_back(dc);
     }
     return STRSIM_OK;
@@ -964,11 +1032,13 @@ static int upload_data_range(ThreadCtx& ctx, Uploader& up, int64_t from, int64_t
     int64_t start = 0;
     for (size_t id = 0; id < up.col->buf_size.size(); id++) {
         const int64_t size = up.col->buf_size[id];
-        const int64_t lo = from > start ? from - start : 0;
-        const int64_t hi = to - start < size ? to - start : size;
+        int64_t lo = from > start ? from - start : 0;
+        int64_t hi = to - start < size ? to - start : size;
+        if (lo < up.col->buf_lo[id]) lo = up.col->buf_lo[id];  // a row shard stores only [buf_lo, buf_hi)
+        if (hi > up.col->buf_hi[id]) hi = up.col->buf_hi[id];
         if (hi > lo) {
             if (do_copy)
-                CUDA_TRY(upload_copy(ctx, base + up.buf_dev_off[id] + lo, static_cast<const char*>(up.buf_src[id]) + lo,
+                CUDA_TRY(upload_copy(ctx, base + up.col->buf_dev_off[id] + lo, static_cast<const char*>(up.buf_src[id]) + lo,
                                      (size_t)(hi - lo), st));
             if (do_stats) {
                 if (do_copy) CUDA_TRY(upload_flush(ctx));  // the kernel below must be queued behind every DMA of the copy
@@ -976,7 +1046,7 @@ static int upload_data_range(ThreadCtx& ctx, Uploader& up, int64_t from, int64_t
                 if (blocks > 148 * 16) blocks = 148 * 16;
                 if (blocks < 1) blocks = 1;
                 stats_bytes_kernel<<<(unsigned)blocks, 256, 0, st>>>(
-                    reinterpret_cast<const unsigned char*>(base + up.buf_dev_off[id] + lo), hi - lo, d_stats);
+                    reinterpret_cast<const unsigned char*>(base + up.col->buf_dev_off[id] + lo), hi - lo, d_stats);
                 g_launches.fetch_add(1, std::memory_order_relaxed);
             }
         }
@@ -1072,23 +1142,34 @@ static void set_resident(strsim_b200_column* col, int64_t uploaded) {
     for (size_t id = 0; id < col->buf_size.size(); id++) {
         const int64_t size = col->buf_size[id];
         int64_t r = uploaded - start;
-        col->buf_resident[id] = r < 0 ? 0 : (r > size ? size : r);
+        r = r < 0 ? 0 : (r > size ? size : r);
+        col->buf_resident[id] = r > col->buf_hi[id] ? col->buf_hi[id] : r;  // bytes above buf_hi never arrive
         start += size;
     }
 }
 
-// residency frontier of one chunk for the kernels (DevCol::res_buf / res_off)
-static void chunk_frontier(const strsim_b200_column* col, size_t chunk, unsigned* res_buf, unsigned* res_off) {
-    *res_buf = 0xFFFFFFFFu;
-    *res_off = 0;
+// residency frontiers of one chunk for the kernels (DevCol::res_* upper, DevCol::lo_* lower)
+static void chunk_frontier(const strsim_b200_column* col, size_t chunk, DevCol* dc) {
+    dc->res_buf = 0xFFFFFFFFu;
+    dc->res_off = 0;
+    dc->lo_buf = 0;
+    dc->lo_off = 0;
     if (chunk >= col->chunk_buf_ids.size()) return;
     const auto& ids = col->chunk_buf_ids[chunk];
     for (size_t b = 0; b < ids.size(); b++) {
         const size_t id = (size_t)ids[b];
         if (col->buf_resident[id] < col->buf_size[id]) {
-            *res_buf = (unsigned)b;
-            *res_off = (unsigned)col->buf_resident[id];
-            return;
+            dc->res_buf = (unsigned)b;
+            dc->res_off = (unsigned)col->buf_resident[id];
+            break;
+        }
+    }
+    for (size_t b = ids.size(); b-- > 0;) {
+        const size_t id = (size_t)ids[b];
+        if (col->buf_lo[id] > 0) {
+            dc->lo_buf = (unsigned)b;
+            dc->lo_off = (unsigned)col->buf_lo[id];
+            break;
         }
     }
 }
@@ -1793,8 +1874,8 @@ static int compute_on_device(ThreadCtx& ctx, const int* measures, size_t n_measu
         s.a.vbit = ca.vbit + (bc_a ? 0 : oa);
         s.a.bufs = ca.bufs;
         s.a.stride = bc_a ? 0 : 1;
-        chunk_frontier(a, bc_a ? 0 : ia, &s.a.res_buf, &s.a.res_off);
-        chunk_frontier(b, bc_b ? 0 : ib, &s.b.res_buf, &s.b.res_off);
+        chunk_frontier(a, bc_a ? 0 : ia, &s.a);
+        chunk_frontier(b, bc_b ? 0 : ib, &s.b);
         s.b.views = cb.views + (bc_b ? 0 : ob);
         s.b.validity = cb.validity;
         s.b.vbit = cb.vbit + (bc_b ? 0 : ob);
@@ -1938,6 +2019,7 @@ int strsim_b200_column_upload(const strsim_view_chunk* chunks, size_t n_chunks, 
 
 void strsim_b200_column_free(strsim_b200_column* col) {
     if (!col) return;
+    for (strsim_b200_column* sh : col->shards) strsim_b200_column_free(sh);
     if (col->block) {
         cudaSetDevice(col->device);
         pool_free(col->device, col->block, col->block_bytes);
@@ -1950,7 +2032,10 @@ int64_t strsim_b200_column_device_bytes(const strsim_b200_column* col) { return 
 int strsim_b200_column_device(const strsim_b200_column* col) { return col ? col->device : -1; }
 int strsim_b200_get_device(void) {
     ThreadCtx* c;
-    return ensure_ctx(&c) == STRSIM_OK ? c->device : -1;
+    if (ensure_ctx(&c) != STRSIM_OK) return -1;
+    // sharded mode: what columns kept by host calls report as their "device" (strsim_b200_column_device)
+    const size_t g = shard_devices().size();
+    return g >= 2 ? SHARD_DEVICE_BASE + (int)g : c->device;
 }
 int64_t strsim_b200_column_algorithmic_bytes(const strsim_b200_column* col) {
     return col ? col->alg_bytes : -1;
@@ -1973,13 +2058,13 @@ int strsim_b200_column_restat(strsim_b200_column* col, void* stream) {
     CUDA_TRY(cudaMemcpyAsync(ctx->d_stats, ctx->h_stats, sizeof(ColumnStats), cudaMemcpyHostToDevice, st));
     char* base = static_cast<char*>(col->block);
     for (size_t id = 0; id < col->buf_size.size(); id++) {
-        const int64_t size = col->buf_size[id];
+        const int64_t lo = col->buf_lo[id], size = col->buf_hi[id] - lo;
         if (size <= 0) continue;
         long long blocks = ((size >> 4) + 255) / 256;
         if (blocks > 148 * 16) blocks = 148 * 16;
         if (blocks < 1) blocks = 1;
-        stats_bytes_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const unsigned char*>(base + col->buf_dev_off[id]),
-                                                            size, ctx->d_stats);
+        stats_bytes_kernel<<<(unsigned)blocks, 256, 0, st>>>(
+            reinterpret_cast<const unsigned char*>(base + col->buf_dev_off[id] + lo), size, ctx->d_stats);
         g_launches.fetch_add(1, std::memory_order_relaxed);
     }
     for (const DevChunk& dc : col->chunks) {
@@ -2057,7 +2142,13 @@ static int host_call_impl(const int* measures, size_t n_measures, const strsim_v
                           const strsim_b200_column* res_a, strsim_b200_column** keep_a, const strsim_view_chunk* b,
                           size_t n_b, const strsim_b200_column* res_b, strsim_b200_column** keep_b,
                           double* const* out_values, uint8_t* out_validity, int64_t* out_null_count,
-                          int32_t* const* dbg_ints);
+                          int32_t* const* dbg_ints, bool trim);
+static bool shard_this_call(int64_t la, int64_t lb, const strsim_b200_column* res_a, const strsim_b200_column* res_b);
+static int host_call_sharded(const int* measures, size_t n_measures, const strsim_view_chunk* a, size_t n_a,
+                             const strsim_b200_column* res_a, strsim_b200_column** keep_a, const strsim_view_chunk* b,
+                             size_t n_b, const strsim_b200_column* res_b, strsim_b200_column** keep_b,
+                             double* const* out_values, uint8_t* out_validity, int64_t* out_null_count,
+                             int32_t* const* dbg_ints);
 
 static int host_call(const int* measures, size_t n_measures, const strsim_view_chunk* a, size_t n_a,
                      const strsim_b200_column* res_a, strsim_b200_column** keep_a, const strsim_view_chunk* b,
@@ -2065,8 +2156,20 @@ static int host_call(const int* measures, size_t n_measures, const strsim_view_c
                      double* const* out_values, uint8_t* out_validity, int64_t* out_null_count,
                      int32_t* const* dbg_ints) {
     return guarded("compute_host", [&] {
+        int64_t la = 0, lb = 0;
+        if (res_a) la = res_a->length;
+        else for (size_t i = 0; a && i < n_a; i++) la += a[i].length;
+        if (res_b) lb = res_b->length;
+        else for (size_t i = 0; b && i < n_b; i++) lb += b[i].length;
+        if (shard_this_call(la, lb, res_a, res_b))
+            return host_call_sharded(measures, n_measures, a, n_a, res_a, keep_a, b, n_b, res_b, keep_b, out_values,
+                                     out_validity, out_null_count, dbg_ints);
+        if ((res_a && !res_a->shards.empty()) || (res_b && !res_b->shards.empty())) {
+            strsim_set_error("a column kept by a sharded call can only be used by sharded calls of the same shape");
+            return (int)STRSIM_ERR_ARGUMENT;
+        }
         return host_call_impl(measures, n_measures, a, n_a, res_a, keep_a, b, n_b, res_b, keep_b, out_values, out_validity,
-                              out_null_count, dbg_ints);
+                              out_null_count, dbg_ints, false);
     });
 }
 
@@ -2074,7 +2177,7 @@ static int host_call_impl(const int* measures, size_t n_measures, const strsim_v
                           const strsim_b200_column* res_a, strsim_b200_column** keep_a, const strsim_view_chunk* b,
                           size_t n_b, const strsim_b200_column* res_b, strsim_b200_column** keep_b,
                           double* const* out_values, uint8_t* out_validity, int64_t* out_null_count,
-                          int32_t* const* dbg_ints) {
+                          int32_t* const* dbg_ints, bool trim) {
     if (keep_a) *keep_a = nullptr;
     if (keep_b) *keep_b = nullptr;
     if ((!res_a && n_a && !a) || (!res_b && n_b && !b) || !measures || n_measures == 0 || n_measures > 8 || !out_values) {
@@ -2131,11 +2234,11 @@ static int host_call_impl(const int* measures, size_t n_measures, const strsim_v
     // duplex) instead of running back to back.
     Uploader ua, ub;
     if (!res_a) {
-        rc = upload_plan(*ctx, a, n_a, &ua);
+        rc = upload_plan(*ctx, a, n_a, &ua, trim && la > 1);
         if (rc) return rc;
     }
     if (!res_b) {
-        rc = upload_plan(*ctx, b, n_b, &ub);
+        rc = upload_plan(*ctx, b, n_b, &ub, trim && lb > 1);
         if (rc) {
             if (!res_a) strsim_b200_column_free(ua.col);
             return rc;
@@ -2352,8 +2455,10 @@ static int host_call_impl(const int* measures, size_t n_measures, const strsim_v
             int64_t deferred = 0;
             run_slice(redo_list[k], true, &deferred);
             if (rc == STRSIM_OK && deferred > 0) {
+                // a row shard uploaded only the stretch of the data its first and last rows delimit and some
+                // view points outside it: the caller repeats the shard with whole buffers
                 strsim_set_error("internal: rows still deferred after the whole upload");
-                rc = STRSIM_ERR_CUDA;
+                rc = trim ? STRSIM_RETRY_UNTRIMMED : (int)STRSIM_ERR_CUDA;
             }
         }
     }
@@ -2425,6 +2530,276 @@ static int host_call_impl(const int* measures, size_t n_measures, const strsim_v
     }
     if (!res_a && ca) strsim_b200_column_free(ca);
     if (!res_b && cb) strsim_b200_column_free(cb);
+    return rc;
+}
+
+// ---- one host call over several GPUs (north_star 4) ---------------------------------------
+// The reference fans one call out over the workers of Polars' pool and re-assembles the chunks in the same
+// call (strsim.rs:72-104: split_offsets, one task per range, from_chunk_iter).  Here the workers are the
+// GPUs named by STRSIM_B200_DEVICES ("0,1,2,3", "0-7" or "all"): the rows are cut into one contiguous range
+// per device with the reference's rule (split_offsets, strsim.rs:21-39: equal ranges, the last one takes the
+// remainder; ranges start at multiples of 64 rows so that no validity byte is shared), every range runs
+// the ordinary host call -- upload of ITS views and of the stretch of the data buffers its rows reference,
+// kernels, download -- on its device's worker thread, and the results land in disjoint ranges of the
+// caller's buffers: the "concatenation" is the layout itself.  No collective, no peer traffic.
+static const std::vector<int>& shard_devices() {
+    static const std::vector<int> devs = [] {
+        std::vector<int> v;
+        const char* e = getenv("STRSIM_B200_DEVICES");
+        if (!e || !*e) return v;
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess) {
+            cudaGetLastError();
+            return v;
+        }
+        if (!strcmp(e, "all")) {
+            for (int d = 0; d < n; d++) v.push_back(d);
+            return v;
+        }
+        for (const char* p = e; *p;) {
+            char* end = nullptr;
+            const long lo = strtol(p, &end, 10);
+            if (end == p) break;
+            long hi = lo;
+            p = end;
+            if (*p == '-') {
+                hi = strtol(p + 1, &end, 10);
+                if (end == p + 1) break;
+                p = end;
+            }
+            for (long d = lo; d <= hi && d < n; d++) {
+                bool dup = false;
+                for (int x : v) dup = dup || x == (int)d;
+                if (d >= 0 && !dup) v.push_back((int)d);
+            }
+            if (*p == ',') p++;
+            else break;
+        }
+        return v;
+    }();
+    return devs;
+}
+
+constexpr int64_t SHARD_MIN_ROWS = 65536;  // below this one device is quicker than the fan-out
+
+static bool shard_this_call(int64_t la, int64_t lb, const strsim_b200_column* res_a, const strsim_b200_column* res_b) {
+    const size_t g = shard_devices().size();
+    if (g < 2) return false;
+    if (la != lb && la != 1 && lb != 1) return false;  // the ordinary path reports the shape error
+    const int64_t n = la == 1 ? lb : la;
+    if (n < SHARD_MIN_ROWS) return false;
+    // resident operands must be columns a sharded call of the same fan-out kept
+    for (const strsim_b200_column* r : {res_a, res_b})
+        if (r && r->length > 1 && r->shards.size() != g) return false;
+    return true;
+}
+
+// one worker thread per device: its thread-local context (streams, pinned buffers, staging rings) lives as
+// long as the process, so a sharded call costs no set-up
+class DeviceWorker {
+   public:
+    static DeviceWorker& of(int device) {
+        static std::mutex m;
+        static std::vector<DeviceWorker*> all;
+        std::lock_guard<std::mutex> lock(m);
+        for (DeviceWorker* w : all)
+            if (w->device_ == device) return *w;
+        all.push_back(new DeviceWorker(device));  // never destroyed: the threads outlive static destructors
+        return *all.back();
+    }
+    struct Job {
+        std::function<int()> fn;
+        int rc = 0;
+        std::string error;
+        int64_t overflow[2] = {0, 0};
+        int redo = 0;
+        bool done = false;
+    };
+    void submit(Job* j) {
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            q_.push_back(j);
+        }
+        cv_.notify_all();
+    }
+    void wait(Job* j) {
+        std::unique_lock<std::mutex> lock(m_);
+        cv_.wait(lock, [j] { return j->done; });
+    }
+
+   private:
+    explicit DeviceWorker(int device) : device_(device) {
+        std::thread([this] { run(); }).detach();
+    }
+    void run() {
+        g_requested_device = device_;
+        for (;;) {
+            Job* j;
+            {
+                std::unique_lock<std::mutex> lock(m_);
+                cv_.wait(lock, [this] { return !q_.empty(); });
+                j = q_.front();
+                q_.pop_front();
+            }
+            g_last_error.clear();
+            const int rc = guarded("sharded call", j->fn);
+            j->error = g_last_error;
+            j->overflow[0] = g_last_overflow[0];
+            j->overflow[1] = g_last_overflow[1];
+            j->redo = g_last_redo_slices;
+            {
+                std::lock_guard<std::mutex> lock(m_);
+                j->rc = rc;
+                j->done = true;
+            }
+            cv_.notify_all();
+        }
+    }
+    int device_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<Job*> q_;
+};
+
+// rows [lo, hi) of a chunk list as a chunk list over the same buffers
+static std::vector<strsim_view_chunk> slice_chunks(const strsim_view_chunk* ch, size_t n, int64_t lo, int64_t hi) {
+    std::vector<strsim_view_chunk> out;
+    int64_t row0 = 0;
+    for (size_t i = 0; i < n; i++) {
+        const int64_t c_lo = lo > row0 ? lo - row0 : 0;
+        const int64_t c_hi = hi - row0 < ch[i].length ? hi - row0 : ch[i].length;
+        if (c_hi > c_lo) {
+            strsim_view_chunk c = ch[i];
+            c.offset += c_lo;
+            c.length = c_hi - c_lo;
+            out.push_back(c);
+        }
+        row0 += ch[i].length;
+    }
+    return out;
+}
+
+static int host_call_sharded(const int* measures, size_t n_measures, const strsim_view_chunk* a, size_t n_a,
+                             const strsim_b200_column* res_a, strsim_b200_column** keep_a, const strsim_view_chunk* b,
+                             size_t n_b, const strsim_b200_column* res_b, strsim_b200_column** keep_b,
+                             double* const* out_values, uint8_t* out_validity, int64_t* out_null_count,
+                             int32_t* const* dbg_ints) {
+    if (keep_a) *keep_a = nullptr;
+    if (keep_b) *keep_b = nullptr;
+    if ((!res_a && n_a && !a) || (!res_b && n_b && !b) || !measures || n_measures == 0 || n_measures > 8 || !out_values) {
+        strsim_set_error("compute_host: NULL / out-of-range argument");
+        return STRSIM_ERR_ARGUMENT;
+    }
+    const std::vector<int>& devs = shard_devices();
+    const size_t G = devs.size();
+    int64_t la = 0, lb = 0;
+    if (res_a) la = res_a->length;
+    else for (size_t i = 0; i < n_a; i++) la += a[i].length;
+    if (res_b) lb = res_b->length;
+    else for (size_t i = 0; i < n_b; i++) lb += b[i].length;
+    const int64_t n = la == 1 ? lb : la;
+    const bool bc_a = la == 1 && n != 1, bc_b = lb == 1 && n != 1;
+    // the row ranges: those of the resident column(s), else split_offsets (strsim.rs:21-39) on 64-row units
+    std::vector<int64_t> cut(G + 1, n);
+    const strsim_b200_column* shaped = (res_a && !res_a->shards.empty()) ? res_a : (res_b && !res_b->shards.empty()) ? res_b : nullptr;
+    if (shaped) {
+        for (size_t g = 0; g <= G; g++) cut[g] = shaped->shard_lo[g];
+        if (res_a && res_b && !res_a->shards.empty() && !res_b->shards.empty() && res_a->shard_lo != res_b->shard_lo) {
+            strsim_set_error("the two resident columns were sharded differently");
+            return STRSIM_ERR_ARGUMENT;
+        }
+    } else {
+        const int64_t units = (n + 63) / 64, per = units / (int64_t)G;
+        for (size_t g = 0; g < G; g++) cut[g] = (int64_t)g * per * 64;
+        cut[G] = n;
+    }
+    static const bool no_trim = [] {
+        const char* k = getenv("STRSIM_B200_KERNEL");
+        const char* t = getenv("STRSIM_B200_SHARD_TRIM");
+        return (k && !strcmp(k, "direct")) || (t && !strcmp(t, "0"));
+    }();
+    struct Shard {
+        std::vector<strsim_view_chunk> a, b;
+        std::vector<double*> outs;
+        std::vector<int32_t*> dbgs;
+        int64_t nulls = 0;
+        strsim_b200_column *kept_a = nullptr, *kept_b = nullptr;
+        DeviceWorker::Job job;
+        bool used = false;
+    };
+    std::vector<Shard> shards(G);
+    for (size_t g = 0; g < G; g++) {
+        Shard& sh = shards[g];
+        const int64_t lo = cut[g], hi = cut[g + 1];
+        if (hi <= lo) continue;
+        sh.used = true;
+        if (!res_a) sh.a = bc_a ? std::vector<strsim_view_chunk>(a, a + n_a) : slice_chunks(a, n_a, lo, hi);
+        if (!res_b) sh.b = bc_b ? std::vector<strsim_view_chunk>(b, b + n_b) : slice_chunks(b, n_b, lo, hi);
+        for (size_t m = 0; m < n_measures; m++) {
+            sh.outs.push_back(out_values[m] ? out_values[m] + lo : nullptr);
+            sh.dbgs.push_back(dbg_ints && dbg_ints[m] ? dbg_ints[m] + 6 * lo : nullptr);
+        }
+        const strsim_b200_column* ra = res_a ? (res_a->shards.empty() ? res_a : res_a->shards[g]) : nullptr;
+        const strsim_b200_column* rb = res_b ? (res_b->shards.empty() ? res_b : res_b->shards[g]) : nullptr;
+        uint8_t* val = out_validity ? out_validity + (lo >> 3) : nullptr;
+        const bool want_dbg = dbg_ints != nullptr;
+        sh.job.fn = [&sh, measures, n_measures, ra, rb, keep_a, keep_b, val, want_dbg, force = force_generic_rows()]() {
+            const bool trim = !no_trim && !force;
+            int rc = host_call_impl(measures, n_measures, sh.a.data(), sh.a.size(), ra, keep_a && !ra ? &sh.kept_a : nullptr,
+                                    sh.b.data(), sh.b.size(), rb, keep_b && !rb ? &sh.kept_b : nullptr, sh.outs.data(), val,
+                                    &sh.nulls, want_dbg ? sh.dbgs.data() : nullptr, trim);
+            if (rc == STRSIM_RETRY_UNTRIMMED)
+                rc = host_call_impl(measures, n_measures, sh.a.data(), sh.a.size(), ra, keep_a && !ra ? &sh.kept_a : nullptr,
+                                    sh.b.data(), sh.b.size(), rb, keep_b && !rb ? &sh.kept_b : nullptr, sh.outs.data(), val,
+                                    &sh.nulls, want_dbg ? sh.dbgs.data() : nullptr, false);
+            return rc;
+        };
+        DeviceWorker::of(devs[g]).submit(&sh.job);
+    }
+    int rc = STRSIM_OK;
+    int64_t nulls = 0;
+    g_last_overflow[0] = g_last_overflow[1] = 0;
+    g_last_redo_slices = 0;
+    for (size_t g = 0; g < G; g++) {
+        Shard& sh = shards[g];
+        if (!sh.used) continue;
+        DeviceWorker::of(devs[g]).wait(&sh.job);
+        if (sh.job.rc != STRSIM_OK && rc == STRSIM_OK) {
+            rc = sh.job.rc;
+            strsim_set_error("device %d: %s", devs[g], sh.job.error.c_str());
+        }
+        nulls += sh.nulls;
+        g_last_overflow[0] += sh.job.overflow[0];
+        g_last_overflow[1] += sh.job.overflow[1];
+        g_last_redo_slices += sh.job.redo;
+    }
+    if (out_null_count) *out_null_count = nulls;
+    // kept columns: one composite per operand (a literal operand is never kept as a composite)
+    auto assemble = [&](bool is_a, strsim_b200_column** keep, int64_t len) {
+        bool all = keep != nullptr && rc == STRSIM_OK && len > 1;
+        for (size_t g = 0; g < G && all; g++)
+            if (shards[g].used && !(is_a ? shards[g].kept_a : shards[g].kept_b)) all = false;
+        if (all) {
+            auto* comp = new strsim_b200_column();
+            comp->device = SHARD_DEVICE_BASE + (int)G;
+            comp->length = len;
+            comp->shard_lo = cut;
+            for (size_t g = 0; g < G; g++) {
+                strsim_b200_column* k = is_a ? shards[g].kept_a : shards[g].kept_b;
+                if (!k) {  // an empty range: a placeholder keeps the indices aligned
+                    k = new strsim_b200_column();
+                    k->device = devs[g];
+                }
+                comp->shards.push_back(k);
+                comp->block_bytes += k->block_bytes;
+            }
+            *keep = comp;
+        } else {
+            for (size_t g = 0; g < G; g++) strsim_b200_column_free(is_a ? shards[g].kept_a : shards[g].kept_b);
+        }
+    };
+    assemble(true, keep_a, la);
+    assemble(false, keep_b, lb);
     return rc;
 }
 

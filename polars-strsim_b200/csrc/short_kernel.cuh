@@ -38,11 +38,16 @@ struct DevCol {
     // progressive upload): buffers with index < res_buf are complete, buffer res_buf holds its first
     // res_off bytes, later buffers nothing yet.  0xFFFFFFFF = everything is resident.
     unsigned int res_buf, res_off;
+    // lower frontier (row shards of a sharded call upload only the stretch of the data their rows
+    // reference): buffers with index < lo_buf and the first lo_off bytes of buffer lo_buf have no storage
+    // on this device.  (0, 0) = everything from the start.
+    unsigned int lo_buf, lo_off;
 };
 
-// is the out-of-line payload of view v (length > 12) on the device yet?
+// is the out-of-line payload of view v (length > 12) on the device (yet)?
 __device__ __forceinline__ bool payload_resident(const uint4& v, const DevCol& c) {
-    return v.z < c.res_buf || (v.z == c.res_buf && v.w + v.x <= c.res_off);
+    return (v.z < c.res_buf || (v.z == c.res_buf && v.w + v.x <= c.res_off)) &&
+           (v.z > c.lo_buf || (v.z == c.lo_buf && v.w >= c.lo_off));
 }
 
 struct Overflow {
