@@ -128,8 +128,9 @@ STRSIM_API int strsim_b200_compute_host_keep(const int *measures, size_t n_measu
                                              int64_t *out_null_count, int32_t *const *dbg_ints);
 
 /* ---- Arrow C Data Interface entry point -----------------------------------------------------------
- * Inputs are BORROWED (not released).  Accepted formats: "vu"/"vz" (Utf8View/BinaryView); "u"/"U"
- * (Utf8/LargeUtf8) are converted to views on the host first.  `out` receives a Float64 array
+ * Inputs are BORROWED (not released).  Accepted formats: "vu" (Utf8View); "u"/"U" (Utf8/LargeUtf8) are
+ * converted to views on the host first; dictionary-encoded arrays of those (integer index format with
+ * `ArrowSchema.dictionary` set).  Binary layouts are a dtype error, as in the reference (strsim.rs:46-47).  `out` receives a Float64 array
  * (format "g") with a release callback; the caller owns it. */
 struct ArrowArray;
 struct ArrowSchema;
@@ -148,6 +149,23 @@ STRSIM_API int strsim_b200_compute_arrow(int measure, const struct ArrowSchema *
  * bytes or NULL.  d_dbg_ints: device pointer, n_rows*STRSIM_DBG_INTS int32 or NULL. */
 STRSIM_API int strsim_b200_column_upload(const strsim_view_chunk *chunks, size_t n_chunks,
                                          strsim_b200_column **out);
+/* Dictionary-encoded input (Arrow dictionary / Polars Categorical; SURVEY.md 8(f).4 -- the reference rejects
+ * such columns at `.str()?`, strsim.rs:46-47, so this widens the drop-in rather than mirroring it).  One
+ * chunk = the indices of the rows + the dictionary they index (one chunk of views, any of the String
+ * layouts after the plugin's conversion).  Only the indices and the dictionary cross PCIe; the device
+ * materialises each row's view from the dictionary (dict_gather_kernel) and the measures run on the result
+ * as on any other resident column.  A row is null when its index is null, out of range, or names a null
+ * dictionary entry. */
+typedef struct strsim_dict_chunk {
+    strsim_view_chunk values;   /* the dictionary */
+    const void *indices;        /* ArrowArray.buffers[1] of the encoded chunk */
+    int32_t index_bytes;        /* 1, 2, 4 or 8 */
+    int32_t index_signed;       /* Arrow int8..int64 (1) or uint8..uint32 (0) */
+    const uint8_t *validity;    /* of the indices, LSB-first, or NULL */
+    int64_t offset, length;     /* ArrowArray.offset / .length of the encoded chunk */
+} strsim_dict_chunk;
+STRSIM_API int strsim_b200_column_upload_dictionary(const strsim_dict_chunk *chunks, size_t n_chunks,
+                                                    strsim_b200_column **out);
 STRSIM_API void strsim_b200_column_free(strsim_b200_column *col);
 STRSIM_API int64_t strsim_b200_column_length(const strsim_b200_column *col);
 /* bytes of HBM the column occupies, and the device it lives on */

@@ -394,12 +394,7 @@ void cache_insert(std::vector<ChunkKey> key, strsim_b200_column* col, strsim_ser
     reaper_ensure();
 }
 
-bool cacheable(const strsim_series_export& s, const Column& c) {
-    if (!cache_enabled() || layout_of(s.field ? s.field->format : nullptr) != L_VIEW) return false;
-    int64_t n = 0;
-    for (const auto& ch : c.chunks) n += ch.length;
-    return n >= CACHE_MIN_ROWS;
-}
+bool cacheable_rows(int64_t n) { return cache_enabled() && n >= CACHE_MIN_ROWS; }
 
 void reaper_wanted() {
     std::lock_guard<std::mutex> lock(g_cache_mutex);
@@ -476,6 +471,8 @@ int compute_to_arrow(int measure, const Column& ca, const Column& cb, ArrowArray
     int64_t la = 0, lb = 0;
     for (const auto& c : ca.chunks) la += c.length;
     for (const auto& c : cb.chunks) lb += c.length;
+    if (res_a) la = strsim_b200_column_length(res_a);
+    if (res_b) lb = strsim_b200_column_length(res_b);
     if (la != lb && la != 1 && lb != 1) {
         strsim_set_error("Inputs must have the same length, or one of them must be a Utf8 literal.");
         return STRSIM_ERR_SHAPE;
@@ -582,6 +579,101 @@ void release_inputs(strsim_series_export* inputs, size_t n_inputs) {
     }
 }
 
+// ---- one operand of a call ---------------------------------------------------------------------------------
+// Either a String column in one of the three layouts (host chunks of views: uploaded by the host call itself,
+// pipelined with the kernels) or a dictionary-encoded one (Arrow dictionary / Polars Categorical: indices
+// and dictionary are uploaded up front and the rows' views materialised on the device,
+// strsim_b200_column_upload_dictionary).  Either way the column may already be in HBM from an earlier call.
+bool index_format(const char* fmt, int* bytes, int* is_signed) {
+    if (!fmt || !fmt[0] || fmt[1]) return false;
+    switch (fmt[0]) {
+        case 'c': *bytes = 1; *is_signed = 1; return true;
+        case 'C': *bytes = 1; *is_signed = 0; return true;
+        case 's': *bytes = 2; *is_signed = 1; return true;
+        case 'S': *bytes = 2; *is_signed = 0; return true;
+        case 'i': *bytes = 4; *is_signed = 1; return true;
+        case 'I': *bytes = 4; *is_signed = 0; return true;
+        case 'l': *bytes = 8; *is_signed = 1; return true;
+        case 'L': *bytes = 8; *is_signed = 0; return true;  // values above 2^63 are out of range anyway
+        default: return false;
+    }
+}
+
+struct Operand {
+    Column col;                               // String layouts
+    bool is_dict = false;
+    std::vector<Column> dict_values;          // dictionary-encoded: one per chunk (owns synthesised views)
+    std::vector<strsim_dict_chunk> dict_chunks;
+    int64_t rows = 0;
+    std::vector<ChunkKey> key;
+    bool cache = false, claimed = false;
+    std::shared_ptr<CacheEntry> hit;
+    strsim_b200_column* owned = nullptr;      // uploaded by this call and not handed to the cache
+    strsim_b200_column* kept = nullptr;       // handed over by the host call: goes to the cache
+    int device = -1;
+    ~Operand() {
+        if (claimed) cache_unclaim(key, device);  // whatever happened, waiting calls are woken
+        if (owned) strsim_b200_column_free(owned);
+    }
+    const strsim_b200_column* resident() const { return hit ? hit->col : owned; }
+};
+
+int operand_from_arrow(const ArrowSchema* schema, const ArrowArray* const* arrays, size_t n, Operand& op) {
+    const char* fmt = schema ? schema->format : nullptr;
+    int ibytes = 0, isigned = 0;
+    if (schema && schema->dictionary && index_format(fmt, &ibytes, &isigned)) {
+        op.is_dict = true;
+        op.dict_values.resize(n);
+        op.dict_chunks.resize(n);
+        for (size_t i = 0; i < n; i++) {
+            const ArrowArray* a = arrays[i];
+            if (!a->dictionary || a->n_buffers < 2) {
+                strsim_set_error("dictionary-encoded chunk %zu carries no dictionary", i);
+                return STRSIM_ERR_ARGUMENT;
+            }
+            const ArrowArray* dict = a->dictionary;
+            int rc = column_from_arrow(schema->dictionary->format, &dict, 1, op.dict_values[i]);
+            if (rc) return rc;
+            strsim_dict_chunk& ch = op.dict_chunks[i];
+            ch.values = op.dict_values[i].chunks[0];
+            ch.indices = a->buffers[1];
+            ch.index_bytes = ibytes;
+            ch.index_signed = isigned;
+            ch.validity = static_cast<const uint8_t*>(a->buffers[0]);
+            ch.offset = a->offset;
+            ch.length = a->length;
+            op.rows += a->length;
+            ChunkKey k;
+            k.views = ch.indices;
+            k.validity = ch.validity;
+            k.offset = ch.offset;
+            k.length = ch.length;
+            k.bufs = {ch.values.views, static_cast<const void*>(ch.values.validity)};
+            k.sizes = {ch.values.length, ch.values.offset};
+            op.key.push_back(std::move(k));
+        }
+        return STRSIM_OK;
+    }
+    int rc = column_from_arrow(fmt, arrays, n, op.col);
+    if (rc) return rc;
+    for (const auto& c : op.col.chunks) op.rows += c.length;
+    if (layout_of(fmt) == L_VIEW) op.key = key_of(op.col);  // synthesised views have no stable identity
+    return STRSIM_OK;
+}
+
+// looks the operand up in the cache (series != nullptr: the call owns its inputs and may cache them) and
+// uploads a dictionary-encoded operand that is not there
+int operand_resolve(Operand& op, int device, bool may_cache, bool may_wait) {
+    op.device = device;
+    op.cache = may_cache && device >= 0 && !op.key.empty() && cacheable_rows(op.rows);
+    if (op.cache) op.hit = cache_lookup(op.key, device, &op.claimed, may_wait);
+    if (op.is_dict && !op.hit) {
+        const int rc = strsim_b200_column_upload_dictionary(op.dict_chunks.data(), op.dict_chunks.size(), &op.owned);
+        if (rc) return rc;
+    }
+    return STRSIM_OK;
+}
+
 void plugin_call(int measure, strsim_series_export* inputs, size_t n_inputs,
                  strsim_series_export* return_value) {
     {   // expired cache entries go before anything new is uploaded
@@ -589,52 +681,45 @@ void plugin_call(int measure, strsim_series_export* inputs, size_t n_inputs,
         cache_trim(0);
     }
     int rc = STRSIM_OK;
-    Column ca, cb;
     ArrowArray* result = nullptr;
     if (n_inputs != 2 || !inputs) {
         strsim_set_error("expected 2 input series, got %zu", n_inputs);
         rc = STRSIM_ERR_ARGUMENT;
     }
-    if (rc == STRSIM_OK)
-        rc = column_from_arrow(inputs[0].field ? inputs[0].field->format : nullptr,
-                               inputs[0].arrays, inputs[0].len, ca);
-    if (rc == STRSIM_OK)
-        rc = column_from_arrow(inputs[1].field ? inputs[1].field->format : nullptr,
-                               inputs[1].arrays, inputs[1].len, cb);
-    if (rc == STRSIM_OK) {
+    {
+        Operand a, b;
+        if (rc == STRSIM_OK) rc = operand_from_arrow(inputs[0].field, inputs[0].arrays, inputs[0].len, a);
+        if (rc == STRSIM_OK) rc = operand_from_arrow(inputs[1].field, inputs[1].arrays, inputs[1].len, b);
         // columns this library already holds in HBM are not uploaded again; the others are uploaded
         // (pipelined with the kernels) and kept
-        const int device = strsim_b200_get_device();
-        const bool cache_a = device >= 0 && cacheable(inputs[0], ca), cache_b = device >= 0 && cacheable(inputs[1], cb);
-        std::vector<ChunkKey> key_a, key_b;
-        std::shared_ptr<CacheEntry> hit_a, hit_b;
-        bool claimed_a = false, claimed_b = false;
-        if (cache_a) hit_a = cache_lookup(key_a = key_of(ca), device, &claimed_a, true);
-        if (cache_b) {
-            key_b = key_of(cb);
-            // the same column on both sides: this call already owns that upload and must not wait for itself
-            if (!(claimed_a && key_b == key_a)) hit_b = cache_lookup(key_b, device, &claimed_b, !claimed_a);
-        }
-        struct Unclaim {  // whatever happens below (errors, exceptions), waiting calls are woken
-            const std::vector<ChunkKey>*key_a, *key_b;
-            bool a, b;
-            int device;
-            ~Unclaim() {
-                if (a) cache_unclaim(*key_a, device);
-                if (b) cache_unclaim(*key_b, device);
+        const int device = rc == STRSIM_OK ? strsim_b200_get_device() : -1;
+        if (rc == STRSIM_OK) rc = operand_resolve(a, device, true, true);
+        // the same column on both sides: this call already owns that upload and must not wait for itself
+        if (rc == STRSIM_OK) rc = operand_resolve(b, device, !(a.claimed && b.key == a.key), !a.claimed);
+        if (rc == STRSIM_OK) {
+            result = new ArrowArray();
+            rc = compute_to_arrow(measure, a.col, b.col, result, a.resident(),
+                                  a.cache && !a.resident() ? &a.kept : nullptr, b.resident(),
+                                  b.cache && !b.resident() ? &b.kept : nullptr);
+            if (rc != STRSIM_OK) {
+                delete result;
+                result = nullptr;
             }
-        } unclaim{&key_a, &key_b, claimed_a, claimed_b, device};
-        strsim_b200_column *kept_a = nullptr, *kept_b = nullptr;
-        result = new ArrowArray();
-        rc = compute_to_arrow(measure, ca, cb, result, hit_a ? hit_a->col : nullptr,
-                              cache_a && !hit_a ? &kept_a : nullptr, hit_b ? hit_b->col : nullptr,
-                              cache_b && !hit_b ? &kept_b : nullptr);
-        if (rc != STRSIM_OK) {
-            delete result;
-            result = nullptr;
         }
-        if (kept_a) cache_insert(key_a, kept_a, inputs[0]);
-        if (kept_b) cache_insert(key_b, kept_b, inputs[1]);
+        if (rc == STRSIM_OK) {
+            // what this call brought to HBM stays there for the calls to come (the cache takes over the
+            // arrays this call owns, so that their addresses keep meaning the same bytes)
+            for (int k = 0; k < 2; k++) {
+                Operand& op = k == 0 ? a : b;
+                strsim_b200_column* col = op.kept ? op.kept : (op.cache && !op.hit ? op.owned : nullptr);
+                if (!col) continue;
+                if (col == op.owned) op.owned = nullptr;
+                op.kept = nullptr;
+                cache_insert(op.key, col, inputs[k]);
+            }
+        }
+        if (a.kept) strsim_b200_column_free(a.kept);
+        if (b.kept) strsim_b200_column_free(b.kept);
     }
     // the callee owns the inputs (polars-ffi import_series_buffer semantics): release every chunk's
     // contents, then the SeriesExport boxes
@@ -690,12 +775,13 @@ int strsim_b200_compute_arrow(int measure, const ArrowSchema* a_schema, const Ar
         return STRSIM_ERR_ARGUMENT;
     }
     try {
-        Column ca, cb;
-        int rc = column_from_arrow(a_schema->format, a_chunks, n_a, ca);
+        Operand a, b;  // borrowed inputs: nothing is cached
+        int rc = operand_from_arrow(a_schema, a_chunks, n_a, a);
+        if (rc == STRSIM_OK) rc = operand_from_arrow(b_schema, b_chunks, n_b, b);
+        if (rc == STRSIM_OK) rc = operand_resolve(a, -1, false, false);
+        if (rc == STRSIM_OK) rc = operand_resolve(b, -1, false, false);
         if (rc) return rc;
-        rc = column_from_arrow(b_schema->format, b_chunks, n_b, cb);
-        if (rc) return rc;
-        return compute_to_arrow(measure, ca, cb, out);
+        return compute_to_arrow(measure, a.col, b.col, out, a.resident(), nullptr, b.resident(), nullptr);
     } catch (const std::exception& e) {
         strsim_set_error("compute_arrow failed: %s", e.what());
         return STRSIM_ERR_NOMEM;

@@ -322,6 +322,52 @@ __global__ void __launch_bounds__(256) stats_bytes_kernel(const unsigned char* d
     stats_commit(out, o, a);
 }
 
+// ---- dictionary-encoded columns: materialise the views of the rows ----------------------------------------
+// A dictionary-encoded (Polars Categorical / Arrow dictionary) chunk holds one small integer per row and the
+// distinct strings once.  Only the indices cross PCIe (1-8 bytes per row instead of a 16-byte view plus
+// payload); on the device row r's view is the dictionary's view of its index -- a 16-byte gather out of a
+// table that sits in L2 -- and everything downstream runs on that view column unchanged (its out-of-line
+// views point into the dictionary's data buffers).  Validity: the row's bit AND the dictionary value's
+// bit AND index in range; one ballot per warp writes 32 rows' bits.
+struct DictGatherArgs {
+    const uint4* dict_views;
+    const uint8_t* dict_validity;  // or nullptr
+    long long dict_vbit;
+    long long dict_len;
+    const void* indices;  // row 0 of the chunk's logical range
+    int index_bytes;      // 1, 2, 4, 8
+    int index_signed;
+    const uint8_t* validity;  // of the indices (device copy), or nullptr
+    long long vbit;
+    long long n;
+    uint4* out_views;
+    uint32_t* out_validity;  // ceil(n/32) words
+};
+
+__global__ void __launch_bounds__(256) dict_gather_kernel(const DictGatherArgs g) {
+    const long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    bool ok = false;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (row < g.n) {
+        long long idx;
+        switch (g.index_bytes) {
+            case 1: idx = g.index_signed ? (long long)static_cast<const int8_t*>(g.indices)[row]
+                                         : (long long)static_cast<const uint8_t*>(g.indices)[row]; break;
+            case 2: idx = g.index_signed ? (long long)static_cast<const int16_t*>(g.indices)[row]
+                                         : (long long)static_cast<const uint16_t*>(g.indices)[row]; break;
+            case 4: idx = g.index_signed ? (long long)static_cast<const int32_t*>(g.indices)[row]
+                                         : (long long)static_cast<const uint32_t*>(g.indices)[row]; break;
+            default: idx = static_cast<const long long*>(g.indices)[row]; break;
+        }
+        ok = bit_valid(g.validity, g.vbit + row) && idx >= 0 && idx < g.dict_len &&
+             bit_valid(g.dict_validity, g.dict_vbit + idx);
+        if (ok) v = __ldg(g.dict_views + idx);
+        g.out_views[row] = v;
+    }
+    const unsigned bits = __ballot_sync(0xFFFFFFFFu, ok);
+    if ((threadIdx.x & 31) == 0 && (row & ~31ll) < g.n) g.out_validity[row >> 5] = bits;
+}
+
 // ---- output validity: bit = both inputs valid (polars-core arity kernels; README.md:69-70) ---------
 struct ValidityArgs {
     const uint8_t* va;

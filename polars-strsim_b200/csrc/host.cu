@@ -20,6 +20,8 @@
 #include <cstring>
 #include <exception>
 #include <functional>
+#include <memory>
+#include <algorithm>
 #include <mutex>
 #include <new>
 #include <deque>
@@ -606,6 +608,9 @@ struct strsim_b200_column {
     // shards and no other field but `length` is used.
     std::vector<strsim_b200_column*> shards;
     std::vector<int64_t> shard_lo;
+    // a column materialised from dictionary-encoded chunks: the dictionaries (resident columns whose data
+    // buffers this column's views point into), freed with it
+    std::vector<strsim_b200_column*> dictionaries;
     void* block = nullptr;  // one allocation holds everything
     size_t block_bytes = 0;
     std::vector<DevChunk> chunks;
@@ -2017,9 +2022,130 @@ int strsim_b200_column_upload(const strsim_view_chunk* chunks, size_t n_chunks, 
     return STRSIM_OK;
 }
 
+int strsim_b200_column_upload_dictionary(const strsim_dict_chunk* chunks, size_t n_chunks, strsim_b200_column** out) {
+    if (!out || (n_chunks && !chunks)) {
+        strsim_set_error("column_upload_dictionary: NULL argument");
+        return STRSIM_ERR_ARGUMENT;
+    }
+    *out = nullptr;
+    ThreadCtx* ctx;
+    int rc = ensure_ctx(&ctx);
+    if (rc) return rc;
+    return guarded("column_upload_dictionary", [&]() -> int {
+        std::unique_ptr<strsim_b200_column, void (*)(strsim_b200_column*)> col(new strsim_b200_column(), strsim_b200_column_free);
+        col->device = ctx->device;
+        // device storage of the materialised column: per chunk views, validity words and a staging area for
+        // the indices (+ their validity bytes)
+        size_t total = 0;
+        std::vector<size_t> off_views(n_chunks), off_valid(n_chunks), off_idx(n_chunks), off_ival(n_chunks);
+        for (size_t i = 0; i < n_chunks; i++) {
+            const strsim_dict_chunk& ch = chunks[i];
+            if (ch.length < 0 || ch.offset < 0 || (ch.length > 0 && !ch.indices) ||
+                (ch.index_bytes != 1 && ch.index_bytes != 2 && ch.index_bytes != 4 && ch.index_bytes != 8)) {
+                strsim_set_error("dictionary chunk %zu: bad length / offset / index width", i);
+                return STRSIM_ERR_ARGUMENT;
+            }
+            off_views[i] = total;
+            total = align_up(total + 16 * (size_t)ch.length, 256);
+            off_valid[i] = total;
+            total = align_up(total + 4 * (size_t)((ch.length + 31) / 32) + 8, 256);
+            off_idx[i] = total;
+            total = align_up(total + (size_t)ch.index_bytes * (size_t)ch.length, 256);
+            off_ival[i] = total;
+            total = align_up(total + (ch.validity ? (size_t)((ch.offset + ch.length + 7) / 8 - ch.offset / 8) : 0) + 8, 256);
+        }
+        total += 256;
+        int rc2 = pool_alloc(ctx->device, total, &col->block);
+        if (rc2) return rc2;
+        col->block_bytes = total;
+        col->has_validity = true;
+        char* base = static_cast<char*>(col->block);
+        // each distinct dictionary is uploaded once (the chunks of a Polars Categorical share theirs)
+        std::vector<std::pair<const void*, strsim_b200_column*>> seen;
+        unsigned or_byte = 0, and_byte = 0xFF;
+        double out_of_line = 0.0;
+        for (size_t i = 0; i < n_chunks; i++) {
+            const strsim_dict_chunk& ch = chunks[i];
+            strsim_b200_column* dict = nullptr;
+            for (auto& s2 : seen)
+                if (s2.first == ch.values.views && s2.second->length == ch.values.length) dict = s2.second;
+            if (!dict) {
+                rc2 = upload_column(*ctx, &ch.values, 1, false, &dict);
+                if (rc2) return rc2;
+                col->dictionaries.push_back(dict);
+                seen.emplace_back(ch.values.views, dict);
+                or_byte |= dict->or_byte;
+                and_byte &= dict->and_byte;
+                col->block_bytes += dict->block_bytes;
+            }
+            if (dict->length > 0) out_of_line = std::max(out_of_line, (double)dict->data_bytes / (double)dict->length);
+            if (ch.length == 0) {
+                DevChunk dc{};
+                dc.length = 0;
+                col->chunks.push_back(dc);
+                col->chunk_buf_ids.emplace_back();
+                continue;
+            }
+            const size_t idx_bytes = (size_t)ch.index_bytes * (size_t)ch.length;
+            CUDA_TRY(upload_copy(*ctx, base + off_idx[i], static_cast<const char*>(ch.indices) + (size_t)ch.index_bytes * (size_t)ch.offset,
+                                 idx_bytes, ctx->stream));
+            const int64_t first_byte = ch.offset >> 3;
+            if (ch.validity)
+                CUDA_TRY(cudaMemcpyAsync(base + off_ival[i], ch.validity + first_byte,
+                                         (size_t)(((ch.offset + ch.length + 7) >> 3) - first_byte), cudaMemcpyHostToDevice,
+                                         ctx->stream));
+            CUDA_TRY(upload_flush(*ctx));
+            const DevChunk& dv = dict->chunks[0];
+            DictGatherArgs g{};
+            g.dict_views = dv.views;
+            g.dict_validity = dv.validity;
+            g.dict_vbit = dv.vbit;
+            g.dict_len = dict->length;
+            g.indices = base + off_idx[i];
+            g.index_bytes = ch.index_bytes;
+            g.index_signed = ch.index_signed;
+            g.validity = ch.validity ? reinterpret_cast<const uint8_t*>(base + off_ival[i]) : nullptr;
+            g.vbit = ch.offset & 7;
+            g.n = ch.length;
+            g.out_views = reinterpret_cast<uint4*>(base + off_views[i]);
+            g.out_validity = reinterpret_cast<uint32_t*>(base + off_valid[i]);
+            dict_gather_kernel<<<(unsigned)((ch.length + 255) / 256), 256, 0, ctx->stream>>>(g);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            CUDA_TRY(cudaGetLastError());
+            DevChunk dc;
+            dc.views = g.out_views;
+            dc.validity = reinterpret_cast<const uint8_t*>(g.out_validity);
+            dc.vbit = 0;
+            dc.bufs = dv.bufs;
+            dc.length = ch.length;
+            dc.data_bytes = 0;
+            col->chunks.push_back(dc);
+            col->chunk_buf_ids.emplace_back();  // no residency bookkeeping: the dictionary is complete
+            col->length += ch.length;
+        }
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        col->or_byte = or_byte;
+        col->and_byte = and_byte;
+        // rows repeat dictionary entries in any order: the stage area is sized for the dictionary's mean
+        // out-of-line bytes per entry
+        col->data_bytes = (int64_t)(out_of_line * (double)col->length);
+        if (col->length == 1) {
+            // a literal must not be null (see null_literal_error): read the one validity bit back
+            uint32_t word = 1;
+            for (size_t i = 0; i < n_chunks; i++)
+                if (chunks[i].length == 1)
+                    CUDA_TRY(cudaMemcpy(&word, base + off_valid[i], 4, cudaMemcpyDeviceToHost));
+            col->scalar_null = !(word & 1u);
+        }
+        *out = col.release();
+        return STRSIM_OK;
+    });
+}
+
 void strsim_b200_column_free(strsim_b200_column* col) {
     if (!col) return;
     for (strsim_b200_column* sh : col->shards) strsim_b200_column_free(sh);
+    for (strsim_b200_column* d : col->dictionaries) strsim_b200_column_free(d);
     if (col->block) {
         cudaSetDevice(col->device);
         pool_free(col->device, col->block, col->block_bytes);

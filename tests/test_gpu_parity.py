@@ -701,6 +701,76 @@ def test_concurrent_plugin_calls_share_one_upload(native, oracle):
     plugin_driver.cache_clear()
 
 
+def test_dictionary_encoded_columns(native, oracle):
+    """Arrow dictionary / Polars Categorical inputs (the reference rejects them at
+    `.str()?`, strsim.rs:46-47): only the indices and the dictionary are uploaded, the rows' views are
+    materialised on the device, and the results equal those of the decoded String columns bit for bit --
+    through the Arrow entry point (borrowed inputs) and through the plugin symbols (owned inputs, cached),
+    with every index width, null indices, null dictionary entries, sliced and multi-chunk arrays, a plain
+    String column on the other side, long entries (> 64 bytes) and a literal."""
+    import pyarrow as pa
+
+    sys.path.insert(0, str(ROOT))
+    from bench_support import plugin_driver
+    from polars_strsim import arrow as strsim_arrow
+
+    rng = random.Random(77)
+    words = ["", "a", "smith", "smyth", "josé maría", "日本語", "phillips", "philips", None,
+             "a-rather-long-surname-over-32-bytes-long", "x" * 70 + "yz", "naïve", "Ünal-Çelik"]
+    words += ["".join(rng.choice("abcdefghijklmnopqrstuvwxyz") for _ in range(rng.randint(1, 24))) for _ in range(200)]
+    n = 70_000
+
+    def encoded(index_type, seed, values_type=pa.string_view()):
+        r = random.Random(seed)
+        idx = [None if r.random() < 0.03 else r.randrange(len(words)) for _ in range(n)]
+        cap = {pa.int8(): 127, pa.uint8(): 255}.get(index_type)
+        if cap is not None:
+            idx = [i if i is None or i <= cap else i % cap for i in idx]
+        arr = pa.DictionaryArray.from_arrays(pa.array(idx, type=index_type), pa.array(words, type=values_type))
+        return arr, [None if i is None else words[i] for i in idx]
+
+    def check_values(measure, got, a, b):
+        ref, rv, _ = oracle.batch(measure, a, b)
+        assert (np.asarray(got.is_valid()) == rv).all(), measure
+        vals = got.fill_null(0.0).to_numpy(zero_copy_only=False)
+        assert (vals[rv].view(np.uint64) == ref[rv].view(np.uint64)).all(), measure
+
+    B_plain_list = [None if rng.random() < 0.02 else rng.choice([w for w in words if w is not None]) for _ in range(n)]
+    B_plain = sv(B_plain_list)
+    for k, (itype, vtype) in enumerate([(pa.int32(), pa.string_view()), (pa.uint32(), pa.large_string()),
+                                        (pa.int8(), pa.string()), (pa.uint16(), pa.string_view()),
+                                        (pa.int64(), pa.string_view())]):
+        A, a = encoded(itype, 100 + k, vtype)
+        Bd, b = encoded(pa.uint32(), 200 + k)
+        measure = oracle.MEASURES[k % 5]
+        check_values(measure, strsim_arrow.compute(measure, A, Bd), a, b)              # both encoded
+        check_values(measure, strsim_arrow.compute(measure, A, B_plain), a, B_plain_list)  # one plain String column
+        check_values(measure, strsim_arrow.compute(measure, A.slice(17, 50_001), Bd.slice(300, 50_001)),
+                     a[17:50_018], b[300:50_301])                                     # ArrowArray.offset on indices + validity
+    # multi-chunk, through the plugin symbols: the second call finds the materialised columns in HBM
+    A, a = encoded(pa.uint32(), 7)
+    Bd, b = encoded(pa.uint32(), 8)
+    CA = pa.chunked_array([A.slice(0, 30_000), A.slice(30_000)])
+    plugin_driver.cache_clear()
+    for measure in oracle.MEASURES:
+        r = plugin_driver.call(measure, CA, Bd)
+        got = np.concatenate(r.values())
+        valid = r.validity()
+        ref, rv, _ = oracle.batch(measure, a, b)
+        assert (valid == rv).all() and r.null_count == int((~rv).sum()), measure
+        assert (got[rv].view(np.uint64) == ref[rv].view(np.uint64)).all(), measure
+        r.release()
+    plugin_driver.cache_clear()
+    # a literal against an encoded column; a null literal still fails the call
+    check_values("jaro_winkler", strsim_arrow.compute("jaro_winkler", A, "smith"), a, ["smith"] * n)
+    with pytest.raises(native.StrsimError, match="literal operand is null"):
+        strsim_arrow.compute("jaro", A, None)
+    # a non-String dictionary is a dtype error like any other non-String column
+    bad = pa.DictionaryArray.from_arrays(pa.array([0, 1], type=pa.int32()), pa.array([1.5, 2.5]))
+    with pytest.raises(native.StrsimError, match="expected `String`"):
+        strsim_arrow.compute("jaro", bad, bad)
+
+
 def test_pageable_inputs_and_outputs_go_through_the_pinned_rings(oracle):
     """Ordinary (pageable) Arrow buffers in, ordinary numpy arrays out: uploads are staged through the
     pinned ring by the copy threads, one row slice ahead of the kernels; downloads likewise."""
