@@ -20,7 +20,7 @@ of length 4..24 per GPU, all five measures; seeds in SURVEY.md 8(d)) over one ba
             the reference's CPU algorithm (the oracle port: no cargo in this image)
             with the reference's static row-range threading on all host cores, same rows, same metric.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2|C3|C4|C5|L1|M1|N1] [--rows R]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2|C3|C4|C5|L1|M1|N1|T1] [--rows R]
     python bench.py --impl reference ...
     python bench.py --strong --gpus N      # ONE plugin call sharded over N GPUs inside the library
     torchrun --nproc-per-node N bench.py --gpus N ...   # one process per GPU, rows sharded by range
@@ -62,6 +62,9 @@ WORKLOADS = {
     "N1": dict(config=8, rows=10_000_000, measures=MEASURES,
                desc="N1 (not a BASELINE config): C2 with real-name spelling -- capitalised words, spaces, hyphens and "
                     "apostrophes (any ASCII: the 7-plane instantiation of the short kernel)"),
+    "T1": dict(config=9, rows=10_000_000, measures=MEASURES,
+               desc="T1 (not a BASELINE config): M1 with a tail -- one row in ten has 100-300 characters and takes the "
+                    "long-row kernels (warp-cooperative Jaro / multiset, multi-word Myers)"),
     "C5": dict(config=5, rows=125_000_000, measures=("jaro_winkler", "sorensen_dice"),
                desc="C5: record-linkage pairs (C2 generator, seed 0xC5), Jaro-Winkler + Sorensen-Dice"),
 }

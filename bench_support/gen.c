@@ -13,6 +13,8 @@
  *                  Latin-1 bit-plane path of the general kernel on its own)
  *   config 8 (N1): C2 with real-name spelling: words start with a capital, positions inside a name are a
  *                  space / hyphen / apostrophe w.p. 0.08 (any ASCII: the 7-plane kernel instantiation)
+ *   config 9 (T1): config 7 (20..60-character ASCII strings) with a tail: one row in ten has 100..300
+ *                  characters (free-text fields next to names: the rows above 64 bytes take the long-row kernels)
  *   config 4 (C4): long text, length U{200..4000} codepoints, 90 % a..z/space, 10 % two- and
  *                  three-byte codepoints; b = a with ~10 % random edits w.p. 0.5, else independent
  * Every row is generated from splitmix64(seed, row), so output is independent of the thread count.
@@ -163,9 +165,13 @@ static void gen_row(int config, uint64_t seed, int64_t row, double null_p, rowbu
             script = S_LATIN; /* the Latin rows of C3 alone: a column of names with diacritics */
         } else if (config == 8) {
             script = S_NAME;
-        } else if (config == 7) {
+        } else if (config == 7 || config == 9) {
             lo = 20; /* medium ASCII strings (street addresses): most rows leave the 32-byte kernels */
             hi = 60;
+            if (config == 9 && rndf(&r) < 0.1) {
+                lo = 100;
+                hi = 300;
+            }
         } else if (config == 3) {
             if (rndf(&r) < 0.7) {
                 script = S_LATIN;

@@ -16,7 +16,7 @@ import pyarrow as pa
 HERE = Path(__file__).resolve().parent
 LIB = HERE / "libgen.so"
 
-SEEDS = {2: 0xC2, 3: 0xC3, 4: 0xC4, 5: 0xC5, 6: 0xC6, 7: 0xC7, 8: 0xC8}
+SEEDS = {2: 0xC2, 3: 0xC3, 4: 0xC4, 5: 0xC5, 6: 0xC6, 7: 0xC7, 8: 0xC8, 9: 0xC9}
 _lib = None
 
 

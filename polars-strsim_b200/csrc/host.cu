@@ -33,6 +33,7 @@
 #include "direct_kernel.cuh"
 #include "generic_kernel.cuh"
 #include "long_lev_kernel.cuh"
+#include "long_pair_kernel.cuh"
 #include "short_kernel.cuh"
 
 using namespace strsim;
@@ -1608,6 +1609,52 @@ static int run_long_lev(ThreadCtx& ctx, const SegArgs& args, const Overflow& ov,
     return STRSIM_OK;
 }
 
+// long rows of Jaro / Jaro-Winkler / Jaccard / Sorensen-Dice -> one pair per warp (long_pair_kernel.cuh), every
+// wanted measure in ONE launch.  `outs` / `dbgs` by measure id (nullptr = not wanted).  Returns
+// STRSIM_ERR_NOMEM-free: *served = false when a slab for the longest row does not fit the scratch budget
+// (the caller then falls back to the one-thread-per-pair kernel).
+static int run_long_pair(ThreadCtx& ctx, const SegArgs& args, double* const outs[5], int* const dbgs[5], const Overflow& ov,
+                         cudaStream_t st, bool* served) {
+    *served = false;
+    LongPairArgs g{};
+    g.a = args.a;
+    g.b = args.b;
+    bool any = false;
+    for (int m = 1; m < 5; m++) {
+        g.outs[m] = outs[m];
+        g.dbgs[m] = dbgs[m];
+        any = any || outs[m] != nullptr;
+    }
+    if (!any) {
+        *served = true;
+        return STRSIM_OK;
+    }
+    g.list = args.listlong;
+    g.list_count = &ctx.d_ovf->nlong;
+    g.cursor = ctx.d_counters + 3;
+    g.cap_a = (int)((ov.max_bytes_a + 32u) & ~31u);
+    g.cap_b = (int)((ov.max_bytes_b + 32u) & ~31u);
+    int hs = 64;
+    while (hs < 2 * g.cap_b) hs <<= 1;
+    g.hash_size = hs;
+    g.slab_bytes = long_pair_slab_bytes(g.cap_a, g.cap_b, g.hash_size);
+    long long warps = (long long)ctx.sm_count * 32;
+    if ((long long)ov.nlong < warps) warps = ov.nlong;
+    const long long budget = 2ll << 30;
+    if (warps * g.slab_bytes > budget) warps = budget / g.slab_bytes;
+    if (warps < 1) return STRSIM_OK;  // not served
+    int rc = ws_reserve(ctx.scratch, (size_t)(warps * g.slab_bytes));
+    if (rc) return rc;
+    g.scratch = static_cast<unsigned char*>(ctx.scratch.ptr);
+    g.n_warps = (int)warps;
+    CUDA_TRY(cudaMemsetAsync(ctx.d_counters + 3, 0, sizeof(unsigned int), st));
+    long_pair_kernel<<<(unsigned)((warps + LONGP_WPB - 1) / LONGP_WPB), 32 * LONGP_WPB, 0, st>>>(g);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    *served = true;
+    return STRSIM_OK;
+}
+
 static bool force_generic_rows() {
     static const bool v = getenv("STRSIM_B200_FORCE_GENERIC") != nullptr && atoi(getenv("STRSIM_B200_FORCE_GENERIC")) != 0;
     return v;
@@ -1674,7 +1721,16 @@ static int finish_long(ThreadCtx& ctx, const SegArgs& args, const Overflow& ov, 
         if (rc) return rc;
         if (left.n > 0) rc = run_generic<MEASURE>(ctx, args, ov, st, left.list, left.count, left.n);
     } else {
-        rc = run_generic<MEASURE>(ctx, args, ov, st);
+        bool served = false;
+        if (!force_generic_rows()) {
+            double* outs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+            int* dbgs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+            outs[MEASURE] = args.out;
+            dbgs[MEASURE] = args.dbg;
+            rc = run_long_pair(ctx, args, outs, dbgs, ov, st, &served);
+            if (rc) return rc;
+        }
+        if (!served) rc = run_generic<MEASURE>(ctx, args, ov, st);
     }
     return rc;
 }
@@ -1787,9 +1843,14 @@ static int run_segment_multi(ThreadCtx& ctx, SegArgs args, int groups, Alphabet 
     }
     g_last_overflow[1] += ov.nlong;
     if (ov.nlong > 0) {
+        bool served = false;  // Jaro / Jaro-Winkler / Jaccard / Sorensen-Dice of the long rows: ONE warp-per-pair launch
+        if (!force_generic_rows()) {
+            rc = run_long_pair(ctx, args, args.outs, args.dbgs, ov, st, &served);
+            if (rc) return rc;
+        }
         for (int k = 0; k < 5; k++) {
             const int m = (k + 1) % 5;  // 1, 2, 3, 4, then Levenshtein
-            if (!args.outs[m]) continue;
+            if (!args.outs[m] || (served && m != 0)) continue;
             SegArgs am = args;
             am.out = args.outs[m];
             am.dbg = args.dbgs[m];

@@ -121,6 +121,44 @@ def test_medium_and_long_strings(native, oracle):
     assert sum(native.last_overflow()) > 0  # the overflow kernels really ran
 
 
+def test_long_rows_one_pair_per_warp(native, oracle):
+    """Rows above 64 bytes of Jaro / Jaro-Winkler / Jaccard / Sorensen-Dice (long_pair_kernel.cuh: one pair per
+    warp -- windowed matching by ballot over 32 positions of b per step, transpositions on compacted flag
+    sets, multiset intersection through a per-pair hash table; the reference treats every length alike,
+    strsim.rs:208-219,297-305): tiny alphabets (every window full of candidates, long runs of equal
+    characters), anagrams, reversals, near-duplicates, unrelated pairs, 1-4 byte UTF-8, lengths around the
+    32-position word boundaries up to 2500 characters, one side short or empty, nulls -- single-measure
+    launches, the fused launch, and the one-thread-per-pair kernel as an independent second opinion."""
+    rng = random.Random(4242)
+    a, b = [], []
+    alphabets = ["ab", "abc", "abcdefghijklmnopqrstuvwxyz ", "aéß日\U0001f600xyz", "日本語中文字漢"]
+    for n in (65, 66, 95, 96, 97, 127, 128, 129, 200, 300, 511, 1000, 2500):
+        for alpha in alphabets:
+            x = "".join(rng.choice(alpha) for _ in range(n))
+            y = list(x)
+            for _ in range(max(1, n // 12)):  # a few edits
+                k = rng.randrange(len(y))
+                op = rng.random()
+                if op < 0.4:
+                    y[k] = rng.choice(alpha)
+                elif op < 0.7:
+                    y.insert(k, rng.choice(alpha))
+                elif len(y) > 1:
+                    del y[k]
+            shuffled = list(x)
+            rng.shuffle(shuffled)
+            z = "".join(rng.choice(alpha) for _ in range(rng.randint(1, n + 40)))
+            a += [x, x, x, x, x, x, x[: n // 2], "", x, None, x + "q"]
+            b += ["".join(y), "".join(shuffled), x[::-1], z, x, x[:3], x, x, "", x, None]
+    a += ["x" * 300, "ab" * 150, "a" * 70 + "b" * 70]
+    b += ["x" * 150 + "y" * 150, "ba" * 150, "b" * 70 + "a" * 70]
+    for measure in oracle.MEASURES:
+        check(native, oracle, measure, a, b)
+    assert native.last_overflow()[1] > 0  # the long-row kernels really ran
+    check_multi(native, oracle, list(range(5)), a, b)
+    check_multi(native, oracle, [2, 4], a, b)
+
+
 def test_nulls_slices_chunks_broadcast(native, oracle):
     import pyarrow as pa
 
