@@ -298,7 +298,8 @@ def run_strong(args, wl):
             ptrs = [o.data_ptr() for o in outs]
             nulls = A.null_count + B.null_count > 0
             val = torch.zeros((hi - lo + 31) // 32, dtype=torch.int32, device=f"cuda:{g}") if nulls else None
-            stream = torch.cuda.current_stream(g)
+            stream = torch.cuda.Stream(device=g)  # not the legacy default stream (see main())
+            torch.cuda.set_stream(stream)
 
             def step():
                 if len(measures) > 1:
@@ -463,8 +464,14 @@ def main():
     out_ptrs = [o.data_ptr() for o in outs]
     val = torch.zeros((n + 31) // 32, dtype=torch.int32, device="cuda") if has_nulls else None
     vptr = val.data_ptr() if val is not None else 0
-    stream = torch.cuda.current_stream()
+    # a stream of our own: torch's current stream is the legacy default stream (handle 0), which the library
+    # would read as "use your per-thread stream" -- and events recorded on the default stream do not order
+    # with the library's non-blocking streams, so kernels launched after a call's last host synchronisation
+    # (validity bitmap, long-row kernels) would fall outside the bracket
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
+    assert sptr != 0
 
     def step():
         if fused:
