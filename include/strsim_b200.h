@@ -214,10 +214,20 @@ STRSIM_API int strsim_b200_get_device(void);
 STRSIM_API int strsim_b200_bind_thread_near_device(int device);
 /* Polars plugin calls keep recently uploaded input columns in HBM (and hold the Arrow arrays they own
  * alive, so that an address can only ever mean the same bytes): at most STRSIM_B200_CACHE_BYTES of
- * HBM (default 8 GiB), 8 columns, dropped after 30 s without use; STRSIM_B200_CACHE=0 disables it.
+ * HBM (default 4 GiB), 8 columns, dropped after STRSIM_B200_CACHE_TTL seconds without use (default 10; a
+ * reaper thread enforces it in an idle process too); STRSIM_B200_CACHE=0 disables it.
  * cache_clear drops everything now; cache_stats: [0] hits, [1] misses, [2] columns held, [3] bytes */
 STRSIM_API void strsim_b200_cache_clear(void);
 STRSIM_API void strsim_b200_cache_stats(int64_t out[4]);
+/* Companion measures (arrow_plugin.cpp): the plugin call that uploads a pair of columns also computes -- in
+ * the same fused pass, downloads overlapped with the upload -- the measures the PREVIOUS query asked for
+ * on its pair of columns, and the later calls of the query (README.md:47-51: five expressions, five calls)
+ * take their result ready-made.  Learned from the calls themselves, never guessed; results wait at most
+ * the cache's time-to-live.  `enabled` switches the mechanism at run time (initial state: on, unless
+ * STRSIM_B200_SPECULATE=0 or the cache is off) and forgets what was learned; returns the previous state.
+ * stats: [0] results handed over ready-made, [1] results waiting, [2] bit mask of the learned companions. */
+STRSIM_API int strsim_b200_speculation(int enabled);
+STRSIM_API void strsim_b200_speculation_stats(int64_t out[3]);
 /* thread-local, NUL-terminated description of the last failure on this thread */
 STRSIM_API const char *strsim_b200_last_error(void);
 /* kernels launched by this library since load (all threads); bench.py reports the delta */

@@ -659,6 +659,7 @@ def test_plugin_calls_reuse_columns_already_in_hbm(native, oracle):
         assert (got[ref_valid].view(np.uint64) == ref[ref_valid].view(np.uint64)).all(), measure
 
     L.strsim_b200_cache_clear()
+    L.strsim_b200_speculation(0)  # this test counts cache hits call by call: no results computed ahead
     rng = random.Random(5)
     n = 120000
     a = [None if rng.random() < 0.02 else "".join(rng.choice("abcdefghij") for _ in range(rng.randint(0, 28))) for _ in range(n)]
@@ -684,6 +685,7 @@ def test_plugin_calls_reuse_columns_already_in_hbm(native, oracle):
     L.strsim_b200_cache_clear()
     assert stats()[2:] == [0, 0]
     check_out("sorensen_dice", call("sorensen_dice", A2, B2), a2, b)
+    L.strsim_b200_speculation(1)
 
 
 def test_concurrent_plugin_calls_share_one_upload(native, oracle):
@@ -711,6 +713,7 @@ def test_concurrent_plugin_calls_share_one_upload(native, oracle):
     A, B = workloads.make_pairs(2, n)
     a, b = A.to_pylist(), B.to_pylist()
     refs = {m: oracle.batch(m, a, b)[0] for m in oracle.MEASURES}
+    L.strsim_b200_speculation(0)  # every call computes its own measure here (test_companion_measures covers the rest)
     for round_ in range(2):
         plugin_driver.cache_clear()
         h0, m0, _, _ = stats()
@@ -737,6 +740,77 @@ def test_concurrent_plugin_calls_share_one_upload(native, oracle):
             assert (got[measure].view(np.uint64) == refs[measure].view(np.uint64)).all(), measure
         time.sleep(0.5)  # lets the background thread pin result buffers for the second round
     plugin_driver.cache_clear()
+    L.strsim_b200_speculation(1)
+
+
+def test_companion_measures_are_computed_with_the_upload(native, oracle):
+    """The README query is five plugin calls over the same two columns (README.md:47-51).  Once the plugin has
+    SEEN such a query, the call that uploads the columns of the next one computes the other four measures in
+    the same fused pass and downloads them behind the upload; the later calls take their result ready-made
+    (no kernel launch at all) -- bit-exact, with the null mask, sequentially and from five threads at once.
+    Nothing is computed ahead for a process that asks for one measure only."""
+    import ctypes
+    import threading
+
+    sys.path.insert(0, str(ROOT))
+    from bench_support import plugin_driver, workloads
+
+    L = native.lib()
+    L.strsim_b200_speculation_stats.argtypes = [ctypes.POINTER(ctypes.c_int64)]
+    L.strsim_b200_speculation_stats.restype = None
+
+    def spec():
+        out = (ctypes.c_int64 * 3)()
+        L.strsim_b200_speculation_stats(out)
+        return list(out)
+
+    n = 300_000
+    plugin_driver.cache_clear()
+    L.strsim_b200_speculation(1)  # also forgets what earlier tests taught it
+    queries = [workloads.make_pairs(3, n, row_base=q * n) for q in range(4)]  # nulls, mixed scripts
+
+    def run_query(A, B, measures, threads=False):
+        got = {}
+
+        def work(m):
+            r = plugin_driver.call(m, A, B)
+            got[m] = (np.concatenate(r.values()).copy(), r.validity(), r.null_count)
+            r.release()
+        if threads:
+            ts = [threading.Thread(target=work, args=(m,)) for m in measures]
+            [t.start() for t in ts]
+            [t.join() for t in ts]
+        else:
+            for m in measures:
+                work(m)
+        a, b = A.to_pylist(), B.to_pylist()
+        for m in measures:
+            ref, rv, _ = oracle.batch(m, a, b)
+            vals, valid, nulls = got[m]
+            assert (valid == rv).all() and nulls == int((~rv).sum()), m
+            assert (vals[rv].view(np.uint64) == ref[rv].view(np.uint64)).all(), m
+
+    served0 = spec()[0]
+    run_query(*queries[0], oracle.MEASURES)              # the first query teaches the companions
+    assert spec()[0] == served0 and spec()[1] == 0
+    launches = native.kernel_launches()
+    run_query(*queries[1], oracle.MEASURES)              # the second one gets four results ready-made
+    assert spec()[0] - served0 == 4 and spec()[1] == 0
+    assert spec()[2] == 0b11111
+    run_query(*queries[2], oracle.MEASURES, threads=True)  # all five calls at once
+    assert spec()[0] - served0 == 8
+    # a query that asks for one measure only: what was computed ahead for it waits, then expires -- and the
+    # query after it computes nothing ahead any more
+    run_query(*queries[3], ["jaro"])
+    assert spec()[1] == 4
+    run_query(*queries[0], ["jaro"])
+    assert spec()[2] == 0b00010
+    waiting = spec()[1]
+    run_query(*queries[1], ["jaro"])
+    assert spec()[1] <= waiting  # nothing new computed ahead (what waited may have expired meanwhile)
+    plugin_driver.cache_clear()
+    assert spec()[1] == 0
+    L.strsim_b200_speculation(1)
 
 
 def test_dictionary_encoded_columns(native, oracle):
