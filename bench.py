@@ -356,8 +356,10 @@ def run_strong(args, wl):
                 r.release()
         return results
 
-    plugin_step()
-    plugin_step()
+    for k in range(4):  # see main(): the plugin learns the measures, the pinned result pool grows
+        plugin_step()
+        if k < 2:
+            time.sleep(0.6)
     e2e_steps = max(1, min(args.steps, 5))
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -587,8 +589,12 @@ def main():
             L.strsim_b200_speculation_stats(o)
             return int(o[0])
 
-        plugin_step()
-        plugin_step()
+        # warm-up: the plugin learns the query's measures from the first step, and its pool of pinned result
+        # buffers grows in a background thread after the first requests (a one-time cost per process)
+        for k in range(4):
+            plugin_step()
+            if k < 2:
+                time.sleep(0.6)
         barrier()
         e2e_steps = max(1, min(args.steps, 5))
         served0 = served()
@@ -615,6 +621,7 @@ def main():
                # columns computed and downloaded the measures the previous step's calls had asked for; this
                # many calls per step took their result ready-made
                "calls_served_from_results_computed_with_the_upload_per_step": (served() - served0) / (e2e_steps + 1),
+               "warmup_steps": 4,
                "result_chunks_per_call": chunks_out,
                "checksum_matches_device": bool(all(
                    abs(s - checksums[m]) <= 1e-9 * max(1.0, abs(checksums[m])) for s, m in zip(sums, measures)))}

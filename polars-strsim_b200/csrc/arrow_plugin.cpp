@@ -738,9 +738,10 @@ void results_clear() {
     {
         std::lock_guard<std::mutex> lock(g_cache_mutex);
         drop.swap(g_results);
+        if (g_query_mask) g_companion_mask = g_query_mask;  // what the process has learned survives a cache clear
         g_query_key_a.clear();
         g_query_key_b.clear();
-        g_query_mask = 0;  // the companion mask survives: it is what the process has learned
+        g_query_mask = 0;
     }
     for (ResultEntry& r : drop) result_destroy(r.res);
 }

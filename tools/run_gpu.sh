@@ -1,9 +1,22 @@
 cd $GRAFT_REPO_ROOT
-for r in 4 6 8; do
-STRSIM_B200_WT_RPT=$r python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/r2i_bench_C2_rpt$r.json 2> gpurun_out/r2i_err.log; python - <<PY
-import json
-d=json.load(open('gpurun_out/r2i_bench_C2_rpt$r.json'))
-print('C2 wt rpt=$r', round(d['ms_per_step'],4), d['overflow_rows_last_call'])
+python - <<'PY'
+import sys, time, json, os
+sys.path[:0]=['.','polars-strsim_b200']
+from bench_support import plugin_driver, workloads
+from polars_strsim import _native
+M=("levenshtein","jaro","jaro_winkler","jaccard","sorensen_dice")
+A,B=workloads.make_pairs(2,10_000_000)
+L=_native.lib()
+def step():
+    plugin_driver.cache_clear()
+    t=[]
+    for m in M:
+        t0=time.perf_counter(); r=plugin_driver.call(m,A,B); t.append((time.perf_counter()-t0)*1e3); r.release()
+    return t
+for spec in (1,0):
+    L.strsim_b200_speculation(spec)
+    for i in range(12):
+        t=step()
+        if i>=8: print('spec',spec,'step',i,'total %.2f'%sum(t),['%.2f'%x for x in t])
+    time.sleep(1.0)
 PY
-done
-tail -2 gpurun_out/r2i_err.log
