@@ -1358,18 +1358,20 @@ static int launch_general(ThreadCtx& ctx, const SegArgs& args, long long rows, c
         return launch_short<uint32_t, MEASURE, 256, RPT_WIDE, false, 128, false, false, true>(ctx, a, rows, st);
     int rc = launch_short<uint32_t, MEASURE, 256, RPT_LATIN, false, 128, false, false, true, true>(ctx, a, rows, st);
     if (rc) return rc;
-    // a column of Latin-1 text (names with diacritics) has nothing left for the second launch
-    CUDA_TRY(publish_to_host(ctx.h_ovf, ctx.d_ovf, sizeof(Overflow), st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    if (g_wide_share && rows > 0) *g_wide_share = (float)ctx.h_ovf->nwide / (float)rows;
-    if (ctx.h_ovf->nwide == 0) return STRSIM_OK;
-    // the pairs the first launch listed: gather mode over that list only (null rows and the overflow
-    // lists were settled by the first launch: skip_latin)
+    // the pairs the first launch listed: gather mode over that list only (null rows and the overflow lists
+    // were settled by the first launch: skip_latin).  The list's length stays on the device -- the second
+    // launch reads it there and its CTAs leave at once when the list is empty -- so the two launches go out
+    // back to back, without the host round trip that used to sit between them; the share of wide pairs
+    // (the hint above) is read with the segment's overflow counters (note_wide_share).
     a.skip_latin = 1;
     a.list = args.listwide;
     a.list_count = &ctx.d_ovf->nwide;
-    a.n = ctx.h_ovf->nwide;
-    return launch_short<uint32_t, MEASURE, 256, RPT_WIDE, true, 128, false, false, true>(ctx, a, (long long)ctx.h_ovf->nwide, st);
+    a.n = rows;
+    return launch_short<uint32_t, MEASURE, 256, RPT_WIDE, true, 128, false, false, true>(ctx, a, rows, st);
+}
+
+static void note_wide_share(const Overflow& ov, long long rows) {
+    if (g_wide_share && rows > 0 && ov.nwide > 0) *g_wide_share = (float)ov.nwide / (float)rows;
 }
 
 // Which instantiation of the fused kernel serves a segment (see DevStore): decided from the union of
@@ -1547,7 +1549,7 @@ static int run_long_lev(ThreadCtx& ctx, const SegArgs& args, const Overflow& ov,
     while (hs < 2 * cap_pat) hs <<= 1;
     g.hash_size = hs;
     g.w_max = (cap_pat + 63) / 64;
-    const long long worst_words = (long long)(cap_pat + 1) * g.w_max;
+    const long long worst_words = (long long)(cap_pat + 1) * ((g.w_max + 1) & ~1);  // rows have an even stride (long_load_eq)
     const long long budget = 8ll << 30;
     // tier 0 reads listlong and defers into spare_list (count d_counters[1]);
     // tier 1 reads spare_list and defers into listlong, free again by then (count d_counters[2])
@@ -1560,7 +1562,7 @@ static int run_long_lev(ThreadCtx& ctx, const SegArgs& args, const Overflow& ov,
         long long peq_words = tier == 0 ? (64ll << 10) : worst_words;  // tier 0: 512 KiB of Peq per slab
         if (peq_words > worst_words) peq_words = worst_words;
         g.peq_words = peq_words;
-        g.slab_bytes = long_lev_slab_bytes(g.cap_a, g.cap_b, g.hash_size, peq_words);
+        g.slab_bytes = long_lev_slab_bytes(g.cap_a, g.cap_b, g.cap_pat, g.hash_size, peq_words);
         static const int tier0_warps = [] {
             const char* e = getenv("STRSIM_B200_LONG_WARPS");  // tuning knob: resident warps per SM
             const int v = e && *e ? atoi(e) : 0;
@@ -1751,6 +1753,7 @@ static int run_segment(ThreadCtx& ctx, SegArgs args, Alphabet al, int stage32, i
     Overflow ov;
     rc = read_overflow(ctx, &ov, st);
     if (rc) return rc;
+    if (al == ALPHA_GENERAL) note_wide_share(ov, seg_rows);
     g_last_overflow[0] += ov.n64;
     if (ov.n64 > 0) {
         rc = finish_64<MEASURE>(ctx, args, ov, st, al != ALPHA_GENERAL);
@@ -1764,15 +1767,6 @@ static int run_segment(ThreadCtx& ctx, SegArgs args, Alphabet al, int stage32, i
     return rc;
 }
 
-static int finish_64_any(int measure, ThreadCtx& ctx, const SegArgs& args, const Overflow& ov, cudaStream_t st) {
-    switch (measure) {
-        case 0: return finish_64<0>(ctx, args, ov, st);
-        case 1: return finish_64<1>(ctx, args, ov, st);
-        case 2: return finish_64<2>(ctx, args, ov, st);
-        case 3: return finish_64<3>(ctx, args, ov, st);
-        default: return finish_64<4>(ctx, args, ov, st);
-    }
-}
 static int finish_long_any(int measure, ThreadCtx& ctx, const SegArgs& args, const Overflow& ov, cudaStream_t st) {
     switch (measure) {
         case 0: return finish_long<0>(ctx, args, ov, st);
@@ -1814,6 +1808,7 @@ static int run_segment_multi(ThreadCtx& ctx, SegArgs args, int groups, Alphabet 
     Overflow ov;
     rc = read_overflow(ctx, &ov, st);
     if (rc) return rc;
+    if (al == ALPHA_GENERAL) note_wide_share(ov, seg_rows);
     g_last_overflow[0] += ov.n64;
     static const bool planes64 = !(getenv("STRSIM_B200_PLANES64") && !strcmp(getenv("STRSIM_B200_PLANES64"), "0"));
     if (ov.n64 > 0 && al != ALPHA_GENERAL && groups >= 2 && planes64) {
@@ -1828,14 +1823,21 @@ static int run_segment_multi(ThreadCtx& ctx, SegArgs args, int groups, Alphabet 
         }
         if (rc) return rc;
     } else if (ov.n64 > 0) {
-        for (int m = 0; m < 5; m++) {
-            if (!args.outs[m]) continue;
-            SegArgs am = args;
-            am.out = args.outs[m];
-            am.dbg = args.dbgs[m];
-            rc = finish_64_any(m, ctx, am, ov, st);
-            if (rc) return rc;
-        }
+        // general columns: the table / hash path with 64-bit masks, every wanted measure in one launch
+        // (blockIdx.y = measure)
+        using L = DirectLayout<uint64_t, 64, 1, 192>;
+        auto kern = direct_multi64_kernel<64, 192>;
+        CUDA_TRY(configure_smem(reinterpret_cast<const void*>(kern), ctx.device, L::bytes));
+        SegArgs a64 = args;
+        a64.list = args.list64;
+        a64.list_count = &ctx.d_ovf->n64;
+        a64.n = ov.n64;
+        long long gx = ((long long)ov.n64 + L::TILE - 1) / L::TILE;
+        if (gx > 8ll * ctx.sm_count) gx = 8ll * ctx.sm_count;
+        if (gx < 1) gx = 1;
+        kern<<<dim3((unsigned)gx, 5), 64, L::bytes, st>>>(a64);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        CUDA_TRY(cudaGetLastError());
     }
     if (ov.n64 > 0) {  // rows the 64-bit kernels could not take are appended to listlong: re-read the counters
         rc = read_overflow(ctx, &ov, st, false);

@@ -54,18 +54,16 @@ struct LongLevArgs {
 };
 
 struct LongLevSlab {
-    uint32_t* cps_a;
-    uint32_t* cps_b;
+    uint32_t* cps_a;  // the PATTERN's code points (cap_pat entries); the text is never stored decoded
     uint16_t* tid;
     uint32_t* hkeys;
     uint32_t* hvals;  // per hash slot: occurrence count while the pattern is inserted, then the character's code
     unsigned long long* peq;
 };
 
-__host__ __device__ inline long long long_lev_slab_bytes(int cap_a, int cap_b, int hash_size, long long peq_words) {
+__host__ __device__ inline long long long_lev_slab_bytes(int cap_a, int cap_b, int cap_pat, int hash_size, long long peq_words) {
     long long b = 0;
-    b += 4ll * cap_a;
-    b += 4ll * cap_b;
+    b += 4ll * cap_pat;
     b += 2ll * ((cap_a > cap_b ? cap_a : cap_b) + 2 * LONG_TID_PAD);
     b = (b + 15) & ~15ll;
     b += 4ll * hash_size;
@@ -79,9 +77,7 @@ __device__ inline LongLevSlab long_lev_carve(unsigned char* base, const LongLevA
     LongLevSlab s;
     long long o = 0;
     s.cps_a = reinterpret_cast<uint32_t*>(base + o);
-    o += 4ll * g.cap_a;
-    s.cps_b = reinterpret_cast<uint32_t*>(base + o);
-    o += 4ll * g.cap_b;
+    o += 4ll * g.cap_pat;
     s.tid = reinterpret_cast<uint16_t*>(base + o);
     o += 2ll * ((g.cap_a > g.cap_b ? g.cap_a : g.cap_b) + 2 * LONG_TID_PAD);
     o = (o + 15) & ~15ll;
@@ -115,6 +111,24 @@ __device__ inline int warp_decode(const unsigned char* p, int nbytes, uint32_t* 
     return count;
 }
 
+// number of characters (bytes that are not UTF-8 continuation bytes) of p[0..nbytes), by the whole warp:
+// aligned 4-byte loads, 128 bytes per step
+__device__ inline int warp_count_chars(const unsigned char* p, int nbytes, int lane) {
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
+    const int head = (int)(addr & 3);  // bytes of the first aligned word that precede the string
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(addr - (uintptr_t)head);
+    const int total = head + nbytes, nwords = (total + 3) >> 2;
+    int cont = 0;
+    for (int i = lane; i < nwords; i += 32) {
+        uint32_t x = w[i];  // reads at most 3 bytes before / after the string: inside the padded device buffer
+        if (i == 0) x &= ~byte_mask(head);
+        if (i == nwords - 1) x &= byte_mask(total - 4 * i);
+        cont += __popc(((x >> 7) & ~(x >> 6)) & 0x01010101u);
+    }
+    cont = __reduce_add_sync(0xFFFFFFFFu, cont);
+    return nbytes - cont;
+}
+
 __device__ __forceinline__ uint32_t long_hash(uint32_t cp, int shift) { return (cp * 2654435761u) >> shift; }
 
 // Character codes (16 bit, what the text is translated to): a character that occurs at least twice in the
@@ -134,6 +148,36 @@ __device__ __forceinline__ uint32_t long_find_slot(const LongLevSlab& s, uint32_
         if (k == key) return slot;
         if (k == 0u) return ~0u;
         slot = (slot + 1u) & hmask;
+    }
+}
+
+// The K Eq words of one lane: consecutive 64-bit words of a Peq row, starting at the lane's first block.
+// Every lane reads another row (its own text column), so a load instruction touches up to 32 sectors
+// whatever its width -- the round-1 kernel issued K separate 64-bit loads and kept the L1 data pipe 82 %
+// busy.  Rows are 16-byte aligned (even stride), so K = 2 and K = 4 are one / two 128-bit loads; K = 3
+// starts at an odd word for odd lanes: two 128-bit loads from the aligned word below, and the three
+// wanted words are picked by the lane's parity.  (Reads one word outside the lane's blocks: inside the
+// row, or inside LONG_PEQ_PAD for the last lane.)
+template <int K>
+__device__ __forceinline__ void long_load_eq(const unsigned long long* row, bool odd, uint64_t (&eq)[K]) {
+    if (K == 1) {
+        eq[0] = row[0];
+    } else if (K == 2) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(row);
+        eq[0] = v.x;
+        eq[1] = v.y;
+    } else if (K == 4) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(row), w = *reinterpret_cast<const ulonglong2*>(row + 2);
+        eq[0] = v.x;
+        eq[1] = v.y;
+        eq[2] = w.x;
+        eq[3] = w.y;
+    } else {  // K == 3
+        const unsigned long long* base = row - (odd ? 1 : 0);
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(base), w = *reinterpret_cast<const ulonglong2*>(base + 2);
+        eq[0] = odd ? v.y : v.x;
+        eq[1] = odd ? w.x : v.y;
+        eq[2] = odd ? w.y : w.x;
     }
 }
 
@@ -158,7 +202,8 @@ __device__ inline int long_wavefront(const LongLevSlab& s, const uint16_t* tid, 
     const int blk0 = lane_on ? lane * K : 0;  // idle lanes prefetch block 0 (harmless) and never compute
     const unsigned n_on = lane_on ? (unsigned)n : 0u;
     const unsigned long long* rowbase = s.peq + blk0;
-    const unsigned W8 = (unsigned)W;
+    const bool odd = (blk0 & 1) != 0;  // K == 3 only: the lane's first block sits at an odd word of its (16-byte aligned) row
+    const unsigned W8 = (unsigned)((W + 1) & ~1);  // row stride of Peq: even, so that rows start 16-byte aligned
     const uint16_t* tp = tid - lane;  // tp[st + c] = id of column (st - lane) + c
     // codes of this lane's columns j, j+1, j+2 sit in tq[1], tq[2], tq[0] at step 0 and rotate from there
     tq[1] = tp[0];
@@ -167,12 +212,10 @@ __device__ inline int long_wavefront(const LongLevSlab& s, const uint16_t* tid, 
     {
         const unsigned long long* r0 = rowbase + (size_t)((tq[1] & LONG_SINGLE) ? zero_row : tq[1]) * W8;
         const unsigned long long* r1 = rowbase + (size_t)((tq[2] & LONG_SINGLE) ? zero_row : tq[2]) * W8;
+        long_load_eq<K>(r0, odd, eq[0]);
+        long_load_eq<K>(r1, odd, eq[1]);
 #pragma unroll
-        for (int k = 0; k < K; k++) {
-            eq[0][k] = r0[k];
-            eq[1][k] = r1[k];
-            eq[2][k] = 0ull;
-        }
+        for (int k = 0; k < K; k++) eq[2][k] = 0ull;
     }
     uint32_t carry_prev = 0;  // bit 0: hp, bit 1: hm of this lane's last block in the previous step
 #pragma unroll 1
@@ -188,8 +231,7 @@ __device__ inline int long_wavefront(const LongLevSlab& s, const uint16_t* tid, 
             {
                 const uint32_t t = tq[u];
                 const unsigned long long* row = rowbase + (size_t)((t & LONG_SINGLE) ? zero_row : t) * W8;
-#pragma unroll
-                for (int k = 0; k < K; k++) eq[(u + 2) % 3][k] = row[k];
+                long_load_eq<K>(row, odd, eq[(u + 2) % 3]);
             }
             if ((unsigned)(j0 + u) < n_on) {
                 // a character that occurs once in the pattern: its bit, if it falls into this lane's blocks
@@ -249,13 +291,18 @@ __device__ __noinline__ void long_prepare(const LongLevArgs& g, const LongLevSla
         o.v = 1.0;
         return;
     }
-    const int la = warp_decode(pa, na, s.cps_a, lane);
-    const int lb = warp_decode(pb, nb, s.cps_b, lane);
+    // Character counts first: they decide which string is the pattern (the shorter one), and only the
+    // PATTERN is kept as code points -- the text is decoded and translated to codes in one pass (step 4).
+    // (The first version stored both strings as code points, 34 KB written and read again per C4 pair; with
+    // thousands of pairs in flight the slabs outgrew the L2 and that traffic went to HBM.)
+    const int la = warp_count_chars(pa, na, lane);
+    const int lb = warp_count_chars(pb, nb, lane);
     o.la = o.pi.la = la;
     o.lb = o.pi.lb = lb;
     const bool pat_is_b = lb <= la;
-    const uint32_t* P = pat_is_b ? s.cps_b : s.cps_a;
-    const uint32_t* T = pat_is_b ? s.cps_a : s.cps_b;
+    const unsigned char* const pat_bytes = pat_is_b ? pb : pa;
+    const unsigned char* const txt_bytes = pat_is_b ? pa : pb;
+    const int pat_nbytes = pat_is_b ? nb : na, txt_nbytes = pat_is_b ? na : nb;
     const int m = pat_is_b ? lb : la, n = pat_is_b ? la : lb;
     o.m = m;
     o.n = n;
@@ -269,27 +316,51 @@ __device__ __noinline__ void long_prepare(const LongLevArgs& g, const LongLevSla
         o.v = lev_value(n, la, lb);
         return;
     }
+    uint32_t* const P = s.cps_a;
+    warp_decode(pat_bytes, pat_nbytes, P, lane);
     const int W = (m + 63) >> 6;
     o.W = W;
-    // 1. hash set of the pattern's codepoints (table sized for this pattern, load <= 1/2)
+    // 1. hash set of the pattern's codepoints.  Sized for the DISTINCT characters, which are few in text (230
+    // of 2100 on C4): start with 1024 slots and grow only when the table turns out more than half full, so a
+    // typical pair zeroes and probes 8 KB instead of the 32 KB a table for 2m keys would take.
     int hbits = 6;
-    while ((1 << hbits) < 2 * m) hbits++;
-    const int hsize = 1 << hbits, hshift = 32 - hbits;
-    const uint32_t hmask = (uint32_t)hsize - 1u;
-    for (int i = lane; i < hsize; i += 32) {
-        s.hkeys[i] = 0u;
-        s.hvals[i] = 0u;
-    }
-    __syncwarp();
-    for (int i = lane; i < m; i += 32) {
-        const uint32_t key = P[i] + 1u;
-        uint32_t slot = long_hash(P[i], hshift);
-        for (;;) {
-            const uint32_t old = atomicCAS(&s.hkeys[slot], 0u, key);
-            if (old == 0u || old == key) break;
-            slot = (slot + 1u) & hmask;
+    while ((1 << hbits) < 2 * m && hbits < 10) hbits++;
+    int hsize, hshift;
+    uint32_t hmask;
+    for (;;) {
+        hsize = 1 << hbits;
+        hshift = 32 - hbits;
+        hmask = (uint32_t)hsize - 1u;
+        for (int i = lane; i < hsize; i += 32) {
+            s.hkeys[i] = 0u;
+            s.hvals[i] = 0u;
         }
-        atomicAdd(&s.hvals[slot], 1u);  // occurrences of this character in the pattern
+        __syncwarp();
+        int fresh = 0;
+        bool full = false;
+        for (int i = lane; i < m; i += 32) {
+            const uint32_t key = P[i] + 1u;
+            uint32_t slot = long_hash(P[i], hshift);
+            int probes = 0;
+            for (;;) {
+                const uint32_t old = atomicCAS(&s.hkeys[slot], 0u, key);
+                if (old == 0u) fresh++;
+                if (old == 0u || old == key) break;
+                slot = (slot + 1u) & hmask;
+                if (++probes > hsize) {
+                    full = true;
+                    break;
+                }
+            }
+            if (full) break;
+            atomicAdd(&s.hvals[slot], 1u);  // occurrences of this character in the pattern
+        }
+        fresh = __reduce_add_sync(0xFFFFFFFFu, fresh);
+        full = __any_sync(0xFFFFFFFFu, full);
+        if (!full && 2 * fresh <= hsize) break;
+        hbits += 2;  // (1 << hbits) stays within the slab: it ends at the first power of two >= 2m
+        while ((1 << (hbits - 1)) >= 2 * m && hbits > 6) hbits--;
+        __syncwarp();
     }
     __syncwarp();
     // 2. dense row ids, in slot order, for the characters that occur at least twice
@@ -306,7 +377,8 @@ __device__ __noinline__ void long_prepare(const LongLevArgs& g, const LongLevSla
     __syncwarp();
     o.zero_row = rows;  // row `rows` stays all zero: characters the pattern does not contain
     // 3. Peq[row][block]; single characters record their position instead
-    const size_t words = (size_t)(rows + 1u) * W;
+    const int Wp = (W + 1) & ~1;  // row stride (see long_load_eq)
+    const size_t words = (size_t)(rows + 1u) * Wp;
     if ((long long)words > g.peq_words) {  // needs a bigger slab: second launch
         if (lane == 0) g.huge_list[atomicAdd(g.huge_count, 1u)] = (unsigned int)row;
         o.status = 2;
@@ -320,15 +392,30 @@ __device__ __noinline__ void long_prepare(const LongLevArgs& g, const LongLevSla
         if (code == LONG_PENDING)
             s.hvals[slot] = LONG_SINGLE | (uint32_t)i;  // the only occurrence: nobody else writes this slot
         else
-            atomicOr(&s.peq[(size_t)code * W + (i >> 6)], 1ull << (i & 63));
+            atomicOr(&s.peq[(size_t)code * Wp + (i >> 6)], 1ull << (i & 63));
     }
     __syncwarp();
     __threadfence();  // the atomics landed in L2; drop possibly stale L1 lines before reading Peq
-    // 4. text -> codes, padded on both sides with the all-zero row
+    // 4. text -> codes, padded on both sides with the all-zero row: decoded 32 bytes per step and looked up
+    // at once (valid UTF-8, as Polars guarantees)
     uint16_t* tid = s.tid + LONG_TID_PAD;
-    for (int j = lane; j < n; j += 32) {
-        const uint32_t slot = long_find_slot(s, hmask, hshift, T[j]);
-        tid[j] = (uint16_t)(slot == ~0u ? rows : __ldcg(&s.hvals[slot]));
+    {
+        int done = 0;
+        for (int base = 0; base < txt_nbytes; base += 32) {
+            const int i = base + lane;
+            const uint32_t c = i < txt_nbytes ? txt_bytes[i] : 0x80u;
+            const bool lead = i < txt_nbytes && (c & 0xC0u) != 0x80u;
+            const unsigned mask = __ballot_sync(0xFFFFFFFFu, lead);
+            if (lead) {
+                int len = c < 0x80u ? 1 : c < 0xE0u ? 2 : c < 0xF0u ? 3 : 4;
+                if (len > txt_nbytes - i) len = txt_nbytes - i;
+                uint32_t cp = len == 1 ? c : (c & (0xFFu >> (len + 1)));
+                for (int e = 1; e < len; e++) cp = (cp << 6) | (txt_bytes[i + e] & 0x3Fu);
+                const uint32_t slot = long_find_slot(s, hmask, hshift, cp);
+                tid[done + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)(slot == ~0u ? rows : __ldcg(&s.hvals[slot]));
+            }
+            done += __popc(mask);
+        }
     }
     for (int j = lane; j < LONG_TID_PAD; j += 32) {
         s.tid[j] = (uint16_t)rows;

@@ -85,41 +85,58 @@ SS_HD void planes_add_word(PlaneTab<NBITS, M>& tab, uint32_t word, int w) {
 // that way, a pair of such strings runs the bit-plane path with 8 planes instead of the register-compare
 // path, whose position masks cost two ALU operations per tabled character per streamed character.
 //
-// Slab: rd(w) / wr(w, word) over the string's words (zero padded).  In place: the output never
-// overtakes the input.  Returns the number of characters.
-template <class Slab>
-SS_HD int transcode_latin1(Slab& s, int nbytes) {
+// Core: rd(w) -> word w of the UTF-8 string (zero beyond nbytes), wr(w, word) receives the output words.
+// `wide` collects the lead bytes >= 0xC4 met on the way (a character above U+00FF: the result is then
+// meaningless and the caller hands the pair to the register-compare path).  A word holds at most two lead
+// bytes (a lead is followed by a continuation byte); they are squeezed out highest first, branch-free --
+// a missing lead turns its step into a no-op.  The output never overtakes the input, so rd and wr may name
+// the same storage.  Returns the number of characters.
+template <class Rd, class Wr>
+SS_HD int transcode_latin1_stream(const Rd& rd, Wr& wr, int nbytes, uint32_t& wide) {
     uint64_t acc = 0;
     int acc_bytes = 0, out_w = 0, total = 0;
     uint32_t carry = 0;  // low bit of a lead byte that ended the previous word
     const int nw = (nbytes + 3) >> 2;
     for (int w = 0; w < nw; w++) {
-        const uint32_t x = s.rd(w);
-        const uint32_t lead = x & (x << 1) & 0x80808080u;  // bit 7 of every 11xxxxxx byte
-        const uint32_t lowbit = x & (lead >> 7);           // bit 0 of the lead bytes ...
-        const uint32_t y = x | (lowbit << 14) | (carry << 6);  // ... into bit 6 of the byte that follows
+        const uint32_t x = rd(w);
+        const uint32_t lead = x & (x << 1) & 0x80808080u;   // bit 7 of every 11xxxxxx byte
+        const uint32_t leadfull = (lead >> 7) * 0xFFu;      // those bytes, all bits
+        wide |= x & leadfull & 0x3C3C3C3Cu;                 // a lead with any of bits 2..5 set is >= 0xC4
+        const uint32_t lowbit = x & (lead >> 7);            // bit 0 of the lead bytes ...
+        uint32_t y = x | (lowbit << 14) | (carry << 6);     // ... into bit 6 of the byte that follows
         carry = lowbit >> 24;
-        uint32_t z = 0;
-        int cnt = 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const bool keep = 4 * w + j < nbytes && !((lead >> (8 * j + 7)) & 1u);
-            if (keep) {
-                z |= ((y >> (8 * j)) & 0xFFu) << (8 * cnt);
-                cnt++;
-            }
-        }
-        acc |= (uint64_t)z << (8 * acc_bytes);
+        const uint32_t l1 = lead & (0u - lead), l2 = lead ^ l1;  // the lower and the higher lead of the word (or 0)
+        const uint32_t m2 = (l2 >> 7) - 1u, m1 = (l1 >> 7) - 1u;  // bytes below the lead; all ones when there is none
+        y = (y & m2) | ((y >> 8) & ~m2);
+        y = (y & m1) | ((y >> 8) & ~m1);
+        const int in_word = nbytes - 4 * w < 4 ? nbytes - 4 * w : 4;
+        const int cnt = in_word - popc(lead);
+        acc |= (uint64_t)y << (8 * acc_bytes);
         acc_bytes += cnt;
         total += cnt;
         if (acc_bytes >= 4) {
-            s.wr(out_w++, (uint32_t)acc);
+            wr(out_w++, (uint32_t)acc);
             acc >>= 32;
             acc_bytes -= 4;
         }
     }
-    if (acc_bytes > 0) s.wr(out_w++, (uint32_t)acc);
+    if (acc_bytes > 0) wr(out_w++, (uint32_t)acc);
     return total;
+}
+
+// Slab: rd(w) / wr(w, word) over the string's words (zero padded), transcoded in place.
+template <class Slab>
+SS_HD int transcode_latin1(Slab& s, int nbytes) {
+    struct Rd {
+        const Slab& s;
+        SS_HD uint32_t operator()(int w) const { return s.rd(w); }
+    } rd{s};
+    struct Wr {
+        Slab& s;
+        SS_HD void operator()(int w, uint32_t v) { s.wr(w, v); }
+    } wr{s};
+    uint32_t wide = 0;
+    return transcode_latin1_stream(rd, wr, nbytes, wide);
 }
 
 // any byte >= 0xC4 (a character above U+00FF) in a zero-padded word?

@@ -488,6 +488,24 @@ struct SlabByteAt {
     }
 };
 
+// A staged string (any byte offset inside the tile) as the word source of transcode_latin1_stream: aligned
+// shared-memory words, funnel-shifted to the string's start, zero beyond its length.
+struct StagedWords {
+    const uint32_t* p;  // aligned word that holds the first byte
+    int sh;             // bit offset of the first byte inside it
+    int len;
+    __device__ __forceinline__ uint32_t operator()(int w) const {
+        const uint32_t word = __funnelshift_r(p[w], p[w + 1], sh);
+        const int left = len - 4 * w;
+        return left >= 4 ? word : word & byte_mask(left);
+    }
+};
+template <int TPB>
+struct SlabWriter {
+    uint32_t* w;  // &slab[tid]
+    __device__ __forceinline__ void operator()(int i, uint32_t v) { w[i * TPB] = v; }
+};
+
 struct WarpMaxDev {  // maximum over the 32 lanes of the warp (all lanes must call it)
     __device__ __forceinline__ int operator()(int v) const { return __reduce_max_sync(0xFFFFFFFFu, v); }
 };
@@ -810,13 +828,24 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
             // multiset kernels: the loops run la times (Levenshtein streams the longer string)
             if (REG && (is_multi(MEASURE) || MEASURE != LEVENSHTEIN)) mx = va.x;
             uint32_t wide = 0;  // UREG: a character above U+00FF somewhere in the pair
-            if (UREG) {
+            if (ULAT) {
+                // The Latin-1 launch looks at the first word of each string only: a name in a script above
+                // U+00FF starts with such a character (C3: every CJK row), and a pair whose first wide
+                // character comes later is caught when it is transcoded in step 4.  The sort key is the
+                // BYTE length of the streamed string -- a few diacritics more or less do not change the cost
+                // class.  (The first version counted the characters of both strings here, word by word with a
+                // third of the lanes active: a fifth of the launch's instructions.)
+                wide = wide_bytes(staged_first_word(smem, staged_str(va, i, (uint32_t)L::off_sva, off_stage_a))) |
+                       wide_bytes(staged_first_word(smem, staged_str(vb, i, (uint32_t)L::off_svb, off_stage_b)));
+                if (is_multi(MEASURE) || MEASURE != LEVENSHTEIN) mx = va.x;  // the plane path streams a
+            } else if (UREG) {
                 // the register-compare path costs (streamed characters) x (tabled characters): bucket by
                 // CHARACTER counts so that e.g. 6-character CJK rows do not share a warp with 18-character
                 // Latin rows of the same byte length.
                 const int ca = staged_char_count(va, stage_a, wide), cb = staged_char_count(vb, stage_b, wide);
                 mx = (uint32_t)(ca > cb ? ca : cb);
-                if (is_multi(MEASURE) && ULAT) mx = (uint32_t)ca;  // the plane path streams a for every group
+            }
+            if (UREG) {
                 // each of the two launches over a general column takes one class; the first one counts what
                 // it leaves to the second (none in a Latin-1 column: the host then skips that launch)
                 if (ULAT && wide != 0u) {
@@ -895,10 +924,27 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
                     continue;
                 }
                 const uint4 va = sva[i], vb = svb[i];
-                load_string<WORDS, TPB>(va, stage_a, store.wa_);
-                load_string<WORDS, TPB>(vb, stage_b, store.wb_);
-                SlabWords<TPB> sa{store.wa_}, sb{store.wb_};
-                const int ca = transcode_latin1(sa, (int)va.x), cb = transcode_latin1(sb, (int)vb.x);
+                // straight from the staged tile into the thread's slab, one byte per character
+                const StagedStr SA = staged_str(va, i, (uint32_t)L::off_sva, off_stage_a),
+                                SB = staged_str(vb, i, (uint32_t)L::off_svb, off_stage_b);
+                uint32_t wide = 0;
+                SlabWriter<TPB> wa{store.wa_}, wb{store.wb_};
+                const int ca = transcode_latin1_stream(
+                    StagedWords{reinterpret_cast<const uint32_t*>(smem + (SA.off & ~3u)), (int)(SA.off & 3u) * 8, SA.len}, wa,
+                    SA.len, wide);
+                const int cb = transcode_latin1_stream(
+                    StagedWords{reinterpret_cast<const uint32_t*>(smem + (SB.off & ~3u)), (int)(SB.off & 3u) * 8, SB.len}, wb,
+                    SB.len, wide);
+                if (wide != 0u) {
+                    // a character above U+00FF behind the first word: the register-compare launch takes the pair
+                    const unsigned m = __activemask();
+                    const int leader = (int)__ffs(m) - 1;
+                    unsigned base = 0;
+                    if (lane == leader) base = atomicAdd(&s.ovf->nwide, (unsigned)__popc(m));
+                    base = __shfl_sync(m, base, leader);
+                    s.listwide[base + __popc(m & ((1u << lane) - 1u))] = (unsigned int)row;
+                    continue;
+                }
                 typedef SlabSrc<TPB, SlabByteAt<TPB>> Src;
                 const Src A{store.wa_, ca, SlabByteAt<TPB>{smem_u32(store.wa_)}},
                           B{store.wb_, cb, SlabByteAt<TPB>{smem_u32(store.wb_)}};

@@ -1,22 +1,8 @@
 cd $GRAFT_REPO_ROOT
-python - <<'PY'
-import sys, time, json, os
-sys.path[:0]=['.','polars-strsim_b200']
-from bench_support import plugin_driver, workloads
-from polars_strsim import _native
-M=("levenshtein","jaro","jaro_winkler","jaccard","sorensen_dice")
-A,B=workloads.make_pairs(2,10_000_000)
-L=_native.lib()
-def step():
-    plugin_driver.cache_clear()
-    t=[]
-    for m in M:
-        t0=time.perf_counter(); r=plugin_driver.call(m,A,B); t.append((time.perf_counter()-t0)*1e3); r.release()
-    return t
-for spec in (1,0):
-    L.strsim_b200_speculation(spec)
-    for i in range(12):
-        t=step()
-        if i>=8: print('spec',spec,'step',i,'total %.2f'%sum(t),['%.2f'%x for x in t])
-    time.sleep(1.0)
+python -m pytest tests -m gpu -x -q -k "not full_size and not c4_by" > gpurun_out/r2m_pytest.log 2>&1; tail -6 gpurun_out/r2m_pytest.log
+python bench.py --workload C3 --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r2m_bench_C3.json 2> gpurun_out/r2m_err.log; python - <<PY
+import json
+d=json.load(open('gpurun_out/r2m_bench_C3.json'))
+print('C3', round(d['ms_per_step'],4), {k:round(v['ms'],3) for k,v in d['per_measure'].items()}, d['overflow_rows_last_call'], d['roofline']['frac'])
 PY
+tail -3 gpurun_out/r2m_err.log
