@@ -248,7 +248,15 @@ __global__ void list_all_kernel(const SegArgs s) {
 struct ColumnStats {
     unsigned int or_bits;   // OR of all bytes, replicated over the four byte lanes
     unsigned int and_bits;  // AND of all bytes (padding treated as 0xFF)
+    // views only: the longest string in bytes, and the largest out-of-line payload (lengths padded to 4) of
+    // any aligned block of STATS_BLOCK consecutive rows of a chunk.  With them the host can PROVE that no row
+    // of a launch will leave the short-string kernel (none longer than its masks, no tile larger than its
+    // stage area) and skip the read-back of the overflow counters -- the device-resident call is then
+    // asynchronous for real.
+    unsigned int max_len;
+    unsigned int max_block_pad;
 };
+constexpr int STATS_BLOCK = 256;
 
 __device__ __forceinline__ void stats_commit(ColumnStats* out, uint32_t o, uint32_t a) {
 #pragma unroll
@@ -277,23 +285,40 @@ __device__ __forceinline__ void stats_of_view(const uint4& v, uint32_t& o, uint3
 
 // Both statistics kernels are pure streaming reads: four independent 16-byte loads per thread and
 // iteration keep enough bytes in flight to run at the HBM rate (one load per iteration: half of it).
-__global__ void __launch_bounds__(256) stats_views_kernel(const uint4* views, long long n, ColumnStats* out) {
-    uint32_t o = 0, a = 0xFFFFFFFFu;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    for (; i + 3 * stride < n; i += 4 * stride) {
-        const uint4 v0 = ld_view(views + i), v1 = ld_view(views + i + stride), v2 = ld_view(views + i + 2 * stride),
-                    v3 = ld_view(views + i + 3 * stride);
-        stats_of_view(v0, o, a);
-        stats_of_view(v1, o, a);
-        stats_of_view(v2, o, a);
-        stats_of_view(v3, o, a);
-    }
-    for (; i < n; i += stride) {
-        const uint4 v = ld_view(views + i);
-        stats_of_view(v, o, a);
+// A CTA of STATS_BLOCK threads takes four aligned blocks of STATS_BLOCK rows per iteration, one row of each
+// per thread, so that the per-block payload sums are CTA reductions.
+__global__ void __launch_bounds__(STATS_BLOCK) stats_views_kernel(const uint4* views, long long n, ColumnStats* out) {
+    __shared__ unsigned int block_sum[4];
+    uint32_t o = 0, a = 0xFFFFFFFFu, mx = 0, best = 0;
+    const long long n_blocks = (n + STATS_BLOCK - 1) / STATS_BLOCK;
+    if (threadIdx.x < 4) block_sum[threadIdx.x] = 0u;
+    __syncthreads();
+    for (long long b0 = 4ll * blockIdx.x; b0 < n_blocks; b0 += 4ll * gridDim.x) {
+        uint4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const long long row = (b0 + j) * STATS_BLOCK + threadIdx.x;
+            v[j] = row < n ? ld_view(views + row) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if ((b0 + j) * STATS_BLOCK + threadIdx.x < n) stats_of_view(v[j], o, a);
+            mx = max(mx, v[j].x);
+            const unsigned int pad = v[j].x > 12u ? ((v[j].x + 3u) & ~3u) : 0u;
+            const unsigned int s = __reduce_add_sync(0xFFFFFFFFu, pad);
+            if ((threadIdx.x & 31) == 0 && s) atomicAdd(&block_sum[j], s);
+        }
+        __syncthreads();
+        if (threadIdx.x < 4) {
+            best = max(best, block_sum[threadIdx.x]);
+            block_sum[threadIdx.x] = 0u;
+        }
+        __syncthreads();
     }
     stats_commit(out, o, a);
+    mx = __reduce_max_sync(0xFFFFFFFFu, mx);
+    if ((threadIdx.x & 31) == 0 && mx) atomicMax(&out->max_len, mx);
+    if (threadIdx.x < 4 && best) atomicMax(&out->max_block_pad, best);
 }
 
 // data: 16-byte aligned device buffer, `bytes` valid bytes

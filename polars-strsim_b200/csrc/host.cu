@@ -163,6 +163,8 @@ static void stream_copy(void* dst, const void* src, size_t bytes) {
 #endif
 }
 
+static const std::vector<int>& shard_devices();  // the GPUs one host call is sharded over (STRSIM_B200_DEVICES)
+
 class StagePool {
    public:
     static StagePool& get() {
@@ -179,9 +181,17 @@ class StagePool {
 
    private:
     StagePool() {
+        // half the cores, at most 8 (16 when one call is sharded over four or more GPUs) -- shared with the
+        // other processes of a one-process-per-GPU launch (torchrun sets LOCAL_WORLD_SIZE), which would
+        // otherwise oversubscribe the host with 8 copy threads each
         unsigned n = std::thread::hardware_concurrency() / 2;
+        if (const char* lw = getenv("LOCAL_WORLD_SIZE")) {
+            const int ranks = atoi(lw);
+            if (ranks > 1) n /= (unsigned)ranks;
+        }
+        const unsigned cap = shard_devices().size() >= 4 ? 16u : 8u;
         if (n < 2) n = 2;
-        if (n > 8) n = 8;
+        if (n > cap) n = cap;
         if (const char* e = getenv("STRSIM_B200_COPY_THREADS")) {
             const int v = atoi(e);
             if (v > 0 && v <= 64) n = (unsigned)v;
@@ -621,6 +631,9 @@ struct strsim_b200_column {
     bool has_validity = false;
     bool scalar_null = false;  // the column has exactly one row and that row is null
     unsigned or_byte = 0, and_byte = 0xFF;  // OR / AND over every string byte of the column
+    // longest string (bytes) and largest padded out-of-line payload of an aligned STATS_BLOCK-row block of a
+    // chunk; 0xFFFFFFFF = not known (columns assembled by host calls, dictionary columns)
+    unsigned max_len = 0xFFFFFFFFu, max_block_pad = 0xFFFFFFFFu;
     // distinct data buffers in upload order (chunks made by slicing share buffers) and how much of each
     // is on the device right now: equal to the size except while a host call uploads progressively
     std::vector<int64_t> buf_size, buf_resident;
@@ -834,6 +847,8 @@ struct Uploader {
 static void stats_init_value(ColumnStats* s) {
     s->or_bits = 0u;
     s->and_bits = 0xFFFFFFFFu;
+    s->max_len = 0u;
+    s->max_block_pad = 0u;
 }
 static void stats_fold(const ColumnStats& s, unsigned* or_byte, unsigned* and_byte) {
     const unsigned o = s.or_bits, a = s.and_bits;
@@ -1202,9 +1217,9 @@ static int upload_rows(ThreadCtx& ctx, Uploader& up, int64_t lo, int64_t hi, cud
         }
         if (!do_stats) continue;
         if (do_copy) CUDA_TRY(upload_flush(ctx));  // the kernel below must be queued behind every DMA of the copy
-        long long blocks = (c_hi - c_lo + 255) / 256;
-        if (blocks > 148 * 16) blocks = 148 * 16;
-        stats_views_kernel<<<(unsigned)blocks, 256, 0, st>>>(
+        long long blocks = (c_hi - c_lo + 4 * STATS_BLOCK - 1) / (4 * STATS_BLOCK);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        stats_views_kernel<<<(unsigned)blocks, STATS_BLOCK, 0, st>>>(
             reinterpret_cast<const uint4*>(base + p.views_off) + c_lo, c_hi - c_lo, d_stats);
         g_launches.fetch_add(1, std::memory_order_relaxed);
     }
@@ -1239,6 +1254,8 @@ static int upload_column(ThreadCtx& ctx, const strsim_view_chunk* chunks, size_t
     }
     strsim_b200_column* col = up.col;
     stats_fold(*ctx.h_stats, &col->or_byte, &col->and_byte);
+    col->max_len = ctx.h_stats->max_len;
+    col->max_block_pad = ctx.h_stats->max_block_pad;
     if (want_alg_bytes) {
         // 16 B of view per row + out-of-line payload (byte length > 12) + validity bits
         int64_t bytes = 0;
@@ -1738,7 +1755,8 @@ static int finish_long(ThreadCtx& ctx, const SegArgs& args, const Overflow& ov, 
 }
 
 template <int MEASURE>
-static int run_segment(ThreadCtx& ctx, SegArgs args, Alphabet al, int stage32, int64_t seg_rows, cudaStream_t st) {
+static int run_segment(ThreadCtx& ctx, SegArgs args, Alphabet al, int stage32, int64_t seg_rows, cudaStream_t st,
+                       bool proven_clean) {
     int rc = prepare_segment(ctx, args, stage32, seg_rows, st);
     if (rc) return rc;
     if (force_generic_rows()) {
@@ -1749,6 +1767,8 @@ static int run_segment(ThreadCtx& ctx, SegArgs args, Alphabet al, int stage32, i
     } else {
         rc = launch_fused<MEASURE>(ctx, al, args, seg_rows, st);
         if (rc) return rc;
+        // the column statistics prove that no row leaves the launch (see compute_on_device): nothing to read back
+        if (proven_clean) return STRSIM_OK;
     }
     Overflow ov;
     rc = read_overflow(ctx, &ov, st);
@@ -1782,7 +1802,7 @@ static int finish_long_any(int measure, ThreadCtx& ctx, const SegArgs& args, con
 // measure with the single-measure follow-up kernels.  Levenshtein goes last: its long-row kernel
 // reuses both lists as scratch.
 static int run_segment_multi(ThreadCtx& ctx, SegArgs args, int groups, Alphabet al, int stage32, int64_t seg_rows,
-                             cudaStream_t st) {
+                             cudaStream_t st, bool proven_clean) {
     int rc = prepare_segment(ctx, args, stage32, seg_rows, st);
     if (rc) return rc;
     args.out = nullptr;
@@ -1804,6 +1824,7 @@ static int run_segment_multi(ThreadCtx& ctx, SegArgs args, int groups, Alphabet 
                 rc = STRSIM_ERR_ARGUMENT;
         }
         if (rc) return rc;
+        if (proven_clean) return STRSIM_OK;  // no row can have left the launch: nothing to read back
     }
     Overflow ov;
     rc = read_overflow(ctx, &ov, st);
@@ -1959,20 +1980,49 @@ static int compute_on_device(ThreadCtx& ctx, const int* measures, size_t n_measu
         const double avg = avg_a > avg_b ? avg_a : avg_b;
         long long stage = -(long long)(avg * 16.0 + 1.0);
         if (stage < -64 * 16) stage = -64 * 16;
+        // Can a row leave the short-string launch at all?  Not when (a) every byte is ASCII (one launch, the
+        // plane path), (b) both columns are completely resident and their statistics carry the longest
+        // string and the largest payload of an aligned 256-row block, (c) no string exceeds the 32-byte
+        // masks, and (d) the stage area holds the payload of any tile -- a tile of 256 x RPT rows covers RPT
+        // aligned blocks, one more when the segment does not start on a block boundary.  Then the stage
+        // area is sized from that bound and the host neither reads the overflow counters back nor waits.
+        bool proven_clean = false;
+        static const bool no_proof = (getenv("STRSIM_B200_READBACK") != nullptr && !strcmp(getenv("STRSIM_B200_READBACK"), "1")) ||
+                                     getenv("STRSIM_B200_TILE") != nullptr || getenv("STRSIM_B200_KERNEL") != nullptr ||
+                                     getenv("STRSIM_B200_REG") != nullptr;  // experiment knobs change the tile shape
+        if (!no_proof && al != ALPHA_GENERAL && !force_generic_rows() && a->max_len <= 32u && b->max_len <= 32u &&
+            a->max_block_pad != 0xFFFFFFFFu && b->max_block_pad != 0xFFFFFFFFu && s.a.res_buf == 0xFFFFFFFFu &&
+            s.b.res_buf == 0xFFFFFFFFu && s.a.lo_off == 0u && s.b.lo_off == 0u) {
+            const long long tile_blocks = n_measures > 1 ? 3 : 4;  // launch_multi: 256 x 3 rows, launch_fused: 256 x 4
+            const long long blocks_a = tile_blocks + ((bc_a || oa % STATS_BLOCK == 0) ? 0 : 1);
+            const long long blocks_b = tile_blocks + ((bc_b || ob % STATS_BLOCK == 0) ? 0 : 1);
+            long long need = blocks_a * (long long)a->max_block_pad;
+            if (blocks_b * (long long)b->max_block_pad > need) need = blocks_b * (long long)b->max_block_pad;
+            need += 48;  // the TMA span is rounded to 16 bytes at both ends
+            // what launch_short would size from the mean (25 % headroom); the proof may ask for a little more,
+            // but not for so much more that a CTA less would fit an SM
+            const long long by_mean = (long long)(avg * 16.0 + 1.0) * (tile_blocks * 256) * 5 / (16 * 4) + 256;
+            if (need <= by_mean + by_mean / 8 && need <= 32ll * tile_blocks * 256) {
+                stage = need > by_mean ? need : by_mean;
+                if (stage < 1024) stage = 1024;
+                stage = (stage + 15) & ~15ll;
+                proven_clean = true;
+            }
+        }
         int rc;
         if (n_measures > 1) {
             for (size_t k = 0; k < n_measures; k++) {
                 s.outs[measures[k]] = d_outs[k] + row;
                 s.dbgs[measures[k]] = (d_dbgs && d_dbgs[k]) ? d_dbgs[k] + 6 * row : nullptr;
             }
-            rc = run_segment_multi(ctx, s, groups, al, (int)stage, len, st);
+            rc = run_segment_multi(ctx, s, groups, al, (int)stage, len, st, proven_clean);
         } else {
             switch (measure) {
-                case 0: rc = run_segment<0>(ctx, s, al, (int)stage, len, st); break;
-                case 1: rc = run_segment<1>(ctx, s, al, (int)stage, len, st); break;
-                case 2: rc = run_segment<2>(ctx, s, al, (int)stage, len, st); break;
-                case 3: rc = run_segment<3>(ctx, s, al, (int)stage, len, st); break;
-                default: rc = run_segment<4>(ctx, s, al, (int)stage, len, st); break;
+                case 0: rc = run_segment<0>(ctx, s, al, (int)stage, len, st, proven_clean); break;
+                case 1: rc = run_segment<1>(ctx, s, al, (int)stage, len, st, proven_clean); break;
+                case 2: rc = run_segment<2>(ctx, s, al, (int)stage, len, st, proven_clean); break;
+                case 3: rc = run_segment<3>(ctx, s, al, (int)stage, len, st, proven_clean); break;
+                default: rc = run_segment<4>(ctx, s, al, (int)stage, len, st, proven_clean); break;
             }
         }
         if (rc) return rc;
@@ -2258,15 +2308,19 @@ int strsim_b200_column_restat(strsim_b200_column* col, void* stream) {
     }
     for (const DevChunk& dc : col->chunks) {
         if (dc.length <= 0) continue;
-        long long blocks = (dc.length + 255) / 256;
-        if (blocks > 148 * 16) blocks = 148 * 16;
-        stats_views_kernel<<<(unsigned)blocks, 256, 0, st>>>(dc.views, dc.length, ctx->d_stats);
+        long long blocks = (dc.length + 4 * STATS_BLOCK - 1) / (4 * STATS_BLOCK);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        stats_views_kernel<<<(unsigned)blocks, STATS_BLOCK, 0, st>>>(dc.views, dc.length, ctx->d_stats);
         g_launches.fetch_add(1, std::memory_order_relaxed);
     }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(publish_to_host(ctx->h_stats, ctx->d_stats, sizeof(ColumnStats), st));
     CUDA_TRY(cudaStreamSynchronize(st));
     stats_fold(*ctx->h_stats, &col->or_byte, &col->and_byte);
+    if (col->dictionaries.empty()) {  // (a materialised dictionary column's rows are not scanned here)
+        col->max_len = ctx->h_stats->max_len;
+        col->max_block_pad = ctx->h_stats->max_block_pad;
+    }
     return STRSIM_OK;
 }
 
