@@ -206,6 +206,17 @@ STRSIM_API int strsim_b200_set_device(int device);
 STRSIM_API int strsim_b200_device_count(void);
 /* device the calling thread's calls use right now (-1: no usable device) */
 STRSIM_API int strsim_b200_get_device(void);
+/* One host / plugin call over several GPUs (north_star 4; the reference fans one call out over the workers of
+ * Polars' pool and re-assembles the chunks in the same call, strsim.rs:72-104).  With the environment
+ * variable STRSIM_B200_DEVICES = "0,1,2,3" | "0-7" | "all", every host call of at least 65536 rows is cut
+ * into one contiguous row range per listed device -- split_offsets (strsim.rs:21-39) on units of 64 rows,
+ * so that no validity byte is shared -- and each range is uploaded (its views and the stretch of the data
+ * buffers its rows reference), computed and downloaded by a worker thread of its device into its range of
+ * the caller's buffers.  No collective, no peer traffic.  Columns kept by such a call
+ * (strsim_b200_compute_host_keep, the plugin's cache) are sharded the same way and
+ * strsim_b200_column_device() reports 1000 + number of shards for them.
+ * strsim_b200_shard_cuts writes the n_shards + 1 boundaries of that partition (no GPU needed). */
+STRSIM_API void strsim_b200_shard_cuts(int64_t n_rows, int n_shards, int64_t *cuts);
 /* Multi-GPU hosts: binds the calling thread (and the threads and pinned buffers it creates from now on,
  * first-touch) to the CPUs of the NUMA node the device's PCIe link hangs off, so that host<->device
  * copies do not cross the socket interconnect.  Returns the node, or -1 when there is nothing to do

@@ -2837,6 +2837,15 @@ static bool shard_this_call(int64_t la, int64_t lb, const strsim_b200_column* re
     return true;
 }
 
+// split_offsets (strsim.rs:21-39) on units of 64 rows: range g starts at g * (units / G) * 64, the last one
+// takes the remainder.  Exported so that the rule can be checked without a GPU (tests/test_sharding.py).
+extern "C" void strsim_b200_shard_cuts(int64_t n_rows, int n_shards, int64_t* cuts) {
+    if (n_shards < 1 || !cuts) return;
+    const int64_t units = (n_rows + 63) / 64, per = units / n_shards;
+    for (int g = 0; g < n_shards; g++) cuts[g] = (int64_t)g * per * 64;
+    cuts[n_shards] = n_rows;
+}
+
 // one worker thread per device: its thread-local context (streams, pinned buffers, staging rings) lives as
 // long as the process, so a sharded call costs no set-up
 class DeviceWorker {
@@ -2952,9 +2961,7 @@ static int host_call_sharded(const int* measures, size_t n_measures, const strsi
             return STRSIM_ERR_ARGUMENT;
         }
     } else {
-        const int64_t units = (n + 63) / 64, per = units / (int64_t)G;
-        for (size_t g = 0; g < G; g++) cut[g] = (int64_t)g * per * 64;
-        cut[G] = n;
+        strsim_b200_shard_cuts(n, (int)G, cut.data());
     }
     static const bool no_trim = [] {
         const char* k = getenv("STRSIM_B200_KERNEL");

@@ -174,7 +174,9 @@ struct ShortLayout {
     static constexpr int NWARP = TPB / 32;
     static constexpr size_t off_sva = 0;
     static constexpr size_t off_svb = off_sva + sizeof(uint4) * TILE;
-    static constexpr size_t off_tab = off_svb + sizeof(uint4) * TILE;
+    // 16 spare bytes behind the views: reading an inline string by whole words looks one word past the
+    // last view, which must not be a word another thread writes (its slab) -- racecheck flagged exactly that
+    static constexpr size_t off_tab = off_svb + sizeof(uint4) * TILE + 16;
     static constexpr size_t off_slab_a = off_tab + ((REG || UREG) ? 0 : sizeof(M) * T * TPB);
     static constexpr size_t off_slab_b = off_slab_a + (REG ? 0 : 4 * WORDS * TPB);
     static constexpr size_t off_hist = off_slab_b + (REG ? 0 : 4 * WORDS * TPB);

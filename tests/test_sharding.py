@@ -30,6 +30,32 @@ def test_split_offsets_matches_reference_rule():
             assert shard_for_rank(n, w, w - 1) == parts[-1]
 
 
+def test_in_call_shard_cuts_follow_split_offsets_on_64_row_units():
+    """The partition one sharded host call uses (STRSIM_B200_DEVICES; include/strsim_b200.h:
+    strsim_b200_shard_cuts): the reference's split_offsets (strsim.rs:21-39) applied to units of 64 rows,
+    so that no validity byte is shared between two devices; the last range takes the remainder."""
+    import ctypes
+
+    sys.path[:0] = [str(ROOT), str(ROOT / "polars-strsim_b200")]
+    from polars_strsim import _native
+    from polars_strsim.sharding import split_offsets
+
+    L = _native.lib()
+    L.strsim_b200_shard_cuts.restype = None
+    L.strsim_b200_shard_cuts.argtypes = [ctypes.c_int64, ctypes.c_int, ctypes.POINTER(ctypes.c_int64)]
+    for n in (0, 1, 63, 64, 65, 65536, 1_000_003, 10_000_000, 2**31 + 5):
+        for g in (1, 2, 3, 4, 8):
+            cuts = (ctypes.c_int64 * (g + 1))()
+            L.strsim_b200_shard_cuts(n, g, cuts)
+            cuts = list(cuts)
+            assert cuts[0] == 0 and cuts[-1] == n and all(x <= y for x, y in zip(cuts, cuts[1:]))
+            assert all(c % 64 == 0 for c in cuts[:-1])
+            units = split_offsets((n + 63) // 64, g)
+            assert cuts[:-1] == [off * 64 for off, _ in units]
+            sizes = [y - x for x, y in zip(cuts, cuts[1:])]
+            assert len(set(sizes[:-1])) <= 1 and (g == 1 or sizes[-1] >= sizes[0] - 63)
+
+
 def _worker(rank, world, port, out_dir):
     sys.path[:0] = [str(ROOT), str(ROOT / "polars-strsim_b200"), str(ROOT / "tests")]
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
