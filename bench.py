@@ -513,6 +513,12 @@ def main():
     elapsed_ms = max_over_ranks(e0.elapsed_time(e1))
     checksum = float(out.sum().item())
     checksums = {m: float(o.sum().item()) for m, o in zip(measures, outs)}
+    # every rank owns other rows: the sum over the ranks of each measure's checksum stands for the whole job
+    checksums_all_ranks = None
+    if world > 1:
+        t = torch.tensor([checksums[m] for m in measures], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        checksums_all_ranks = {m: float(v) for m, v in zip(measures, t.tolist())}
 
     # ---- the column-statistics pre-pass (an upload runs it once per column; it picks the kernel
     # instantiation): the same kernels again over the resident columns, CUDA events on the same stream
@@ -724,7 +730,7 @@ def main():
                   "value_is": "device-resident: both columns (and their byte statistics) already in HBM"},
         "per_measure": per_measure, "roofline": roofline, "clocks": clocks, "gpu_launches": launches,
         "overflow_rows_last_call": {"to_64bit_kernel": overflow[0], "to_long_kernel": overflow[1]},
-        "checksum": checksum, "checksums": checksums,
+        "checksum": checksum, "checksums": checksums, "checksums_all_ranks": checksums_all_ranks,
         "step": ("one fused launch for all measures (strsim_b200_compute_device_multi)" if fused
                  else "one single-measure launch per measure"),
         "fused_matches_single_measure_kernel": fused_matches_single,

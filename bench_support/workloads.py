@@ -49,7 +49,8 @@ def make_chunk(config: int, n: int, row_base: int = 0, null_p: float = 0.0, pinn
     """One chunk of `n` pairs -> (A, B) pyarrow string_view arrays (+ host bytes held)."""
     L = lib()
     seed = SEEDS.get(config, config) if seed is None else seed
-    threads = threads or len(os.sched_getaffinity(0))
+    if not threads:  # the ranks of a one-process-per-GPU launch share the host's cores
+        threads = max(1, len(os.sched_getaffinity(0)) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
     gen_config = 2 if config == 5 else config
     sizes = (ctypes.c_int64 * 2)()
     va, pva = _alloc(16 * n, pinned)
