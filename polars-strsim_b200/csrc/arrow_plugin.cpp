@@ -282,9 +282,12 @@ void cache_trim(int64_t incoming_bytes) {
 bool g_reaper_running = false;  // guarded by g_cache_mutex
 int results_reap();  // drops results computed ahead that nobody came for; returns how many are left
 
+std::atomic<bool>& g_exiting = *new std::atomic<bool>(false);  // set by an atexit hook: background threads stand still
+
 void reaper_main() {
     for (;;) {
         std::this_thread::sleep_for(std::chrono::seconds(1));
+        if (g_exiting.load()) return;  // the process is tearing down (CUDA runtime included): touch nothing
         std::vector<std::shared_ptr<CacheEntry>> expired;  // destroyed outside the lock (frees HBM, releases arrays)
         bool done = false;
         {
@@ -318,6 +321,11 @@ void reaper_main() {
 // mutex held
 void reaper_ensure() {
     if (g_reaper_running) return;
+    static const bool hooked = [] {
+        std::atexit([] { g_exiting.store(true); });
+        return true;
+    }();
+    (void)hooked;
     try {
         std::thread(reaper_main).detach();
         g_reaper_running = true;
