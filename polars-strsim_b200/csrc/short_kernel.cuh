@@ -571,6 +571,19 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
     store.wb_ = slab_b + tid;
     __syncthreads();
 
+    // Gather launches (overflow lists, the wide pairs of a general column) reach a row through its list entry:
+    // two dependent trips to memory per row, and the profile of the wide-pair launch of C3 showed the CTAs
+    // waiting on exactly that (40 % of the issue slots used, long-scoreboard and barrier stalls on top).  The
+    // entries of this CTA's NEXT tile are therefore fetched into registers while the current tile is loaded,
+    // and the views they name are pulled into L2 at the start of the compute phase.
+    unsigned int next_row[RPT];
+    if (GATHER) {
+#pragma unroll
+        for (int k = 0; k < RPT; k++) {
+            const long long idx = (long long)blockIdx.x * TILE + k * TPB + tid;
+            next_row[k] = idx < n ? s.list[idx] : 0u;
+        }
+    }
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long tile0 = tile * TILE;
         for (int i = tid; i < NB; i += TPB) hist[i] = 0;
@@ -586,9 +599,13 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
             const long long idx = tile0 + i;
             uint4 va = make_uint4(0, 0, 0, 0), vb = make_uint4(0, 0, 0, 0);
             if (idx < n) {
-                const long long row = GATHER ? (long long)s.list[idx] : idx;
+                const long long row = GATHER ? (long long)next_row[k] : idx;
                 va = ld_view(s.a.views + row * s.a.stride);
                 vb = ld_view(s.b.views + row * s.b.stride);
+                if (GATHER) {
+                    const long long nxt = idx + (long long)gridDim.x * TILE;
+                    if (nxt < n) next_row[k] = s.list[nxt];  // used by the next tile; its views are prefetched in step 4
+                }
                 if (!GATHER) {
                     // pull this CTA's NEXT tile of views into L2 while the current one is processed
                     const long long nxt = idx + (long long)gridDim.x * TILE;
@@ -909,6 +926,16 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
         __syncthreads();
 
         // ---------------- 4. compute -----------------------------------------------------------------
+        if (GATHER) {
+#pragma unroll
+            for (int k = 0; k < RPT; k++) {
+                const long long nxt = tile0 + (long long)gridDim.x * TILE + k * TPB + tid;
+                if (nxt < n) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(s.a.views + (long long)next_row[k] * s.a.stride));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(s.b.views + (long long)next_row[k] * s.b.stride));
+                }
+            }
+        }
 #pragma unroll 1
         for (int k = 0; k < RPT; k++) {
             const int p = k * TPB + ((k & 1) ? (TPB - 1 - tid) : tid);  // snake order balances warps
