@@ -69,8 +69,31 @@ def main():
             traffic[key] = t
             insts[key] = float(r[ix["smsp__inst_executed.sum"]].replace(",", ""))
     Path(out_md).write_text("\n".join(lines) + "\n")
+    if traffic_path and len(sys.argv) > 5:  # C4: argv[5] = DP cells of the captured launch
+        cells = float(sys.argv[5])
+        for r in rows[2:]:
+            if "long_lev_kernel" in r[ix["Kernel Name"]]:
+                sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+                from bench import kernel_source_hash
+
+                cur = json.loads(traffic_path.read_text()) if traffic_path.exists() else {}
+                if cur.get("source_hash") != kernel_source_hash():
+                    cur = {"source_hash": kernel_source_hash()}
+                inst = float(r[ix["smsp__inst_executed.sum"]].replace(",", ""))
+                t = to_bytes(r[ix["dram__bytes_read.sum"]], units[ix["dram__bytes_read.sum"]]) + \
+                    to_bytes(r[ix["dram__bytes_write.sum"]], units[ix["dram__bytes_write.sum"]])
+                cur["C4_warp_instructions_per_cell"] = {"long_lev_kernel": inst / cells,
+                                                        "_note": "smsp__inst_executed.sum / DP cells of the captured launch"}
+                cur["C4_dram_bytes_per_cell"] = {"long_lev_kernel": t / cells}
+                traffic_path.write_text(json.dumps(cur, indent=1) + "\n")
     if traffic_path and traffic:
         cur = json.loads(traffic_path.read_text()) if traffic_path.exists() else {}
+        # the capture belongs to the kernel sources it was taken on: bench.py quotes it only for the same hash
+        sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+        from bench import kernel_source_hash
+
+        if cur.get("source_hash") != kernel_source_hash():
+            cur = {"source_hash": kernel_source_hash()}
         cur.setdefault(workload, {}).update(traffic)
         cur.setdefault(workload + "_warp_instructions", {}).update(insts)
         cur["_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch of short_kernel<measure>, "
