@@ -27,6 +27,7 @@
 extern "C" void strsim_set_error(const char* fmt, ...);
 extern "C" void* strsim_result_alloc(size_t bytes);  // host.cu: pool of pinned result buffers
 extern "C" int strsim_result_free(void* p);
+extern "C" void strsim_result_unpinned_released(size_t bytes);
 extern "C" int strsim_result_pool_trim(int idle_seconds);
 extern "C" void strsim_pool_trim(int idle_seconds);  // host.cu: idle device blocks back to the driver
 
@@ -421,6 +422,7 @@ struct ResultPrivate {
     uint8_t* validity;
     const void* buffers[2];
     bool pinned;       // `values` is a block of the pinned result pool (DMA'd into directly)
+    size_t value_bytes;  // as asked of the pool
     void* map_base;    // large results: an anonymous mapping (2 MiB aligned start inside it) ...
     size_t map_bytes;  // ... so that the kernel may back it with huge pages: 40 first-touch faults for
                        // 80 MB instead of 20,000
@@ -432,6 +434,7 @@ double* alloc_values(ResultPrivate* p, size_t n) {
     p->map_base = nullptr;
     p->map_bytes = 0;
     p->pinned = false;
+    p->value_bytes = bytes;
     if (void* pin = strsim_result_alloc(bytes)) {
         p->pinned = true;
         reaper_wanted();  // someone has to unpin the block once it has come back and sat idle
@@ -460,6 +463,7 @@ void free_values(ResultPrivate* p) {
         p->pinned = false;
         return;
     }
+    strsim_result_unpinned_released(p->value_bytes);
 #if defined(__linux__)
     if (p->map_base) {
         munmap(p->map_base, p->map_bytes);

@@ -542,6 +542,11 @@ static void pinned_grower_main() {
     }
 }
 
+// results of (roughly) this size that live in pageable memory right now because the pool had no block for them
+static std::vector<std::pair<size_t, int>>& g_unpinned_live = *new std::vector<std::pair<size_t, int>>();  // guarded by g_pinned_mutex
+
+static bool same_class(size_t block, size_t want) { return block >= want && block <= want + want / 2 + (1u << 20); }
+
 extern "C" void* strsim_result_alloc(size_t bytes) {
     if (bytes < (1u << 20) || pinned_limit() == 0) return nullptr;
     const size_t want = (bytes + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
@@ -549,15 +554,31 @@ extern "C" void* strsim_result_alloc(size_t bytes) {
     size_t best = g_pinned.size();
     for (size_t i = 0; i < g_pinned.size(); i++) {
         const PinnedBlock& b = g_pinned[i];
-        if (!b.in_use && b.bytes >= bytes && b.bytes <= want + want / 2 + (1u << 20) &&
-            (best == g_pinned.size() || b.bytes < g_pinned[best].bytes))
-            best = i;
+        if (!b.in_use && same_class(b.bytes, want) && (best == g_pinned.size() || b.bytes < g_pinned[best].bytes)) best = i;
     }
     if (best != g_pinned.size()) {
         g_pinned[best].in_use = true;
         return g_pinned[best].ptr;
     }
-    if (g_pinned_requests.size() < 16) {
+    // No block: this result goes to pageable memory.  The pool should hold as many blocks of this size as
+    // there are results of this size alive at once (held by the engine, or computed ahead and waiting): ask
+    // the background thread for one more block only while blocks + pending requests fall short of that --
+    // every miss used to queue a request, and a dozen 80 MB cudaHostAlloc calls (35 ms each, serialised
+    // with the streams by the driver) then ran into the calls that followed.
+    int live = 1;
+    bool found = false;
+    for (auto& u : g_unpinned_live)
+        if (u.first == want) {
+            live = ++u.second;
+            found = true;
+        }
+    if (!found) g_unpinned_live.emplace_back(want, 1);
+    int have = 0;
+    for (const PinnedBlock& b : g_pinned)
+        if (same_class(b.bytes, want)) have += b.in_use ? 0 : 1;  // (free blocks of the class: none, or we would not be here)
+    int pending = 0;
+    for (size_t r : g_pinned_requests) pending += r == want ? 1 : 0;
+    if (pending + have < live && g_pinned_requests.size() < 16) {
         g_pinned_requests.push_back(want);
         if (!g_pinned_grower_running) {
             try {
@@ -570,6 +591,15 @@ extern "C" void* strsim_result_alloc(size_t bytes) {
         g_pinned_cv.notify_one();
     }
     return nullptr;
+}
+
+// a result that strsim_result_alloc() turned away (pageable memory, `bytes` as asked for then) has been freed
+extern "C" void strsim_result_unpinned_released(size_t bytes) {
+    if (bytes < (1u << 20)) return;
+    const size_t want = (bytes + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
+    std::lock_guard<std::mutex> lock(g_pinned_mutex);
+    for (auto& u : g_unpinned_live)
+        if (u.first == want && u.second > 0) u.second--;
 }
 
 // true when `p` was a block of the pool (now free again); callable from any thread, makes no CUDA call
