@@ -525,12 +525,11 @@ static void pinned_grower_main() {
             }
             want = g_pinned_requests.front();
             g_pinned_requests.pop_front();
-            size_t total = want, free_fit = 0;
-            for (const PinnedBlock& b : g_pinned) {
-                total += b.bytes;
-                if (!b.in_use && b.bytes >= want && b.bytes <= want + want / 2 + (1u << 20)) free_fit++;
-            }
-            if (total > pinned_limit() || free_fit > 0) continue;  // over budget, or a fitting block came back meanwhile
+            size_t total = want;
+            for (const PinnedBlock& b : g_pinned) total += b.bytes;
+            // (a free block of this size does not cancel the request: requests are counted against the results
+            // alive at once, and the burst that raised them has usually been released by now)
+            if (total > pinned_limit()) continue;  // over budget
         }
         void* p = nullptr;
         if (cudaHostAlloc(&p, want, cudaHostAllocPortable) != cudaSuccess) {

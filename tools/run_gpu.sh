@@ -1,10 +1,20 @@
 cd $GRAFT_REPO_ROOT
-python -m pytest tests -m gpu -x -q -k "not full_size and not c4_by" > gpurun_out/r2p_pytest.log 2>&1; tail -4 gpurun_out/r2p_pytest.log
-for w in C3 M1; do
-python bench.py --workload $w --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r2p_bench_$w.json 2> gpurun_out/r2p_err.log; python - <<PY
-import json
-d=json.load(open('gpurun_out/r2p_bench_$w.json'))
-print('$w', round(d['ms_per_step'],4), {k:round(v['ms'],3) for k,v in d['per_measure'].items()}, d['overflow_rows_last_call'], d['roofline']['frac'])
+python - <<'PY'
+import sys, time, ctypes
+sys.path[:0]=['.','polars-strsim_b200']
+from bench_support import plugin_driver, workloads
+from polars_strsim import _native
+M=("levenshtein","jaro","jaro_winkler","jaccard","sorensen_dice")
+A,B=workloads.make_pairs(2,10_000_000)
+L=_native.lib()
+t_start=time.perf_counter()
+def step(tag):
+    plugin_driver.cache_clear()
+    t=[]
+    for m in M:
+        t0=time.perf_counter(); r=plugin_driver.call(m,A,B); t.append((time.perf_counter()-t0)*1e3); r.release()
+    print('%6.2f s' % (time.perf_counter()-t_start), tag,'total %.2f'%sum(t),['%.2f'%x for x in t], flush=True)
+for k in range(12):
+    step('step %d'%k)
+    if k<2: time.sleep(0.6)
 PY
-done
-tail -3 gpurun_out/r2p_err.log
