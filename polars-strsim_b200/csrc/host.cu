@@ -1336,6 +1336,7 @@ static int launch_short(ThreadCtx& ctx, SegArgs args, long long n_upper, cudaStr
         if (stage > (long long)L::CAP * L::TILE) stage = (long long)L::CAP * L::TILE;
         args.stage_bytes = (int)((stage + 15) & ~15ll);
     }
+    if (args.stage_bytes > L::CAP * L::TILE) args.stage_bytes = L::CAP * L::TILE;  // nothing longer than CAP bytes is staged
     const size_t smem = L::bytes(args.stage_bytes);
     // cudaFuncAttributeMaxDynamicSharedMemorySize belongs to (device, kernel) and is shared by every host
     // thread (Polars calls the plugin from several): it is raised ONCE per device to the most this
@@ -2032,10 +2033,11 @@ static int compute_on_device(ThreadCtx& ctx, const int* measures, size_t n_measu
             need += 48;  // the TMA span is rounded to 16 bytes at both ends
             // what launch_short would size from the mean (25 % headroom); the proof may ask for a little more,
             // but not for so much more that a CTA less would fit an SM
-            const long long by_mean = (long long)(avg * 16.0 + 1.0) * (tile_blocks * 256) * 5 / (16 * 4) + 256;
+            const long long by_mean = (long long)((avg < 64.0 ? avg : 64.0) * 16.0 + 1.0) * (tile_blocks * 256) * 5 / (16 * 4) + 256;
             if (need <= by_mean + by_mean / 8 && need <= 32ll * tile_blocks * 256) {
-                stage = need > by_mean ? need : by_mean;
-                if (stage < 1024) stage = 1024;
+                // the bound itself, not the mean-based size: a column uploaded from a SLICE of a longer array
+                // brings whole data buffers along, and their bytes per row say nothing about its rows
+                stage = need < 1024 ? 1024 : need;
                 stage = (stage + 15) & ~15ll;
                 proven_clean = true;
             }
