@@ -1388,22 +1388,16 @@ static thread_local float* g_wide_share = nullptr;  // the current column pair's
 
 template <int MEASURE, int RPT_LATIN, int RPT_WIDE>
 static int launch_general(ThreadCtx& ctx, const SegArgs& args, long long rows, cudaStream_t st) {
-    static const bool latin = !(getenv("STRSIM_B200_LATIN") && !strcmp(getenv("STRSIM_B200_LATIN"), "0"));
     SegArgs a = args;
     a.skip_latin = 0;
     // The first launch (ULAT) reads every row, computes the Latin-1 pairs and LISTS the others; the second
     // one (UREG) gathers the listed rows only.  Measured per 50 M rows x 5 measures on C3 (30 % of the rows
-    // CJK): 8.9 ms against 10.2 ms for the register-compare kernel alone (single measures: within 3 % either
-    // way, Jaro 13 % faster); L1 (no wide pairs, one launch): 1.49 ms vs 2.23 ms per 10 M rows.  When most
-    // pairs are wide the first launch is a wasted pass: once a segment of this column pair has shown more
-    // than half of its pairs wide, the following segments / slices / calls go to the register-compare
-    // kernel alone.
-    static const float wide_limit = [] {
-        const char* e = getenv("STRSIM_B200_WIDE_SHARE");  // tuning knob: share of wide pairs above which one launch serves all
-        return e && *e ? (float)atof(e) : 0.5f;
-    }();
-    const bool mostly_latin = !(g_wide_share && *g_wide_share > wide_limit);
-    if (!latin || !mostly_latin)
+    // CJK): 8.9 ms against 10.2 ms for the register-compare kernel alone (round 1); L1 (no wide pairs): 1.2 ms
+    // vs 2.2 ms per 10 M rows.  When most pairs are wide the first launch is a wasted pass: once a segment of
+    // this column pair has shown more than half of its pairs wide, the following segments / slices / calls
+    // go to the register-compare kernel alone.
+    const bool mostly_latin = !(g_wide_share && *g_wide_share > 0.5f);
+    if (!mostly_latin)
         return launch_short<uint32_t, MEASURE, 256, RPT_WIDE, false, 128, false, false, true>(ctx, a, rows, st);
     int rc = launch_short<uint32_t, MEASURE, 256, RPT_LATIN, false, 128, false, false, true, true>(ctx, a, rows, st);
     if (rc) return rc;
@@ -1428,7 +1422,6 @@ static void note_wide_share(const Overflow& ov, long long rows) {
 enum Alphabet { ALPHA_GENERAL = 0, ALPHA_ASCII128 = 1, ALPHA_ASCII64 = 2, ALPHA_ASCII32 = 3 };
 
 static Alphabet classify_alphabet(unsigned o, unsigned n) {  // OR / AND over every byte of both columns
-    static const char* force = getenv("STRSIM_B200_ALPHABET");  // test / tuning knob: 0..3 caps the choice
     Alphabet al;
     if (o & 0x80u)
         al = ALPHA_GENERAL;
@@ -1438,65 +1431,27 @@ static Alphabet classify_alphabet(unsigned o, unsigned n) {  // OR / AND over ev
         al = ALPHA_ASCII64;
     else
         al = ALPHA_ASCII128;
-    if (force && *force) {
-        const int cap = atoi(force);
-        if (al != ALPHA_GENERAL && (int)al > cap) al = (Alphabet)cap;
-    }
     return al;
 }
 
+// One measure over a segment: the plane path for ASCII-only columns (tiles of 256 x 4 rows), the two
+// launches of launch_general otherwise.  Variants that were measured and dropped -- a kernel without
+// shared-memory staging (0.70 vs 0.58 ms: the sorted threads' scattered global loads cost 32 L1TEX
+// wavefronts per warp instruction), the per-thread table path for ASCII columns (0.58 vs 0.48 ms), other
+// tile shapes -- are in the git history of round 1, not in the build.
 template <int MEASURE>
 static int launch_fused(ThreadCtx& ctx, Alphabet al, const SegArgs& args, long long rows, cudaStream_t st) {
-    static const char* cfg_env = getenv("STRSIM_B200_TILE");  // tuning knob
-    const int cfg = cfg_env && *cfg_env ? atoi(cfg_env) : 0;
-    // "direct" = direct_kernel.cuh (no shared-memory staging).  Measured on C2 (profiles/README.md): it
-    // doubles the resident warps but is SLOWER (levenshtein 0.70 ms vs 0.58 ms per 10M pairs) because the
-    // sorted threads' scattered global loads cost 32 L1TEX wavefronts per warp instruction, where the
-    // staged kernel reads shared memory conflict-free.  Kept as an experiment knob and for the gather
-    // (overflow-list) launches, whose rows are scattered anyway.
-    static const char* kern_env = getenv("STRSIM_B200_KERNEL");
-    const bool direct = kern_env && !strcmp(kern_env, "direct");
-    (void)cfg;
-    if (direct) {
-        switch (al) {
-            case ALPHA_ASCII32:
-                return launch_direct<uint32_t, MEASURE, 128, 2, false, 32, true>(ctx, args, rows, st);
-            case ALPHA_ASCII64:
-                return launch_direct<uint32_t, MEASURE, 128, 4, false, 64, true>(ctx, args, rows, st);
-            case ALPHA_ASCII128:
-                return launch_direct<uint32_t, MEASURE, 128, 4, false, 128, true>(ctx, args, rows, st);
-            default:
-                return launch_direct<uint32_t, MEASURE, 128, 4, false, 128, false>(ctx, args, rows, st);
-        }
-    }
-    static const char* reg_env = getenv("STRSIM_B200_REG");  // "0": table-driven ASCII path instead
-    const bool reg = !(reg_env && !strcmp(reg_env, "0"));
-    if (reg) {
-        switch (al) {
-            case ALPHA_ASCII32:
-                if (cfg == 1) return launch_short<uint32_t, MEASURE, 128, 4, false, 32, true, true>(ctx, args, rows, st);
-                return launch_short<uint32_t, MEASURE, 256, 4, false, 32, true, true>(ctx, args, rows, st);
-            case ALPHA_ASCII64:
-                return launch_short<uint32_t, MEASURE, 256, 4, false, 64, true, true>(ctx, args, rows, st);
-            case ALPHA_ASCII128:
-                return launch_short<uint32_t, MEASURE, 256, 4, false, 128, true, true>(ctx, args, rows, st);
-            default:
-                // any script: Latin-1 pairs by the plane path, the others by the register-compare path
-                // (row_unicode_reg.cuh); no table in shared memory
-                if (cfg == 1) return launch_short<uint32_t, MEASURE, 128, 4, false, 128, false, false, true>(ctx, args, rows, st);
-                if (cfg == 2) return launch_short<uint32_t, MEASURE, 128, 2, false, 128, false, false, true>(ctx, args, rows, st);
-                return launch_general<MEASURE, 4, 4>(ctx, args, rows, st);
-        }
-    }
     switch (al) {
         case ALPHA_ASCII32:
-            return launch_short<uint32_t, MEASURE, 128, 4, false, 32, true>(ctx, args, rows, st);
+            return launch_short<uint32_t, MEASURE, 256, 4, false, 32, true, true>(ctx, args, rows, st);
         case ALPHA_ASCII64:
-            return launch_short<uint32_t, MEASURE, 128, 4, false, 64, true>(ctx, args, rows, st);
+            return launch_short<uint32_t, MEASURE, 256, 4, false, 64, true, true>(ctx, args, rows, st);
         case ALPHA_ASCII128:
-            return launch_short<uint32_t, MEASURE, 128, 4, false, 128, true>(ctx, args, rows, st);
+            return launch_short<uint32_t, MEASURE, 256, 4, false, 128, true, true>(ctx, args, rows, st);
         default:
-            return launch_short<uint32_t, MEASURE, 128, 4, false, 128, false>(ctx, args, rows, st);
+            // any script: Latin-1 pairs by the plane path, the others by the register-compare path
+            // (row_unicode_reg.cuh); no table in shared memory
+            return launch_general<MEASURE, 4, 4>(ctx, args, rows, st);
     }
 }
 
@@ -1506,20 +1461,6 @@ static int launch_multi(ThreadCtx& ctx, Alphabet al, const SegArgs& args, long l
     constexpr int ME = MULTI_BASE + GROUPS;
     // tiles of 256 x 3 rows: 48 KB of shared memory per CTA, so four CTAs (32 warps) share an SM; measured
     // on C2 (all five measures): 256x4 0.775 ms, 256x3 0.748 ms, 128x4 0.81 ms, 256x2 0.80 ms, 512x2 1.05 ms
-    static const char* cfg_env = getenv("STRSIM_B200_TILE");  // tuning knob (all-groups kernel only)
-    const int cfg = cfg_env && *cfg_env ? atoi(cfg_env) : 0;
-    if (GROUPS == 7 && cfg != 0) {
-        if (al == ALPHA_ASCII32) {
-            if (cfg == 1) return launch_short<uint32_t, MULTI_BASE + 7, 256, 4, false, 32, true, true>(ctx, args, rows, st);
-            if (cfg == 2) return launch_short<uint32_t, MULTI_BASE + 7, 128, 4, false, 32, true, true>(ctx, args, rows, st);
-            if (cfg == 3) return launch_short<uint32_t, MULTI_BASE + 7, 256, 2, false, 32, true, true>(ctx, args, rows, st);
-            if (cfg == 4) return launch_short<uint32_t, MULTI_BASE + 7, 128, 3, false, 32, true, true>(ctx, args, rows, st);
-        } else if (al == ALPHA_GENERAL) {
-            if (cfg == 1) return launch_short<uint32_t, MULTI_BASE + 7, 256, 4, false, 128, false, false, true>(ctx, args, rows, st);
-            if (cfg == 2) return launch_short<uint32_t, MULTI_BASE + 7, 128, 4, false, 128, false, false, true>(ctx, args, rows, st);
-            if (cfg == 3) return launch_short<uint32_t, MULTI_BASE + 7, 256, 3, false, 128, false, false, true>(ctx, args, rows, st);
-        }
-    }
     switch (al) {
         case ALPHA_ASCII32:
             return launch_short<uint32_t, ME, 256, 3, false, 32, true, true>(ctx, args, rows, st);
@@ -1612,11 +1553,7 @@ static int run_long_lev(ThreadCtx& ctx, const SegArgs& args, const Overflow& ov,
         if (peq_words > worst_words) peq_words = worst_words;
         g.peq_words = peq_words;
         g.slab_bytes = long_lev_slab_bytes(g.cap_a, g.cap_b, g.cap_pat, g.hash_size, peq_words);
-        static const int tier0_warps = [] {
-            const char* e = getenv("STRSIM_B200_LONG_WARPS");  // tuning knob: resident warps per SM
-            const int v = e && *e ? atoi(e) : 0;
-            return v > 0 ? v : 32;
-        }();
+        constexpr int tier0_warps = 32;  // resident warps per SM (24 / 16 measured 4 % / 20 % slower on C4)
         // a warp works on two pairs at a time (long_lev_kernel.cuh): two slabs per warp
         long long warps = (long long)ctx.sm_count * (tier == 0 ? tier0_warps : 8);
         if (((long long)src.n + 1) / 2 < warps) warps = ((long long)src.n + 1) / 2;
@@ -1751,8 +1688,7 @@ static int finish_64_planes(ThreadCtx& ctx, const SegArgs& args, const Overflow&
 // rows of 33..64 bytes -> 64-bit instantiation in gather mode
 template <int MEASURE>
 static int finish_64(ThreadCtx& ctx, const SegArgs& args, const Overflow& ov, cudaStream_t st, bool ascii = false) {
-    static const bool planes64 = !(getenv("STRSIM_B200_PLANES64") && !strcmp(getenv("STRSIM_B200_PLANES64"), "0"));
-    if (ascii && planes64) return finish_64_planes<MEASURE>(ctx, args, ov, st);
+    if (ascii) return finish_64_planes<MEASURE>(ctx, args, ov, st);
     SegArgs a64 = args;
     a64.list = args.list64;
     a64.list_count = &ctx.d_ovf->n64;
@@ -1863,8 +1799,7 @@ static int run_segment_multi(ThreadCtx& ctx, SegArgs args, int groups, Alphabet 
     if (rc) return rc;
     if (al == ALPHA_GENERAL) note_wide_share(ov, seg_rows);
     g_last_overflow[0] += ov.n64;
-    static const bool planes64 = !(getenv("STRSIM_B200_PLANES64") && !strcmp(getenv("STRSIM_B200_PLANES64"), "0"));
-    if (ov.n64 > 0 && al != ALPHA_GENERAL && groups >= 2 && planes64) {
+    if (ov.n64 > 0 && al != ALPHA_GENERAL && groups >= 2) {
         // ASCII-only columns: ONE fused launch of the 64-bit plane path over list64
         switch (groups) {
             case 2: rc = finish_64_planes<MULTI_BASE + 2>(ctx, args, ov, st); break;
@@ -2019,9 +1954,7 @@ static int compute_on_device(ThreadCtx& ctx, const int* measures, size_t n_measu
         // aligned blocks, one more when the segment does not start on a block boundary.  Then the stage
         // area is sized from that bound and the host neither reads the overflow counters back nor waits.
         bool proven_clean = false;
-        static const bool no_proof = (getenv("STRSIM_B200_READBACK") != nullptr && !strcmp(getenv("STRSIM_B200_READBACK"), "1")) ||
-                                     getenv("STRSIM_B200_TILE") != nullptr || getenv("STRSIM_B200_KERNEL") != nullptr ||
-                                     getenv("STRSIM_B200_REG") != nullptr;  // experiment knobs change the tile shape
+        static const bool no_proof = getenv("STRSIM_B200_READBACK") != nullptr && !strcmp(getenv("STRSIM_B200_READBACK"), "1");
         if (!no_proof && al != ALPHA_GENERAL && !force_generic_rows() && a->max_len <= 32u && b->max_len <= 32u &&
             a->max_block_pad != 0xFFFFFFFFu && b->max_block_pad != 0xFFFFFFFFu && s.a.res_buf == 0xFFFFFFFFu &&
             s.b.res_buf == 0xFFFFFFFFu && s.a.lo_off == 0u && s.b.lo_off == 0u) {
@@ -2560,8 +2493,7 @@ static int host_call_impl(const int* measures, size_t n_measures, const strsim_v
     // bypass the residency check) all data first, as before.
     static const bool no_progressive = [] {
         const char* e = getenv("STRSIM_B200_PROGRESSIVE");
-        const char* k = getenv("STRSIM_B200_KERNEL");
-        return (e && !strcmp(e, "0")) || (k && !strcmp(k, "direct"));
+        return e && !strcmp(e, "0");
     }();
     n_slices = (int)((n + slice_rows - 1) / slice_rows);
     const bool progressive = !no_progressive && !force_generic_rows() && la == lb && n_slices > 1 &&
@@ -2997,9 +2929,8 @@ static int host_call_sharded(const int* measures, size_t n_measures, const strsi
         strsim_b200_shard_cuts(n, (int)G, cut.data());
     }
     static const bool no_trim = [] {
-        const char* k = getenv("STRSIM_B200_KERNEL");
         const char* t = getenv("STRSIM_B200_SHARD_TRIM");
-        return (k && !strcmp(k, "direct")) || (t && !strcmp(t, "0"));
+        return t && !strcmp(t, "0");
     }();
     struct Shard {
         std::vector<strsim_view_chunk> a, b;
