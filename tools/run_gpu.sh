@@ -1,20 +1,11 @@
 cd $GRAFT_REPO_ROOT
-python - <<'PY'
-import sys, time, ctypes
-sys.path[:0]=['.','polars-strsim_b200']
-from bench_support import plugin_driver, workloads
-from polars_strsim import _native
-M=("levenshtein","jaro","jaro_winkler","jaccard","sorensen_dice")
-A,B=workloads.make_pairs(2,10_000_000)
-L=_native.lib()
-t_start=time.perf_counter()
-def step(tag):
-    plugin_driver.cache_clear()
-    t=[]
-    for m in M:
-        t0=time.perf_counter(); r=plugin_driver.call(m,A,B); t.append((time.perf_counter()-t0)*1e3); r.release()
-    print('%6.2f s' % (time.perf_counter()-t_start), tag,'total %.2f'%sum(t),['%.2f'%x for x in t], flush=True)
-for k in range(12):
-    step('step %d'%k)
-    if k<2: time.sleep(0.6)
+python -m pytest tests -m gpu -x -q > gpurun_out/r2r_pytest.log 2>&1; tail -3 gpurun_out/r2r_pytest.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+for lib in "" exp/libvariant_ulat_rpt2.so; do
+STRSIM_B200_LIB=$lib python bench.py --workload C3 --rows 50000000 --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r2r_c3.json 2> gpurun_out/r2r_err.log; python - <<PY
+import json
+d=json.load(open('gpurun_out/r2r_c3.json'))
+print('C3 50M lib=[$lib]', round(d['ms_per_step'],4))
 PY
+done
+python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-e2e | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('C2', d['ms_per_step'], d['roofline']['traffic'])"
