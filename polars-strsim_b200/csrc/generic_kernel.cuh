@@ -424,8 +424,7 @@ __global__ void validity_kernel(const ValidityArgs v) {
     const long long w = w_lo + blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long r_begin = max(w << 5, v.out_row0);
     const long long r_end = min((w + 1) << 5, v.out_row0 + v.n);
-    if (r_begin >= r_end) return;
-    const int rows = (int)(r_end - r_begin);
+    const int rows = r_begin < r_end ? (int)(r_end - r_begin) : 0;  // (no early return: the reduction below names every lane)
     uint32_t bits = 0;
     if (rows == 32 && (reinterpret_cast<uintptr_t>(v.va) & 3) == 0 && (reinterpret_cast<uintptr_t>(v.vb) & 3) == 0) {
         const long long s = r_begin - v.out_row0;
@@ -439,14 +438,13 @@ __global__ void validity_kernel(const ValidityArgs v) {
     }
     if (rows == 32)
         v.out[w] = bits;
-    else
+    else if (rows > 0)
         atomicOr(&v.out[w], bits);
     // one atomic per warp: with nulls in most 32-row words, a million atomics per segment on ONE address
     // serialised in the L2 and made this kernel 12 % of a C3 step (658 us per 33 M rows; now a few us)
     const int nulls = rows - __popc(bits);
-    const unsigned peers = __activemask();
-    const int total = __reduce_add_sync(peers, nulls);
-    if (total && (threadIdx.x & 31) == __ffs((int)peers) - 1) atomicAdd(v.null_count, (unsigned long long)total);
+    const int total = __reduce_add_sync(0xFFFFFFFFu, nulls);
+    if (total && (threadIdx.x & 31) == 0) atomicAdd(v.null_count, (unsigned long long)total);
 }
 
 }  // namespace strsim

@@ -492,7 +492,7 @@ extern "C" void strsim_pool_trim(int idle_seconds) {
 // milliseconds per 80 MB), so buffers are pooled: a call takes a free block when there is one -- otherwise
 // it falls back to pageable memory AND asks a background thread to pin a block of that size for the calls
 // to come; the release callback of the Arrow array hands the block back.  At most
-// STRSIM_B200_PINNED_RESULT_BYTES (default 1 GiB) are pinned at any time; blocks idle for the cache's
+// STRSIM_B200_PINNED_RESULT_BYTES (default 4 GiB) are pinned at any time; blocks idle for the cache's
 // time-to-live are unpinned by the plugin's reaper (strsim_result_pool_trim).
 struct PinnedBlock {
     void* ptr;
@@ -509,7 +509,7 @@ static bool g_pinned_grower_running = false;
 static size_t pinned_limit() {
     static const size_t lim = [] {
         const char* e = getenv("STRSIM_B200_PINNED_RESULT_BYTES");
-        return e && *e ? (size_t)strtoull(e, nullptr, 10) : ((size_t)1 << 30);
+        return e && *e ? (size_t)strtoull(e, nullptr, 10) : ((size_t)4 << 30);
     }();
     return lim;
 }

@@ -393,6 +393,28 @@ struct StagedSrc {
 // data sets dominated by equal pairs.
 constexpr bool PREFILTER_EQUAL = false;
 
+// ULAT launch: appends the rows a thread flagged (bit k of `flags` = its k-th row of the tile) to the list the
+// register-compare launch gathers, with one atomic per warp.  EVERY lane of the warp calls it from converged
+// code (the ballots name the full mask).  It replaces the opportunistic form -- __activemask() inside the
+// divergent branch, then __shfl_sync over that mask -- in which nothing ties the point where the compiler reads
+// the active mask to the lanes that take the branch.
+template <int RPT, typename RowOf>
+__device__ __forceinline__ void list_wide_rows(const SegArgs& s, uint32_t flags, int lane, RowOf row_of) {
+    if (!__any_sync(0xFFFFFFFFu, flags != 0u)) return;
+    unsigned total = 0;
+#pragma unroll
+    for (int k = 0; k < RPT; k++) total += (unsigned)__popc(__ballot_sync(0xFFFFFFFFu, (flags >> k) & 1u));
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(&s.ovf->nwide, total);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+#pragma unroll
+    for (int k = 0; k < RPT; k++) {
+        const unsigned b = __ballot_sync(0xFFFFFFFFu, (flags >> k) & 1u);
+        if ((flags >> k) & 1u) s.listwide[base + (unsigned)__popc(b & ((1u << lane) - 1u))] = row_of(k);
+        base += (unsigned)__popc(b);
+    }
+}
+
 // first four bytes of an out-of-line string (its view's prefix word was replaced by the stage offset)
 __device__ __forceinline__ uint32_t sva_prefix(const uint4& v, const unsigned char* stage) {
     const uint32_t* p = reinterpret_cast<const uint32_t*>(stage) + (v.y >> 2);
@@ -739,14 +761,14 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
                 if (v.x <= 12u) continue;
                 const uint32_t padded = (v.x + 3u) & ~3u;
                 if (pos + padded > (uint32_t)s.stage_bytes) {
-                    // stage full: finish this row in the long kernel (listed once: by the first launch)
+                    // stage full: finish this row in the long kernel.  (Also in the second launch over a general
+                    // column: its tiles hold wide pairs only, which can be longer than the column's mean -- the
+                    // first launch staged this row and listed it as wide, so it is on no other list yet.)
                     const long long idx = tile0 + i;
                     const long long row = GATHER ? (long long)s.list[idx] : idx;
-                    if (!(UREG && !ULAT && s.skip_latin)) {
-                        s.listlong[atomicAdd(&s.ovf->nlong, 1u)] = (unsigned int)row;
-                        atomicMax(&s.ovf->max_bytes_a, sva[i].x);
-                        atomicMax(&s.ovf->max_bytes_b, svb[i].x);
-                    }
+                    s.listlong[atomicAdd(&s.ovf->nlong, 1u)] = (unsigned int)row;
+                    atomicMax(&s.ovf->max_bytes_a, sva[i].x);
+                    atomicMax(&s.ovf->max_bytes_b, svb[i].x);
                     active &= ~(1u << k);
                     continue;
                 }
@@ -799,6 +821,7 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
                                                  ((active >> k) & 1u) != 0u);
             }
         }
+        uint32_t listed = 0;  // ULAT: bit k = this thread's k-th row goes to the register-compare launch
 #pragma unroll
         for (int k = 0; k < RPT; k++) {
             const int i = k * TPB + tid;
@@ -868,15 +891,7 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
                 // each of the two launches over a general column takes one class; the first one counts what
                 // it leaves to the second (none in a Latin-1 column: the host then skips that launch)
                 if (ULAT && wide != 0u) {
-                    // listed (one atomic per warp), so that the second launch gathers these rows only
-                    const unsigned m = __activemask();
-                    const int leader = (int)__ffs(m) - 1;
-                    unsigned base = 0;
-                    if (lane == leader) base = atomicAdd(&s.ovf->nwide, (unsigned)__popc(m));
-                    base = __shfl_sync(m, base, leader);
-                    const long long idx = tile0 + i;
-                    s.listwide[base + __popc(m & ((1u << lane) - 1u))] =
-                        (unsigned int)(GATHER ? (long long)s.list[idx] : idx);
+                    listed |= 1u << k;  // the second launch gathers these rows only (list_wide_rows below)
                     continue;
                 }
                 if (!ULAT && s.skip_latin && wide == 0u) continue;
@@ -891,6 +906,11 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
                                         ((hi_bits & 0x80808080u) ? (uint32_t)(CAP + 1) : 0u);
             rank[k] = atomicAdd(&hist[key[k]], 1u);
         }
+        if constexpr (ULAT)
+            list_wide_rows<RPT>(s, listed, lane, [&](int k) {
+                const long long idx = tile0 + k * TPB + tid;
+                return (unsigned int)(GATHER ? (long long)s.list[idx] : idx);
+            });
         __syncthreads();
         if (warp == 0) {
             // start[key] = number of rows with a larger key; lane l owns bins [l*CH, (l+1)*CH)
@@ -936,6 +956,7 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
                 }
             }
         }
+        uint32_t late = 0;  // ULAT: bit k = the pair of round k turned out wide while it was transcoded
 #pragma unroll 1
         for (int k = 0; k < RPT; k++) {
             const int p = k * TPB + ((k & 1) ? (TPB - 1 - tid) : tid);  // snake order balances warps
@@ -966,12 +987,7 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
                     SB.len, wide);
                 if (wide != 0u) {
                     // a character above U+00FF behind the first word: the register-compare launch takes the pair
-                    const unsigned m = __activemask();
-                    const int leader = (int)__ffs(m) - 1;
-                    unsigned base = 0;
-                    if (lane == leader) base = atomicAdd(&s.ovf->nwide, (unsigned)__popc(m));
-                    base = __shfl_sync(m, base, leader);
-                    s.listwide[base + __popc(m & ((1u << lane) - 1u))] = (unsigned int)row;
+                    late |= 1u << k;
                     continue;
                 }
                 typedef SlabSrc<TPB, SlabByteAt<TPB>> Src;
@@ -1093,6 +1109,11 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
                 d[5] = ints.x2;
             }
         }
+        if constexpr (ULAT)
+            list_wide_rows<RPT>(s, late, lane, [&](int k) {
+                const long long idx = tile0 + perm[k * TPB + ((k & 1) ? (TPB - 1 - tid) : tid)];
+                return (unsigned int)(GATHER ? (long long)s.list[idx] : idx);
+            });
         __syncthreads();  // smem is reused by the next tile
     }
 }

@@ -121,6 +121,30 @@ def test_medium_and_long_strings(native, oracle):
     assert sum(native.last_overflow()) > 0  # the overflow kernels really ran
 
 
+def test_wide_rows_longer_than_the_column_mean(native, oracle):
+    """A general column of short Latin-1 rows with one row in ten a long CJK string: the launch over the wide
+    pairs (short_kernel.cuh, second launch of launch_general) sizes its staging area from the COLUMN's mean
+    payload, so its tiles -- wide pairs only -- overflow it.  Those rows must finish in the long kernel, not
+    vanish (they did: the second launch assumed the first had listed them)."""
+    rng = random.Random(4242)
+    cjk = [chr(c) for c in range(0x4E00, 0x4E40)]
+    a, b = [], []
+    for r in range(60000):
+        if r % 10 == 3:
+            x = "".join(rng.choice(cjk) for _ in range(rng.randint(7, 10)))
+            y = list(x)
+            y[rng.randrange(len(y))] = rng.choice(cjk)
+            y = "".join(y[: rng.randint(6, len(y))])
+        else:
+            x = "".join(rng.choice("abcdé") for _ in range(rng.randint(1, 5)))
+            y = "".join(rng.choice("abcdé") for _ in range(rng.randint(1, 5)))
+        a.append(x)
+        b.append(y)
+    for measure in ("levenshtein", "jaro_winkler", "sorensen_dice"):
+        check(native, oracle, measure, a, b)
+    check_multi(native, oracle, list(range(5)), a, b)
+
+
 def test_long_rows_one_pair_per_warp(native, oracle):
     """Rows above 64 bytes of Jaro / Jaro-Winkler / Jaccard / Sorensen-Dice (long_pair_kernel.cuh: one pair per
     warp -- windowed matching by ballot over 32 positions of b per step, transpositions on compacted flag
