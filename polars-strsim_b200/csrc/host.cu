@@ -248,7 +248,9 @@ struct ThreadCtx {
     ColumnStats* d_slice_stats = nullptr;  // [0] data of a, [1] data of b, [2+s] views of slice s
     ColumnStats* h_slice_stats = nullptr;  // pinned
     int sm_count = 0;
-    Overflow* d_ovf = nullptr;
+    Overflow* d_ovf = nullptr;      // the counters the current launches fill
+    Overflow* d_ovf_alt = nullptr;  // a second set: a follow-up launch that reads one list and fills another (finish_wide)
+    Overflow* d_ovf_base = nullptr; // the allocation behind the two (they swap roles)
     Overflow* h_ovf = nullptr;  // pinned
     unsigned long long* d_nulls = nullptr;
     unsigned long long* h_nulls = nullptr;  // pinned
@@ -291,7 +293,7 @@ static void destroy_ctx(ThreadCtx& c) {
     for (auto& ev : c.done_event) if (ev) cudaEventDestroy(ev);
     for (auto& ev : c.slice_event) if (ev) cudaEventDestroy(ev);
     for (auto& ev : c.up_event) if (ev) cudaEventDestroy(ev);
-    for (void* p : {(void*)c.d_slice_stats, (void*)c.d_ovf, (void*)c.d_nulls, (void*)c.d_stats, (void*)c.d_counters,
+    for (void* p : {(void*)c.d_slice_stats, (void*)c.d_ovf_base, (void*)c.d_nulls, (void*)c.d_stats, (void*)c.d_counters,
                     c.lists.ptr, c.scratch.ptr})
         if (p) cudaFree(p);
     for (void* p : {(void*)c.h_slice_stats, (void*)c.h_ovf, (void*)c.h_nulls, (void*)c.h_counters, (void*)c.h_stats})
@@ -321,7 +323,9 @@ static int init_ctx(ThreadCtx& c, int device) {
     CUDA_TRY(cudaMallocHost(&c.h_slice_stats, sizeof(ColumnStats) * (2 + MAX_SLICES)));
     for (auto& ev : c.done_event) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CUDA_TRY(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, c.device));
-    CUDA_TRY(cudaMalloc(&c.d_ovf, sizeof(Overflow)));
+    CUDA_TRY(cudaMalloc(&c.d_ovf_base, 2 * sizeof(Overflow)));
+    c.d_ovf = c.d_ovf_base;
+    c.d_ovf_alt = c.d_ovf_base + 1;
     CUDA_TRY(cudaMallocHost(&c.h_ovf, sizeof(Overflow)));
     CUDA_TRY(cudaMalloc(&c.d_nulls, sizeof(unsigned long long)));
     CUDA_TRY(cudaMallocHost(&c.h_nulls, sizeof(unsigned long long)));
@@ -1643,6 +1647,13 @@ static int run_long_pair(ThreadCtx& ctx, const SegArgs& args, double* const outs
     return STRSIM_OK;
 }
 
+// test hook: STRSIM_B200_WIDE_ROWS=0 sends the 65..320-byte rows of ASCII columns to the warp-per-pair kernels,
+// as before finish_wide existed (the parity tests run both ways)
+static bool wide_rows_enabled() {
+    static const bool v = !(getenv("STRSIM_B200_WIDE_ROWS") != nullptr && atoi(getenv("STRSIM_B200_WIDE_ROWS")) == 0);
+    return v;
+}
+
 static bool force_generic_rows() {
     static const bool v = getenv("STRSIM_B200_FORCE_GENERIC") != nullptr && atoi(getenv("STRSIM_B200_FORCE_GENERIC")) != 0;
     return v;
@@ -1683,6 +1694,36 @@ static int finish_64_planes(ThreadCtx& ctx, const SegArgs& args, const Overflow&
     a64.n = ov.n64;
     a64.stage_bytes = 64 * 128 * 3;
     return launch_short<uint64_t, MEASURE, 128, 3, true, 128, true, true>(ctx, a64, ov.n64, st);
+}
+
+// Rows of 65..320 bytes of ASCII-only columns: the plane path again, with masks of ten 32-bit words
+// (wide_mask.cuh) -- one pair per thread, gather mode over listlong, tiles of 128 rows.  The launch reads
+// listlong (count: the current counters) and appends what it cannot take -- a string above 320 bytes, a tile
+// whose payload does not fit the stage area -- to the OTHER list buffer under the second set of counters;
+// then the two sets and the two buffers swap roles, so that the warp-per-pair kernels behind it find "their"
+// list where they always do.  `ov` is re-read: it describes what is left.
+// Measured on T1 (10 M address-like rows, one in ten of 100-300 characters, all five measures): see
+// DESIGN.md 3.3b.
+constexpr int WIDE_WORDS = 10;
+template <int MEASURE>
+static int finish_wide(ThreadCtx& ctx, SegArgs& args, Overflow* ov, cudaStream_t st) {
+    SegArgs aw = args;
+    aw.list = args.listlong;
+    aw.list_count = &ctx.d_ovf->nlong;
+    aw.n = ov->nlong;
+    aw.ovf = ctx.d_ovf_alt;
+    aw.listlong = args.list64;  // free: the 64-bit launch has consumed it (same stream)
+    aw.list64 = nullptr;        // never written by this instantiation (CAP != 32)
+    CUDA_TRY(cudaMemsetAsync(ctx.d_ovf_alt, 0, sizeof(Overflow), st));
+    // stage area: the listed strings are all out of line; 224 bytes a row on average fit 100-300-character
+    // rows, longer tiles send their last rows on to the warp kernels
+    aw.stage_bytes = 224 * 128;
+    int rc = launch_short<Wide<WIDE_WORDS>, MEASURE, 128, 1, true, 128, true, true>(ctx, aw, ov->nlong, st);
+    if (rc) return rc;
+    std::swap(ctx.d_ovf, ctx.d_ovf_alt);
+    std::swap(args.listlong, args.list64);
+    args.ovf = ctx.d_ovf;
+    return read_overflow(ctx, ov, st, false);
 }
 
 // rows of 33..64 bytes -> 64-bit instantiation in gather mode
@@ -1751,6 +1792,10 @@ static int run_segment(ThreadCtx& ctx, SegArgs args, Alphabet al, int stage32, i
         if (rc) return rc;
     }
     g_last_overflow[1] += ov.nlong;
+    if (ov.nlong > 0 && al != ALPHA_GENERAL && !force_generic_rows() && wide_rows_enabled()) {
+        rc = finish_wide<MEASURE>(ctx, args, &ov, st);
+        if (rc) return rc;
+    }
     if (ov.nlong > 0) rc = finish_long<MEASURE>(ctx, args, ov, st);
     return rc;
 }
@@ -1832,6 +1877,17 @@ static int run_segment_multi(ThreadCtx& ctx, SegArgs args, int groups, Alphabet 
         if (rc) return rc;
     }
     g_last_overflow[1] += ov.nlong;
+    if (ov.nlong > 0 && al != ALPHA_GENERAL && groups >= 2 && !force_generic_rows() && wide_rows_enabled()) {
+        switch (groups) {
+            case 2: rc = finish_wide<MULTI_BASE + 2>(ctx, args, &ov, st); break;
+            case 3: rc = finish_wide<MULTI_BASE + 3>(ctx, args, &ov, st); break;
+            case 4: rc = finish_wide<MULTI_BASE + 4>(ctx, args, &ov, st); break;
+            case 5: rc = finish_wide<MULTI_BASE + 5>(ctx, args, &ov, st); break;
+            case 6: rc = finish_wide<MULTI_BASE + 6>(ctx, args, &ov, st); break;
+            default: rc = finish_wide<MULTI_BASE + 7>(ctx, args, &ov, st); break;
+        }
+        if (rc) return rc;
+    }
     if (ov.nlong > 0) {
         bool served = false;  // Jaro / Jaro-Winkler / Jaccard / Sorensen-Dice of the long rows: ONE warp-per-pair launch
         if (!force_generic_rows()) {

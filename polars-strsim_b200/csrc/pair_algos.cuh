@@ -96,6 +96,16 @@ SS_HD int ctz64(uint64_t x) {  // x != 0
 #endif
 }
 
+// masks wider than 64 bits (wide_mask.cuh): N 32-bit words behind the same operators
+template <int N>
+struct Wide;
+
+// bits < m of a mask (m >= 0; m >= bits(M) gives all ones)
+template <class M>
+struct LowMask {
+    SS_HD static M get(int m) { return m >= (int)(sizeof(M) * 8) ? ~M(0) : ((M(1) << m) - M(1)); }
+};
+
 // bits lo..hi inclusive (0 <= lo, hi < bits(M)); empty when lo > hi
 template <class M>
 SS_HD M mask_range(int lo, int hi) {
@@ -232,7 +242,7 @@ struct MyersStep {
         Mv = Ph & Xv;
     }
     SS_HD int distance(int m, int n) const {
-        const M mask = m >= (int)(sizeof(M) * 8) ? ~M(0) : ((M(1) << m) - M(1));
+        const M mask = LowMask<M>::get(m);
         return n + popc(Pv & mask) - popc(Mv & mask);
     }
 };
@@ -326,7 +336,7 @@ struct JaroMatchStep {
     int m;             // valid after finish()
     SS_HD JaroMatchStep(const Tab& t, int lb, int bound_) : tab(t), rev_a(M(0)), flag_a(M(0)), flag_b(M(0)), m(0) {
         window.init(bound_);
-        lbmask = lb >= (int)(sizeof(M) * 8) ? ~M(0) : ((M(1) << lb) - M(1));
+        lbmask = LowMask<M>::get(lb);
         avail = lbmask;
     }
     SS_HD void operator()(uint32_t c) { step(tab(c)); }
@@ -401,6 +411,11 @@ struct TransByBytes {
         }
         return t;
     }
+    // masks of several words: wide_mask.cuh
+    template <int N, class Tab, class Each>
+    SS_HD int operator()(const Tab&, const Each&, int, const Wide<N>& flag_a, const Wide<N>& flag_b) const {
+        return trans_by_bytes_wide(flag_a, flag_b, A, B);
+    }
 };
 
 // multiset intersection (strsim.rs:297-305); `used` starts with the padding positions >= lb set
@@ -411,7 +426,7 @@ struct MultisetStep {
     int pad;    // padding positions >= lb, set in `used` from the start
     int inter;  // valid after finish()
     SS_HD MultisetStep(const Tab& t, int lb)
-        : tab(t), used(lb >= (int)(sizeof(M) * 8) ? M(0) : ~((M(1) << lb) - M(1))),
+        : tab(t), used(~LowMask<M>::get(lb)),
           pad(lb >= (int)(sizeof(M) * 8) ? 0 : (int)(sizeof(M) * 8) - lb), inter(0) {}
     SS_HD void operator()(uint32_t c) { step(tab(c)); }
     SS_HD void step(const M Eq) {  // branch-free: the lowest unused equal position of b is consumed

@@ -16,6 +16,7 @@
 // Arithmetic and row rules are those of row_short.cuh (same step functors, same f64 formulas).
 #pragma once
 #include "row_short.cuh"
+#include "wide_mask.cuh"
 
 namespace strsim {
 
@@ -33,10 +34,18 @@ SS_HD uint32_t sign_fill_byte(uint32_t x, int byte) {  // all-ones if bit 7 of b
 #endif
 }
 
-// a 32-bit pattern over every 32-bit half of M
+// a 32-bit pattern over every 32-bit word of M
+template <class M>
+struct Rep32 {
+    SS_HD static M get(uint32_t s) { return sizeof(M) == 4 ? (M)s : (M)(((uint64_t)s << 32) | s); }
+};
+template <int N>
+struct Rep32<Wide<N>> {
+    SS_HD static Wide<N> get(uint32_t s) { return Wide<N>::fill(s); }
+};
 template <class M>
 SS_HD M rep32(uint32_t s) {
-    return sizeof(M) == 4 ? (M)s : (M)(((uint64_t)s << 32) | s);
+    return Rep32<M>::get(s);
 }
 
 // M = uint32_t: strings of at most 32 characters; uint64_t: at most 64 (every plane is two registers)
@@ -58,9 +67,7 @@ struct PlaneTab {
         if (NBITS > 7) X |= B[7] ^ rep32<M>(sign_fill_byte(c, 0));  // one byte per character up to U+00FF (Latin-1 rows)
         return ~X & valid;
     }
-    SS_HD void set_valid(int m) {
-        valid = m >= (int)(sizeof(M) * 8) ? ~M(0) : ((M(1) << m) - M(1));
-    }
+    SS_HD void set_valid(int m) { valid = LowMask<M>::get(m); }
 };
 
 // adds the four characters of word w (characters 4w..4w+3) to the planes
@@ -75,6 +82,16 @@ SS_HD void planes_add_word(PlaneTab<NBITS, M>& tab, uint32_t word, int w) {
             tab.B[k] |= (M)(w == 7 ? (prod & 0xF0000000u) : ((prod >> (28 - 4 * w)) & (0xFu << (4 * w))));
         else
             tab.B[k] |= (M)(prod >> 28) << (4 * w);
+    }
+}
+
+// masks of several words (wide_mask.cuh): word w of the string fills nibble w % 8 of mask word w / 8
+template <int NBITS, int N>
+SS_HD void planes_add_word(PlaneTab<NBITS, Wide<N>>& tab, uint32_t word, int w) {
+#pragma unroll
+    for (int k = 0; k < NBITS; k++) {
+        const uint32_t prod = (word & (0x01010101u << k)) * (0x10204080u >> k);
+        tab.B[k].w[w >> 3] |= (prod >> 28) << (4 * (w & 7));
     }
 }
 
@@ -268,7 +285,7 @@ SS_HD double row_planes(const Src& A, const Src& B, PairInts& out) {
             d = step.distance(P.len, X.len);
         }
         out.x0 = d;
-        v = lev_value<true>(d, la, lb);
+        v = lev_value<(sizeof(M) <= 8)>(d, la, lb);  // (the quotient table ends at 64)
     } else {
         B.planes(tab);
         if (IS_JARO) {
@@ -283,7 +300,7 @@ SS_HD double row_planes(const Src& A, const Src& B, PairInts& out) {
             const int t = match.m > 0 ? trans(tab, each_a, outer, match.flag_a, match.flag_b) : 0;
             out.x0 = match.m;
             out.x1 = t;
-            v = match.m == 0 ? 0.0 : jaro_value<true>(match.m, t, la, lb);
+            v = match.m == 0 ? 0.0 : jaro_value<(sizeof(M) <= 8)>(match.m, t, la, lb);
             if (MEASURE == JARO_WINKLER && v > 0.7) {  // strsim.rs:260-267
                 PrefixOf<Src> prefix{A, B};
                 const int l = prefix();

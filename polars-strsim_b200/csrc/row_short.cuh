@@ -246,7 +246,7 @@ SS_HD void multi_body(const Tab& tab, const Each& each_a, int la, int lb, bool o
         // Pv all ones -> d = lb, an empty pattern (lb = 0) scores no vertical delta -> d = la
         const int d = f.my.distance(lb, la);
         o.x0 = d;
-        emit(LEVENSHTEIN, lev_value<true>(d, la, lb), o);
+        emit(LEVENSHTEIN, lev_value<(sizeof(M) <= 8)>(d, la, lb), o);  // (the quotient table ends at 64)
     }
     PairInts z;
     z.flag = F_ONE_EMPTY;
@@ -265,7 +265,7 @@ SS_HD void multi_body(const Tab& tab, const Each& each_a, int la, int lb, bool o
             const int t = f.jm.m > 0 ? trans_count(tab, each_a, la, f.jm.flag_a, f.jm.flag_b) : 0;
             o.x0 = f.jm.m;
             o.x1 = t;
-            double v = f.jm.m == 0 ? 0.0 : jaro_value<true>(f.jm.m, t, la, lb);
+            double v = f.jm.m == 0 ? 0.0 : jaro_value<(sizeof(M) <= 8)>(f.jm.m, t, la, lb);
             emit(JARO, v, o);
             if (v > 0.7) {  // strsim.rs:260-267
                 const int l = prefix();

@@ -321,3 +321,64 @@ extern "C" int algos_batch_latin1_multi(int groups, int64_t n, const uint8_t* ad
     }
     return 0;
 }
+
+// masks of several words (wide_mask.cuh): ASCII strings of up to 32 * N characters, one pair per thread on
+// the device; here the same templates with N = 10 (320 characters) and N = 5, 7 planes
+template <int N, int MEASURE>
+static double wide_single(const uint32_t* a, const uint32_t* b, int na, int nb, PairInts& pi) {
+    return row_planes<MEASURE, 7, Wide<N>>(host_src(a, na), host_src(b, nb), pi);
+}
+template <int N>
+static int wide_batch(int measure, int groups, int64_t n, const uint8_t* ad, const int64_t* ao, const uint8_t* bd,
+                      const int64_t* bo, int* ints, double* values) {
+    constexpr int CAPB = 32 * N;
+    for (int64_t r = 0; r < n; r++) {
+        const int na = (int)(ao[r + 1] - ao[r]), nb = (int)(bo[r + 1] - bo[r]);
+        if (na > CAPB || nb > CAPB) return -2;
+        uint32_t a[CAPB / 4 + 2], b[CAPB / 4 + 2];
+        std::memset(a, 0xA5, sizeof a);  // bytes past the string are arbitrary for a source
+        std::memset(b, 0x5A, sizeof b);
+        std::memcpy(a, ad + ao[r], na);
+        std::memcpy(b, bd + bo[r], nb);
+        const bool equal = na == nb && std::memcmp(ad + ao[r], bd + bo[r], na) == 0;
+        if (groups) {
+            HostEmit e{r, n, ints, values};
+            const PairInts o = {F_EQUAL, 0, 0, 0, 0, 0};
+            const HostSrc A = host_src(a, na), B = host_src(b, nb);
+            switch (groups) {
+                case 1: if (equal) emit_groups<1>(e, 1.0, o); else row_planes_multi<1, 7, Wide<N>>(A, B, e); break;
+                case 2: if (equal) emit_groups<2>(e, 1.0, o); else row_planes_multi<2, 7, Wide<N>>(A, B, e); break;
+                case 3: if (equal) emit_groups<3>(e, 1.0, o); else row_planes_multi<3, 7, Wide<N>>(A, B, e); break;
+                case 4: if (equal) emit_groups<4>(e, 1.0, o); else row_planes_multi<4, 7, Wide<N>>(A, B, e); break;
+                case 5: if (equal) emit_groups<5>(e, 1.0, o); else row_planes_multi<5, 7, Wide<N>>(A, B, e); break;
+                case 6: if (equal) emit_groups<6>(e, 1.0, o); else row_planes_multi<6, 7, Wide<N>>(A, B, e); break;
+                case 7: if (equal) emit_groups<7>(e, 1.0, o); else row_planes_multi<7, 7, Wide<N>>(A, B, e); break;
+                default: return -3;
+            }
+            continue;
+        }
+        PairInts pi;
+        double v;
+        if (equal) {
+            pi = {F_EQUAL, 0, 0, 0, 0, 0};
+            v = 1.0;
+        } else
+            switch (measure) {
+                case 0: v = wide_single<N, 0>(a, b, na, nb, pi); break;
+                case 1: v = wide_single<N, 1>(a, b, na, nb, pi); break;
+                case 2: v = wide_single<N, 2>(a, b, na, nb, pi); break;
+                case 3: v = wide_single<N, 3>(a, b, na, nb, pi); break;
+                default: v = wide_single<N, 4>(a, b, na, nb, pi); break;
+            }
+        values[r] = v;
+        int* o = ints + 6 * r;
+        o[0] = pi.flag; o[1] = pi.la; o[2] = pi.lb; o[3] = pi.x0; o[4] = pi.x1; o[5] = pi.x2;
+    }
+    return 0;
+}
+// groups == 0: one measure (values[n], ints[n][6]); else the fused form (values[5][n], ints[5][n][6])
+extern "C" int algos_batch_wide(int words, int measure, int groups, int64_t n, const uint8_t* ad, const int64_t* ao,
+                                const uint8_t* bd, const int64_t* bo, int* ints, double* values) {
+    return words == 5 ? wide_batch<5>(measure, groups, n, ad, ao, bd, bo, ints, values)
+                      : wide_batch<10>(measure, groups, n, ad, ao, bd, bo, ints, values);
+}

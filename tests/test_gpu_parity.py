@@ -145,6 +145,61 @@ def test_wide_rows_longer_than_the_column_mean(native, oracle):
     check_multi(native, oracle, list(range(5)), a, b)
 
 
+def test_wide_rows_of_ascii_columns(native, oracle):
+    """Rows of 65..320 bytes of ASCII-only columns: one pair per thread with masks of ten words
+    (wide_mask.cuh, host.cu: finish_wide) -- between the 64-bit plane launch and the warp-per-pair kernels,
+    which still take what is longer.  Lengths around every 32-character word boundary, near-duplicates,
+    moved blocks, tiny alphabets, equal pairs, one side short or empty, nulls; every measure alone, all
+    five fused, and group subsets."""
+    rng = random.Random(777)
+    alpha = "abcdefghijklmnopqrstuvwxyz ABCDEFGH0123456789-,.'#/"
+    a, b = [], []
+    for _ in range(6000):
+        n = rng.choice([rng.randint(65, 320), rng.randint(65, 320), rng.randint(1, 64), rng.randint(321, 420)])
+        al = alpha if rng.random() < 0.8 else "ab"
+        x = "".join(rng.choice(al) for _ in range(n))
+        r = rng.random()
+        if r < 0.65:
+            y = list(x)
+            for _ in range(rng.randint(0, 10)):
+                k = rng.randrange(len(y))
+                op = rng.random()
+                if op < 0.35:
+                    y[k] = rng.choice(al)
+                elif op < 0.6:
+                    y.insert(k, rng.choice(al))
+                elif op < 0.85 and len(y) > 1:
+                    del y[k]
+                elif len(y) > 40:
+                    blk = y[k:k + 12]
+                    del y[k:k + 12]
+                    q = rng.randrange(len(y) + 1)
+                    y[q:q] = blk
+            y = "".join(y)
+        elif r < 0.85:
+            y = "".join(rng.choice(al) for _ in range(rng.randint(0, 340)))
+        elif r < 0.93:
+            y = x
+        else:
+            y = x[: rng.randint(0, 5)]
+        if rng.random() < 0.03:
+            x = None
+        if rng.random() < 0.03:
+            y = None
+        a.append(x)
+        b.append(y)
+    for la in (64, 65, 96, 97, 128, 129, 160, 161, 288, 289, 319, 320, 321):
+        for lb in (0, 1, 33, 65, 160, 319, 320, 321):
+            a += ["a" * la, "".join(rng.choice(alpha) for _ in range(la))]
+            b += ["b" * lb, "".join(rng.choice(alpha) for _ in range(lb))]
+    for measure in oracle.MEASURES:
+        check(native, oracle, measure, a, b)
+    assert native.last_overflow()[1] > 0
+    check_multi(native, oracle, list(range(5)), a, b)
+    for ids in ([1, 2], [3, 4], [0, 3], [0, 1]):
+        check_multi(native, oracle, ids, a, b)
+
+
 def test_long_rows_one_pair_per_warp(native, oracle):
     """Rows above 64 bytes of Jaro / Jaro-Winkler / Jaccard / Sorensen-Dice (long_pair_kernel.cuh: one pair per
     warp -- windowed matching by ballot over 32 positions of b per step, transpositions on compacted flag

@@ -297,3 +297,79 @@ def test_fused_measures_unicode_reg(algos, oracle):
     check_multi(oracle, lambda g, ints, vals: algos.algos_batch_ureg_multi(
         g, len(a), ad.ctypes.data, ao.ctypes.data, bd.ctypes.data, bo.ctypes.data, ints.ctypes.data,
         vals.ctypes.data), a, b)
+
+
+@pytest.mark.parametrize("words", [5, 10])
+def test_wide_masks_long_ascii_rows(algos, oracle, words):
+    """wide_mask.cuh: masks of `words` 32-bit words behind the same step functors -- ASCII strings of up to
+    32 * words characters, single measures and every fused group set, against the oracle (bits and integer
+    records).  Lengths around every word boundary, empty sides, long common runs, transposed blocks."""
+    from oracle.oracle import _pack, MEASURE_ID
+
+    algos.algos_batch_wide.restype = ctypes.c_int
+    algos.algos_batch_wide.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64] + [ctypes.c_void_p] * 6
+    cap = 32 * words
+    alphabet = "ab yz-'09AZ~\x01\x7f!,.#"
+    rng = random.Random(4100 + words)
+    a, b = [], []
+    for _ in range(1500):
+        n = rng.choice([rng.randint(0, cap), rng.randint(cap // 2, cap), rng.randint(60, 70)])
+        x = "".join(rng.choice(alphabet) for _ in range(n))
+        r = rng.random()
+        if r < 0.6:
+            y = list(x)
+            for _ in range(rng.randint(0, 12)):
+                op, pos = rng.randint(0, 4), rng.randint(0, len(y))
+                if op == 0 and y:
+                    y[min(pos, len(y) - 1)] = rng.choice(alphabet)
+                elif op == 1 and len(y) < cap:
+                    y.insert(pos, rng.choice(alphabet))
+                elif op == 2 and y:
+                    del y[min(pos, len(y) - 1)]
+                elif op == 3 and len(y) > 1:
+                    q = min(pos, len(y) - 2)
+                    y[q], y[q + 1] = y[q + 1], y[q]
+                elif op == 4 and len(y) > 40:  # a block moves: matches far from the diagonal
+                    q = rng.randint(0, len(y) - 20)
+                    blk = y[q:q + 15]
+                    del y[q:q + 15]
+                    p2 = rng.randint(0, len(y))
+                    y[p2:p2] = blk
+            y = "".join(y)
+        elif r < 0.8:
+            y = "".join(rng.choice(alphabet) for _ in range(rng.randint(0, cap)))
+        else:
+            y = "".join(rng.choice("ab") for _ in range(rng.randint(0, cap)))
+            x = "".join(rng.choice("ab") for _ in range(len(x)))
+        a.append(x)
+        b.append(y)
+    edges = sorted({0, 1, 2, 31, 32, 33, 63, 64, 65, 95, 96, 97, cap // 2 - 1, cap // 2, cap // 2 + 1, cap - 33, cap - 32,
+                    cap - 31, cap - 1, cap})
+    for la in edges:
+        for lb in edges:
+            a.append("a" * la)
+            b.append("b" * lb)
+            a.append("".join(rng.choice(alphabet) for _ in range(la)))
+            b.append("".join(rng.choice(alphabet) for _ in range(lb)))
+            s = "".join(rng.choice("abc") for _ in range(max(la, lb)))
+            a.append(s[:la])
+            b.append(s[max(la, lb) - lb:])
+    a += ["x" * cap, "xy" * (cap // 2), "x" * cap]
+    b += ["x" * cap, "yx" * (cap // 2), "x" * (cap - 1) + "y"]
+    ad, ao, _ = _pack(a)
+    bd, bo, _ = _pack(b)
+    n = len(a)
+    for measure in oracle.MEASURES:
+        ints = np.zeros((n, 6), dtype=np.int32)
+        vals = np.zeros(n, dtype=np.float64)
+        rc = algos.algos_batch_wide(words, MEASURE_ID[measure], 0, n, ad.ctypes.data, ao.ctypes.data, bd.ctypes.data,
+                                    bo.ctypes.data, ints.ctypes.data, vals.ctypes.data)
+        assert rc == 0
+        ref, _, ref_ints = oracle.batch(measure, a, b)
+        bad = np.nonzero(vals.view(np.uint64) != ref.view(np.uint64))[0]
+        assert bad.size == 0, (measure, a[bad[0]], b[bad[0]], vals[bad[0]], ref[bad[0]], ints[bad[0]], ref_ints[bad[0]])
+        ib = np.nonzero((ints != ref_ints).any(axis=1))[0]
+        assert ib.size == 0, (measure, a[ib[0]], b[ib[0]], ints[ib[0]], ref_ints[ib[0]])
+    check_multi(oracle, lambda g, ints, vals: algos.algos_batch_wide(
+        words, 0, g, n, ad.ctypes.data, ao.ctypes.data, bd.ctypes.data, bo.ctypes.data, ints.ctypes.data,
+        vals.ctypes.data), a, b)
