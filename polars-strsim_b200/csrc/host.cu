@@ -1411,6 +1411,7 @@ static int launch_general(ThreadCtx& ctx, const SegArgs& args, long long rows, c
     // back to back, without the host round trip that used to sit between them; the share of wide pairs
     // (the hint above) is read with the segment's overflow counters (note_wide_share).
     a.skip_latin = 1;
+    a.ctr = 1;
     a.list = args.listwide;
     a.list_count = &ctx.d_ovf->nwide;
     a.n = rows;
@@ -1693,6 +1694,7 @@ static int finish_64_planes(ThreadCtx& ctx, const SegArgs& args, const Overflow&
     a64.list_count = &ctx.d_ovf->n64;
     a64.n = ov.n64;
     a64.stage_bytes = 64 * 128 * 3;
+    a64.ctr = 2;
     return launch_short<uint64_t, MEASURE, 128, 3, true, 128, true, true>(ctx, a64, ov.n64, st);
 }
 
