@@ -1422,6 +1422,14 @@ static void note_wide_share(const Overflow& ov, long long rows) {
     if (g_wide_share && rows > 0 && ov.nwide > 0) *g_wide_share = (float)ov.nwide / (float)rows;
 }
 
+// Tile shapes (256 threads x rows per thread).  Since the tiles are handed out through a counter, smaller tiles
+// cost no balance, and their smaller stage areas let one more CTA share an SM: measured on one box, 3 / 4 / 3
+// rows per thread -> 2 / 3 / 2: C2 fused 0.535 -> 0.515 ms, single measures 0.353 -> 0.336 (Levenshtein),
+// L1 1.07 -> 0.96 ms, C3 6.30 -> 5.95 ms per 50 M rows, M1 2.96 -> 2.87 ms.
+constexpr int FUSED_RPT = 2;   // fused ASCII launches
+constexpr int SINGLE_RPT = 3;  // single-measure ASCII launches
+constexpr int LATIN_RPT = 2;   // the fused Latin-1 launch over a general column
+
 // Which instantiation of the fused kernel serves a segment (see DevStore): decided from the union of
 // the two columns' byte statistics.
 enum Alphabet { ALPHA_GENERAL = 0, ALPHA_ASCII128 = 1, ALPHA_ASCII64 = 2, ALPHA_ASCII32 = 3 };
@@ -1448,11 +1456,11 @@ template <int MEASURE>
 static int launch_fused(ThreadCtx& ctx, Alphabet al, const SegArgs& args, long long rows, cudaStream_t st) {
     switch (al) {
         case ALPHA_ASCII32:
-            return launch_short<uint32_t, MEASURE, 256, 4, false, 32, true, true>(ctx, args, rows, st);
+            return launch_short<uint32_t, MEASURE, 256, SINGLE_RPT, false, 32, true, true>(ctx, args, rows, st);
         case ALPHA_ASCII64:
-            return launch_short<uint32_t, MEASURE, 256, 4, false, 64, true, true>(ctx, args, rows, st);
+            return launch_short<uint32_t, MEASURE, 256, SINGLE_RPT, false, 64, true, true>(ctx, args, rows, st);
         case ALPHA_ASCII128:
-            return launch_short<uint32_t, MEASURE, 256, 4, false, 128, true, true>(ctx, args, rows, st);
+            return launch_short<uint32_t, MEASURE, 256, SINGLE_RPT, false, 128, true, true>(ctx, args, rows, st);
         default:
             // any script: Latin-1 pairs by the plane path, the others by the register-compare path
             // (row_unicode_reg.cuh); no table in shared memory
@@ -1468,14 +1476,14 @@ static int launch_multi(ThreadCtx& ctx, Alphabet al, const SegArgs& args, long l
     // on C2 (all five measures): 256x4 0.775 ms, 256x3 0.748 ms, 128x4 0.81 ms, 256x2 0.80 ms, 512x2 1.05 ms
     switch (al) {
         case ALPHA_ASCII32:
-            return launch_short<uint32_t, ME, 256, 3, false, 32, true, true>(ctx, args, rows, st);
+            return launch_short<uint32_t, ME, 256, FUSED_RPT, false, 32, true, true>(ctx, args, rows, st);
         case ALPHA_ASCII64:
-            return launch_short<uint32_t, ME, 256, 3, false, 64, true, true>(ctx, args, rows, st);
+            return launch_short<uint32_t, ME, 256, FUSED_RPT, false, 64, true, true>(ctx, args, rows, st);
         case ALPHA_ASCII128:
-            return launch_short<uint32_t, ME, 256, 3, false, 128, true, true>(ctx, args, rows, st);
+            return launch_short<uint32_t, ME, 256, FUSED_RPT, false, 128, true, true>(ctx, args, rows, st);
         default:
             // register-compare path: 256 x 2 measured best on C3 (4.82 ms vs 5.11 ms per 10M rows x 5 measures)
-            return launch_general<ME, 3, 2>(ctx, args, rows, st);
+            return launch_general<ME, LATIN_RPT, 2>(ctx, args, rows, st);
     }
 }
 
@@ -2016,7 +2024,7 @@ static int compute_on_device(ThreadCtx& ctx, const int* measures, size_t n_measu
         if (!no_proof && al != ALPHA_GENERAL && !force_generic_rows() && a->max_len <= 32u && b->max_len <= 32u &&
             a->max_block_pad != 0xFFFFFFFFu && b->max_block_pad != 0xFFFFFFFFu && s.a.res_buf == 0xFFFFFFFFu &&
             s.b.res_buf == 0xFFFFFFFFu && s.a.lo_off == 0u && s.b.lo_off == 0u) {
-            const long long tile_blocks = n_measures > 1 ? 3 : 4;  // launch_multi: 256 x 3 rows, launch_fused: 256 x 4
+            const long long tile_blocks = n_measures > 1 ? FUSED_RPT : SINGLE_RPT;
             const long long blocks_a = tile_blocks + ((bc_a || oa % STATS_BLOCK == 0) ? 0 : 1);
             const long long blocks_b = tile_blocks + ((bc_b || ob % STATS_BLOCK == 0) ? 0 : 1);
             long long need = blocks_a * (long long)a->max_block_pad;

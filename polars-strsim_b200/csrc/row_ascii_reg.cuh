@@ -6,7 +6,7 @@
 // and that its load/store traffic kept the LSU half busy.  For strings of at most 32 characters:
 //   * instead of table[c], the position mask of a character is computed from BIT PLANES of the
 //     tabled string: plane k holds bit k of every character (bit i of B[k] = bit k of char i), and
-//         Eq(c) = valid & ~( OR_k ( B[k] ^ S_k(c) ) ),   S_k(c) = all-ones if bit k of c is set.
+//         Eq(c) = ~( OR_k ( B[k] ^ S_k(c) ) ),   S_k(c) = all-ones if bit k of c is set.
 //     The S_k come from two multiplies that park bit k in the sign bit of some byte, and one
 //     byte-permute with sign replication each (PRMT); with the column statistics proving a 32- or
 //     64-code-point alphabet block only 5 or 6 planes are needed, 7 for any ASCII, 8 for Latin-1;
@@ -34,6 +34,15 @@ SS_HD uint32_t sign_fill_byte(uint32_t x, int byte) {  // all-ones if bit 7 of b
 #endif
 }
 
+// byte 1 or 2 of a word, zero-extended: one PRMT on the device where a shift and a mask are two operations
+SS_HD uint32_t byte_of(uint32_t word, int byte) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(word, 0u, 0x4440u + (uint32_t)byte);
+#else
+    return (word >> (8 * byte)) & 0xFFu;
+#endif
+}
+
 // a 32-bit pattern over every 32-bit word of M
 template <class M>
 struct Rep32 {
@@ -53,7 +62,11 @@ template <int NBITS, class M = uint32_t>
 struct PlaneTab {
     typedef M mask_type;
     M B[NBITS];
-    M valid;  // bits < m
+    // The mask is exact on the positions of the tabled string and ARBITRARY above them (the planes hold
+    // whatever followed the string in its last word).  No consumer looks there: Myers' carries and shifts only
+    // move upwards and its distance is read below m, Jaro's candidates are cut by `avail` and the multiset's
+    // by `used`, both of which start from the length of b.  (A `valid` mask here was one more operation per
+    // character of a, on the pipe that bounds the kernel.)
     SS_HD M operator()(uint32_t c) const {
         // u: bits 6,5,4,3 of c in the sign bits of bytes 0..3; v: bits 2,1,0 in bytes 0..2
         const uint32_t u = c * 0x10080402u, v = c * 0x00804020u;
@@ -65,9 +78,8 @@ struct PlaneTab {
         if (NBITS > 5) X |= B[5] ^ rep32<M>(sign_fill_byte(u, 1));
         if (NBITS > 6) X |= B[6] ^ rep32<M>(sign_fill_byte(u, 0));
         if (NBITS > 7) X |= B[7] ^ rep32<M>(sign_fill_byte(c, 0));  // one byte per character up to U+00FF (Latin-1 rows)
-        return ~X & valid;
+        return ~X;
     }
-    SS_HD void set_valid(int m) { valid = LowMask<M>::get(m); }
 };
 
 // adds the four characters of word w (characters 4w..4w+3) to the planes
@@ -201,7 +213,6 @@ struct SlabSrc {
             if (4 * i >= len) break;
             planes_add_word<NBITS, M>(tab, w[i * STRIDE], i);
         }
-        tab.set_valid(len);
     }
     template <class F>
     SS_HD void each(int n, F& f) const {
@@ -212,8 +223,8 @@ struct SlabSrc {
         for (; n >= 4; n -= 4, p += STRIDE) {
             const uint32_t word = p[0];
             f(word & 0xFFu);
-            f((word >> 8) & 0xFFu);
-            f((word >> 16) & 0xFFu);
+            f(byte_of(word, 1));
+            f(byte_of(word, 2));
             f(word >> 24);
         }
         if (n > 0) {

@@ -332,8 +332,8 @@ struct EachByteStaged {
             const uint32_t word = __funnelshift_r(lo, hi, sh);
             lo = hi;
             f(word & 0xFFu);
-            f((word >> 8) & 0xFFu);
-            f((word >> 16) & 0xFFu);
+            f(byte_of(word, 1));
+            f(byte_of(word, 2));
             f(word >> 24);
         }
         if (n > 0) {
@@ -348,7 +348,7 @@ struct EachByteStaged {
 };
 
 // bit planes of a staged string of m <= 32 characters, word by word from shared memory.  The bytes after
-// the string need no masking: PlaneTab::valid keeps them out of every position mask.
+// the string need no masking: no consumer of a position mask looks above the string (PlaneTab).
 template <int NBITS, class M>
 __device__ __forceinline__ void build_planes_staged(const unsigned char* smem, const StagedStr& S,
                                                     PlaneTab<NBITS, M>& tab) {
@@ -366,7 +366,6 @@ __device__ __forceinline__ void build_planes_staged(const unsigned char* smem, c
         lo = hi;
         planes_add_word<NBITS, M>(tab, word, w);
     }
-    tab.set_valid(m);
 }
 
 // first word (zero-masked to the string's length) of a staged string
@@ -619,6 +618,9 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
     // start of the current one (the round trip to L2 hides behind the loads of the views) and the answer crosses
     // the CTA through shared memory behind the barrier that opens the stage phase.
     uint32_t* next_slot = reinterpret_cast<uint32_t*>(smem + L::off_mbar + 8);
+    // both columns complete on the device (no upload in flight, no row shard): no view needs the residency test
+    const bool all_resident = s.a.res_buf == 0xFFFFFFFFu && s.b.res_buf == 0xFFFFFFFFu &&
+                              (s.a.lo_buf | s.a.lo_off | s.b.lo_buf | s.b.lo_off) == 0u;
     long long tile_after = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile = tile_after) {
         const long long tile0 = tile * TILE;
@@ -646,7 +648,8 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
                 const bool second = UREG && !ULAT && s.skip_latin;  // the first launch settled these rows
                 if (!valid) {
                     if (!second) store_settled<MEASURE>(s, row, 0.0, 0);
-                } else if ((va.x > 12u && !payload_resident(va, s.a)) || (vb.x > 12u && !payload_resident(vb, s.b))) {
+                } else if (!all_resident &&
+                           ((va.x > 12u && !payload_resident(va, s.a)) || (vb.x > 12u && !payload_resident(vb, s.b)))) {
                     if (!second) atomicAdd(&s.ovf->ndefer, 1u);  // nothing is written for this row in this pass
                 } else if (mx > (uint32_t)CAP) {
                     if (second) {
@@ -708,17 +711,16 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
         int mode[2];          // 0 nothing out of line, 1 TMA bulk span, 2 cooperative gather copy
         uint32_t base16[2];   // TMA mode: 16-aligned start offset of the span in the data buffer
         uint32_t span[2], bufidx[2];
+        // every warp folds the NWARP partials again, lane l taking warp l % NWARP's (one load and one REDUX per
+        // field; each thread looping over all of them was 160 instructions per thread and tile)
+        const uint32_t* my_red = red + (lane & (NWARP - 1)) * 16;
 #pragma unroll
         for (int c = 0; c < 2; c++) {
-            uint32_t a0 = 0xFFFFFFFFu, a1 = 0, a2 = 0xFFFFFFFFu, a3 = 0, a4 = 0;
-#pragma unroll
-            for (int w = 0; w < NWARP; w++) {
-                a0 = min(a0, red[w * 16 + c * 5 + 0]);
-                a1 = max(a1, red[w * 16 + c * 5 + 1]);
-                a2 = min(a2, red[w * 16 + c * 5 + 2]);
-                a3 = max(a3, red[w * 16 + c * 5 + 3]);
-                a4 += red[w * 16 + c * 5 + 4];
-            }
+            const uint32_t a0 = __reduce_min_sync(0xFFFFFFFFu, my_red[c * 5 + 0]);
+            const uint32_t a1 = __reduce_max_sync(0xFFFFFFFFu, my_red[c * 5 + 1]);
+            const uint32_t a2 = __reduce_min_sync(0xFFFFFFFFu, my_red[c * 5 + 2]);
+            const uint32_t a3 = __reduce_max_sync(0xFFFFFFFFu, my_red[c * 5 + 3]);
+            const uint32_t a4 = __reduce_max_sync(0xFFFFFFFFu, my_red[c * 5 + 4]);  // only "any at all" matters
             base16[c] = a0 & ~15u;
             span[c] = ((a1 + 15u) & ~15u) - base16[c];
             bufidx[c] = a2;
