@@ -1429,6 +1429,8 @@ static void note_wide_share(const Overflow& ov, long long rows) {
 constexpr int FUSED_RPT = 2;   // fused ASCII launches
 constexpr int SINGLE_RPT = 3;  // single-measure ASCII launches
 constexpr int LATIN_RPT = 2;   // the fused Latin-1 launch over a general column
+constexpr int M64_TPB = 128, M64_RPT = 2;  // the 64-bit plane launch over list64 (M1: 128 x 3 -> 128 x 2: 2.87 -> 2.54 ms;
+                                           // 128 x 1: 2.67, 256 x 1: 2.57, 256 x 2: 2.74, 64 x 2: 2.72, 128 x 4: 3.41)
 
 // Which instantiation of the fused kernel serves a segment (see DevStore): decided from the union of
 // the two columns' byte statistics.
@@ -1692,7 +1694,7 @@ static int read_overflow(ThreadCtx& ctx, Overflow* ov, cudaStream_t st, bool fir
 }
 
 // rows of 33..64 bytes of ASCII-only columns: the plane path with 64-bit masks (two registers per plane),
-// gather mode over list64; tiles of 128 x 3 rows with a worst-case stage area (every listed string is
+// gather mode over list64; tiles of 128 x 2 rows with a worst-case stage area (every listed string is
 // out of line).  MEASURE may be a fused set (MULTI_BASE + groups).  Medium ASCII strings (M1 workload,
 // 20-60 characters, 73 % of the rows on this list): 22.8 -> see profiles/r1_bench_M1.json ms per 10 M rows.
 template <int MEASURE>
@@ -1701,9 +1703,9 @@ static int finish_64_planes(ThreadCtx& ctx, const SegArgs& args, const Overflow&
     a64.list = args.list64;
     a64.list_count = &ctx.d_ovf->n64;
     a64.n = ov.n64;
-    a64.stage_bytes = 64 * 128 * 3;
+    a64.stage_bytes = 64 * M64_TPB * M64_RPT;
     a64.ctr = 2;
-    return launch_short<uint64_t, MEASURE, 128, 3, true, 128, true, true>(ctx, a64, ov.n64, st);
+    return launch_short<uint64_t, MEASURE, M64_TPB, M64_RPT, true, 128, true, true>(ctx, a64, ov.n64, st);
 }
 
 // Rows of 65..320 bytes of ASCII-only columns: the plane path again, with masks of ten 32-bit words

@@ -14,8 +14,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 90 --csv --log-file
 # C2: the timed fused launch and the per-measure pass behind it
 ncu --set full --clock-control none --import-source on -k regex:short_kernel -s 3 -c 6 -f -o $T/c2 python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > $O/${R}_ncu_full_C2.log 2>&1
 python tools/summarize_ncu.py $T/c2.ncu-rep C2 $O/${R}_ncu_short_kernel_C2.md profiles/traffic.json
-python tools/ncu_regions.py $T/c2.ncu-rep "(int)15, (int)256" short_kernelIjLi15ELi256ELi3ELb0ELi32ELb1ELb1ELb0ELb0E polars-strsim_b200/csrc/host.o > $O/${R}_ncu_regions_C2_fused.txt 2>&1
-python tools/ncu_lines.py $T/c2.ncu-rep 0 short_kernelIjLi15ELi256ELi3ELb0ELi32ELb1ELb1ELb0ELb0E polars-strsim_b200/csrc/host.o "(int)15, (int)256" > $O/${R}_ncu_lines_C2_fused.txt 2>&1
+python tools/ncu_regions.py $T/c2.ncu-rep "(int)15, (int)256" short_kernelIjLi15ELi256ELi2ELb0ELi32ELb1ELb1ELb0ELb0E polars-strsim_b200/csrc/host.o > $O/${R}_ncu_regions_C2_fused.txt 2>&1
+python tools/ncu_lines.py $T/c2.ncu-rep 0 short_kernelIjLi15ELi256ELi2ELb0ELi32ELb1ELb1ELb0ELb0E polars-strsim_b200/csrc/host.o "(int)15, (int)256" > $O/${R}_ncu_lines_C2_fused.txt 2>&1
 ncu -i $T/c2.ncu-rep --page raw --csv > $O/${R}_ncu_raw_C2.csv 2>/dev/null
 python tools/ncu_raw_summary.py $O/${R}_ncu_raw_C2.csv > $O/${R}_ncu_stalls_C2.txt 2>&1
 # C3: the Latin-1 launch and the register-compare (gather) launch of the first segment
@@ -23,7 +23,7 @@ ncu --set full --clock-control none --import-source on -k regex:short_kernel -c 
 python tools/summarize_ncu.py $T/c3.ncu-rep C3 $O/${R}_ncu_short_kernel_C3.md
 ncu -i $T/c3.ncu-rep --page raw --csv > $O/${R}_ncu_raw_C3.csv 2>/dev/null
 python tools/ncu_raw_summary.py $O/${R}_ncu_raw_C3.csv > $O/${R}_ncu_stalls_C3.txt 2>&1
-python tools/ncu_regions.py $T/c3.ncu-rep "(bool)1, (bool)1>" short_kernelIjLi15ELi256ELi3ELb0ELi128ELb0ELb0ELb1ELb1E polars-strsim_b200/csrc/host.o > $O/${R}_ncu_regions_C3_latin1_launch.txt 2>&1
+python tools/ncu_regions.py $T/c3.ncu-rep "(bool)1, (bool)1>" short_kernelIjLi15ELi256ELi2ELb0ELi128ELb0ELb0ELb1ELb1E polars-strsim_b200/csrc/host.o > $O/${R}_ncu_regions_C3_latin1_launch.txt 2>&1
 # C4: long_lev_kernel on 40,000 pairs (cells from the bench line of the same rows)
 python bench.py --workload C4 --rows 40000 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > $O/${R}_bench_C4_40k.json 2> $O/${R}_c4.err
 CELLS=$(python -c "import json; print(json.load(open('$O/${R}_bench_C4_40k.json'))['long_levenshtein']['cells_per_launch'])")

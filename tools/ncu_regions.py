@@ -3,7 +3,7 @@
 
     python tools/ncu_regions.py REPORT.ncu-rep DEMANGLED_SUBSTRING MANGLED_SUBSTRING [host.o]
 
-e.g. "(int)15, (int)256" "short_kernelIjLi15ELi256ELi3ELb0ELi32ELb1ELb1ELb0ELb0E" for the fused ASCII launch.
+e.g. "(int)15, (int)256" "short_kernelIjLi15ELi256ELi2ELb0ELi32ELb1ELb1ELb0ELb0E" for the fused ASCII launch.
 
 Joins `ncu --page source --csv` (SASS rows: executed warp / thread instructions, stall samples) with
 the inline chains of `nvdisasm -gi` (built with -lineinfo) by instruction offset.  Every instruction is

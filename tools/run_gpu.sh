@@ -7,11 +7,7 @@ for l in sys.stdin:
     except Exception: continue
     print('$1', round(d['ms_per_step'],4), [round(v['ms'],3) for v in d.get('per_measure',{}).values()], d.get('gpu_launches'), d['checksum'], (d.get('long_levenshtein') or {}).get('gcups',''))
 "; }
-timeout 300 python -m pytest tests -m gpu -x -q -k "golden or random_short or fused or readme or mixed or wide or latin or gather or scatter" 2>&1 | tail -2
-for v in head H I J main; do
+for v in m128_2 m128_1 m64_2 m64_3; do
  if [ $v = main ]; then unset STRSIM_B200_LIB; else export STRSIM_B200_LIB=$PWD/exp/variants/lib$v.so; fi
- timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-e2e 2>$O/err_C2.log | show C2-$v
- timeout 300 python bench.py --workload L1 --steps 10 --warmup 3 --no-cpu-baseline --no-e2e 2>$O/err_L1.log | show L1-$v
- timeout 300 python bench.py --workload C3 --rows 50000000 --steps 5 --warmup 3 --no-cpu-baseline --no-e2e 2>$O/err_C3.log | show C3-$v
  timeout 300 python bench.py --workload M1 --steps 10 --warmup 3 --no-cpu-baseline --no-e2e 2>$O/err_M1.log | show M1-$v
 done
