@@ -1,13 +1,8 @@
 cd $GRAFT_REPO_ROOT
-O=gpurun_out; mkdir -p $O
-show() { python -c "
-import sys, json
-for l in sys.stdin:
-    try: d=json.loads(l)
-    except Exception: continue
-    print('$1', round(d['ms_per_step'],4), [round(v['ms'],3) for v in d.get('per_measure',{}).values()], d.get('gpu_launches'), d['checksum'], (d.get('long_levenshtein') or {}).get('gcups',''))
-"; }
-for v in m128_2 m128_1 m64_2 m64_3; do
- if [ $v = main ]; then unset STRSIM_B200_LIB; else export STRSIM_B200_LIB=$PWD/exp/variants/lib$v.so; fi
- timeout 300 python bench.py --workload M1 --steps 10 --warmup 3 --no-cpu-baseline --no-e2e 2>$O/err_M1.log | show M1-$v
+R=r2
+K="random_short_mixed or length_boundaries or wide_rows or fused_measures_subsets or scattered_views"
+for tool in racecheck memcheck; do
+  timeout 500 compute-sanitizer --tool $tool --log-file gpurun_out/${R}_sanitizer_$tool.log \
+      python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "$K" > gpurun_out/${R}_sanitizer_${tool}_pytest.log 2>&1
+  echo "$tool: exit $?"; tail -3 gpurun_out/${R}_sanitizer_${tool}_pytest.log; tail -4 gpurun_out/${R}_sanitizer_$tool.log
 done
