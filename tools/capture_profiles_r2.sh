@@ -32,6 +32,12 @@ python tools/summarize_ncu.py $T/c4.ncu-rep C4 $O/${R}_ncu_long_lev_C4.md profil
 ncu -i $T/c4.ncu-rep --page raw --csv > $O/${R}_ncu_raw_C4.csv 2>/dev/null
 python tools/ncu_raw_summary.py $O/${R}_ncu_raw_C4.csv > $O/${R}_ncu_stalls_C4.txt 2>&1
 python tools/ncu_lines.py $T/c4.ncu-rep 0 long_lev_kernel polars-strsim_b200/csrc/host.o > $O/${R}_ncu_lines_C4_long_lev.txt 2>&1
+# T1: the ten-word plane launch over the 65-320-byte rows of an ASCII column (4 M rows, a tenth of them long)
+ncu --set full --clock-control none --import-source on -k regex:short_kernel -s 2 -c 1 -f -o $T/t1 python tools/prof_one.py T1 fused 4000000 1 > $O/${R}_ncu_full_T1.log 2>&1
+python tools/summarize_ncu.py $T/t1.ncu-rep T1 $O/${R}_ncu_wide_rows_T1.md
+ncu -i $T/t1.ncu-rep --page raw --csv > $O/${R}_ncu_raw_T1.csv 2>/dev/null
+python tools/ncu_raw_summary.py $O/${R}_ncu_raw_T1.csv > $O/${R}_ncu_stalls_T1.txt 2>&1
+rm -f $O/${R}_ncu_raw_T1.csv
 cp profiles/traffic.json $O/traffic.json
 rm -f $O/${R}_ncu_raw_C2.csv $O/${R}_ncu_raw_C3.csv $O/${R}_ncu_raw_C4.csv
 ls -la $O | tail -30; cat $O/traffic.json
