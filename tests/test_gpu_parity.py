@@ -374,6 +374,43 @@ def test_device_resident_api(native, oracle):
         assert (got[ref_valid].view(np.uint64) == ref[ref_valid].view(np.uint64)).all()
 
 
+@pytest.mark.parametrize("n", [1, 511, 512, 513, 1536, 148 * 5 * 512 + 7])
+def test_tiles_from_the_counter_cover_every_row_once(native, oracle, n):
+    """short_kernel hands its tiles out through a counter that the last CTA of a launch resets: row counts
+    around one tile (512 rows fused, 768 single measure), fewer tiles than CTAs, one tile more than the CTAs of
+    a full grid; several launches back to back over the same overflow record -- single measures, the fused
+    launch, and (medium rows mixed in) the 64-bit gather launch behind each of them -- must keep giving the
+    oracle's rows, all of them, none twice (an output slot left from the run before would show)."""
+    torch = pytest.importorskip("torch")
+    rng = random.Random(1000 + n)
+    base = [rand_pair(rng, 24) for _ in range(min(n, 4000))]
+    medium = ("".join(rng.choice("abcdefgh") for _ in range(45)), "".join(rng.choice("abcdefgh") for _ in range(50)))
+    a = [(medium[0] if i % 97 == 5 else base[i % len(base)][0]) for i in range(n)]
+    b = [(medium[1] if i % 97 == 5 else base[i % len(base)][1]) for i in range(n)]
+    ca, cb = native.DeviceColumn(sv(a)), native.DeviceColumn(sv(b))
+    st = torch.cuda.current_stream().cuda_stream
+    val = torch.zeros((n + 31) // 32, dtype=torch.int32, device="cuda")
+    refs = {m: oracle.batch(m, a[: len(base) * 2 + 100], b[: len(base) * 2 + 100])[0] for m in oracle.MEASURES}
+    for rep in range(3):
+        outs = [torch.full((n,), -1.0, dtype=torch.float64, device="cuda") for _ in oracle.MEASURES]
+        native.compute_device_multi(list(oracle.MEASURES), ca, cb, [o.data_ptr() for o in outs], val.data_ptr(), None, st)
+        single = torch.full((n,), -1.0, dtype=torch.float64, device="cuda")
+        native.compute_device("jaro_winkler", ca, cb, single.data_ptr(), val.data_ptr(), 0, st)
+        torch.cuda.synchronize()
+        for m, o in zip(oracle.MEASURES, outs):
+            got = o.cpu().numpy()
+            k = len(refs[m])
+            assert (got[:k].view(np.uint64) == refs[m].view(np.uint64)).all(), (m, rep)
+            # the rows repeat with period len(base) except where the medium pair sits: same row, same bits
+            if n > len(base):
+                idx = np.arange(len(base), n)
+                plain = (idx % 97 != 5) & ((idx % len(base)) % 97 != 5)
+                assert (got[idx[plain]].view(np.uint64) == got[idx[plain] % len(base)].view(np.uint64)).all(), (m, rep)
+            assert (got >= 0.0).all(), (m, rep, "a row was not written")
+            if m == "jaro_winkler":
+                assert (single.cpu().numpy().view(np.uint64) == got.view(np.uint64)).all(), rep
+
+
 def test_multi_measure_single_upload(native, oracle):
     rng = random.Random(23)
     pairs = [rand_pair(rng, 40) for _ in range(20000)]
