@@ -1,23 +1,34 @@
-// short_kernel.cuh -- the fused short-string kernel (one pair per thread, strings <= bits(M) bytes).
+// short_kernel.cuh -- the short-string kernel: one pair per thread, strings of at most bits(M) bytes
+// (M = u32, u64, or Wide<10> = 320 bits), one measure or a fused set of measures per launch.
 //
-// One persistent CTA walks tiles of TILE = TPB*RPT consecutive rows:
-//   1. load   : coalesced 16-byte loads of both columns' Arrow views (+ validity bits) -> smem
+// Persistent CTAs walk tiles of TILE = TPB*RPT consecutive rows (gather launches: consecutive entries of a
+// row list).  Tiles are handed out through a counter (Overflow::tile_ctr), not by a fixed stride: a CTA starts
+// on tile blockIdx.x and asks for its next tile while it works on the current one.  Per tile:
+//   1. load   : coalesced 16-byte loads of both columns' Arrow views (+ validity bits) -> shared memory;
+//               null rows are settled, rows that cannot be served here go to the overflow lists
 //   2. stage  : the tile's out-of-line payload (byte length > 12) is one contiguous span of the data
 //               buffer when the column was built sequentially, so ONE TMA bulk copy
 //               (cp.async.bulk.shared.global, SASS UBLKCP) per column brings it into shared memory,
-//               completion on an mbarrier; columns whose views are scattered (gather/filter
-//               results) fall back to a cooperative word copy into the same stage area
-//   3. bucket : every row gets a cost key (Unicode?, max byte length); a shared-memory counting
-//               sort yields a permutation so that the 32 lanes of a warp work on pairs of (nearly)
-//               equal length and the same code path -- the length-bucketing pre-pass, done per tile
-//               on chip, no extra HBM traffic and no global reordering
-//   4. compute: each thread copies its pair into a private, bank-conflict-free slab
-//               ([slot][thread] layout), then runs row_short<M>() (Myers / bitmask Jaro / multiset)
-//               with its private 128-entry position-mask table, and writes the f64 result
-// Rows that do not fit (longer than bits(M) bytes, or the stage area is full) are appended to an
-// overflow list and finished by the 64-bit instantiation of this kernel (gather mode) or by
-// long_kernel.cuh.  Null rows (either input null, README.md:69-70) get 0.0 and are never
-// dereferenced beyond their view.
+//               completion on an mbarrier; columns whose views are scattered (gather/filter results,
+//               dictionary columns) fall back to a cooperative word copy into the same stage area
+//   3. bucket : byte-equal pairs are found by all lanes in lock step; every other row gets a cost key (the
+//               length of the streamed string / its character count); a shared-memory counting sort yields
+//               a permutation so that the 32 lanes of a warp work on pairs of (nearly) equal cost -- the
+//               length-bucketing pre-pass, done per tile on chip, no extra HBM traffic, output order untouched
+//   4. compute: each thread takes one sorted pair and runs one of the register paths on it --
+//               REG  (ASCII-only columns): bit planes of the tabled string, the streamed one read byte by byte,
+//                    both straight from the staged tile (row_ascii_reg.cuh);
+//               ULAT (general columns, first launch): the pairs without a character above U+00FF, transcoded to
+//                    one byte per character into the thread's slab, then the plane path with 8 planes; the
+//                    other pairs are listed for
+//               UREG (general columns, second launch, gather mode): the tabled string decoded into registers,
+//                    position masks by compares (row_unicode_reg.cuh)
+//               -- and writes the f64 result(s).
+// Rows that do not fit (longer than bits(M) bytes, or the stage area is full) are appended to an overflow list
+// and finished by the wider instantiations of this kernel in gather mode (64-bit and ten-word masks, ASCII
+// columns), by direct_kernel.cuh (33..64-byte rows of general columns) or by the warp-per-pair kernels
+// (long_lev_kernel.cuh, long_pair_kernel.cuh).  Null rows (either input null, README.md:69-70) get 0.0 and
+// are never dereferenced beyond their view.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -183,8 +194,7 @@ struct ShortLayout {
     static constexpr size_t off_svb = off_sva + sizeof(uint4) * TILE;
     // 16 spare bytes behind the views: reading an inline string by whole words looks one word past the
     // last view, which must not be a word another thread writes (its slab) -- racecheck flagged exactly that
-    static constexpr size_t off_tab = off_svb + sizeof(uint4) * TILE + 16;
-    static constexpr size_t off_slab_a = off_tab + ((REG || UREG) ? 0 : sizeof(M) * T * TPB);
+    static constexpr size_t off_slab_a = off_svb + sizeof(uint4) * TILE + 16;
     static constexpr size_t off_slab_b = off_slab_a + (REG ? 0 : 4 * WORDS * TPB);
     static constexpr size_t off_hist = off_slab_b + (REG ? 0 : 4 * WORDS * TPB);
     static constexpr size_t off_red = off_hist + 4 * ((NB + 3) & ~3);
@@ -401,12 +411,6 @@ struct StagedSrc {
     }
 };
 
-// Settling byte-equal pairs before the sort frees their lanes but costs every row a prefix compare;
-// measured on C2 (20 % equal pairs) it LOSES 5-8 % (table path: latency-bound rounds; register path:
-// the extra prefix reads and compares cost more ALU work than the freed lanes give back).  Kept for
-// data sets dominated by equal pairs.
-constexpr bool PREFILTER_EQUAL = false;
-
 // ULAT launch: appends the rows a thread flagged (bit k of `flags` = its k-th row of the tile) to the list the
 // register-compare launch gathers, with one atomic per warp.  EVERY lane of the warp calls it from converged
 // code (the ballots name the full mask).  It replaces the opportunistic form -- __activemask() inside the
@@ -427,38 +431,6 @@ __device__ __forceinline__ void list_wide_rows(const SegArgs& s, uint32_t flags,
         if ((flags >> k) & 1u) s.listwide[base + (unsigned)__popc(b & ((1u << lane) - 1u))] = row_of(k);
         base += (unsigned)__popc(b);
     }
-}
-
-// first four bytes of an out-of-line string (its view's prefix word was replaced by the stage offset)
-__device__ __forceinline__ uint32_t sva_prefix(const uint4& v, const unsigned char* stage) {
-    const uint32_t* p = reinterpret_cast<const uint32_t*>(stage) + (v.y >> 2);
-    return __funnelshift_r(p[0], p[1], (int)(v.y & 3) * 8);
-}
-
-// Exact byte equality of two strings of the same length `len` described by their staged views.
-__device__ __forceinline__ bool staged_equal(const uint4& va, const uint4& vb, const unsigned char* stage_a,
-                                             const unsigned char* stage_b) {
-    const int len = (int)va.x;
-    if (len <= 12) {
-        const uint32_t m0 = byte_mask(len), m1 = byte_mask(len - 4 < 0 ? 0 : len - 4),
-                       m2 = byte_mask(len - 8 < 0 ? 0 : len - 8);
-        return (((va.y ^ vb.y) & m0) | ((va.z ^ vb.z) & m1) | ((va.w ^ vb.w) & m2)) == 0u;
-    }
-    const uint32_t* pa = reinterpret_cast<const uint32_t*>(stage_a) + (va.y >> 2);
-    const uint32_t* pb = reinterpret_cast<const uint32_t*>(stage_b) + (vb.y >> 2);
-    const int sa = (int)(va.y & 3) * 8, sb = (int)(vb.y & 3) * 8;
-    uint32_t la = pa[0], lb = pb[0];
-    const int full = len >> 2;
-    int w = 0;
-    for (; w < full; w++) {
-        const uint32_t ha = pa[w + 1], hb = pb[w + 1];
-        if (__funnelshift_r(la, ha, sa) != __funnelshift_r(lb, hb, sb)) return false;
-        la = ha;
-        lb = hb;
-    }
-    if (len & 3)
-        return ((__funnelshift_r(la, pa[w + 1], sa) ^ __funnelshift_r(lb, pb[w + 1], sb)) & byte_mask(len & 3)) == 0u;
-    return true;
 }
 
 __device__ __forceinline__ void store_dbg(int* d, const PairInts& o) {
@@ -557,8 +529,7 @@ template <class M, int MEASURE, int TPB, int RPT, bool GATHER, int T, bool ASCII
           bool UREG = false, bool ULAT = false>
 __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
     static_assert(!ULAT || UREG, "the Latin-1 instantiation uses the general kernel's slabs");
-    static_assert(ASCII_ONLY || UREG || T >= DevStore<M, TPB, T>::HASH_ENTRIES,
-                  "the Unicode path keeps its hash slots in the table memory");
+    static_assert(REG || UREG, "register paths only (the table / hash path lives in direct_kernel.cuh)");
     static_assert(!UREG || (!ASCII_ONLY && !REG && sizeof(M) == 4), "register-compare path: general u32 kernel");
     static_assert(!REG || (ASCII_ONLY && (T == 32 || T == 64 || T == 128)),
                   "the plane path serves ASCII-only columns (strings of at most 32 bytes for M = u32, 64 for u64)");
@@ -575,7 +546,6 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
     extern __shared__ __align__(16) unsigned char smem[];
     uint4* sva = reinterpret_cast<uint4*>(smem + L::off_sva);
     uint4* svb = reinterpret_cast<uint4*>(smem + L::off_svb);
-    M* tab = reinterpret_cast<M*>(smem + L::off_tab);
     uint32_t* slab_a = reinterpret_cast<uint32_t*>(smem + L::off_slab_a);
     uint32_t* slab_b = reinterpret_cast<uint32_t*>(smem + L::off_slab_b);
     uint32_t* hist = reinterpret_cast<uint32_t*>(smem + L::off_hist);
@@ -591,18 +561,10 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
     const long long n = GATHER ? (long long)*s.list_count : s.n;
     const long long n_tiles = (n + TILE - 1) / TILE;
 
-    // one-time: zero the position-mask tables (row_short keeps them zero), init the mbarrier
-    {
-        if (!REG && !UREG) {
-            uint4* t4 = reinterpret_cast<uint4*>(tab);
-            constexpr int N4 = (int)(sizeof(M) * T * TPB / 16);
-            for (int i = tid; i < N4; i += TPB) t4[i] = make_uint4(0, 0, 0, 0);
-        }
-        if (tid == 0) mbar_init(mbar, 1);
-    }
+    if (tid == 0) mbar_init(mbar, 1);
     uint32_t mbar_phase = 0;
     DevStore<M, TPB, T> store;
-    store.tab_ = tab + tid;
+    store.tab_ = nullptr;  // (the register paths keep no table; the slabs serve ULAT / UREG)
     store.wa_ = slab_a + tid;
     store.wb_ = slab_b + tid;
     __syncthreads();
@@ -860,42 +822,11 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
             rank[k] = 0;
             if (!((active >> k) & 1u)) continue;
             const uint4 va = sva[i], vb = svb[i];
-            // byte-equal pairs score 1.0 (strsim.rs:128,182,288,324): settle them here so that they do
-            // not occupy lanes of the compute phase (the 4-byte prefix in the view rejects most rows)
-            // (always in the fused kernel: its per-pair loops are three measures long, so the lanes that a
-            // fifth of equal pairs would idle are worth far more than the prefix compare)
+            // byte-equal pairs score 1.0 (strsim.rs:128,182,288,324).  The plane launches and every fused launch
+            // found them above (all lanes in lock step) and give them the cheapest key; the single-measure
+            // register-compare launch finds them in step 4
             bool settle_equal = false;
-            if constexpr (REG || ULAT || is_multi(MEASURE)) {
-                settle_equal = row_equal[k];
-            } else if (PREFILTER_EQUAL) {
-                settle_equal = va.x == vb.x &&
-                               (va.x == 0u || ((va.x <= 12u ? va.y : sva_prefix(va, stage_a)) ==
-                                               (vb.x <= 12u ? vb.y : sva_prefix(vb, stage_b)))) &&
-                               staged_equal(va, vb, stage_a, stage_b);
-            }
-            if (settle_equal && !is_multi(MEASURE) && !REG && !ULAT) {
-                const long long idx = tile0 + i;
-                const long long row = GATHER ? (long long)s.list[idx] : idx;
-                store_settled<MEASURE>(s, row, 1.0, F_EQUAL);
-                continue;
-            }
-            uint32_t hi_bits = 0;  // conservative (unmasked) non-ASCII test; exact test in step 4
-            if (!ASCII_ONLY && !UREG) {
-                if (va.x <= 12u) {
-                    hi_bits |= va.y | va.z | va.w;
-                } else {
-                    const uint32_t* p = reinterpret_cast<const uint32_t*>(stage_a) + (va.y >> 2);
-                    const int nwords = (int)(((va.y & 3u) + va.x + 3u) >> 2);
-                    for (int w = 0; w < nwords; w++) hi_bits |= p[w];
-                }
-                if (vb.x <= 12u) {
-                    hi_bits |= vb.y | vb.z | vb.w;
-                } else {
-                    const uint32_t* p = reinterpret_cast<const uint32_t*>(stage_b) + (vb.y >> 2);
-                    const int nwords = (int)(((vb.y & 3u) + vb.x + 3u) >> 2);
-                    for (int w = 0; w < nwords; w++) hi_bits |= p[w];
-                }
-            }
+            if constexpr (REG || ULAT || is_multi(MEASURE)) settle_equal = row_equal[k];
             uint32_t mx = va.x > vb.x ? va.x : vb.x;
             // fused evaluation streams a against the tabled b for every group, and so do the single Jaro and
             // multiset kernels: the loops run la times (Levenshtein streams the longer string)
@@ -932,9 +863,7 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
             // first test, and the stores stay dense
             // (the register kernels read "key 1" as "byte-equal" in step 4: there a pair with an empty a and a
             // non-empty b must not share that key, so their other keys start at 2)
-            key[k] = settle_equal ? 1u
-                                  : (REG || ULAT ? 2u : 1u) + mx +
-                                        ((hi_bits & 0x80808080u) ? (uint32_t)(CAP + 1) : 0u);
+            key[k] = settle_equal ? 1u : (REG || ULAT ? 2u : 1u) + mx;
             rank[k] = atomicAdd(&hist[key[k]], 1u);
         }
         if constexpr (ULAT)
@@ -1103,29 +1032,17 @@ __global__ void __launch_bounds__(TPB) short_kernel(const SegArgs s) {
                 row_planes_multi<GROUPS, NBITS, M>(StagedSrc{smem, A.off, A.len}, StagedSrc{smem, B.off, B.len}, emit);
                 continue;
             }
-            if constexpr (REG) {
-                // the sort put the byte-equal pairs (key 1) last: whole warps of them leave here
-                if (p >= (int)hist[1]) {
-                    const long long idx = tile0 + i;
-                    store_settled<MEASURE>(s, GATHER ? (long long)s.list[idx] : idx, 1.0, F_EQUAL);
-                    continue;
-                }
+            // REG, one measure.  The sort put the byte-equal pairs (key 1) last: whole warps of them leave here
+            if (p >= (int)hist[1]) {
+                const long long idx = tile0 + i;
+                store_settled<MEASURE>(s, GATHER ? (long long)s.list[idx] : idx, 1.0, F_EQUAL);
+                continue;
+            }
+            {
                 const StagedStr A = staged_str(va, i, (uint32_t)L::off_sva, off_stage_a),
                                 B = staged_str(vb, i, (uint32_t)L::off_svb, off_stage_b);
                 v = row_planes<is_multi(MEASURE) ? 0 : MEASURE, NBITS, M>(StagedSrc{smem, A.off, A.len},
                                                                          StagedSrc{smem, B.off, B.len}, ints);
-            } else {
-                const uint32_t or_a = load_string<WORDS, TPB>(va, stage_a, store.wa_);
-                const uint32_t or_b = load_string<WORDS, TPB>(vb, stage_b, store.wb_);
-                bool equal = false;  // with the prefilter, byte-equal pairs were settled before the sort
-                if (!PREFILTER_EQUAL && na == nb) {
-                    const int nw = (na + 3) >> 2;
-                    uint32_t diff = 0;
-                    for (int w = 0; w < nw; w++) diff |= store.wa(w) ^ store.wb(w);
-                    equal = diff == 0;
-                }
-                const bool ascii = ASCII_ONLY || ((or_a | or_b) & 0x80808080u) == 0;
-                v = row_short<M>(is_multi(MEASURE) ? 0 : MEASURE, store, na, nb, equal, ascii, ints);
             }
             const long long idx = tile0 + i;
             const long long row = GATHER ? (long long)s.list[idx] : idx;
