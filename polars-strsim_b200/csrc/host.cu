@@ -1449,7 +1449,7 @@ static Alphabet classify_alphabet(unsigned o, unsigned n) {  // OR / AND over ev
     return al;
 }
 
-// One measure over a segment: the plane path for ASCII-only columns (tiles of 256 x 4 rows), the two
+// One measure over a segment: the plane path for ASCII-only columns (tiles of 256 x SINGLE_RPT rows), the two
 // launches of launch_general otherwise.  Variants that were measured and dropped -- a kernel without
 // shared-memory staging (0.70 vs 0.58 ms: the sorted threads' scattered global loads cost 32 L1TEX
 // wavefronts per warp instruction), the per-thread table path for ASCII columns (0.58 vs 0.48 ms), other
@@ -1474,8 +1474,8 @@ static int launch_fused(ThreadCtx& ctx, Alphabet al, const SegArgs& args, long l
 template <int GROUPS>
 static int launch_multi(ThreadCtx& ctx, Alphabet al, const SegArgs& args, long long rows, cudaStream_t st) {
     constexpr int ME = MULTI_BASE + GROUPS;
-    // tiles of 256 x 3 rows: 48 KB of shared memory per CTA, so four CTAs (32 warps) share an SM; measured
-    // on C2 (all five measures): 256x4 0.775 ms, 256x3 0.748 ms, 128x4 0.81 ms, 256x2 0.80 ms, 512x2 1.05 ms
+    // tiles of 256 x FUSED_RPT rows: 33 KB of shared memory per CTA, five CTAs (40 warps) share an SM (see the
+    // tile shapes above; with a fixed stride of tiles per CTA, in round 1, 256 x 3 was the best shape)
     switch (al) {
         case ALPHA_ASCII32:
             return launch_short<uint32_t, ME, 256, FUSED_RPT, false, 32, true, true>(ctx, args, rows, st);
